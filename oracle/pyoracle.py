@@ -1,0 +1,264 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_build/liboracle.so (the C++ f64 restatement of the reference hot path,
+see rtw_oracle.hpp).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+W64, W32 = 0, 1
+LIBM, PORTABLE = 0, 1
+LAMBERTIAN, METAL, DIELECTRIC, INVISIBLE = 0, 1, 2, 3
+V_MISS, V_ABSORB, V_SPECULAR, V_DIFFUSE = 0, 1, 2, 3
+EPS = 2.220446049250313e-16
+
+
+def build(force: bool = False) -> str:
+    """Compile the restatement with g++ (make); returns the .so path."""
+    srcs = [os.path.join(_HERE, f) for f in ("rtw_oracle.hpp", "oracle_capi.cpp", "oracle_cli.cpp", "Makefile")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("r", C.c_double), ("g", C.c_double), ("b", C.c_double), ("param", C.c_double)]
+
+
+class Camera(C.Structure):
+    _fields_ = [(n, C.c_double * 3) for n in ("center", "pixel00", "du", "dv", "ddu", "ddv", "background")] + [
+        ("defocus_angle", C.c_double), ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32),
+        ("max_depth", C.c_uint32)]
+
+
+class CameraBuilder(C.Structure):
+    _fields_ = [("aspect_ratio", C.c_double), ("has_aspect", C.c_uint32), ("width", C.c_uint32), ("has_width", C.c_uint32),
+                ("height", C.c_uint32), ("has_height", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
+                ("background", C.c_double * 3), ("vfov", C.c_double), ("lookfrom", C.c_double * 3),
+                ("lookat", C.c_double * 3), ("vup", C.c_double * 3), ("defocus_angle", C.c_double),
+                ("focus_dist", C.c_double)]
+
+
+class Options(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("tmin", C.c_double), ("rng_mode", C.c_uint32), ("math_mode", C.c_uint32),
+                ("faithful_bvh", C.c_uint32), ("threads", C.c_int32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "paths", "box_tests", "box_builds", "node_visits", "sphere_tests",
+                                          "plane_tests", "light_tests", "lambertian", "metal", "dielectric", "absorbed",
+                                          "missed", "depth_out")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class BvhStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("nodes", "leaves", "depth", "max_leaf", "prims")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_uniform.restype = C.c_double
+        L.orc_uniform.argtypes = [C.c_uint64] + [C.c_uint32] * 6
+        L.orc_uniform_index.restype = C.c_uint32
+        L.orc_uniform_index.argtypes = [C.c_uint64] + [C.c_uint32] * 6
+        L.orc_sincos.argtypes = [C.c_double, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_desc_simple.restype = C.c_void_p
+        L.orc_desc_simple.argtypes = [C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_int32]
+        L.orc_desc_destroy.argtypes = [C.c_void_p]
+        L.orc_desc_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_desc_copy.argtypes = [C.c_void_p] * 8
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_bvh_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_trace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                      C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_scatter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 12
+        L.orc_get_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
+        L.orc_render.restype = C.c_double
+        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_path_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+        L.orc_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_hardware_threads.restype = C.c_uint32
+        L.orc_camera_build.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def philox4x32_10(ctr, key):
+    ctr = np.asarray(ctr, dtype=np.uint32)
+    key = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_p(ctr), _p(key), _p(out))
+    return out
+
+
+def uniform(seed, pixel, sample, vertex, k, rng_mode=W64, kind=0):
+    return lib().orc_uniform(seed, pixel, sample, vertex, k, rng_mode, kind)
+
+
+def uniform_index(seed, pixel, sample, vertex, k, n, rng_mode=W64):
+    return lib().orc_uniform_index(seed, pixel, sample, vertex, k, rng_mode, n)
+
+
+def sincos(phi, math_mode=LIBM):
+    s, c = C.c_double(), C.c_double()
+    lib().orc_sincos(phi, math_mode, C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+class SceneDesc:
+    """Plain-data scene: what scenes::simple builds (scenes/src/lib.rs:155-233), as arrays."""
+
+    def __init__(self, spheres, sphere_mat, materials, planes, plane_mat, lights, cam_builder=None):
+        self.spheres = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        self.sphere_mat = np.ascontiguousarray(sphere_mat, dtype=np.uint32)
+        self.materials = materials  # ctypes array of Material
+        self.planes = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 6)
+        self.plane_mat = np.ascontiguousarray(plane_mat, dtype=np.uint32)
+        self.lights = np.ascontiguousarray(lights, dtype=np.float64).reshape(-1, 4)
+        self.cam_builder = cam_builder
+
+    def materials_array(self):
+        return np.array([[m.kind, m.r, m.g, m.b, m.param] for m in self.materials], dtype=np.float64).reshape(-1, 5)
+
+
+def make_materials(rows):
+    arr = (Material * len(rows))()
+    for i, (kind, r, g, b, param) in enumerate(rows):
+        arr[i] = Material(int(kind), float(r), float(g), float(b), float(param))
+    return arr
+
+
+def scene_simple(seed=20261018, n=11, p_lambertian=0.8, p_metal=0.95, ground=0) -> SceneDesc:
+    L = lib()
+    h = L.orc_desc_simple(seed, n, p_lambertian, p_metal, ground)
+    try:
+        cnt = np.zeros(4, dtype=np.uint64)
+        L.orc_desc_counts(h, _p(cnt))
+        ns, nm, npl, nl = (int(x) for x in cnt)
+        spheres = np.zeros((ns, 4)); smat = np.zeros(ns, dtype=np.uint32)
+        mats = (Material * nm)()
+        planes = np.zeros((npl, 6)); pmat = np.zeros(npl, dtype=np.uint32)
+        lights = np.zeros((nl, 4))
+        cb = CameraBuilder()
+        L.orc_desc_copy(h, _p(spheres), _p(smat), C.cast(mats, C.c_void_p), _p(planes), _p(pmat), _p(lights),
+                        C.cast(C.pointer(cb), C.c_void_p))
+    finally:
+        L.orc_desc_destroy(h)
+    return SceneDesc(spheres, smat, mats, planes, pmat, lights, cb)
+
+
+def camera_build(cb: CameraBuilder) -> Camera:
+    cam = Camera()
+    lib().orc_camera_build(C.byref(cb), C.byref(cam))
+    return cam
+
+
+def camera_for(desc: SceneDesc, width, height, spp, max_depth, vfov=40.0) -> Camera:
+    """What bin/src/main.rs:72-79 does with the scene's CameraBuilder."""
+    cb = CameraBuilder.from_buffer_copy(desc.cam_builder)
+    cb.vfov = vfov
+    cb.aspect_ratio = width / height
+    cb.has_aspect = 1
+    cb.width, cb.has_width, cb.height, cb.has_height = width, 1, height, 1
+    cb.spp, cb.max_depth = spp, max_depth
+    return camera_build(cb)
+
+
+class Scene:
+    def __init__(self, desc: SceneDesc):
+        self.desc = desc
+        L = lib()
+        self.h = L.orc_scene_create(len(desc.sphere_mat), _p(desc.spheres), _p(desc.sphere_mat), len(desc.materials),
+                                    C.cast(desc.materials, C.c_void_p), len(desc.plane_mat), _p(desc.planes),
+                                    _p(desc.plane_mat), len(desc.lights), _p(desc.lights))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_scene_destroy(self.h)
+            self.h = None
+
+    def bvh_stats(self):
+        s = BvhStats()
+        lib().orc_scene_bvh_stats(self.h, C.byref(s))
+        return {n: int(getattr(s, n)) for n, _ in s._fields_}
+
+    def trace_batch(self, o, d, tmin=EPS, tmax=float("inf"), faithful=False):
+        o = np.ascontiguousarray(o, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+        n = o.shape[0]
+        prim = np.zeros(n, dtype=np.int32); t = np.zeros(n)
+        cnt = Counters()
+        lib().orc_trace_batch(self.h, n, _p(o), _p(d), tmin, tmax, _p(prim), _p(t), int(faithful), C.byref(cnt))
+        return prim, t, cnt.as_dict()
+
+    def scatter_batch(self, o, d, pixel, sample, vertex, opts: Options):
+        o = np.ascontiguousarray(o, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+        n = o.shape[0]
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        vertex = np.ascontiguousarray(vertex, dtype=np.uint32)
+        prim = np.zeros(n, dtype=np.int32); t = np.zeros(n); kind = np.zeros(n, dtype=np.uint32)
+        p = np.zeros((n, 3)); normal = np.zeros((n, 3)); dr = np.zeros((n, 3)); w = np.zeros((n, 3))
+        lib().orc_scatter_batch(self.h, C.byref(opts), n, _p(o), _p(d), _p(pixel), _p(sample), _p(vertex), _p(prim), _p(t),
+                                _p(kind), _p(p), _p(normal), _p(dr), _p(w))
+        return dict(prim=prim, t=t, kind=kind, p=p, normal=normal, dir=dr, weight=w)
+
+    def render(self, cam: Camera, opts: Options, row_begin=0, row_end=0xFFFFFFFF):
+        img = np.zeros((cam.height, cam.width, 3))
+        cnt = Counters(); pan = C.c_uint32(0)
+        sec = lib().orc_render(self.h, C.byref(cam), C.byref(opts), _p(img), row_begin, row_end, C.byref(cnt), C.byref(pan))
+        return img, sec, cnt.as_dict(), bool(pan.value)
+
+    def path_radiance(self, cam: Camera, opts: Options, i, j, sample):
+        i = np.ascontiguousarray(i, dtype=np.uint32); j = np.ascontiguousarray(j, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(i), 3))
+        lib().orc_path_radiance(self.h, C.byref(cam), C.byref(opts), len(i), _p(i), _p(j), _p(sample), _p(out))
+        return out
+
+
+def get_rays(cam: Camera, opts: Options, i, j, sample):
+    i = np.ascontiguousarray(i, dtype=np.uint32); j = np.ascontiguousarray(j, dtype=np.uint32)
+    sample = np.ascontiguousarray(sample, dtype=np.uint32)
+    o = np.zeros((len(i), 3)); d = np.zeros((len(i), 3))
+    lib().orc_get_rays(C.byref(cam), C.byref(opts), len(i), _p(i), _p(j), _p(sample), _p(o), _p(d))
+    return o, d
+
+
+def resolve(rgb_sum, spp):
+    a = np.ascontiguousarray(rgb_sum, dtype=np.float64)
+    out = np.zeros(a.shape, dtype=np.uint8)
+    lib().orc_resolve(_p(a), a.size, spp, _p(out))
+    return out
+
+
+def options(seed=20261018, tmin=EPS, rng_mode=W64, math_mode=LIBM, faithful_bvh=False, threads=0) -> Options:
+    return Options(seed, tmin, rng_mode, math_mode, int(faithful_bvh), threads)
+
+
+def hardware_threads():
+    return int(lib().orc_hardware_threads())

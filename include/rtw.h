@@ -1,0 +1,183 @@
+/* rtw.h — C ABI of the B200 (sm_100a) CUDA path-tracing backend for N9199/ray_tracing_weekend.
+ *
+ * This is the drop-in boundary for ONE path of the reference: Camera::render(world, lights)
+ * (shared/src/camera.rs:295-297 -> render_internal :315-388 -> ray_colour_tail_call :460-522) and
+ * the per-ray operations it is made of.  The reference has no FFI of its own; these are the entry
+ * points a `cuda` crate of the Rust workspace binds (see INTEGRATION.md for the extern "C" block).
+ *
+ * Conventions: all structs are plain little-endian POD; the caller owns every buffer it passes and
+ * the library keeps no pointer after a call returns; handles are opaque and owned by the library;
+ * calls are blocking; a handle must not be used from two threads at once (distinct handles may).
+ * Every function returns RTW_OK (0) or a negative RTW_E_* code and never aborts/unwinds;
+ * rtw_last_error() gives the thread-local message of the last failure.
+ * There is NO CPU fallback: without a CUDA device every compute call returns RTW_E_NO_DEVICE.
+ */
+#ifndef RTW_H
+#define RTW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RTW_API __attribute__((visibility("default")))
+#else
+#define RTW_API
+#endif
+
+enum {
+    RTW_OK = 0,
+    RTW_E_INVALID = -1,      /* bad argument / inconsistent scene (the reference would panic) */
+    RTW_E_CUDA = -2,         /* CUDA runtime error, text in rtw_last_error()                  */
+    RTW_E_NO_DEVICE = -3,    /* no CUDA device visible                                        */
+    RTW_E_UNSUPPORTED = -4,  /* valid in the reference but outside this backend's scope       */
+    RTW_E_NOMEM = -5
+};
+
+/* DynMaterial flattened (shared/src/material.rs:251-325).  Textures: SolidColour only
+ * (shared/src/texture.rs:15-22). */
+enum {
+    RTW_LAMBERTIAN = 0, /* Lambertian{SolidColour(r,g,b)}        material.rs:327-376 */
+    RTW_METAL = 1,      /* Metal{albedo=(r,g,b), fuzz=param}     material.rs:378-421 */
+    RTW_DIELECTRIC = 2, /* Dialectric{index_of_refraction=param} material.rs:423-488 */
+    RTW_INVISIBLE = 3   /* Invisible: never scatters, emits 0    material.rs:319-325 */
+};
+typedef struct { uint32_t kind; uint32_t reserved; double r, g, b, param; } rtw_material;
+
+/* Sphere{center, radius} (shared/src/entities/sphere.rs:25-30) */
+typedef struct { double cx, cy, cz, r; } rtw_sphere;
+/* Plane{point, normal}; normal is normalised by the library like Plane::new (entities/plane.rs:27-39).
+ * One-sided: only rays with dir.normal > EPSILON hit (plane.rs:62-63). */
+typedef struct { double px, py, pz, nx, ny, nz; } rtw_plane;
+
+/* The fields of Camera the render loop reads (shared/src/camera.rs:231-260). */
+typedef struct {
+    double center[3], pixel00_loc[3], pixel_delta_u[3], pixel_delta_v[3];
+    double defocus_disk_u[3], defocus_disk_v[3], background[3];
+    double defocus_angle;
+    uint32_t image_width, image_height, samples_per_pixel, max_depth;
+} rtw_camera;
+
+/* CameraBuilder (shared/src/camera.rs:28-112); has_* mirror the Option<> fields. */
+typedef struct {
+    double aspect_ratio; uint32_t has_aspect_ratio;
+    uint32_t image_width, has_image_width, image_height, has_image_height;
+    uint32_t samples_per_pixel, max_depth;
+    double background[3], vfov, lookfrom[3], lookat[3], vup[3], defocus_angle, focus_dist;
+} rtw_camera_builder;
+
+enum { RTW_F32 = 0,   /* fast path: FP32 arithmetic, 24-bit uniforms (stream layout W32)            */
+       RTW_F64 = 1 }; /* reference-exact path: the reference's f64 operation order, no FMA
+                         contraction, 53-bit uniforms (stream layout W64)                           */
+enum { RTW_MEGAKERNEL = 0, RTW_WAVEFRONT = 1 };
+enum { RTW_FLAG_FIX_NAN = 1u,       /* zero NaN components of a sample before accumulation (the dead
+                                       ray_colour twin did, camera.rs:434); OFF = reference behaviour */
+       RTW_FLAG_COUNT_EVENTS = 2u };/* fill the event counters of rtw_stats (slower)                 */
+
+typedef struct {
+    uint64_t seed;        /* Philox4x32-10 key                                                      */
+    double   tmin;        /* lower end of the world.hit range; reference value DBL_EPSILON (camera.rs:473) */
+    uint32_t precision;   /* RTW_F32 | RTW_F64                                                      */
+    uint32_t mode;        /* RTW_MEGAKERNEL | RTW_WAVEFRONT                                         */
+    uint32_t flags;
+    uint32_t reserved;
+} rtw_opts;
+
+typedef struct {
+    uint64_t paths;        /* ray_colour_call invocations (camera.rs:326)                           */
+    uint64_t rays;         /* world.hit invocations (camera.rs:473): primary + every bounce         */
+    uint64_t node_visits;  /* inner BVH nodes visited (two child-box tests each)   [COUNT_EVENTS]   */
+    uint64_t sphere_tests; /* ray-sphere tests during world.hit                    [COUNT_EVENTS]   */
+    uint64_t light_tests;  /* Sphere::hit calls made by lights.pdf_value           [COUNT_EVENTS]   */
+    uint64_t lambertian, metal, dielectric; /* scatter calls by material           [COUNT_EVENTS]   */
+    uint64_t absorbed, missed, depth_out;   /* path terminations by reason         [COUNT_EVENTS]   */
+    double   kernel_ms;    /* CUDA-event time of the render kernels of this call                    */
+    double   total_ms;     /* CUDA-event time of the whole call's device work incl. copies          */
+    uint32_t launches;     /* kernels launched by this call                                         */
+    uint32_t reserved;
+} rtw_stats;
+
+typedef struct rtw_scene rtw_scene;
+
+/* ---- host-side helpers (no GPU needed) -------------------------------------------------------- */
+RTW_API int         rtw_abi_version(void);
+RTW_API const char* rtw_last_error(void);
+/* CameraBuilder::build (shared/src/camera.rs:114-218), bit-identical f64 arithmetic. */
+RTW_API int         rtw_camera_build(const rtw_camera_builder* builder, rtw_camera* out);
+/* Philox4x32-10 block function; the device code runs the same rounds (KATs in tests/). */
+RTW_API void        rtw_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Image partition used by the tile entry points: tiles of RTW_TILE_W x RTW_TILE_H pixels in
+ * row-major tile order; tile k belongs to rank k % world and is that rank's local tile k / world. */
+#define RTW_TILE_W 16
+#define RTW_TILE_H 16
+RTW_API uint32_t    rtw_tiles_total(uint32_t width, uint32_t height);
+RTW_API uint32_t    rtw_tiles_per_rank(uint32_t width, uint32_t height, uint32_t world); /* padded: same on every rank */
+
+/* ---- device management ------------------------------------------------------------------------ */
+RTW_API int rtw_device_count(void);           /* >= 0, or RTW_E_* */
+
+/* ---- scene ------------------------------------------------------------------------------------ */
+/* Replaces what scenes::simple hands to render: `world` = BoundedVolumeHierarchy::from(HittableList)
+ * of planes + spheres (scenes/src/lib.rs:228), `lights` = HittableList of spheres (:229).
+ * Copies the inputs, builds and flattens a BVH on the host and uploads it to the current device.
+ * Primitive ids reported by the batch calls: planes first (0..n_planes-1), then spheres, each in
+ * input order.  A scene with Lambertian materials and no lights is RTW_E_INVALID (the reference
+ * panics on the first light sample, hittable_list.rs:414-419). */
+RTW_API int  rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material, size_t n_spheres,
+                      const rtw_plane* planes, const uint32_t* plane_material, size_t n_planes,
+                      const rtw_material* materials, size_t n_materials,
+                      const rtw_sphere* lights, size_t n_lights,
+                      rtw_scene** out);
+RTW_API void rtw_scene_destroy(rtw_scene* scene);
+/* nodes, leaves, depth, max leaf size, bytes resident on the device */
+RTW_API int  rtw_scene_info(const rtw_scene* scene, uint64_t out[5]);
+
+/* ---- Camera::render ---------------------------------------------------------------------------- */
+/* Replaces Camera::render (shared/src/camera.rs:295-297).  Host buffers, both optional:
+ *   rgb_sum: [height][width][3] f64, un-normalised sample sums == the Colour inside each
+ *            SampledColour (camera.rs:381-387); row j = 0 is the BOTTOM row like the reference.
+ *   rgb8:    [height][width][3] u8, resolved like Colour::write_colour (shared/src/colour.rs:15-36),
+ *            same row order (bin/src/main.rs:94-98 reverses rows when writing the PPM). */
+RTW_API int rtw_render(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts,
+               double* rgb_sum, uint8_t* rgb8, rtw_stats* stats);
+
+/* Multi-GPU building blocks (one process per GPU; the caller gathers tile buffers with NCCL).
+ * d_tiles is a DEVICE buffer of rtw_tiles_per_rank() * RTW_TILE_H * RTW_TILE_W * 3 elements
+ * (float for RTW_F32, double for RTW_F64) that receives this rank's tiles; `stream` is a
+ * cudaStream_t (0 = default stream). */
+RTW_API int rtw_render_tiles_device(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts,
+                            uint32_t rank, uint32_t world, void* d_tiles, void* stream, rtw_stats* stats);
+/* d_tiles_all: [world][tiles_per_rank][TILE_H][TILE_W][3] as gathered on the root; writes DEVICE
+ * buffers d_rgb_sum ([h][w][3] f64, may be NULL) and d_rgb8 ([h][w][3] u8, may be NULL). */
+RTW_API int rtw_untile_resolve_device(const void* d_tiles_all, uint32_t precision, uint32_t width, uint32_t height,
+                              uint32_t world, uint32_t samples_per_pixel, double* d_rgb_sum, uint8_t* d_rgb8,
+                              void* stream);
+
+/* ---- per-ray operations (parity surface) ------------------------------------------------------- */
+/* Hittable::hit of the world for a batch of rays (shared/src/hittable.rs:173; bvh.rs:163-188).
+ * o, d: [n][3] f64 host arrays; prim_id: -1 = miss; t: +inf on a miss.  precision as in rtw_opts. */
+RTW_API int rtw_trace_batch(rtw_scene* scene, const double* o, const double* d, size_t n, double tmin, double tmax,
+                    uint32_t precision, int32_t* prim_id, double* t);
+/* One path vertex for a batch of rays: world.hit(tmin..inf) + Material::scatter + for Lambertian the
+ * MixturePdf sample and weight (camera.rs:473-521), drawing from stream (seed; pixel, sample, vertex).
+ * kind: 0 miss, 1 absorbed, 2 specular (Reflect), 3 diffuse (Scatter).  Outputs [n] / [n][3] f64. */
+RTW_API int rtw_scatter_batch(rtw_scene* scene, const rtw_opts* opts, const double* o, const double* d, size_t n,
+                      const uint32_t* pixel, const uint32_t* sample, const uint32_t* vertex,
+                      int32_t* prim_id, double* t, uint32_t* kind, double* p, double* normal,
+                      double* dir, double* weight);
+/* Camera::get_ray (camera.rs:274-293) for a batch of (i, j, sample). */
+RTW_API int rtw_get_rays(const rtw_camera* camera, const rtw_opts* opts, const uint32_t* i, const uint32_t* j,
+                 const uint32_t* sample, size_t n, double* o, double* d);
+/* Radiance of individual paths: ray_colour_call for (i, j, sample) (camera.rs:439-457). */
+RTW_API int rtw_path_radiance(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, const uint32_t* i,
+                      const uint32_t* j, const uint32_t* sample, size_t n, double* rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTW_H */

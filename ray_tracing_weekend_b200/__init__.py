@@ -1,0 +1,13 @@
+"""ray_tracing_weekend_b200 — B200 (sm_100a) CUDA backend for the render path of
+N9199/ray_tracing_weekend: Camera::render -> BVH traversal + Sphere::hit -> Material::scatter ->
+spp accumulation -> gamma, behind the C ABI of include/rtw.h.
+
+The CUDA library is the product; this package is the host-side mirror of the reference's interface
+used by tests and bench.py.  Importing works without a GPU (nvcc builds the library), computing
+does not: there is no CPU fallback."""
+from . import scenes  # noqa: F401
+from ._lib import (EPSILON, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_MEGAKERNEL, RTW_WAVEFRONT,  # noqa: F401
+                   RtwError, library_path, load)
+from .api import (INVISIBLE, BoundedVolumeHierarchy, Camera, CameraBuilder, Dialectric, HittableList, Lambertian, Material,  # noqa: F401
+                  Metal, Plane, RenderOptions, Scene, Sphere, device_count, philox4x32_10, tiles_per_rank, tiles_total,
+                  untile_resolve_device, write_ppm)

@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference's render interface over the C ABI (include/rtw.h).
+
+Names follow the reference (N9199/ray_tracing_weekend) so tests read like its own:
+  CameraBuilder().with_image_width(3)...build() -> Camera         shared/src/camera.rs:44-219
+  Camera.render(world, lights) -> rows of sample sums               shared/src/camera.rs:295-297
+  Sphere / Plane / Lambertian / Metal / Dialectric / INVISIBLE      shared/src/entities, material.rs
+  HittableList.add, BoundedVolumeHierarchy.from_list                shared/src/hittable_collections
+  scenes.simple(seed)                                               scenes/src/lib.rs:155-233
+All arithmetic happens in librtw_cuda.so; nothing here computes pixels, and nothing falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (EPSILON, RTW_DIELECTRIC, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_INVISIBLE,
+                   RTW_LAMBERTIAN, RTW_MEGAKERNEL, RTW_METAL, RTW_WAVEFRONT, RtwError, rtw_camera, rtw_camera_builder,
+                   rtw_material, rtw_opts, rtw_plane, rtw_sphere, rtw_stats)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---- materials (shared/src/material.rs) --------------------------------------------------------------
+@dataclass(frozen=True)
+class Material:
+    kind: int
+    colour: tuple = (0.0, 0.0, 0.0)
+    param: float = 0.0
+
+    def pod(self) -> rtw_material:
+        return rtw_material(self.kind, 0, float(self.colour[0]), float(self.colour[1]), float(self.colour[2]), float(self.param))
+
+
+def Lambertian(colour) -> Material:            # Lambertian::new_with_colour, material.rs:349-351
+    return Material(RTW_LAMBERTIAN, tuple(colour), 0.0)
+
+
+def Metal(albedo, fuzz) -> Material:           # Metal::new, material.rs:401-405
+    return Material(RTW_METAL, tuple(albedo), float(fuzz))
+
+
+def Dialectric(index_of_refraction) -> Material:   # Dialectric::new, material.rs:443-448  (the reference's spelling)
+    return Material(RTW_DIELECTRIC, (1.0, 1.0, 1.0), float(index_of_refraction))
+
+
+INVISIBLE = Material(RTW_INVISIBLE)             # INVISIBLE_PTR, material.rs:319-322
+
+
+# ---- entities -------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Sphere:                                   # entities/sphere.rs:25-47
+    center: tuple
+    radius: float
+    material: Material
+
+
+@dataclass(frozen=True)
+class Plane:                                    # entities/plane.rs:21-39
+    point: tuple
+    normal: tuple
+    material: Material
+
+
+class HittableList:                             # hittable_collections/hittable_list.rs:247-294
+    def __init__(self):
+        self.spheres: List[Sphere] = []
+        self.planes: List[Plane] = []
+
+    def add(self, obj):
+        if isinstance(obj, Sphere):
+            self.spheres.append(obj)
+        elif isinstance(obj, Plane):
+            self.planes.append(obj)
+        else:
+            raise TypeError(f"{type(obj).__name__} is outside the CUDA backend's scope (Sphere, Plane)")
+
+    def len(self):
+        return len(self.spheres) + len(self.planes)
+
+    __len__ = len
+
+    def is_empty(self):
+        return self.len() == 0
+
+
+class BoundedVolumeHierarchy:                   # hittable_collections/bvh.rs:106-143
+    """Carries the primitives; the device BVH is built by rtw_scene_create."""
+
+    def __init__(self, hlist: HittableList):
+        self.list = hlist
+
+    @classmethod
+    def from_list(cls, hlist: HittableList):
+        return cls(hlist)
+
+    def len(self):
+        return self.list.len()
+
+
+def _as_list(world) -> HittableList:
+    if isinstance(world, BoundedVolumeHierarchy):
+        return world.list
+    if isinstance(world, HittableList):
+        return world
+    raise TypeError("world / lights must be a HittableList or a BoundedVolumeHierarchy")
+
+
+@dataclass
+class RenderOptions:
+    seed: int = 20261018
+    tmin: float = EPSILON                      # camera.rs:473
+    precision: int = RTW_F32
+    mode: int = RTW_MEGAKERNEL
+    flags: int = 0
+
+    def pod(self) -> rtw_opts:
+        return rtw_opts(self.seed, self.tmin, self.precision, self.mode, self.flags, 0)
+
+
+class Scene:
+    """rtw_scene handle: world (planes + spheres) and lights uploaded to the current CUDA device."""
+
+    def __init__(self, world, lights):
+        w, l = _as_list(world), _as_list(lights)
+        if l.planes:
+            raise RtwError(_lib.RTW_E_UNSUPPORTED, "lights: only spheres are supported")
+        ns, npl, nl = len(w.spheres), len(w.planes), len(l.spheres)
+        mats = (rtw_material * max(1, ns + npl))()
+        sph = (rtw_sphere * max(1, ns))()
+        smat = np.arange(ns, dtype=np.uint32)
+        pl = (rtw_plane * max(1, npl))()
+        pmat = np.arange(ns, ns + npl, dtype=np.uint32)
+        li = (rtw_sphere * max(1, nl))()
+        for k, s in enumerate(w.spheres):
+            sph[k] = rtw_sphere(*map(float, s.center), float(s.radius))
+            mats[k] = s.material.pod()
+        for k, p in enumerate(w.planes):
+            pl[k] = rtw_plane(*map(float, p.point), *map(float, p.normal))
+            mats[ns + k] = p.material.pod()
+        for k, s in enumerate(l.spheres):
+            li[k] = rtw_sphere(*map(float, s.center), float(s.radius))
+        self._h = C.c_void_p()
+        L = _lib.load()
+        _lib.check(L.rtw_scene_create(C.cast(sph, C.c_void_p), _p(smat), ns, C.cast(pl, C.c_void_p), _p(pmat), npl,
+                                      C.cast(mats, C.c_void_p), ns + npl, C.cast(li, C.c_void_p), nl, C.byref(self._h)))
+        self.n_spheres, self.n_planes, self.n_lights = ns, npl, nl
+        self.upload_bytes = ns * 32 + ns * 4 + npl * 48 + npl * 4 + (ns + npl) * 40 + nl * 32
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.load().rtw_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def info(self):
+        out = np.zeros(5, dtype=np.uint64)
+        _lib.check(_lib.load().rtw_scene_info(self._h, _p(out)))
+        return dict(nodes=int(out[0]), leaves=int(out[1]), depth=int(out[2]), max_leaf=int(out[3]), device_bytes=int(out[4]))
+
+    # Hittable::hit for a batch (hittable.rs:173)
+    def trace_batch(self, o, d, tmin=EPSILON, tmax=float("inf"), precision=RTW_F32):
+        o = np.ascontiguousarray(o, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(d, dtype=np.float64).reshape(-1, 3)
+        n = o.shape[0]
+        prim = np.full(n, -1, dtype=np.int32)
+        t = np.full(n, np.inf)
+        _lib.check(_lib.load().rtw_trace_batch(self._h, _p(o), _p(d), n, tmin, tmax, precision, _p(prim), _p(t)))
+        return prim, t
+
+    def scatter_batch(self, o, d, pixel, sample, vertex, opts: RenderOptions):
+        o = np.ascontiguousarray(o, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(d, dtype=np.float64).reshape(-1, 3)
+        n = o.shape[0]
+        pixel, sample, vertex = (np.ascontiguousarray(a, dtype=np.uint32) for a in (pixel, sample, vertex))
+        prim = np.zeros(n, dtype=np.int32); t = np.zeros(n); kind = np.zeros(n, dtype=np.uint32)
+        p, normal, dr, w = (np.zeros((n, 3)) for _ in range(4))
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_scatter_batch(self._h, C.byref(po), _p(o), _p(d), n, _p(pixel), _p(sample), _p(vertex),
+                                                 _p(prim), _p(t), _p(kind), _p(p), _p(normal), _p(dr), _p(w)))
+        return dict(prim=prim, t=t, kind=kind, p=p, normal=normal, dir=dr, weight=w)
+
+    def path_radiance(self, camera: "Camera", opts: RenderOptions, i, j, sample):
+        i, j, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (i, j, sample))
+        out = np.zeros((len(i), 3))
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_path_radiance(self._h, C.byref(camera.pod), C.byref(po), _p(i), _p(j), _p(sample), len(i), _p(out)))
+        return out
+
+    def render(self, camera: "Camera", opts: Optional[RenderOptions] = None, want_sum=True, want_rgb8=True):
+        """rtw_render: host buffers out.  Returns (rgb_sum [h,w,3] f64 | None, rgb8 [h,w,3] u8 | None, stats dict)."""
+        opts = opts or RenderOptions()
+        h, w = camera.pod.image_height, camera.pod.image_width
+        rgb_sum = np.zeros((h, w, 3)) if want_sum else None
+        rgb8 = np.zeros((h, w, 3), dtype=np.uint8) if want_rgb8 else None
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render(self._h, C.byref(camera.pod), C.byref(po), _p(rgb_sum), _p(rgb8), C.byref(st)))
+        return rgb_sum, rgb8, st.as_dict()
+
+    def render_tiles_device(self, camera: "Camera", opts: RenderOptions, rank: int, world: int, d_tiles_ptr: int, stream: int = 0,
+                            want_stats=True):
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render_tiles_device(self._h, C.byref(camera.pod), C.byref(po), rank, world, C.c_void_p(d_tiles_ptr),
+                                                       C.c_void_p(stream), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+
+def untile_resolve_device(d_tiles_all_ptr, precision, width, height, world, spp, d_rgb_sum_ptr=0, d_rgb8_ptr=0, stream=0):
+    _lib.check(_lib.load().rtw_untile_resolve_device(C.c_void_p(d_tiles_all_ptr), precision, width, height, world, spp,
+                                                     C.c_void_p(d_rgb_sum_ptr) if d_rgb_sum_ptr else None,
+                                                     C.c_void_p(d_rgb8_ptr) if d_rgb8_ptr else None, C.c_void_p(stream)))
+
+
+def tiles_per_rank(width, height, world):
+    return int(_lib.load().rtw_tiles_per_rank(width, height, world))
+
+
+def tiles_total(width, height):
+    return int(_lib.load().rtw_tiles_total(width, height))
+
+
+# ---- camera (shared/src/camera.rs) -------------------------------------------------------------------------
+class Camera:
+    def __init__(self, pod: rtw_camera):
+        self.pod = pod
+
+    @property
+    def image_width(self):
+        return self.pod.image_width
+
+    @property
+    def image_height(self):
+        return self.pod.image_height
+
+    def get_rays(self, i, j, sample, opts: Optional[RenderOptions] = None):
+        """Camera::get_ray for a batch (camera.rs:274-293)."""
+        opts = opts or RenderOptions()
+        i, j, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (i, j, sample))
+        o = np.zeros((len(i), 3)); d = np.zeros((len(i), 3))
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_get_rays(C.byref(self.pod), C.byref(po), _p(i), _p(j), _p(sample), len(i), _p(o), _p(d)))
+        return o, d
+
+    def render(self, world, lights, opts: Optional[RenderOptions] = None):
+        """Camera::render (camera.rs:295-297): [height][width][3] f64 sample sums, row 0 = bottom row."""
+        scene = Scene(world, lights)
+        try:
+            rgb_sum, _, _ = scene.render(self, opts, want_sum=True, want_rgb8=False)
+        finally:
+            scene.close()
+        return rgb_sum
+
+
+class CameraBuilder:                            # camera.rs:28-219
+    def __init__(self, pod: Optional[rtw_camera_builder] = None):
+        if pod is None:
+            pod = rtw_camera_builder()
+            pod.samples_per_pixel, pod.max_depth, pod.vfov, pod.focus_dist = 10, 10, 90.0, 10.0
+            pod.lookat[2] = -1.0
+            pod.vup[1] = 1.0
+        self.pod = pod
+
+    def _with(self, **kw):
+        pod = rtw_camera_builder.from_buffer_copy(self.pod)
+        for k, v in kw.items():
+            if isinstance(v, (tuple, list, np.ndarray)):
+                getattr(pod, k)[:] = [float(x) for x in v]
+            else:
+                setattr(pod, k, v)
+        return CameraBuilder(pod)
+
+    def with_aspect_ratio(self, a): return self._with(aspect_ratio=float(a), has_aspect_ratio=1)
+    def with_image_width(self, w): return self._with(image_width=int(w), has_image_width=1)
+    def with_image_height(self, h): return self._with(image_height=int(h), has_image_height=1)
+    def with_samples_per_pixel(self, s): return self._with(samples_per_pixel=int(s))
+    def with_max_depth(self, d): return self._with(max_depth=int(d))
+    def with_background(self, c): return self._with(background=c)
+    def with_vfov(self, v): return self._with(vfov=float(v))
+    def with_lookfrom(self, p): return self._with(lookfrom=p)
+    def with_lookat(self, p): return self._with(lookat=p)
+    def with_vup(self, p): return self._with(vup=p)
+    def with_defocus_angle(self, a): return self._with(defocus_angle=float(a))
+    def with_focus_dist(self, f): return self._with(focus_dist=float(f))
+
+    def build(self) -> Camera:
+        cam = rtw_camera()
+        _lib.check(_lib.load().rtw_camera_build(C.byref(self.pod), C.byref(cam)))
+        return Camera(cam)
+
+
+def philox4x32_10(ctr: Sequence[int], key: Sequence[int]) -> np.ndarray:
+    ctr = np.asarray(ctr, dtype=np.uint32); key = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    _lib.load().rtw_philox4x32_10(_p(ctr), _p(key), _p(out))
+    return out
+
+
+def device_count() -> int:
+    n = _lib.load().rtw_device_count()
+    if n < 0:
+        _lib.check(n)
+    return n
+
+
+def write_ppm(path, rgb8):
+    """bin/src/main.rs:89-104: ASCII P3, rows reversed (row 0 of the render is the bottom row)."""
+    h, w, _ = rgb8.shape
+    with open(path, "w") as f:
+        f.write(f"P3\n{w} {h}\n255\n")
+        for j in range(h - 1, -1, -1):
+            f.write("\n".join(f"{r} {g} {b}" for r, g, b in rgb8[j]) + "\n")

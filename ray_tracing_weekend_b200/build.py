@@ -1,0 +1,90 @@
+"""Build librtw_cuda.so (the C-ABI library of include/rtw.h) in-tree with nvcc for sm_100a.
+
+Three translation units: kernels_f32.cu (fast path, FMA on), kernels_f64.cu (reference-exact path,
+-fmad=false), capi.cu (extern "C" surface + host BVH builder).  cudart is linked statically so the
+.so loads next to torch's own runtime without LD_LIBRARY_PATH games.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB_PATH = os.path.join(LIB_DIR, "librtw_cuda.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+UNITS = [
+    ("kernels_f32.cu", []),
+    ("kernels_f64.cu", ["-fmad=false"]),
+    ("capi.cu", []),
+    ("../host/rtw_host_capi.cpp", []),
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: cannot build librtw_cuda.so")
+    return exe
+
+
+def _sources():
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    host = os.path.join(HERE, "host")
+    out += [os.path.join(host, f) for f in os.listdir(host)]
+    out.append(os.path.join(os.path.dirname(HERE), "include", "rtw_host.h"))
+    out.append(os.path.join(os.path.dirname(HERE), "include", "rtw.h"))
+    out.append(os.path.abspath(__file__))
+    return out
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out, file=sys.stderr)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + (out or ""))
+    link = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", LIB_PATH, *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)
+    # the reference's `bin` with --backend cuda (host mirror CLI)
+    cli = [shutil.which("g++") or "g++", "-O2", "-std=c++17", os.path.join(HERE, "host", "rtw_bin.cpp"), "-o",
+           os.path.join(LIB_DIR, "rtw_bin"), "-L" + LIB_DIR, "-lrtw_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("rtw_bin build failed: " + " ".join(cli) + "\n" + r.stdout)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

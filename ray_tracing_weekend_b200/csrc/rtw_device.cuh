@@ -1,0 +1,220 @@
+// rtw_device.cuh — device-side building blocks of the B200 path tracer: vectors, Philox4x32-10
+// streams, the two arithmetic policies and the flattened scene views.
+//
+// Two instantiations of everything below exist:
+//   Fast  (T = float,  EXACT = false): FP32, FMA contraction allowed, reciprocal-direction slab
+//          tests, 24-bit uniforms (stream layout W32).  This is the throughput path.
+//   Exact (T = double, EXACT = true ): the reference's f64 operation order (compiled with
+//          -fmad=false so nothing is contracted), division-based slab tests, per-sphere AABB
+//          pre-test, 53-bit uniforms (stream layout W64).  Bit-compatible with an f64 CPU run of the
+//          same algorithm and stream.
+// Reference citations are relative to the reference repository (N9199/ray_tracing_weekend).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace rtw {
+
+#define RTW_HD __host__ __device__ __forceinline__
+#define RTW_D __device__ __forceinline__
+
+constexpr int kStackDepth = 32;      // traversal stack entries per thread (shared memory)
+constexpr int kMaxTreeDepth = 31;    // enforced by the host builder
+constexpr int kTileW = 16, kTileH = 16, kWarpTileW = 8, kWarpTileH = 4;
+constexpr int kWarpTilesPerTile = (kTileW * kTileH) / 32;
+
+// ---------------------------------------------------------------------------------------------
+template <class T> struct V3 { T x, y, z; };
+template <class T> RTW_HD V3<T> mk(T x, T y, T z) { return V3<T>{x, y, z}; }
+template <class T> RTW_HD V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <class T> RTW_HD V3<T> operator-(V3<T> a, V3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <class T> RTW_HD V3<T> operator-(V3<T> a) { return {-a.x, -a.y, -a.z}; }
+template <class T> RTW_HD V3<T> operator*(V3<T> a, T s) { return {a.x * s, a.y * s, a.z * s}; }
+template <class T> RTW_HD V3<T> operator*(V3<T> a, V3<T> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+template <class T> RTW_HD V3<T> operator/(V3<T> a, T s) { return {a.x / s, a.y / s, a.z / s}; }
+template <class T> RTW_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }       // vec.rs:68-72
+template <class T> RTW_HD V3<T> cross(V3<T> a, V3<T> b) {                                              // vec.rs:74-82
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <class T> RTW_HD T sqlen(V3<T> a) { return dot(a, a); }
+
+template <class T> struct Ray { V3<T> o, d; };
+template <class T> RTW_HD V3<T> at(const Ray<T>& r, T t) { return r.o + r.d * t; }                     // ray.rs:25-28
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Same constants as curand_philox4x32_x.h.
+RTW_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+#ifdef __CUDA_ARCH__
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Uniform stream of one (pixel, sample, vertex): counter = (pixel, sample, vertex, block), key = seed.
+// The 32-bit outputs of consecutive blocks form one word sequence x[0], x[1], ...
+//   W32 (fast):  uniform k <- x[k]                      24-bit
+//   W64 (exact): uniform k <- x[2k] | x[2k+1] << 32     53-bit, rand 0.8 `Standard` / `Open01` semantics
+template <bool EXACT> struct Stream {
+    uint32_t k0, k1, pixel, sample, vertex;
+    uint32_t k, blk, b0, b1, b2, b3;
+    RTW_HD Stream(uint64_t seed, uint32_t pixel_, uint32_t sample_, uint32_t vertex_)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), pixel(pixel_), sample(sample_), vertex(vertex_), k(0), blk(0xffffffffu),
+          b0(0), b1(0), b2(0), b3(0) {}
+    RTW_HD uint32_t word32(uint32_t idx) {
+        uint32_t block = idx >> 2;
+        if (block != blk) {
+            uint32_t o[4];
+            philox4x32_10(pixel, sample, vertex, block, k0, k1, o);
+            b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+            blk = block;
+        }
+        uint32_t lo = (idx & 1) ? b1 : b0, hi = (idx & 1) ? b3 : b2;
+        return (idx & 2) ? hi : lo;
+    }
+    RTW_HD uint64_t next64() { uint64_t lo = word32(2 * k), hi = word32(2 * k + 1); k++; return lo | (hi << 32); }
+    RTW_HD uint32_t next32() { return word32(k++); }
+};
+// Standard: [0,1)
+RTW_HD double standard(Stream<true>& s) { return (double)(s.next64() >> 11) * 0x1.0p-53; }
+RTW_HD float standard(Stream<false>& s) { return (float)(s.next32() >> 8) * 0x1.0p-24f; }
+// Open01: (0,1)
+RTW_HD double open01(Stream<true>& s) { return (double)(s.next64() >> 12) * 0x1.0p-52 + 0x1.0p-53; }
+RTW_HD float open01(Stream<false>& s) { return (float)(s.next32() >> 9) * 0x1.0p-23f + 0x1.0p-24f; }
+// Uniform::new_inclusive(-0.5, 0.5) (camera.rs:275): rand's scale = 1/(1-eps) nudged down, see oracle.
+RTW_HD double jitter(Stream<true>& s, double scale) { return (double)(s.next64() >> 12) * 0x1.0p-52 * scale + (-0.5); }
+RTW_HD float jitter(Stream<false>& s, float) { return (float)(s.next32() >> 8) * 0x1.0p-24f * 1.0f + (-0.5f); }
+// uniform index in [0, n)
+RTW_HD uint32_t uindex(Stream<true>& s, uint32_t n) {
+    uint64_t w = s.next64();
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__umul64hi(w, (uint64_t)n);
+#else
+    return (uint32_t)(((unsigned __int128)w * n) >> 64);
+#endif
+}
+RTW_HD uint32_t uindex(Stream<false>& s, uint32_t n) {
+    uint32_t w = s.next32();
+#ifdef __CUDA_ARCH__
+    return __umulhi(w, n);
+#else
+    return (uint32_t)(((uint64_t)w * n) >> 32);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic policies.
+template <class T, bool EXACT> struct M;
+
+template <> struct M<double, true> {
+    static constexpr double PI = 3.14159265358979323846264338327950288;
+    static constexpr double EPS = 2.220446049250313e-16;
+    static RTW_HD double inf() { return __builtin_huge_val(); }
+    static RTW_HD double max_(double a, double b) { return fmax(a, b); }    // f64::max ignores NaN
+    static RTW_HD double min_(double a, double b) { return fmin(a, b); }
+    static RTW_HD double sqrt_(double a) { return sqrt(a); }
+    static RTW_HD V3<double> normalize(V3<double> a) { return a / sqrt(sqlen(a)); }                  // vec.rs:84-94
+    static RTW_HD double div_pi(double a) { return a / PI; }
+    // sin/cos of phi = 2*PI*r: fixed IEEE operation sequence (Cody-Waite by pi/2 + fdlibm kernels),
+    // no FMA — repeated bit for bit by any f64 implementation of the same sequence.
+    static RTW_HD void sincos_2pi(double r, double* s, double* c) {
+        double phi = 2. * PI * r;
+        const double two_over_pi = 6.36619772367581382433e-01;
+        const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+        int n = (int)(phi * two_over_pi + 0.5);
+        double fn = (double)n;
+        double y = (phi - fn * pio2_1) - fn * pio2_1t;
+        double z = y * y;
+        const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                     S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+        const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                     C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+        double ps = S1 + z * (S2 + z * (S3 + z * (S4 + z * (S5 + z * S6))));
+        double pc = C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6))));
+        double sy = y + (y * z) * ps;
+        double cy = (1. - 0.5 * z) + (z * z) * pc;
+        switch (n & 3) {
+            case 0: *s = sy; *c = cy; break;
+            case 1: *s = cy; *c = -sy; break;
+            case 2: *s = -sy; *c = -cy; break;
+            default: *s = -cy; *c = sy; break;
+        }
+    }
+};
+
+template <> struct M<float, false> {
+    static constexpr float PI = 3.14159265358979323846f;
+    static constexpr float EPS = 2.220446049250313e-16f;   // the reference's f64::EPSILON, representable in f32
+    static RTW_HD float inf() { return __builtin_huge_valf(); }
+    static RTW_HD float max_(float a, float b) { return fmaxf(a, b); }
+    static RTW_HD float min_(float a, float b) { return fminf(a, b); }
+    static RTW_HD float sqrt_(float a) { return sqrtf(a); }
+    static RTW_HD V3<float> normalize(V3<float> a) {
+#ifdef __CUDA_ARCH__
+        return a * rsqrtf(sqlen(a));
+#else
+        return a / sqrtf(sqlen(a));
+#endif
+    }
+    static RTW_HD float div_pi(float a) { return a * 0.318309886183790671538f; }
+    static RTW_HD void sincos_2pi(float r, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+        sincospif(2.f * r, s, c);
+#else
+        *s = sinf(2.f * PI * r); *c = cosf(2.f * PI * r);
+#endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Flattened scene.  Spheres are stored in BVH-leaf order ("sorted" index); info = prim_id << 2 | kind.
+enum MatKind : uint32_t { LAMBERTIAN = 0, METAL = 1, DIELECTRIC = 2, INVISIBLE = 3 };
+
+template <class T> struct Vec4T { T x, y, z, w; };
+template <> struct __align__(16) Vec4T<float> { float x, y, z, w; };
+template <> struct __align__(16) Vec4T<double> { double x, y, z, w; };
+
+// Inner node with both child boxes.  child >= 0: inner node index; child < 0: leaf, ~child =
+// first_sorted_sphere << 4 | (count - 1), count in 0..16 encoded as (count-1)&15 with a flag for 0
+template <class T> struct __align__(16) Node {
+    T lmin[3], lmax[3], rmin[3], rmax[3];
+    int32_t left, right;
+    int32_t pad[2];
+};
+constexpr int32_t kEmptyLeaf = (int32_t)0x80000000;   // leaf with no spheres
+RTW_HD int32_t encode_leaf(uint32_t first, uint32_t count) { return count == 0 ? kEmptyLeaf : ~(int32_t)((first << 4) | (count - 1)); }
+
+template <class T> struct PlaneT { V3<T> point, normal; uint32_t info; uint32_t pad; T albedo[3]; T param; };
+
+template <class T> struct SceneView {
+    const Node<T>* nodes;          // BFS order, node 0 = root (global memory)
+    const Node<T>* top_nodes;      // the first n_top nodes again, possibly in shared memory
+    const Vec4T<T>* spheres;       // sorted: (cx, cy, cz, r)
+    const Vec4T<T>* sphere_mat;    // sorted: (albedo r, g, b, param)
+    const uint32_t* sphere_info;   // sorted: prim_id << 2 | kind
+    const PlaneT<T>* planes;
+    const Vec4T<T>* lights;        // (cx, cy, cz, r) in the lights list's insertion order
+    int32_t n_nodes, n_top, n_spheres, n_planes, n_lights;
+};
+
+template <class T> struct CameraT {
+    V3<T> center, pixel00, du, dv, ddu, ddv, background;
+    T defocus_angle, jitter_scale;
+    uint32_t width, height, spp, max_depth;
+};
+
+struct DeviceCounters {   // u64 slots in global memory
+    unsigned long long paths, rays, node_visits, sphere_tests, light_tests, lambertian, metal, dielectric, absorbed, missed, depth_out;
+};
+
+}  // namespace rtw

@@ -1,0 +1,645 @@
+// rtw_kernels.cuh — intersection, shading and the render / batch kernels, templated on the
+// arithmetic policy (see rtw_device.cuh).  Included by kernels_f32.cu (fast) and kernels_f64.cu (exact).
+#pragma once
+#include "rtw_device.cuh"
+
+namespace rtw {
+
+template <class T> struct Hit {
+    V3<T> p, normal;       // HitRecord p / normal (shared/src/hittable.rs:102-129)
+    T t;
+    bool front_face;
+    uint32_t info;         // prim_id << 2 | kind
+    V3<T> albedo;
+    T param;
+};
+
+struct Tally {             // per-thread event counters (only live when COUNT)
+    uint32_t node_visits = 0, sphere_tests = 0, light_tests = 0, lambertian = 0, metal = 0, dielectric = 0,
+             absorbed = 0, missed = 0, depth_out = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Ray / box.  Exact: AABoxHit for AABBox::hit (shared/src/hittable.rs:38-87) verbatim.
+RTW_D bool box_hit_exact(const double* mn, const double* mx, const Ray<double>& r, double start, double end) {
+    using Md = M<double, true>;
+    double x_tmin = (mn[0] - r.o.x) / r.d.x, x_tmax = (mx[0] - r.o.x) / r.d.x;
+    if (signbit(r.d.x)) { double s = x_tmin; x_tmin = x_tmax; x_tmax = s; }
+    double tmin = x_tmin, tmax = x_tmax;
+    double y_tmin = (mn[1] - r.o.y) / r.d.y, y_tmax = (mx[1] - r.o.y) / r.d.y;
+    if (signbit(r.d.y)) { double s = y_tmin; y_tmin = y_tmax; y_tmax = s; }
+    if (tmax < y_tmin || tmin > y_tmax) return false;
+    tmin = Md::max_(tmin, y_tmin); tmax = Md::min_(tmax, y_tmax);
+    double z_tmin = (mn[2] - r.o.z) / r.d.z, z_tmax = (mx[2] - r.o.z) / r.d.z;
+    if (signbit(r.d.z)) { double s = z_tmin; z_tmin = z_tmax; z_tmax = s; }
+    if (tmax < z_tmin || tmin > z_tmax) return false;
+    tmin = Md::max_(tmin, z_tmin); tmax = Md::min_(tmax, z_tmax);
+    return Md::max_(start, tmin) <= Md::min_(end, tmax);
+}
+
+// Fast: reciprocal-direction slabs, one FMA per plane.  oi = o * inv_d.  NaNs (0 * inf) drop out of
+// fminf/fmaxf, which makes the axis unconstrained — conservative.
+struct RayAux { float ix, iy, iz, ox, oy, oz; };
+RTW_D bool box_hit_fast(const float* mn, const float* mx, const RayAux& a, float tmin, float tmax, float* tnear) {
+    float x0 = fmaf(mn[0], a.ix, -a.ox), x1 = fmaf(mx[0], a.ix, -a.ox);
+    float y0 = fmaf(mn[1], a.iy, -a.oy), y1 = fmaf(mx[1], a.iy, -a.oy);
+    float z0 = fmaf(mn[2], a.iz, -a.oz), z1 = fmaf(mx[2], a.iz, -a.oz);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    *tnear = tn;
+    return tn <= tf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ray / sphere: Sphere::hit (shared/src/entities/sphere.rs:61-80).  Returns the accepted root.
+// sphere_root: the reference's textbook quadratic, verbatim (used by the exact path in f64).
+template <class T> RTW_D bool sphere_root(const Vec4T<T>& s, const Ray<T>& r, T a, T start, T end, T* t_out) {
+    V3<T> oc = mk<T>(r.o.x - s.x, r.o.y - s.y, r.o.z - s.z);
+    T half_b = dot(r.d, oc);
+    T c = sqlen(oc) - s.w * s.w;
+    T disc = half_b * half_b - a * c;
+    if (!(disc > T(0))) return false;
+    T sq = sqrt(disc);
+    T root = (-half_b - sq) / a;
+    if (!(start <= root && root <= end)) {
+        root = (-half_b + sq) / a;
+        if (!(start <= root && root <= end)) return false;
+    }
+    *t_out = root;
+    return true;
+}
+
+// FP32 version of the same test.  hb^2 - a*c cancels catastrophically in FP32 for distant origins
+// (|oc| >> r), so the discriminant is taken from the perpendicular residual l = oc - (hb/a) d
+// (disc/a = r^2 - |l|^2, all terms of magnitude r), and the root that would cancel in -k -/+ s is
+// obtained from the product of the roots (c/a)/q.  The sign of c = |oc|^2 - r^2 — which side of the
+// surface the origin is on — decides the sign of the small root exactly as in the f64 reference.
+// Root selection and the inclusive range test are the reference's.
+RTW_D bool sphere_root_fast(const Vec4T<float>& s, const Ray<float>& r, float inv_a, float start, float end, float* t_out) {
+    float ocx = r.o.x - s.x, ocy = r.o.y - s.y, ocz = r.o.z - s.z;
+    float hb = r.d.x * ocx + r.d.y * ocy + r.d.z * ocz;
+    float k = hb * inv_a;
+    float lx = fmaf(-k, r.d.x, ocx), ly = fmaf(-k, r.d.y, ocy), lz = fmaf(-k, r.d.z, ocz);
+    float r2 = s.w * s.w;
+    float dq = r2 - (lx * lx + ly * ly + lz * lz);          // disc / a
+    if (!(dq > 0.f)) return false;
+    float sq = sqrtf(dq * inv_a);                             // sqrt(disc) / a
+    float c_a = ((ocx * ocx + ocy * ocy + ocz * ocz) - r2) * inv_a;
+    float q = -(k + copysignf(sq, k));
+    float other = c_a / q;
+    float near_root = k < 0.f ? other : q, far_root = k < 0.f ? q : other;
+    float root = near_root;
+    if (!(start <= root && root <= end)) {
+        root = far_root;
+        if (!(start <= root && root <= end)) return false;
+    }
+    *t_out = root;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Closest hit: Hittable::hit of the world (bvh.rs:163-188 + hittable_list.rs:394-406), i.e.
+// argmin-t over planes passing Plane::hit and spheres passing (own AABB test) && Sphere::hit.
+// The reference visits both children with the un-shrunk range and keeps the first minimum; here the
+// range is shrunk to the best t so far and children are visited near-first — the argmin is the same
+// except for exact-t ties and the documented grazing cases.
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    bool found = false;
+    T best_t = tmax;
+    int32_t best = -1;      // >= 0 sorted sphere index; <= -2: plane ~index
+    // planes: Plane::hit (entities/plane.rs:61-76), one-sided
+    for (int i = 0; i < sc.n_planes; ++i) {
+        const PlaneT<T>& pl = sc.planes[i];
+        T denom = dot(r.d, pl.normal);
+        if (!(denom > Mt::EPS)) continue;
+        T t = -dot(r.o - pl.point, pl.normal) / denom;
+        if (!(tmin <= t && t <= tmax)) continue;
+        if (!found || t < best_t) { found = true; best_t = t; best = -2 - i; }
+    }
+    T a = sqlen(r.d);
+    RayAux aux;
+    float inv_a = 0.f;
+    if constexpr (!EXACT) {
+        inv_a = 1.f / a;
+        aux.ix = 1.f / r.d.x; aux.iy = 1.f / r.d.y; aux.iz = 1.f / r.d.z;
+        aux.ox = r.o.x * aux.ix; aux.oy = r.o.y * aux.iy; aux.oz = r.o.z * aux.iz;
+    }
+    int sp = 0;
+    int32_t cur = 0;        // root inner node
+    for (;;) {
+        if (cur >= 0) {
+            const Node<T>& nd = cur < sc.n_top ? sc.top_nodes[cur] : sc.nodes[cur];
+            if (COUNT) tl.node_visits++;
+            bool hl, hr; T tl_near = T(0), tr_near = T(0);
+            if constexpr (EXACT) {
+                hl = box_hit_exact(nd.lmin, nd.lmax, r, tmin, best_t);
+                hr = box_hit_exact(nd.rmin, nd.rmax, r, tmin, best_t);
+            } else {
+                hl = box_hit_fast(nd.lmin, nd.lmax, aux, tmin, best_t, &tl_near);
+                hr = box_hit_fast(nd.rmin, nd.rmax, aux, tmin, best_t, &tr_near);
+            }
+            int32_t l = nd.left, rr = nd.right;
+            if (hl && hr) {
+                bool swap = !EXACT && tr_near < tl_near;
+                int32_t near = swap ? rr : l, far = swap ? l : rr;
+                stack[sp * stride] = far; sp++;
+                cur = near;
+                continue;
+            }
+            if (hl) { cur = l; continue; }
+            if (hr) { cur = rr; continue; }
+        } else if (cur != kEmptyLeaf) {
+            uint32_t enc = (uint32_t)~cur;
+            uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                Vec4T<T> s = sc.spheres[i];
+                if constexpr (EXACT) {
+                    // BoundedHittable::bounded_hit (hittable.rs:191-196): the sphere's own box first
+                    // (Sphere::new's box, sphere.rs:42-45), with the un-shrunk range like the reference
+                    double mn[3] = {s.x - s.w, s.y - s.w, s.z - s.w}, mx[3] = {s.x + s.w, s.y + s.w, s.z + s.w};
+                    if (!box_hit_exact(mn, mx, r, tmin, tmax)) continue;
+                }
+                if (COUNT) tl.sphere_tests++;
+                T t;
+                bool hs;
+                if constexpr (EXACT) hs = sphere_root<T>(s, r, a, tmin, tmax, &t);
+                else hs = sphere_root_fast(s, r, inv_a, tmin, tmax, &t);
+                if (hs && (!found || t < best_t)) { found = true; best_t = t; best = (int32_t)i; }
+            }
+        }
+        if (sp == 0) break;
+        sp--;
+        cur = stack[sp * stride];
+    }
+    if (!found) return false;
+    // HitRecord::new (hittable.rs:102-129) for the winner only
+    V3<T> outward;
+    h->t = best_t;
+    h->p = at(r, best_t);
+    if (best >= 0) {
+        Vec4T<T> s = sc.spheres[best];
+        outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;                                 // sphere.rs:82-83
+        Vec4T<T> m = sc.sphere_mat[best];
+        h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = sc.sphere_info[best];
+    } else {
+        const PlaneT<T>& pl = sc.planes[-2 - best];
+        outward = pl.normal;
+        h->albedo = mk<T>(pl.albedo[0], pl.albedo[1], pl.albedo[2]); h->param = pl.param; h->info = pl.info;
+    }
+    h->front_face = dot(r.d, outward) < T(0);
+    h->normal = h->front_face ? outward : -outward;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry/src/onb.rs:8-35
+template <class T, bool EXACT> struct Onb {
+    V3<T> u, v, w;
+    RTW_D explicit Onb(V3<T> n) {
+        w = M<T, EXACT>::normalize(n);
+        V3<T> a = fabs(w.x) > T(0.9) ? mk<T>(0, 1, 0) : mk<T>(1, 0, 0);
+        v = M<T, EXACT>::normalize(cross(w, a));
+        u = cross(w, v);
+    }
+    RTW_D V3<T> transform(V3<T> a) const { return ((mk<T>(0, 0, 0) + u * a.x) + v * a.y) + w * a.z; }
+};
+
+template <class T> RTW_D V3<T> reflect(V3<T> s, V3<T> o) { return s - (o * T(2)) * dot(s, o); }       // vec.rs:103-107
+template <class T, bool EXACT> RTW_D V3<T> refract(V3<T> s, V3<T> o, T eta) {                         // vec.rs:109-116
+    T cos_theta = M<T, EXACT>::min_(dot(s, -o), T(1));
+    V3<T> perp = (s + o * cos_theta) * eta;
+    V3<T> par = o * (-M<T, EXACT>::sqrt_(T(1) - sqlen(perp)));
+    return perp + par;
+}
+
+// Sphere::pdf_value (sphere.rs:101-111) summed over the lights list (hittable_list.rs:408-412).
+// Fast path: Sphere::hit(ray, 0..=inf) succeeds iff disc > 0 and the larger root is >= 0, i.e. iff
+// disc > 0 && (hb <= 0 || c <= 0) — no square root or division until a light is actually hit.
+template <class T, bool EXACT, bool COUNT>
+RTW_D T lights_pdf_value(const SceneView<T>& sc, V3<T> origin, V3<T> dir, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    T acc = T(0);
+    T a = sqlen(dir);
+    Ray<T> r{origin, dir};
+    for (int i = 0; i < sc.n_lights; ++i) {
+        Vec4T<T> s = sc.lights[i];
+        if (COUNT) tl.light_tests++;
+        T v = T(0);
+        V3<T> cd = mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z);
+        bool hit;
+        T distance_squared;
+        if constexpr (EXACT) {
+            T t;
+            hit = sphere_root<T>(s, r, a, T(0), Mt::inf(), &t);
+            distance_squared = sqlen(cd);
+        } else {
+            T hb = -dot(dir, cd);
+            distance_squared = sqlen(cd);
+            T c = distance_squared - s.w * s.w;
+            T k = hb / a;
+            V3<T> l = mk<T>(-cd.x - k * dir.x, -cd.y - k * dir.y, -cd.z - k * dir.z);
+            hit = (s.w * s.w - sqlen(l) > T(0)) && (hb <= T(0) || c <= T(0));
+        }
+        if (hit) {
+            T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
+            T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
+            v = T(1) / solid_angle;
+        }
+        acc = acc + v;
+    }
+    return acc / (T)sc.n_lights;
+}
+
+// Sphere::random (sphere.rs:114-127)
+template <class T, bool EXACT>
+RTW_D V3<T> sphere_random(const Vec4T<T>& s, V3<T> origin, Stream<EXACT>& rng) {
+    using Mt = M<T, EXACT>;
+    V3<T> direction = mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z);
+    T distance = Mt::sqrt_(sqlen(direction));
+    Onb<T, EXACT> uvw(direction);
+    T r1 = standard(rng);
+    T r2 = standard(rng);
+    T z = T(1) + r1 * (Mt::sqrt_(T(1) - s.w * s.w / (distance * distance)) - T(1));
+    T sn, cs;
+    Mt::sincos_2pi(r2, &sn, &cs);
+    T x = cs * Mt::sqrt_(T(1) - z * z);
+    T y = sn * Mt::sqrt_(T(1) - z * z);
+    return uvw.transform(mk<T>(x, y, z));
+}
+
+enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE = 3 };
+
+// Material::scatter (+ the Scatter branch of ray_colour_tail_call, camera.rs:484-521).
+// Returns the vertex kind; on V_SPECULAR / V_DIFFUSE writes the next ray and the factor for `mult`.
+template <class T, bool EXACT, bool COUNT>
+RTW_D uint32_t shade(const SceneView<T>& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    uint32_t kind = h.info & 3u;
+    if (kind == LAMBERTIAN) {                                   // material.rs:357-376
+        if (COUNT) tl.lambertian++;
+        Onb<T, EXACT> uvw(h.normal);                            // CosinePdf::new, pdf.rs:39-43
+        V3<T> dir;
+        if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
+            uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
+            dir = sphere_random<T, EXACT>(sc.lights[idx], h.p, rng);
+        } else {                                                // CosineWeightedHemisphere, utils.rs:146-161
+            T r1 = standard(rng);
+            T r2 = standard(rng);
+            T sn, cs;
+            Mt::sincos_2pi(r1, &sn, &cs);
+            T x = cs * Mt::sqrt_(r2);
+            T y = sn * Mt::sqrt_(r2);
+            T z = Mt::sqrt_(T(1) - r2);
+            dir = uvw.transform(mk<T>(x, y, z));
+        }
+        T light_v = lights_pdf_value<T, EXACT, COUNT>(sc, h.p, dir, tl);
+        V3<T> nd = Mt::normalize(dir);
+        T cos_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));   // CosinePdf::value, pdf.rs:46-49
+        T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
+        T scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));  // material.rs:372-375
+        *next = Ray<T>{h.p, dir};
+        *weight = (h.albedo * scattering_pdf) / pdf_value;      // camera.rs:518
+        return V_DIFFUSE;
+    }
+    if (kind == METAL) {                                        // material.rs:407-421
+        if (COUNT) tl.metal++;
+        V3<T> reflected = reflect(Mt::normalize(r.d), h.normal);
+        V3<T> ball;
+        for (;;) {                                              // UnitSphere: uniform in the unit ball, utils.rs:99-122
+            T a = T(2) * standard(rng) - T(1);
+            T b = T(2) * standard(rng) - T(1);
+            T c = T(2) * standard(rng) - T(1);
+            ball = mk<T>(a, b, c);
+            if (sqlen(ball) < T(1)) break;
+        }
+        V3<T> dir = reflected + ball * h.param;
+        if (dot(dir, h.normal) > T(0)) { *next = Ray<T>{h.p, dir}; *weight = h.albedo; return V_SPECULAR; }
+        if (COUNT) tl.absorbed++;
+        return V_ABSORB;
+    }
+    if (kind == DIELECTRIC) {                                   // material.rs:457-488
+        if (COUNT) tl.dielectric++;
+        T ratio = h.front_face ? T(1) / h.param : h.param;
+        V3<T> unit = Mt::normalize(r.d);
+        T cos_theta = Mt::min_(dot(unit, -h.normal), T(1));
+        T sin_theta = Mt::sqrt_(T(1) - cos_theta * cos_theta);
+        bool do_reflect = ratio * sin_theta > T(1);
+        if (!do_reflect) {
+            T r0 = (T(1) - ratio) / (T(1) + ratio);             // reflectance, material.rs:450-454
+            r0 = r0 * r0;
+            T om = T(1) - cos_theta;
+            T p5 = ((om * om) * (om * om)) * om;
+            do_reflect = (r0 + (T(1) - r0) * p5) > open01(rng);
+        }
+        V3<T> dir = do_reflect ? reflect(unit, h.normal) : refract<T, EXACT>(unit, h.normal, ratio);
+        *next = Ray<T>{h.p, dir};
+        *weight = mk<T>(1, 1, 1);
+        return V_SPECULAR;
+    }
+    if (COUNT) tl.absorbed++;                                   // Invisible: Material defaults, material.rs:32-49
+    return V_ABSORB;
+}
+
+// Camera::get_ray (camera.rs:274-293)
+template <class T, bool EXACT>
+RTW_D Ray<T> get_ray(const CameraT<T>& cam, uint32_t i, uint32_t j, Stream<EXACT>& rng) {
+    T ox = jitter(rng, cam.jitter_scale);
+    T oy = jitter(rng, cam.jitter_scale);
+    V3<T> pixel_sample = (cam.pixel00 + cam.du * ((T)i + ox)) + cam.dv * ((T)j + oy);
+    V3<T> origin = cam.center;
+    if (!(cam.defocus_angle <= M<T, EXACT>::EPS)) {
+        T a, b;
+        for (;;) {                                              // UnitDisk, utils.rs:124-144
+            a = T(2) * standard(rng) - T(1);
+            b = T(2) * standard(rng) - T(1);
+            if (a * a + T(0) * T(0) + b * b < T(1)) break;
+        }
+        origin = (cam.center + cam.ddu * a) + cam.ddv * b;
+    }
+    return Ray<T>{origin, pixel_sample - origin};
+}
+
+// One step of ray_colour_tail_call (camera.rs:460-522) for a live path.  Returns true when the path
+// finished and *value holds its radiance.
+template <class T> struct PathState {
+    Ray<T> r;
+    V3<T> mult, res;
+    uint32_t depth;
+};
+
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool path_step(const SceneView<T>& sc, const CameraT<T>& cam, uint64_t seed, T tmin, uint32_t pixel, uint32_t sample,
+                     PathState<T>& ps, V3<T>* value, int32_t* stack, int stride, uint32_t& nrays, Tally& tl) {
+    if (ps.depth == 0) {                                        // camera.rs:470-472
+        if (COUNT) tl.depth_out++;
+        *value = mk<T>(0, 0, 0) + ps.res;
+        return true;
+    }
+    nrays++;
+    Hit<T> h;
+    if (!closest_hit<T, EXACT, COUNT>(sc, ps.r, tmin, M<T, EXACT>::inf(), &h, stack, stride, tl)) {   // camera.rs:473-475
+        if (COUNT) tl.missed++;
+        *value = ps.mult * cam.background + ps.res;
+        return true;
+    }
+    V3<T> emitted = mk<T>(0, 0, 0);                             // Material::emitted default, material.rs:42-44
+    Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u);
+    Ray<T> next;
+    V3<T> w;
+    uint32_t kind = shade<T, EXACT, COUNT>(sc, ps.r, h, rng, &next, &w, tl);
+    if (kind == V_ABSORB) { *value = ps.mult * emitted + ps.res; return true; }       // camera.rs:484-486
+    if (kind == V_DIFFUSE) ps.res = ps.res + ps.mult * emitted;                       // camera.rs:519
+    ps.mult = ps.mult * w;
+    ps.r = next;
+    ps.depth -= 1;
+    return false;
+}
+
+template <class T> RTW_D V3<T> fix_nan(V3<T> v) { return mk<T>(v.x != v.x ? T(0) : v.x, v.y != v.y ? T(0) : v.y, v.z != v.z ? T(0) : v.z); }
+
+// ---------------------------------------------------------------------------------------------
+template <class T> struct RenderParams {
+    SceneView<T> scene;
+    CameraT<T> cam;
+    uint64_t seed;
+    T tmin;
+    uint32_t flags;
+    uint32_t rank, world, tiles_x, tiles_total, n_local_tiles;
+    T* tiles;                       // [n_local_tiles][kTileH][kTileW][3]
+    unsigned int* work_counter;
+    DeviceCounters* counters;
+    // shared-memory staging of the scene (fast path only): bytes of each section, 0 = keep in global
+    uint32_t smem_nodes, smem_spheres, smem_lights;
+};
+
+RTW_D uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool COUNT>
+RTW_D void flush_counters(DeviceCounters* c, uint32_t npaths, uint32_t nrays, const Tally& tl) {
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t p = warp_sum(npaths), r = warp_sum(nrays);
+    if (lane == 0) { atomicAdd(&c->paths, (unsigned long long)p); atomicAdd(&c->rays, (unsigned long long)r); }
+    if (COUNT) {
+        uint32_t v[9] = {tl.node_visits, tl.sphere_tests, tl.light_tests, tl.lambertian, tl.metal, tl.dielectric, tl.absorbed, tl.missed, tl.depth_out};
+        unsigned long long* dst = &c->node_visits;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            uint32_t s = warp_sum(v[i]);
+            if (lane == 0) atomicAdd(dst + i, (unsigned long long)s);
+        }
+    }
+}
+
+// Megakernel: persistent CTAs; each warp pulls 8x4-pixel warp tiles from this GPU's work queue
+// (an atomic counter); each lane owns one pixel and runs its spp paths back to back, regenerating a
+// camera ray as soon as its previous path ends (render_internal + ray_colour_tail_call,
+// camera.rs:315-388, 460-522).  Samples of a pixel are summed in sample order.
+template <class T, bool EXACT, bool COUNT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
+    SceneView<T> sc = P.scene;
+    if constexpr (!EXACT) {
+        // stage the scene in shared memory when the host decided it fits
+        unsigned char* cur = smem_raw + sizeof(int32_t) * kStackDepth * BLOCK;
+        if (P.smem_nodes) {
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
+            for (uint32_t i = threadIdx.x; i < P.smem_nodes / 16; i += BLOCK) dst[i] = src[i];
+            sc.top_nodes = reinterpret_cast<const Node<T>*>(cur);
+            sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<T>));
+            cur += P.smem_nodes;
+        }
+        if (P.smem_spheres) {
+            uint32_t n16 = P.smem_spheres / 16;       // one float4 per sphere, twice (geometry + material) + info
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.spheres);
+            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
+            sc.spheres = reinterpret_cast<const Vec4T<T>*>(cur);
+            cur += P.smem_spheres;
+            dst = reinterpret_cast<uint4*>(cur);
+            src = reinterpret_cast<const uint4*>(P.scene.sphere_mat);
+            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
+            sc.sphere_mat = reinterpret_cast<const Vec4T<T>*>(cur);
+            cur += P.smem_spheres;
+            uint32_t* dsti = reinterpret_cast<uint32_t*>(cur);
+            for (uint32_t i = threadIdx.x; i < (uint32_t)P.scene.n_spheres; i += BLOCK) dsti[i] = P.scene.sphere_info[i];
+            sc.sphere_info = dsti;
+            cur += (P.scene.n_spheres * 4 + 15) / 16 * 16;
+        }
+        if (P.smem_lights) {
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.lights);
+            for (uint32_t i = threadIdx.x; i < P.smem_lights / 16; i += BLOCK) dst[i] = src[i];
+            sc.lights = reinterpret_cast<const Vec4T<T>*>(cur);
+        }
+        __syncthreads();
+    }
+    const CameraT<T>& cam = P.cam;
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t* stack = stack_base + threadIdx.x;
+    const uint32_t n_warp_tiles = P.n_local_tiles * kWarpTilesPerTile;
+    uint32_t npaths = 0, nrays = 0;
+    Tally tl;
+    for (;;) {
+        uint32_t wt = 0;
+        if (lane == 0) wt = atomicAdd(P.work_counter, 1u);
+        wt = __shfl_sync(0xffffffffu, wt, 0);
+        if (wt >= n_warp_tiles) break;
+        uint32_t local_tile = wt / kWarpTilesPerTile, sub = wt % kWarpTilesPerTile;
+        uint32_t tile = local_tile * P.world + P.rank;
+        uint32_t lx = (sub % (kTileW / kWarpTileW)) * kWarpTileW + (lane % kWarpTileW);
+        uint32_t ly = (sub / (kTileW / kWarpTileW)) * kWarpTileH + (lane / kWarpTileW);
+        uint32_t i = (tile % P.tiles_x) * kTileW + lx, j = (tile / P.tiles_x) * kTileH + ly;
+        bool valid = tile < P.tiles_total && i < cam.width && j < cam.height;
+        uint32_t pixel = j * cam.width + i;
+        V3<T> acc = mk<T>(0, 0, 0);
+        uint32_t sample = 0;
+        bool alive = false;
+        PathState<T> ps;
+        ps.depth = 0;
+        for (;;) {
+            if (!alive && valid && sample < cam.spp) {
+                Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                ps.r = get_ray<T, EXACT>(cam, i, j, rng);
+                ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
+                alive = true;
+                npaths++;
+            }
+            if (!__any_sync(0xffffffffu, alive)) break;
+            if (alive) {
+                V3<T> value;
+                if (path_step<T, EXACT, COUNT>(sc, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+                    if (P.flags & 1u) value = fix_nan(value);
+                    acc = acc + value;                          // fold(Colour::default(), +), camera.rs:335
+                    alive = false;
+                    sample++;
+                }
+            }
+        }
+        T* out = P.tiles + ((size_t)local_tile * (kTileW * kTileH) + (size_t)ly * kTileW + lx) * 3;
+        out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;         // zeros for padding pixels
+    }
+    flush_counters<COUNT>(P.counters, npaths, nrays, tl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batch kernels (one thread per ray) — the parity surface.
+template <class T> struct BatchParams {
+    SceneView<T> scene;
+    CameraT<T> cam;
+    uint64_t seed;
+    T tmin, tmax;
+    uint32_t flags;
+    size_t n;
+    const double *o, *d;                     // [n][3]
+    const uint32_t *a, *b, *c;               // (pixel, sample, vertex) or (i, j, sample)
+    int32_t* prim; double* t; uint32_t* kind;
+    double *p, *normal, *dir, *weight, *rgb;
+};
+
+template <class T> RTW_D V3<T> load3(const double* p, size_t i) { return mk<T>((T)p[3 * i], (T)p[3 * i + 1], (T)p[3 * i + 2]); }
+template <class T> RTW_D void store3(double* p, size_t i, V3<T> v) { p[3 * i] = (double)v.x; p[3 * i + 1] = (double)v.y; p[3 * i + 2] = (double)v.z; }
+
+template <class T, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) trace_batch_kernel(BatchParams<T> P) {
+    __shared__ int32_t stack_s[kStackDepth * BLOCK];
+    size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= P.n) return;
+    Ray<T> r{load3<T>(P.o, idx), load3<T>(P.d, idx)};
+    Hit<T> h;
+    Tally tl;
+    bool hit = closest_hit<T, EXACT, false>(P.scene, r, P.tmin, P.tmax, &h, stack_s + threadIdx.x, BLOCK, tl);
+    P.prim[idx] = hit ? (int32_t)(h.info >> 2) : -1;
+    P.t[idx] = hit ? (double)h.t : __builtin_huge_val();
+}
+
+template <class T, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) {
+    __shared__ int32_t stack_s[kStackDepth * BLOCK];
+    size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= P.n) return;
+    Ray<T> r{load3<T>(P.o, idx), load3<T>(P.d, idx)};
+    Hit<T> h;
+    Tally tl;
+    V3<T> zero = mk<T>(0, 0, 0);
+    if (!closest_hit<T, EXACT, false>(P.scene, r, P.tmin, M<T, EXACT>::inf(), &h, stack_s + threadIdx.x, BLOCK, tl)) {
+        P.prim[idx] = -1; P.t[idx] = __builtin_huge_val(); P.kind[idx] = V_MISS;
+        store3(P.p, idx, zero); store3(P.normal, idx, zero); store3(P.dir, idx, zero); store3(P.weight, idx, zero);
+        return;
+    }
+    Stream<EXACT> rng(P.seed, P.a[idx], P.b[idx], P.c[idx]);
+    Ray<T> next{zero, zero};
+    V3<T> w = zero;
+    uint32_t kind = shade<T, EXACT, false>(P.scene, r, h, rng, &next, &w, tl);
+    P.prim[idx] = (int32_t)(h.info >> 2); P.t[idx] = (double)h.t; P.kind[idx] = kind;
+    store3(P.p, idx, h.p); store3(P.normal, idx, h.normal);
+    store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
+    store3(P.weight, idx, kind >= V_SPECULAR ? w : zero);
+}
+
+template <class T, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) get_rays_kernel(BatchParams<T> P, double* o, double* d) {
+    size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= P.n) return;
+    uint32_t i = P.a[idx], j = P.b[idx], s = P.c[idx];
+    Stream<EXACT> rng(P.seed, j * P.cam.width + i, s, 0u);
+    Ray<T> r = get_ray<T, EXACT>(P.cam, i, j, rng);
+    store3(o, idx, r.o); store3(d, idx, r.d);
+}
+
+template <class T, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) path_radiance_kernel(BatchParams<T> P) {
+    __shared__ int32_t stack_s[kStackDepth * BLOCK];
+    size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= P.n) return;
+    uint32_t i = P.a[idx], j = P.b[idx], s = P.c[idx];
+    uint32_t pixel = j * P.cam.width + i;
+    Stream<EXACT> rng(P.seed, pixel, s, 0u);
+    PathState<T> ps;
+    ps.r = get_ray<T, EXACT>(P.cam, i, j, rng);
+    ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = P.cam.max_depth;
+    V3<T> value;
+    uint32_t nrays = 0;
+    Tally tl;
+    while (!path_step<T, EXACT, false>(P.scene, P.cam, P.seed, P.tmin, pixel, s, ps, &value, stack_s + threadIdx.x, BLOCK, nrays, tl)) {}
+    if (P.flags & 1u) value = fix_nan(value);
+    store3(P.rgb, idx, value);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Untile + resolve: [world][tiles_per_rank][kTileH][kTileW][3] (T) -> rgb_sum f64 and / or rgb8.
+// Colour::write_colour (shared/src/colour.rs:15-36): c/spp -> sqrt -> clamp(0,1) -> (256*x) as u8
+// (`as u8` saturates and maps NaN to 0).  Done in f64 on the widened value in both precisions.
+template <class T>
+__global__ void untile_resolve_kernel(const T* tiles, uint32_t width, uint32_t height, uint32_t world, uint32_t tiles_per_rank,
+                                      uint32_t tiles_x, uint32_t spp, double* rgb_sum, uint8_t* rgb8) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= width || j >= height) return;
+    uint32_t tile = (j / kTileH) * tiles_x + (i / kTileW);
+    uint32_t rank = tile % world, local = tile / world;
+    const T* src = tiles + (((size_t)rank * tiles_per_rank + local) * (kTileW * kTileH) + (size_t)(j % kTileH) * kTileW + (i % kTileW)) * 3;
+    size_t dst = ((size_t)j * width + i) * 3;
+    double scale = 1. / (double)(int32_t)spp;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double v = (double)src[c];
+        if (rgb_sum) rgb_sum[dst + c] = v;
+        if (rgb8) {
+            double g = sqrt(v * scale);
+            if (g < 0.) g = 0.;
+            if (g > 1.) g = 1.;
+            double q = 256. * g;
+            uint8_t b = (q != q) ? 0 : (q >= 255. ? 255 : (q <= 0. ? 0 : (uint8_t)q));
+            rgb8[dst + c] = b;
+        }
+    }
+}
+
+}  // namespace rtw

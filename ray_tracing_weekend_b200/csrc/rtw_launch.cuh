@@ -1,0 +1,95 @@
+// rtw_launch.cuh — launcher bodies, instantiated once per arithmetic policy.
+#pragma once
+#include "rtw_launch.hpp"
+
+namespace rtw {
+
+constexpr int kRenderBlock = 256;
+constexpr int kBatchBlock = 128;
+constexpr size_t kSmemSceneBudget = 64 * 1024;   // per-CTA budget for staged scene data (fast path)
+
+template <class T, bool EXACT, bool COUNT>
+cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    auto kernel = render_mega_kernel<T, EXACT, COUNT, kRenderBlock>;
+    size_t smem = sizeof(int32_t) * kStackDepth * kRenderBlock;
+    P.smem_nodes = P.smem_spheres = P.smem_lights = 0;
+    if (!EXACT) {
+        size_t budget = kSmemSceneBudget;
+        size_t lights = (size_t)P.scene.n_lights * sizeof(Vec4T<T>);
+        if (lights && lights <= budget) { P.smem_lights = (uint32_t)lights; budget -= lights; }
+        size_t sph = (size_t)P.scene.n_spheres * sizeof(Vec4T<T>);
+        size_t sph_total = 2 * sph + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16;
+        size_t nodes = (size_t)P.scene.n_nodes * sizeof(Node<T>);
+        if (nodes + sph_total <= budget) {
+            P.smem_nodes = (uint32_t)nodes; P.smem_spheres = (uint32_t)sph;
+        } else {
+            // large scene: pin as many top levels (BFS prefix) as fit
+            size_t top = std::min(nodes, budget) / sizeof(Node<T>) * sizeof(Node<T>);
+            P.smem_nodes = (uint32_t)top;
+        }
+        smem += P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRenderBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count * per_sm;
+    if (info) { info->grid = grid; info->block = kRenderBlock; info->smem = smem; info->blocks_per_sm = per_sm; }
+    kernel<<<grid, kRenderBlock, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <class T, bool EXACT>
+cudaError_t launch_render_t(RenderParams<T> P, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    return count ? launch_render_impl<T, EXACT, true>(P, sm_count, s, info) : launch_render_impl<T, EXACT, false>(P, sm_count, s, info);
+}
+
+inline int batch_grid(size_t n) { return (int)((n + kBatchBlock - 1) / kBatchBlock); }
+
+template <class T, bool EXACT> cudaError_t launch_trace_t(const BatchParams<T>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    trace_batch_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template <class T, bool EXACT> cudaError_t launch_scatter_t(const BatchParams<T>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    scatter_batch_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template <class T, bool EXACT> cudaError_t launch_get_rays_t(const BatchParams<T>& P, double* o, double* d, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    get_rays_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P, o, d);
+    return cudaGetLastError();
+}
+template <class T, bool EXACT> cudaError_t launch_path_radiance_t(const BatchParams<T>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    path_radiance_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template <class T>
+cudaError_t launch_untile_t(const T* tiles, uint32_t width, uint32_t height, uint32_t world, uint32_t tiles_per_rank, uint32_t spp,
+                            double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
+    dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    uint32_t tiles_x = (width + kTileW - 1) / kTileW;
+    untile_resolve_kernel<T><<<grid, block, 0, s>>>(tiles, width, height, world, tiles_per_rank, tiles_x, spp, rgb_sum, rgb8);
+    return cudaGetLastError();
+}
+
+#define RTW_DEFINE_LAUNCHERS(SUFFIX, T, EXACT)                                                                                   \
+    cudaError_t launch_render_##SUFFIX(RenderParams<T> P, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {           \
+        return launch_render_t<T, EXACT>(P, count, sm_count, s, info);                                                            \
+    }                                                                                                                            \
+    cudaError_t launch_trace_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_trace_t<T, EXACT>(P, s); }         \
+    cudaError_t launch_scatter_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_scatter_t<T, EXACT>(P, s); }     \
+    cudaError_t launch_get_rays_##SUFFIX(const BatchParams<T>& P, double* o, double* d, cudaStream_t s) {                         \
+        return launch_get_rays_t<T, EXACT>(P, o, d, s);                                                                           \
+    }                                                                                                                            \
+    cudaError_t launch_path_radiance_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_path_radiance_t<T, EXACT>(P, s); } \
+    cudaError_t launch_untile_##SUFFIX(const T* tiles, uint32_t width, uint32_t height, uint32_t world, uint32_t tiles_per_rank,  \
+                                       uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {                            \
+        return launch_untile_t<T>(tiles, width, height, world, tiles_per_rank, spp, rgb_sum, rgb8, s);                            \
+    }
+
+}  // namespace rtw

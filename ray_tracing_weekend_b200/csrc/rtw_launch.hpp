@@ -1,0 +1,21 @@
+// rtw_launch.hpp — host-callable launchers exported by kernels_f32.cu (fast) and kernels_f64.cu (exact).
+#pragma once
+#include "rtw_kernels.cuh"
+
+namespace rtw {
+
+struct LaunchInfo { int grid = 0, block = 0; size_t smem = 0; int blocks_per_sm = 0; };
+
+#define RTW_DECLARE_LAUNCHERS(SUFFIX, T)                                                                         \
+    cudaError_t launch_render_##SUFFIX(RenderParams<T> P, bool count, int sm_count, cudaStream_t s, LaunchInfo*); \
+    cudaError_t launch_trace_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                                   \
+    cudaError_t launch_scatter_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                                 \
+    cudaError_t launch_get_rays_##SUFFIX(const BatchParams<T>& P, double* o, double* d, cudaStream_t s);          \
+    cudaError_t launch_path_radiance_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                           \
+    cudaError_t launch_untile_##SUFFIX(const T* tiles, uint32_t width, uint32_t height, uint32_t world,           \
+                                       uint32_t tiles_per_rank, uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
+
+RTW_DECLARE_LAUNCHERS(f32, float)
+RTW_DECLARE_LAUNCHERS(f64, double)
+
+}  // namespace rtw

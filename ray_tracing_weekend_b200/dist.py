@@ -1,0 +1,114 @@
+"""Multi-GPU render: one process per GPU (torchrun), image tiles partitioned across ranks, one gather
+of the framebuffer tiles to rank 0 at the end (NCCL over NVLink; gloo on CPU for the host-logic tests).
+
+The reference has no distributed path; its only parallelism is rayon over pixels
+(shared/src/camera.rs:353).  Pixels are independent and the RNG is keyed by the absolute pixel index, so
+the image does not depend on the number of GPUs or on which GPU renders which tile.
+
+Partition (same constants as include/rtw.h): tiles of 16x16 pixels in row-major tile order; global tile k
+is owned by rank k % world and is that rank's local tile k // world.  Every rank holds
+tiles_per_rank = ceil(tiles_total / world) local tiles (the tail is padding and stays zero), so the gather
+moves equally sized buffers and needs no size exchange.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+TILE_W = TILE_H = 16
+
+
+def tiles_xy(width: int, height: int):
+    return (width + TILE_W - 1) // TILE_W, (height + TILE_H - 1) // TILE_H
+
+
+def tiles_total(width: int, height: int) -> int:
+    tx, ty = tiles_xy(width, height)
+    return tx * ty
+
+
+def tiles_per_rank(width: int, height: int, world: int) -> int:
+    return (tiles_total(width, height) + world - 1) // world
+
+
+def tile_owner(tile: int, world: int):
+    """(rank, local index) of global tile `tile`."""
+    return tile % world, tile // world
+
+
+def local_tile_ids(width: int, height: int, rank: int, world: int):
+    """Global tile ids of this rank's local tiles, in local order (padding slots excluded)."""
+    return list(range(rank, tiles_total(width, height), world))
+
+
+def tile_rect(tile: int, width: int, height: int):
+    """Pixel rectangle (i0, j0, i1, j1) of a tile, clipped to the image; j = 0 is the bottom row."""
+    tx, _ = tiles_xy(width, height)
+    i0, j0 = (tile % tx) * TILE_W, (tile // tx) * TILE_H
+    return i0, j0, min(i0 + TILE_W, width), min(j0 + TILE_H, height)
+
+
+def init_from_env(backend: Optional[str] = None):
+    """Join the process group torchrun described (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local_rank
+
+
+def gather_tiles(local_tiles: torch.Tensor, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """The one collective of the render: gather every rank's [tiles_per_rank, 16, 16, 3] buffer on `dst`.
+    Returns [world, tiles_per_rank, 16, 16, 3] on dst and None elsewhere."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_tiles.unsqueeze(0)
+    rank = dist.get_rank(group)
+    if rank == dst:
+        out = torch.empty((world,) + tuple(local_tiles.shape), dtype=local_tiles.dtype, device=local_tiles.device)
+        dist.gather(local_tiles, gather_list=list(out.unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(local_tiles, gather_list=None, dst=dst, group=group)
+    return None
+
+
+class DistributedRenderer:
+    """Holds the per-rank device buffers so repeated renders (bench steps) allocate nothing."""
+
+    def __init__(self, scene, camera, opts, rank: int, world: int, want_sum: bool = False, want_rgb8: bool = True):
+        from . import api
+        self.api = api
+        self.scene, self.camera, self.opts, self.rank, self.world = scene, camera, opts, rank, world
+        w, h = camera.image_width, camera.image_height
+        self.tpr = tiles_per_rank(w, h, world)
+        dt = torch.float32 if opts.precision == api.RTW_F32 else torch.float64
+        self.local = torch.zeros((self.tpr, TILE_H, TILE_W, 3), dtype=dt, device="cuda")
+        self.rgb_sum = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda") if (want_sum and rank == 0) else None
+        self.rgb8 = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda") if (want_rgb8 and rank == 0) else None
+
+    def render(self, want_stats: bool = False):
+        """One frame: render this rank's tiles, gather on rank 0, untile + resolve there.
+        Work is enqueued on torch's current stream; returns the kernel stats dict when asked (that syncs)."""
+        stream = torch.cuda.current_stream().cuda_stream
+        st = self.scene.render_tiles_device(self.camera, self.opts, self.rank, self.world, self.local.data_ptr(), stream,
+                                            want_stats=want_stats)
+        allt = gather_tiles(self.local, 0)
+        if self.rank == 0:
+            cam = self.camera.pod
+            self.api.untile_resolve_device(allt.data_ptr(), self.opts.precision, cam.image_width, cam.image_height, self.world,
+                                           cam.samples_per_pixel, self.rgb_sum.data_ptr() if self.rgb_sum is not None else 0,
+                                           self.rgb8.data_ptr() if self.rgb8 is not None else 0, stream)
+            self._keep = allt       # keep the gathered buffer alive until the stream has consumed it
+        return st

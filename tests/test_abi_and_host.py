@@ -1,0 +1,147 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol,
+host helpers (camera builder, Philox, tile partition, scene generator) agree with the oracle, and compute
+entry points fail loudly without a GPU.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = 20261018
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"RTW_API[^;(]*?\b(rtwh?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(rtw):
+    names = _declared("rtw.h") + _declared("rtw_host.h")
+    assert len(names) >= 21
+    lib = C.CDLL(rtw.library_path())
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+    from ray_tracing_weekend_b200 import _lib
+    assert sorted(_lib.RTW_SYMBOLS + _lib.RTWH_SYMBOLS) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", rtw.library_path()], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == names, "the library exports exactly the declared C ABI"
+    assert lib.rtw_abi_version() == 1
+
+
+def test_library_contains_sm100a_kernels(rtw):
+    out = subprocess.run(["cuobjdump", "-lelf", rtw.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_philox_host_matches_kat_and_oracle(rtw, oracle):
+    assert [int(x) for x in rtw.philox4x32_10([0, 0, 0, 0], [0, 0])] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        ctr = rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32); key = rng.integers(0, 2 ** 32, 2, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(rtw.philox4x32_10(ctr, key), oracle.philox4x32_10(ctr, key))
+
+
+def test_scene_generator_matches_oracle(rtw, oracle):
+    for args in ((SEED, 11, 0.8, 0.95, 0), (7, 5, 0.1, 0.2, 1), (9, 3, 0.5, 0.6, 2)):
+        world, lights, cb = rtw.scenes.simple(*args)
+        d = oracle.scene_simple(*args)
+        sp = np.array([[*s.center, s.radius] for s in world.list.spheres])
+        assert np.array_equal(sp, d.spheres)
+        assert np.array_equal(np.array([[*s.center, s.radius] for s in lights.spheres]).reshape(-1, 4), d.lights)
+        mats = np.array([[s.material.kind, *s.material.colour, s.material.param] for s in world.list.spheres])
+        assert np.array_equal(mats, d.materials_array()[d.sphere_mat])
+        assert len(world.list.planes) == d.planes.shape[0]
+    world, lights, _ = rtw.scenes.simple(SEED)
+    kinds = np.bincount([s.material.kind for s in world.list.spheres], minlength=3)
+    assert kinds[0] > 5 * kinds[2] and lights.len() == kinds[2]      # every glass sphere is mirrored in `lights` (lib.rs:203,217)
+
+
+def test_camera_builder_matches_oracle(rtw, oracle):
+    d = oracle.scene_simple(SEED)
+    _, _, cb = rtw.scenes.simple(SEED)
+    for (w, h) in ((400, 225), (1920, 1080), (3, 2)):
+        cam = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(7).build()
+        oc = oracle.camera_for(d, w, h, 7, 50)
+        for f, g in (("center", "center"), ("pixel00_loc", "pixel00"), ("pixel_delta_u", "du"), ("pixel_delta_v", "dv"),
+                     ("defocus_disk_u", "ddu"), ("defocus_disk_v", "ddv"), ("background", "background")):
+            assert list(getattr(cam.pod, f)) == list(getattr(oc, g)), f
+        assert (cam.pod.image_width, cam.pod.image_height, cam.pod.samples_per_pixel, cam.pod.max_depth) == (w, h, 7, 50)
+    # the Option<> resolution table (camera.rs:130-156)
+    assert (rtw.CameraBuilder().build().image_width, rtw.CameraBuilder().build().image_height) == (100, 100)
+    c = rtw.CameraBuilder().with_aspect_ratio(16 / 9).build()
+    assert (c.image_width, c.image_height) == (100, 56)
+    c = rtw.CameraBuilder().with_aspect_ratio(2.0).with_image_height(30).build()
+    assert (c.image_width, c.image_height) == (60, 30)
+    c = rtw.CameraBuilder().with_image_width(33).build()
+    assert (c.image_width, c.image_height) == (33, 33)
+
+
+def test_tile_partition_helpers(rtw):
+    from ray_tracing_weekend_b200 import dist as D
+    for (w, h, world) in ((1920, 1080, 8), (400, 225, 3), (3, 2, 2), (16, 16, 4), (100, 70, 1)):
+        assert rtw.tiles_total(w, h) == D.tiles_total(w, h)
+        assert rtw.tiles_per_rank(w, h, world) == D.tiles_per_rank(w, h, world)
+        seen = []
+        for r in range(world):
+            ids = D.local_tile_ids(w, h, r, world)
+            assert len(ids) <= D.tiles_per_rank(w, h, world)
+            assert all(D.tile_owner(k, world) == (r, n) for n, k in enumerate(ids))
+            seen += ids
+        assert sorted(seen) == list(range(D.tiles_total(w, h)))
+        cover = np.zeros((h, w), dtype=int)
+        for k in range(D.tiles_total(w, h)):
+            i0, j0, i1, j1 = D.tile_rect(k, w, h)
+            cover[j0:j1, i0:i1] += 1
+        assert (cover == 1).all()
+
+
+def test_argument_validation_needs_no_gpu(rtw):
+    from ray_tracing_weekend_b200 import _lib
+    L = rtw.load()
+    # a Lambertian world with an empty lights list: the reference panics (hittable_list.rs:414-419)
+    world = rtw.HittableList(); world.add(rtw.Sphere((0, 0, 0), 1.0, rtw.Lambertian((0.5, 0.5, 0.5))))
+    with pytest.raises(rtw.RtwError) as e:
+        rtw.Scene(world, rtw.HittableList())
+    assert e.value.code == _lib.RTW_E_INVALID and "lights" in str(e.value)
+    world = rtw.HittableList(); world.add(rtw.Sphere((0, 0, 0), -1.0, rtw.Metal((1, 1, 1), 0.0)))
+    with pytest.raises(rtw.RtwError) as e:
+        rtw.Scene(world, rtw.HittableList())
+    assert e.value.code == _lib.RTW_E_INVALID
+    out = C.c_void_p()
+    assert L.rtw_scene_create(None, None, 1, None, None, 0, None, 0, None, 0, C.byref(out)) == _lib.RTW_E_INVALID
+    assert L.rtw_camera_build(None, None) == _lib.RTW_E_INVALID
+    with pytest.raises(TypeError):
+        rtw.HittableList().add("quad")
+
+
+def test_no_cpu_fallback(rtw, simple_scene):
+    """Without a CUDA device every compute call must fail loudly (RTW_E_NO_DEVICE), never compute on the CPU."""
+    from ray_tracing_weekend_b200 import _lib
+    if rtw.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(rtw.RtwError) as e:
+        rtw.Scene(simple_scene["world"], simple_scene["lights"])
+    assert e.value.code == _lib.RTW_E_NO_DEVICE and "no CPU fallback" in str(e.value)
+    cam = rtw.CameraBuilder().with_image_width(4).with_image_height(4).build()
+    with pytest.raises(rtw.RtwError) as e:
+        cam.get_rays([0], [0], [0])
+    assert e.value.code == _lib.RTW_E_NO_DEVICE
+    r = subprocess.run([os.path.join(os.path.dirname(rtw.library_path()), "rtw_bin"), "simple", "--width", "4", "--height", "4", "--spp", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or execute it."""
+    pkg = os.path.join(ROOT, "ray_tracing_weekend_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "rtw_oracle" not in txt, os.path.join(dirpath, f)

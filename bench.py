@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s / Mpaths/s of the CUDA render path on BASELINE config C2:
+random-spheres (scenes::simple, seeded) 1920x1080, 500 spp, depth 50, megakernel, N B200s.
+
+A step is one full render of that frame: rtw_render_tiles_device on every rank (tiles interleaved across
+ranks), one NCCL gather of the tile buffers on rank 0, untile + resolve there.  Contract: see the task
+brief — prints ONE JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261018
+WIDTH, HEIGHT, SPP, DEPTH = 1920, 1080, 500, 50
+WORKLOAD = f"random-spheres (scenes::simple seed {SEED}, reference ground plane) {WIDTH}x{HEIGHT}, {SPP} spp, depth {DEPTH}"
+
+# Algorithmic FP32 flop per event (SURVEY §8d / DESIGN.md §Roofline); FMA = 2.
+FLOP = dict(ray_setup=8, node_visit=2 * 22, sphere_test=21, hit_record=20, lambertian=84, light_test=34, metal=46,
+            dielectric=45, path_setup=30)
+
+
+def algorithmic_flops(st):
+    return (st["rays"] * (FLOP["ray_setup"]) + st["node_visits"] * FLOP["node_visit"] + st["sphere_tests"] * FLOP["sphere_test"]
+            + (st["rays"] - st["missed"]) * FLOP["hit_record"] + st["lambertian"] * FLOP["lambertian"]
+            + st["light_tests"] * FLOP["light_test"] + st["metal"] * FLOP["metal"] + st["dielectric"] * FLOP["dielectric"]
+            + st["paths"] * FLOP["path_setup"])
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_run(steps, warmup, sample_spp, faithful=False):
+    """The reference's CPU renderer restated (oracle/, C++ f64 port — the Rust reference cannot be built here),
+    all host threads, on a bounded sample of the workload: the full 1080p frame at `sample_spp` spp."""
+    from oracle import pyoracle as O
+    desc = O.scene_simple(SEED)
+    sc = O.Scene(desc)
+    cam = O.camera_for(desc, WIDTH, HEIGHT, sample_spp, DEPTH)
+    opt = O.options(seed=SEED, faithful_bvh=faithful)
+    for _ in range(warmup):
+        sc.render(cam, opt)
+    secs, rays, paths = 0.0, 0, 0
+    for _ in range(steps):
+        _, s, cnt, _ = sc.render(cam, opt)
+        secs += s; rays += cnt["rays"]; paths += cnt["paths"]
+    return dict(seconds=secs, rays=rays, paths=paths, cores=O.hardware_threads(),
+                sample=f"{WIDTH}x{HEIGHT} at {sample_spp} spp (of {SPP}), depth {DEPTH}, same scene/seed; "
+                       f"{'faithful (boxes recomputed per visit, bvh.rs:145-151)' if faithful else 'cached node boxes'}")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, sample_spp=1)
+    mrays = r["rays"] / r["seconds"] * 1e-6
+    line = dict(impl="reference", metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["seconds"] / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=WORKLOAD, note="C++ restatement of the reference's CPU renderer (oracle/), not the reference "
+                                              "binary: no Rust toolchain in this image"),
+                mpaths_per_s=r["paths"] / r["seconds"] * 1e-6,
+                cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=r["cores"], kind="port", sample=r["sample"] + "; each step is one such frame"),
+                e2e=dict(value=mrays, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ray_tracing_weekend_b200 as R
+    from ray_tracing_weekend_b200 import dist as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback (use --impl reference for the CPU baseline)")
+    rank, world, local_rank = D.init_from_env()
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun --nproc-per-node {args.gpus}")
+    R.load()
+    world_h, lights_h, cb = R.scenes.simple(SEED)
+    cam = (cb.with_vfov(40.).with_aspect_ratio(WIDTH / HEIGHT).with_max_depth(DEPTH).with_image_width(WIDTH).with_image_height(HEIGHT)
+           .with_samples_per_pixel(SPP).build())
+    base_flags = R.RTW_FLAG_LANE_PER_PIXEL if args.lane_per_pixel else 0
+    opts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=R.RTW_MEGAKERNEL, flags=base_flags)
+    scene = R.Scene(world_h, lights_h)
+    renderer = D.DistributedRenderer(scene, cam, opts, rank, world, want_sum=False, want_rgb8=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # event counts of one step (deterministic: counter-based RNG) — an untimed pass with counters on
+    copts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, flags=R.RTW_FLAG_COUNT_EVENTS | base_flags)
+    cnt = scene.render_tiles_device(cam, copts, rank, world, renderer.local.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    keys = ["paths", "rays", "node_visits", "sphere_tests", "light_tests", "lambertian", "metal", "dielectric", "absorbed", "missed", "depth_out"]
+    tot = torch.tensor([cnt[k] for k in keys], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    total = {k: float(v) for k, v in zip(keys, tot.tolist())}
+    local_flops = algorithmic_flops(cnt)
+
+    for _ in range(args.warmup):
+        renderer.render()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    stream = torch.cuda.current_stream().cuda_stream
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                                # evict L2 between timed iterations (outside the event pairs)
+        ev[k][0].record()
+        ev[k][2].record()
+        scene.render_tiles_device(cam, opts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+        ev[k][3].record()
+        allt = D.gather_tiles(renderer.local, 0)
+        if rank == 0:
+            R.untile_resolve_device(allt.data_ptr(), opts.precision, WIDTH, HEIGHT, world, SPP, 0, renderer.rgb8.data_ptr(), stream)
+        ev[k][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
+    kern_ms = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps))
+    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms = t.tolist()
+
+    # ---- end to end through the public host API: scene upload + render + read-back, every step --------------
+    def e2e_step():
+        if world == 1:
+            sc = R.Scene(world_h, lights_h)                              # H2D: BVH build + upload
+            _, rgb8, _ = sc.render(cam, opts, want_sum=False, want_rgb8=True)       # D2H: resolved image
+            sc.close()
+            return rgb8
+        sc = R.Scene(world_h, lights_h)
+        rr = D.DistributedRenderer(sc, cam, opts, rank, world, want_sum=False, want_rgb8=True)
+        rr.render()
+        out = rr.rgb8.cpu() if rank == 0 else None
+        torch.cuda.synchronize()
+        sc.close()
+        return out
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                      # TFLOP/s at max clock
+        secs = step_ms * 1e-3
+        mrays = total["rays"] * args.steps / secs * 1e-6
+        achieved = local_flops / (kern_ms / args.steps * 1e-3) / 1e12        # this rank's kernel: flop / its duration
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = dict(
+            metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload=WORKLOAD, mode="megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)", parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
+                        tmin="f64::EPSILON (reference)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
+            mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
+            kernel_ms_per_step=kern_ms / args.steps,
+            roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,
+                          peak_source=f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json); no FP32 figure is in that file",
+                          kernel="render_mega_kernel<float>" if args.lane_per_pixel else "render_pool_kernel", flop_per_launch=local_flops,
+                          frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None),
+            e2e=dict(value=total["rays"] * e2e_steps / e2e_s * 1e-6, unit="Mrays/s", h2d_bytes_per_step=scene.upload_bytes * world,
+                     d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
+            gpu_launches=args.steps * ((1 if args.lane_per_pixel else 2) * world + 1),
+            clocks=clocks,
+            events_per_step={k: total[k] for k in keys},
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                c = cpu_reference_run(1, 0, sample_spp=4)
+                line["cpu_baseline"] = dict(value=c["rays"] / c["seconds"] * 1e-6, unit="Mrays/s", cores=c["cores"], kind="port",
+                                            sample=c["sample"], mpaths_per_s=c["paths"] / c["seconds"] * 1e-6)
+                f = cpu_reference_run(1, 0, sample_spp=1, faithful=True)
+                line["cpu_baseline"]["faithful_bvh_value"] = f["rays"] / f["seconds"] * 1e-6
+            except Exception as e:                                         # the oracle is only a reported baseline
+                line["cpu_baseline"] = dict(value=None, unit="Mrays/s", cores=0, kind="port", sample=f"unavailable: {e}")
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    global SPP, WORKLOAD
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    # profiling aids — any non-default value is recorded in config and is NOT the headline workload
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
+    args = ap.parse_args()
+    if args.spp != SPP:
+        SPP = args.spp
+        WORKLOAD = WORKLOAD.replace("500 spp", f"{SPP} spp [NON-DEFAULT profiling workload]")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

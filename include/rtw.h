@@ -75,13 +75,20 @@ enum { RTW_F32 = 0,   /* fast path: FP32 arithmetic, 24-bit uniforms (stream lay
        RTW_F64 = 1 }; /* reference-exact path: the reference's f64 operation order, no FMA
                          contraction, 53-bit uniforms (stream layout W64)                           */
 enum { RTW_MEGAKERNEL = 0, RTW_WAVEFRONT = 1 };
+#define RTW_TMIN_REFERENCE (-1.0)
 enum { RTW_FLAG_FIX_NAN = 1u,       /* zero NaN components of a sample before accumulation (the dead
                                        ray_colour twin did, camera.rs:434); OFF = reference behaviour */
-       RTW_FLAG_COUNT_EVENTS = 2u };/* fill the event counters of rtw_stats (slower)                 */
+       RTW_FLAG_COUNT_EVENTS = 2u, /* fill the event counters of rtw_stats (slower)                 */
+       RTW_FLAG_LANE_PER_PIXEL = 4u };/* RTW_F32 only, diagnostic: one lane per pixel instead of the pooled
+                                       path stream (the baseline the pooled megakernel is measured against) */
 
 typedef struct {
     uint64_t seed;        /* Philox4x32-10 key                                                      */
-    double   tmin;        /* lower end of the world.hit range; reference value DBL_EPSILON (camera.rs:473) */
+    double   tmin;        /* lower end of the world.hit range (camera.rs:473).  RTW_TMIN_REFERENCE (any negative
+                             value) = the reference's choice, machine epsilon of the working precision: 2^-52 on
+                             the RTW_F64 path (== f64::EPSILON), 2^-23 on the RTW_F32 path.  The reference's image
+                             depends on how this compares with the rounding noise of hit points (self-intersection),
+                             which is a relation in ulps, not in absolute terms. */
     uint32_t precision;   /* RTW_F32 | RTW_F64                                                      */
     uint32_t mode;        /* RTW_MEGAKERNEL | RTW_WAVEFRONT                                         */
     uint32_t flags;

@@ -20,7 +20,7 @@ struct orc_camera_builder {
     uint32_t spp, max_depth;
     double background[3], vfov, lookfrom[3], lookat[3], vup[3], defocus_angle, focus_dist;
 };
-struct orc_options { uint64_t seed; double tmin; uint32_t rng_mode, math_mode, faithful_bvh; int32_t threads; };
+struct orc_options { uint64_t seed; double tmin; uint32_t rng_mode, math_mode, faithful_bvh; int32_t threads; uint32_t fix_nan, reserved; };
 struct orc_counters {
     uint64_t rays, paths, box_tests, box_builds, node_visits, sphere_tests, plane_tests, light_tests,
         lambertian, metal, dielectric, absorbed, missed, depth_out;
@@ -41,7 +41,7 @@ static Camera to_camera(const orc_camera* c) {
 static Options to_options(const orc_options* o) {
     Options k;
     k.seed = o->seed; k.tmin = o->tmin; k.rng_mode = o->rng_mode; k.math_mode = o->math_mode;
-    k.faithful_bvh = o->faithful_bvh != 0; k.threads = o->threads;
+    k.faithful_bvh = o->faithful_bvh != 0; k.threads = o->threads; k.fix_nan = o->fix_nan != 0;
     return k;
 }
 static void from_counters(const Counters& c, orc_counters* o) {
@@ -196,7 +196,9 @@ void orc_path_radiance(const Scene* s, const orc_camera* cam, const orc_options*
         uint32_t pixel = j[k] * c.image_width + i[k];
         Stream rng(op.seed, pixel, sample[k], 0, op.rng_mode);
         Ray r = get_ray(c, i[k], j[k], rng);
-        put(rgb + 3 * k, ray_colour(*s, c, op, r, pixel, sample[k], nullptr, &pan));
+        V3 v = ray_colour(*s, c, op, r, pixel, sample[k], nullptr, &pan);
+        if (op.fix_nan) { if (v.x != v.x) v.x = 0.; if (v.y != v.y) v.y = 0.; if (v.z != v.z) v.z = 0.; }
+        put(rgb + 3 * k, v);
     }
 }
 

@@ -52,7 +52,7 @@ class CameraBuilder(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("tmin", C.c_double), ("rng_mode", C.c_uint32), ("math_mode", C.c_uint32),
-                ("faithful_bvh", C.c_uint32), ("threads", C.c_int32)]
+                ("faithful_bvh", C.c_uint32), ("threads", C.c_int32), ("fix_nan", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -256,8 +256,8 @@ def resolve(rgb_sum, spp):
     return out
 
 
-def options(seed=20261018, tmin=EPS, rng_mode=W64, math_mode=LIBM, faithful_bvh=False, threads=0) -> Options:
-    return Options(seed, tmin, rng_mode, math_mode, int(faithful_bvh), threads)
+def options(seed=20261018, tmin=EPS, rng_mode=W64, math_mode=LIBM, faithful_bvh=False, threads=0, fix_nan=False) -> Options:
+    return Options(seed, tmin, rng_mode, math_mode, int(faithful_bvh), threads, int(fix_nan), 0)
 
 
 def hardware_threads():

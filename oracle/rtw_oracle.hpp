@@ -589,6 +589,8 @@ struct Options {
     double tmin = EPS;                  // camera.rs:473
     uint32_t rng_mode = W64, math_mode = LIBM;
     bool faithful_bvh = false;          // true: recompute node boxes per visit like bvh.rs:145-151
+    bool fix_nan = false;               // NOT reference behaviour: zero NaN components of a sample (Colour::fix_nan, colour.rs:52-58,
+                                        // which only the dead recursive ray_colour applies, camera.rs:434)
     int threads = 0;
 };
 
@@ -776,7 +778,9 @@ inline void render(const Scene& sc, const Camera& cam, const Options& opt, doubl
                 for (uint32_t s = 0; s < cam.samples_per_pixel; ++s) {
                     Stream rng(opt.seed, pixel, s, 0, opt.rng_mode);
                     Ray r = get_ray(cam, i, j, rng);
-                    acc = acc + ray_colour(sc, cam, opt, r, pixel, s, &c, &panicked);
+                    V3 v = ray_colour(sc, cam, opt, r, pixel, s, &c, &panicked);
+                    if (opt.fix_nan) { if (v.x != v.x) v.x = 0.; if (v.y != v.y) v.y = 0.; if (v.z != v.z) v.z = 0.; }
+                    acc = acc + v;
                 }
                 rgb_sum[3 * (size_t)pixel + 0] = acc.x;
                 rgb_sum[3 * (size_t)pixel + 1] = acc.y;

@@ -6,7 +6,7 @@ The CUDA library is the product; this package is the host-side mirror of the ref
 used by tests and bench.py.  Importing works without a GPU (nvcc builds the library), computing
 does not: there is no CPU fallback."""
 from . import scenes  # noqa: F401
-from ._lib import (EPSILON, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_MEGAKERNEL, RTW_WAVEFRONT,  # noqa: F401
+from ._lib import (EPSILON, TMIN_REFERENCE, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_FLAG_LANE_PER_PIXEL, RTW_MEGAKERNEL, RTW_WAVEFRONT,  # noqa: F401
                    RtwError, library_path, load)
 from .api import (INVISIBLE, BoundedVolumeHierarchy, Camera, CameraBuilder, Dialectric, HittableList, Lambertian, Material,  # noqa: F401
                   Metal, Plane, RenderOptions, Scene, Sphere, device_count, philox4x32_10, tiles_per_rank, tiles_total,

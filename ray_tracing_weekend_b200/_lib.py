@@ -14,9 +14,10 @@ RTW_OK, RTW_E_INVALID, RTW_E_CUDA, RTW_E_NO_DEVICE, RTW_E_UNSUPPORTED, RTW_E_NOM
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC, RTW_INVISIBLE = 0, 1, 2, 3
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
-RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS = 1, 2
+RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL = 1, 2, 4
 RTW_TILE_W = RTW_TILE_H = 16
 EPSILON = 2.220446049250313e-16
+TMIN_REFERENCE = -1.0      # rtw_opts.tmin: machine epsilon of the working precision (the reference's f64::EPSILON analogue)
 
 # every symbol include/rtw.h and include/rtw_host.h declare
 RTW_SYMBOLS = (

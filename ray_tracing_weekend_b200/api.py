@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (EPSILON, RTW_DIELECTRIC, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_INVISIBLE,
+from ._lib import (EPSILON, TMIN_REFERENCE, RTW_DIELECTRIC, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_INVISIBLE,
                    RTW_LAMBERTIAN, RTW_MEGAKERNEL, RTW_METAL, RTW_WAVEFRONT, RtwError, rtw_camera, rtw_camera_builder,
                    rtw_material, rtw_opts, rtw_plane, rtw_sphere, rtw_stats)
 
@@ -114,7 +114,7 @@ def _as_list(world) -> HittableList:
 @dataclass
 class RenderOptions:
     seed: int = 20261018
-    tmin: float = EPSILON                      # camera.rs:473
+    tmin: float = TMIN_REFERENCE               # camera.rs:473: EPSILON of the working precision
     precision: int = RTW_F32
     mode: int = RTW_MEGAKERNEL
     flags: int = 0

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(LIB_DIR, "librtw_cuda.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

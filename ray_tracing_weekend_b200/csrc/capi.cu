@@ -83,9 +83,11 @@ struct rtw_scene {
     int device = 0, sm_count = 0;
     unsigned int* d_work = nullptr; DeviceCounters* d_counters = nullptr;
     DevBuf<double> d_rgb_sum; DevBuf<uint8_t> d_rgb8;
+    DevBuf<unsigned long long> d_accum; DevBuf<uint32_t> d_poison;   // pooled megakernel accumulators
     DevBuf<double> d_in0, d_in1, d_out0, d_out1, d_out2, d_out3, d_out4; DevBuf<uint32_t> d_u0, d_u1, d_u2, d_k; DevBuf<int32_t> d_prim;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     LaunchInfo last_launch;
+    uint32_t last_launches = 1;
 };
 
 namespace {
@@ -138,6 +140,12 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
     return RTW_OK;
 }
 
+// opts.tmin < 0 (RTW_TMIN_REFERENCE): machine epsilon of the working precision, the reference's f64::EPSILON analogue
+template <class T> static inline T resolve_tmin(double tmin) {
+    if (tmin < 0.) return sizeof(T) == 8 ? (T)2.220446049250313e-16 : (T)1.1920928955078125e-07;
+    return (T)tmin;
+}
+
 template <class T> CameraT<T> to_camera(const rtw_camera* c) {
     CameraT<T> k{};
     auto v = [](const double* p) { return V3<T>{(T)p[0], (T)p[1], (T)p[2]}; };
@@ -165,7 +173,7 @@ int check_opts(const rtw_opts* o) {
     if (o->precision != RTW_F32 && o->precision != RTW_F64) return fail(RTW_E_INVALID, "opts.precision");
     if (o->mode != RTW_MEGAKERNEL && o->mode != RTW_WAVEFRONT) return fail(RTW_E_INVALID, "opts.mode");
     if (o->mode == RTW_WAVEFRONT) return fail(RTW_E_UNSUPPORTED, "wavefront mode is not built yet");
-    if (!(o->tmin >= 0.)) return fail(RTW_E_INVALID, "opts.tmin");
+    if (o->tmin != o->tmin) return fail(RTW_E_INVALID, "opts.tmin is NaN");
     return RTW_OK;
 }
 
@@ -179,7 +187,7 @@ template <class T, class Launch>
 int render_tiles_t(rtw_scene* s, SceneDev<T>& d, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, T* tiles,
                    cudaStream_t stream, Launch launch) {
     RenderParams<T> P{};
-    P.scene = d.view; P.cam = to_camera<T>(cam); P.seed = o->seed; P.tmin = (T)o->tmin; P.flags = o->flags;
+    P.scene = d.view; P.cam = to_camera<T>(cam); P.seed = o->seed; P.tmin = resolve_tmin<T>(o->tmin); P.flags = o->flags;
     P.rank = rank; P.world = world;
     P.tiles_x = (cam->image_width + kTileW - 1) / kTileW;
     P.tiles_total = rtw_tiles_total(cam->image_width, cam->image_height);
@@ -346,7 +354,7 @@ void rtw_scene_destroy(rtw_scene* s) {
     s->f32.release(); s->f64.release();
     if (s->d_work) cudaFree(s->d_work);
     if (s->d_counters) cudaFree(s->d_counters);
-    s->d_rgb_sum.release(); s->d_rgb8.release();
+    s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release();
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
@@ -367,10 +375,28 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
     rc = check_opts(o); if (rc) return rc;
     if (world == 0 || rank >= world) return fail(RTW_E_INVALID, "rank/world");
     cudaStream_t st = (cudaStream_t)stream;
+    uint32_t launches = 1;
+    bool pooled = o->precision == RTW_F32 && !(o->flags & RTW_FLAG_LANE_PER_PIXEL);
+    if (pooled) {
+        size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
+        CU(s->d_accum.reserve(n_slots * 3)); CU(s->d_poison.reserve(n_slots));
+    }
     CU(cudaEventRecord(s->ev[0], st));
-    if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch_render_f32);
+    if (pooled) {
+        PoolParams Q{};
+        Q.accum = s->d_accum.p; Q.poison = s->d_poison.p;
+        Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
+        uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
+        Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+        auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
+            return launch_render_pool_f32(P, Q, count, sms, str, info);
+        };
+        rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch);
+        launches = 2;
+    } else if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch_render_f32);
     else rc = render_tiles_t<double>(s, s->f64, cam, o, rank, world, (double*)d_tiles, st, launch_render_f64);
     if (rc) return rc;
+    s->last_launches = launches;
     CU(cudaEventRecord(s->ev[1], st));
     if (stats) {
         DeviceCounters c;
@@ -380,7 +406,7 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         read_stats(c, stats);
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
-        stats->kernel_ms = ms; stats->total_ms = ms; stats->launches = 1;
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->launches = launches;
     }
     return RTW_OK;
 }
@@ -410,7 +436,7 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, double* r
     CU(cudaEventRecord(s->ev[2], 0));
     rc = rtw_render_tiles_device(s, cam, o, 0, 1, tiles, nullptr, nullptr);
     if (rc) return rc;
-    uint32_t launches = 1;
+    uint32_t launches = s->last_launches;
     if (rgb_sum || rgb8) {
         rc = rtw_untile_resolve_device(tiles, o->precision, cam->image_width, cam->image_height, 1, cam->samples_per_pixel,
                                        rgb_sum ? s->d_rgb_sum.p : nullptr, rgb8 ? s->d_rgb8.p : nullptr, nullptr);
@@ -473,11 +499,11 @@ int rtw_scatter_batch(rtw_scene* s, const rtw_opts* opts, const double* o, const
     CU(cudaMemcpy(s->d_u2.p, vertex, n * 4, cudaMemcpyHostToDevice));
     if (opts->precision == RTW_F32) {
         BatchParams<float> P = batch_params<float>(s, s->f32, n);
-        P.seed = opts->seed; P.tmin = (float)opts->tmin; P.flags = opts->flags;
+        P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
         CU(launch_scatter_f32(P, 0));
     } else {
         BatchParams<double> P = batch_params<double>(s, s->f64, n);
-        P.seed = opts->seed; P.tmin = opts->tmin; P.flags = opts->flags;
+        P.seed = opts->seed; P.tmin = resolve_tmin<double>(opts->tmin); P.flags = opts->flags;
         CU(launch_scatter_f64(P, 0));
     }
     CU(cudaMemcpy(prim_id, s->d_prim.p, n * 4, cudaMemcpyDeviceToHost));
@@ -529,11 +555,11 @@ int rtw_path_radiance(rtw_scene* s, const rtw_camera* cam, const rtw_opts* opts,
     CU(cudaMemcpy(s->d_u2.p, sample, n * 4, cudaMemcpyHostToDevice));
     if (opts->precision == RTW_F32) {
         BatchParams<float> P = batch_params<float>(s, s->f32, n);
-        P.cam = to_camera<float>(cam); P.seed = opts->seed; P.tmin = (float)opts->tmin; P.flags = opts->flags;
+        P.cam = to_camera<float>(cam); P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
         CU(launch_path_radiance_f32(P, 0));
     } else {
         BatchParams<double> P = batch_params<double>(s, s->f64, n);
-        P.cam = to_camera<double>(cam); P.seed = opts->seed; P.tmin = opts->tmin; P.flags = opts->flags;
+        P.cam = to_camera<double>(cam); P.seed = opts->seed; P.tmin = resolve_tmin<double>(opts->tmin); P.flags = opts->flags;
         CU(launch_path_radiance_f64(P, 0));
     }
     CU(cudaMemcpy(rgb, s->d_out1.p, 3 * n * 8, cudaMemcpyDeviceToHost));

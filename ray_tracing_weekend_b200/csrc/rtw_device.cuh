@@ -112,6 +112,18 @@ RTW_HD uint32_t uindex(Stream<false>& s, uint32_t n) {
 #endif
 }
 
+// 1-ulp reciprocal on the SFU (MUFU.RCP): the fast path's divisions
+RTW_HD float frcp(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.f / x;
+#endif
+}
+RTW_HD double frcp(double x) { return 1. / x; }
+
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policies.
 template <class T, bool EXACT> struct M;
@@ -192,6 +204,7 @@ template <class T> struct __align__(16) Node {
     int32_t pad[2];
 };
 constexpr int32_t kEmptyLeaf = (int32_t)0x80000000;   // leaf with no spheres
+constexpr int32_t kStop = (int32_t)0x80000001;        // bottom-of-stack code: traversal finished
 RTW_HD int32_t encode_leaf(uint32_t first, uint32_t count) { return count == 0 ? kEmptyLeaf : ~(int32_t)((first << 4) | (count - 1)); }
 
 template <class T> struct PlaneT { V3<T> point, normal; uint32_t info; uint32_t pad; T albedo[3]; T param; };

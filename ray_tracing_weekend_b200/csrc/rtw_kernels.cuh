@@ -86,7 +86,7 @@ RTW_D bool sphere_root_fast(const Vec4T<float>& s, const Ray<float>& r, float in
     float sq = sqrtf(dq * inv_a);                             // sqrt(disc) / a
     float c_a = ((ocx * ocx + ocy * ocy + ocz * ocz) - r2) * inv_a;
     float q = -(k + copysignf(sq, k));
-    float other = c_a / q;
+    float other = c_a * frcp(q);
     float near_root = k < 0.f ? other : q, far_root = k < 0.f ? q : other;
     float root = near_root;
     if (!(start <= root && root <= end)) {
@@ -122,14 +122,17 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
     RayAux aux;
     float inv_a = 0.f;
     if constexpr (!EXACT) {
-        inv_a = 1.f / a;
-        aux.ix = 1.f / r.d.x; aux.iy = 1.f / r.d.y; aux.iz = 1.f / r.d.z;
+        inv_a = frcp(a);
+        aux.ix = frcp(r.d.x); aux.iy = frcp(r.d.y); aux.iz = frcp(r.d.z);
         aux.ox = r.o.x * aux.ix; aux.oy = r.o.y * aux.iy; aux.oz = r.o.z * aux.iz;
     }
-    int sp = 0;
+    // while-while traversal: descend inner nodes until a leaf is reached, then test its spheres; a
+    // stop code at the bottom of the stack ends the walk.
+    stack[0] = kStop;
+    int sp = 1;
     int32_t cur = 0;        // root inner node
     for (;;) {
-        if (cur >= 0) {
+        while (cur >= 0) {
             const Node<T>& nd = cur < sc.n_top ? sc.top_nodes[cur] : sc.nodes[cur];
             if (COUNT) tl.node_visits++;
             bool hl, hr; T tl_near = T(0), tr_near = T(0);
@@ -146,11 +149,17 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
                 int32_t near = swap ? rr : l, far = swap ? l : rr;
                 stack[sp * stride] = far; sp++;
                 cur = near;
-                continue;
+            } else if (hl) {
+                cur = l;
+            } else if (hr) {
+                cur = rr;
+            } else {
+                sp--;
+                cur = stack[sp * stride];
             }
-            if (hl) { cur = l; continue; }
-            if (hr) { cur = rr; continue; }
-        } else if (cur != kEmptyLeaf) {
+        }
+        if (cur == kStop) break;
+        if (cur != kEmptyLeaf) {
             uint32_t enc = (uint32_t)~cur;
             uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
@@ -169,7 +178,6 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
                 if (hs && (!found || t < best_t)) { found = true; best_t = t; best = (int32_t)i; }
             }
         }
-        if (sp == 0) break;
         sp--;
         cur = stack[sp * stride];
     }
@@ -180,7 +188,8 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
     h->p = at(r, best_t);
     if (best >= 0) {
         Vec4T<T> s = sc.spheres[best];
-        outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;                                 // sphere.rs:82-83
+        if constexpr (EXACT) outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;            // sphere.rs:82-83
+        else outward = (h->p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
         Vec4T<T> m = sc.sphere_mat[best];
         h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = sc.sphere_info[best];
     } else {
@@ -221,35 +230,46 @@ template <class T, bool EXACT, bool COUNT>
 RTW_D T lights_pdf_value(const SceneView<T>& sc, V3<T> origin, V3<T> dir, Tally& tl) {
     using Mt = M<T, EXACT>;
     T acc = T(0);
-    T a = sqlen(dir);
-    Ray<T> r{origin, dir};
-    for (int i = 0; i < sc.n_lights; ++i) {
-        Vec4T<T> s = sc.lights[i];
-        if (COUNT) tl.light_tests++;
-        T v = T(0);
-        V3<T> cd = mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z);
-        bool hit;
-        T distance_squared;
-        if constexpr (EXACT) {
+    if constexpr (EXACT) {
+        T a = sqlen(dir);
+        Ray<T> r{origin, dir};
+        for (int i = 0; i < sc.n_lights; ++i) {
+            Vec4T<T> s = sc.lights[i];
+            if (COUNT) tl.light_tests++;
             T t;
-            hit = sphere_root<T>(s, r, a, T(0), Mt::inf(), &t);
-            distance_squared = sqlen(cd);
-        } else {
-            T hb = -dot(dir, cd);
-            distance_squared = sqlen(cd);
-            T c = distance_squared - s.w * s.w;
-            T k = hb / a;
-            V3<T> l = mk<T>(-cd.x - k * dir.x, -cd.y - k * dir.y, -cd.z - k * dir.z);
-            hit = (s.w * s.w - sqlen(l) > T(0)) && (hb <= T(0) || c <= T(0));
+            T v = T(0);
+            if (sphere_root<T>(s, r, a, T(0), Mt::inf(), &t)) {
+                V3<T> cd = mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z);
+                T distance_squared = sqlen(cd);
+                T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
+                T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
+                v = T(1) / solid_angle;
+            }
+            acc = acc + v;
         }
-        if (hit) {
-            T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
-            T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
-            v = T(1) / solid_angle;
+        return acc / (T)sc.n_lights;
+    } else {
+        // unit direction once; per light: towards = nd.(c - o), perpendicular residual l = (c - o) - towards nd,
+        // hit iff |l|^2 < r^2 and (towards >= 0 or the origin is inside): 13 flop, no division or root on a miss
+        V3<T> nd = Mt::normalize(dir);
+        for (int i = 0; i < sc.n_lights; ++i) {
+            Vec4T<T> s = sc.lights[i];
+            if (COUNT) tl.light_tests++;
+            T cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
+            T towards = nd.x * cx + nd.y * cy + nd.z * cz;
+            T lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
+            T r2 = s.w * s.w;
+            if (r2 - (lx * lx + ly * ly + lz * lz) > T(0)) {
+                T distance_squared = cx * cx + cy * cy + cz * cz;
+                if (towards >= T(0) || distance_squared <= r2) {
+                    T cos_theta_max = Mt::sqrt_(T(1) - r2 * frcp(distance_squared));
+                    T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
+                    acc += frcp(solid_angle);
+                }
+            }
         }
-        acc = acc + v;
+        return acc * frcp((T)sc.n_lights);
     }
-    return acc / (T)sc.n_lights;
 }
 
 // Sphere::random (sphere.rs:114-127)
@@ -300,7 +320,8 @@ RTW_D uint32_t shade(const SceneView<T>& sc, const Ray<T>& r, const Hit<T>& h, S
         T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
         T scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));  // material.rs:372-375
         *next = Ray<T>{h.p, dir};
-        *weight = (h.albedo * scattering_pdf) / pdf_value;      // camera.rs:518
+        if constexpr (EXACT) *weight = (h.albedo * scattering_pdf) / pdf_value;      // camera.rs:518
+        else *weight = h.albedo * (scattering_pdf * frcp(pdf_value));
         return V_DIFFUSE;
     }
     if (kind == METAL) {                                        // material.rs:407-421
@@ -527,6 +548,188 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
         out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;         // zeros for padding pixels
     }
     flush_counters<COUNT>(P.counters, npaths, nrays, tl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pooled megakernel (fast path).  The lane-per-pixel kernel above leaves two thirds of the lanes idle
+// (ncu: 10.6 of 32 threads active — a lane whose pixel shows only background finishes its spp paths
+// long before a neighbour looking at glass).  Here lanes are decoupled from pixels: the image's paths
+// form one pixel-major stream (all samples of a pixel are consecutive), warps pull chunks of it from
+// a global queue and every idle lane takes the next path of its warp's chunk.  So the 32 lanes of a
+// warp mostly trace samples of the SAME pixel (coherent primary rays, same first material) and no
+// lane idles until the stream is dry.
+// Radiance is accumulated in 64-bit fixed point (2^-32 units): integer adds commute, so the image is
+// bit-identical no matter which lane, warp or GPU traces which path.  A lane keeps a private partial
+// sum while it stays on one pixel and flushes it with one 64-bit reduction per channel when it moves on.
+// NaN / overflow samples set per-pixel poison bits (a NaN sample poisons the pixel like in the
+// reference, where the f64 sum becomes NaN and `as u8` maps it to 0).
+constexpr float kFixedScale = 4294967296.f;            // 2^32
+constexpr float kFixedMax = 1073741824.f;              // samples >= 2^30 saturate the pixel anyway
+
+struct PoolParams {
+    unsigned long long* accum;      // [n_local_tiles * 256][3]
+    uint32_t* poison;               // [n_local_tiles * 256]: bit c = NaN in channel c, bit 3 + c = overflow / +inf
+    uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
+    uint32_t n_chunks;
+};
+
+RTW_D void pool_flush(const PoolParams& Q, uint32_t q, unsigned long long a0, unsigned long long a1, unsigned long long a2) {
+    if (a0) atomicAdd(Q.accum + 3 * (size_t)q + 0, a0);
+    if (a1) atomicAdd(Q.accum + 3 * (size_t)q + 1, a1);
+    if (a2) atomicAdd(Q.accum + 3 * (size_t)q + 2, a2);
+}
+
+RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
+    if (!(v < kFixedMax)) {                                    // NaN, +inf or absurdly large
+        bad |= (v != v) ? (1u << channel) : (8u << channel);
+        return 0ull;
+    }
+    return __float2ull_rn(v * kFixedScale);                    // negative values clamp to 0
+}
+
+template <bool COUNT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) render_pool_kernel(RenderParams<float> P, PoolParams Q) {
+    using T = float;
+    constexpr bool EXACT = false;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
+    SceneView<T> sc = P.scene;
+    {
+        unsigned char* cur = smem_raw + sizeof(int32_t) * kStackDepth * BLOCK;
+        if (P.smem_nodes) {
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
+            for (uint32_t i = threadIdx.x; i < P.smem_nodes / 16; i += BLOCK) dst[i] = src[i];
+            sc.top_nodes = reinterpret_cast<const Node<T>*>(cur);
+            sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<T>));
+            cur += P.smem_nodes;
+        }
+        if (P.smem_spheres) {
+            uint32_t n16 = P.smem_spheres / 16;
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.spheres);
+            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
+            sc.spheres = reinterpret_cast<const Vec4T<T>*>(cur);
+            cur += P.smem_spheres;
+            dst = reinterpret_cast<uint4*>(cur);
+            src = reinterpret_cast<const uint4*>(P.scene.sphere_mat);
+            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
+            sc.sphere_mat = reinterpret_cast<const Vec4T<T>*>(cur);
+            cur += P.smem_spheres;
+            uint32_t* dsti = reinterpret_cast<uint32_t*>(cur);
+            for (uint32_t i = threadIdx.x; i < (uint32_t)P.scene.n_spheres; i += BLOCK) dsti[i] = P.scene.sphere_info[i];
+            sc.sphere_info = dsti;
+            cur += (P.scene.n_spheres * 4 + 15) / 16 * 16;
+        }
+        if (P.smem_lights) {
+            uint4* dst = reinterpret_cast<uint4*>(cur);
+            const uint4* src = reinterpret_cast<const uint4*>(P.scene.lights);
+            for (uint32_t i = threadIdx.x; i < P.smem_lights / 16; i += BLOCK) dst[i] = src[i];
+            sc.lights = reinterpret_cast<const Vec4T<T>*>(cur);
+        }
+        __syncthreads();
+    }
+    const CameraT<T>& cam = P.cam;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int32_t* stack = stack_base + threadIdx.x;
+    const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
+    const uint32_t spp = cam.spp, G = Q.pixels_per_chunk;
+    uint32_t npaths = 0, nrays = 0;
+    Tally tl;
+    // warp-uniform chunk cursor
+    uint32_t chunk_next = 0, chunk_end = 0, chunk_q0 = 0;
+    bool exhausted = (spp == 0);
+    // lane state
+    bool alive = false;
+    uint32_t q = 0xffffffffu, pixel = 0, sample = 0;
+    uint32_t acc_q = 0xffffffffu, bad = 0;
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+    PathState<T> ps;
+    ps.depth = 0;
+    for (;;) {
+        uint32_t need = __ballot_sync(0xffffffffu, !alive);
+        if (need) {
+            if (chunk_next == chunk_end && !exhausted) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(P.work_counter, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= Q.n_chunks) {
+                    exhausted = true;
+                } else {
+                    chunk_q0 = c * G;
+                    uint32_t npx = min(G, n_slots - chunk_q0);
+                    chunk_next = 0;
+                    chunk_end = npx * spp;
+                    if (G == 1) {       // skip padding pixels (outside the image / padding tiles) as a whole
+                        uint32_t tile = (chunk_q0 >> 8) * P.world + P.rank, in = chunk_q0 & 255u;
+                        uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                        if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) chunk_end = 0;
+                    }
+                }
+            }
+            if (!alive && chunk_next < chunk_end) {
+                uint32_t r = chunk_next + __popc(need & lt_mask);
+                if (r < chunk_end) {
+                    uint32_t pin = r / spp;
+                    sample = r - pin * spp;
+                    q = chunk_q0 + pin;
+                    uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
+                    uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                    if (tile < P.tiles_total && i < cam.width && j < cam.height) {
+                        pixel = j * cam.width + i;
+                        Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                        ps.r = get_ray<T, EXACT>(cam, i, j, rng);
+                        ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
+                        alive = true;
+                        npaths++;
+                    }
+                }
+            }
+            chunk_next = min(chunk_end, chunk_next + (uint32_t)__popc(need));
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (alive) {
+            V3<T> value;
+            if (path_step<T, EXACT, COUNT>(sc, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+                alive = false;
+                if (P.flags & 1u) value = fix_nan(value);
+                if (q != acc_q) {
+                    if (acc_q != 0xffffffffu) {
+                        pool_flush(Q, acc_q, a0, a1, a2);
+                        if (bad) atomicOr(Q.poison + acc_q, bad);
+                    }
+                    acc_q = q; a0 = a1 = a2 = 0ull; bad = 0;
+                }
+                a0 += pool_fixed(value.x, 0, bad);
+                a1 += pool_fixed(value.y, 1, bad);
+                a2 += pool_fixed(value.z, 2, bad);
+            }
+        }
+    }
+    if (acc_q != 0xffffffffu) {
+        pool_flush(Q, acc_q, a0, a1, a2);
+        if (bad) atomicOr(Q.poison + acc_q, bad);
+    }
+    flush_counters<COUNT>(P.counters, npaths, nrays, tl);
+}
+
+// fixed-point accumulators -> the float tile buffer of the ABI
+template <int UNUSED = 0>
+__global__ void pool_finalize_kernel(const unsigned long long* accum, const uint32_t* poison, float* tiles, uint32_t n_slots) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots) return;
+    uint32_t bad = poison[q];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = (float)((double)accum[3 * (size_t)q + c] * (1.0 / 4294967296.0));
+        if (bad & (8u << c)) v = __int_as_float(0x7f800000);
+        if (bad & (1u << c)) v = __int_as_float(0x7fc00000);
+        tiles[3 * (size_t)q + c] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -8,10 +8,10 @@ constexpr int kRenderBlock = 256;
 constexpr int kBatchBlock = 128;
 constexpr size_t kSmemSceneBudget = 64 * 1024;   // per-CTA budget for staged scene data (fast path)
 
-template <class T, bool EXACT, bool COUNT>
-cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    auto kernel = render_mega_kernel<T, EXACT, COUNT, kRenderBlock>;
-    size_t smem = sizeof(int32_t) * kStackDepth * kRenderBlock;
+// decide which scene sections the fast kernels stage in shared memory; returns the dynamic smem size
+template <class T, bool EXACT>
+size_t plan_smem(RenderParams<T>& P, int block) {
+    size_t smem = sizeof(int32_t) * kStackDepth * block;
     P.smem_nodes = P.smem_spheres = P.smem_lights = 0;
     if (!EXACT) {
         size_t budget = kSmemSceneBudget;
@@ -29,14 +29,29 @@ cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, 
         }
         smem += P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     }
+    return smem;
+}
+
+template <class K>
+cudaError_t persistent_grid(K kernel, int block, size_t smem, int sm_count, int* grid, LaunchInfo* info) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRenderBlock, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    int grid = sm_count * per_sm;
-    if (info) { info->grid = grid; info->block = kRenderBlock; info->smem = smem; info->blocks_per_sm = per_sm; }
+    *grid = sm_count * per_sm;
+    if (info) { info->grid = *grid; info->block = block; info->smem = smem; info->blocks_per_sm = per_sm; }
+    return cudaSuccess;
+}
+
+template <class T, bool EXACT, bool COUNT>
+cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    auto kernel = render_mega_kernel<T, EXACT, COUNT, kRenderBlock>;
+    size_t smem = plan_smem<T, EXACT>(P, kRenderBlock);
+    int grid = 0;
+    cudaError_t e = persistent_grid(kernel, kRenderBlock, smem, sm_count, &grid, info);
+    if (e != cudaSuccess) return e;
     kernel<<<grid, kRenderBlock, smem, s>>>(P);
     return cudaGetLastError();
 }
@@ -74,6 +89,25 @@ cudaError_t launch_untile_t(const T* tiles, uint32_t width, uint32_t height, uin
     dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
     uint32_t tiles_x = (width + kTileW - 1) / kTileW;
     untile_resolve_kernel<T><<<grid, block, 0, s>>>(tiles, width, height, world, tiles_per_rank, tiles_x, spp, rgb_sum, rgb8);
+    return cudaGetLastError();
+}
+
+template <bool COUNT>
+cudaError_t launch_render_pool_impl(RenderParams<float> P, PoolParams Q, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    auto kernel = render_pool_kernel<COUNT, kRenderBlock>;
+    size_t smem = plan_smem<float, false>(P, kRenderBlock);
+    int grid = 0;
+    cudaError_t e = persistent_grid(kernel, kRenderBlock, smem, sm_count, &grid, info);
+    if (e != cudaSuccess) return e;
+    uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
+    e = cudaMemsetAsync(Q.accum, 0, (size_t)n_slots * 3 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(Q.poison, 0, (size_t)n_slots * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kRenderBlock, smem, s>>>(P, Q);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pool_finalize_kernel<0><<<(n_slots + 255) / 256, 256, 0, s>>>(Q.accum, Q.poison, P.tiles, n_slots);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,8 @@ struct LaunchInfo { int grid = 0, block = 0; size_t smem = 0; int blocks_per_sm 
                                        uint32_t tiles_per_rank, uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
 
 RTW_DECLARE_LAUNCHERS(f32, float)
+cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
+uint32_t pool_pixels_per_chunk(uint32_t spp);
 RTW_DECLARE_LAUNCHERS(f64, double)
 
 }  // namespace rtw

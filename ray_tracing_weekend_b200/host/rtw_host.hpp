@@ -104,7 +104,7 @@ struct World {
 enum class Precision : uint32_t { F32 = RTW_F32, F64 = RTW_F64 };
 struct RenderOptions {
     uint64_t seed = 20261018;
-    double tmin = 2.220446049250313e-16;            // f64::EPSILON, camera.rs:473
+    double tmin = RTW_TMIN_REFERENCE;               // camera.rs:473: machine epsilon of the working precision
     Precision precision = Precision::F32;
     uint32_t mode = RTW_MEGAKERNEL, flags = 0;
 };

@@ -147,7 +147,8 @@ def run_cuda(args):
     cam = (cb.with_vfov(40.).with_aspect_ratio(WIDTH / HEIGHT).with_max_depth(DEPTH).with_image_width(WIDTH).with_image_height(HEIGHT)
            .with_samples_per_pixel(SPP).build())
     base_flags = R.RTW_FLAG_LANE_PER_PIXEL if args.lane_per_pixel else 0
-    opts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=R.RTW_MEGAKERNEL, flags=base_flags)
+    mode = R.RTW_WAVEFRONT if args.mode == "wavefront" else R.RTW_MEGAKERNEL
+    opts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=base_flags)
     scene = R.Scene(world_h, lights_h)
     renderer = D.DistributedRenderer(scene, cam, opts, rank, world, want_sum=False, want_rgb8=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
@@ -159,7 +160,7 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # event counts of one step (deterministic: counter-based RNG) — an untimed pass with counters on
-    copts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, flags=R.RTW_FLAG_COUNT_EVENTS | base_flags)
+    copts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=R.RTW_FLAG_COUNT_EVENTS | base_flags)
     cnt = scene.render_tiles_device(cam, copts, rank, world, renderer.local.data_ptr(), torch.cuda.current_stream().cuda_stream)
     keys = ["paths", "rays", "node_visits", "sphere_tests", "light_tests", "lambertian", "metal", "dielectric", "absorbed", "missed", "depth_out"]
     tot = torch.tensor([cnt[k] for k in keys], dtype=torch.float64, device="cuda")
@@ -236,13 +237,14 @@ def run_cuda(args):
         line = dict(
             metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload=WORKLOAD, mode="megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)", parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
+            config=dict(workload=WORKLOAD, mode=("wavefront (CTA-local queues in shared memory)" if args.mode == "wavefront" else
+                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
                         tmin="f64::EPSILON (reference)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
             mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
             kernel_ms_per_step=kern_ms / args.steps,
             roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,
                           peak_source=f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json); no FP32 figure is in that file",
-                          kernel="render_mega_kernel<float>" if args.lane_per_pixel else "render_pool_kernel", flop_per_launch=local_flops,
+                          kernel="render_wavefront_kernel" if args.mode == "wavefront" else ("render_mega_kernel<float>" if args.lane_per_pixel else "render_pool_kernel"), flop_per_launch=local_flops,
                           frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None),
             e2e=dict(value=total["rays"] * e2e_steps / e2e_s * 1e-6, unit="Mrays/s", h2d_bytes_per_step=scene.upload_bytes * world,
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
@@ -277,6 +279,7 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
+    ap.add_argument("--mode", default="megakernel", choices=["megakernel", "wavefront"])
     args = ap.parse_args()
     if args.spp != SPP:
         SPP = args.spp

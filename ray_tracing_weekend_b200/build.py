@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(LIB_DIR, "librtw_cuda.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = [
-    ("kernels_f32.cu", []),
+    ("kernels_f32.cu", ["-fmad=false"]),    # FMAs are explicit (fmaf) so every kernel rounds alike
     ("kernels_f64.cu", ["-fmad=false"]),
     ("capi.cu", []),
     ("../host/rtw_host_capi.cpp", []),

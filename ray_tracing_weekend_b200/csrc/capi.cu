@@ -172,7 +172,7 @@ int check_opts(const rtw_opts* o) {
     if (!o) return fail(RTW_E_INVALID, "opts is NULL");
     if (o->precision != RTW_F32 && o->precision != RTW_F64) return fail(RTW_E_INVALID, "opts.precision");
     if (o->mode != RTW_MEGAKERNEL && o->mode != RTW_WAVEFRONT) return fail(RTW_E_INVALID, "opts.mode");
-    if (o->mode == RTW_WAVEFRONT) return fail(RTW_E_UNSUPPORTED, "wavefront mode is not built yet");
+    if (o->mode == RTW_WAVEFRONT && o->precision != RTW_F32) return fail(RTW_E_UNSUPPORTED, "wavefront mode exists on the RTW_F32 path only");
     if (o->tmin != o->tmin) return fail(RTW_E_INVALID, "opts.tmin is NaN");
     return RTW_OK;
 }
@@ -376,7 +376,7 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
     if (world == 0 || rank >= world) return fail(RTW_E_INVALID, "rank/world");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t launches = 1;
-    bool pooled = o->precision == RTW_F32 && !(o->flags & RTW_FLAG_LANE_PER_PIXEL);
+    bool pooled = o->precision == RTW_F32 && (o->mode == RTW_WAVEFRONT || !(o->flags & RTW_FLAG_LANE_PER_PIXEL));
     if (pooled) {
         size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         CU(s->d_accum.reserve(n_slots * 3)); CU(s->d_poison.reserve(n_slots));
@@ -388,8 +388,12 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
         uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+        const bool wavefront = o->mode == RTW_WAVEFRONT;
+        if (wavefront && cam->max_depth > 0xffffu) return fail(RTW_E_UNSUPPORTED, "wavefront mode: max_depth > 65535");
+        const uint32_t bvh_depth = s->bvh.depth;
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
-            return launch_render_pool_f32(P, Q, count, sms, str, info);
+            return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)
+                             : launch_render_pool_f32(P, Q, count, sms, str, info);
         };
         rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch);
         launches = 2;

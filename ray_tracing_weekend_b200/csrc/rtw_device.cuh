@@ -37,10 +37,18 @@ template <class T> RTW_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y
 template <class T> RTW_HD V3<T> cross(V3<T> a, V3<T> b) {                                              // vec.rs:74-82
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
+// FP32 overloads with EXPLICIT fused multiply-adds.  Both kernel translation units are compiled with
+// -fmad=false, so the compiler never decides where an FMA goes: every kernel (megakernel, wavefront, batch)
+// evaluates a given expression with the same roundings, which makes their results bit-identical.
+RTW_HD float dot(V3<float> a, V3<float> b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RTW_HD V3<float> cross(V3<float> a, V3<float> b) {
+    return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))};
+}
 template <class T> RTW_HD T sqlen(V3<T> a) { return dot(a, a); }
 
 template <class T> struct Ray { V3<T> o, d; };
 template <class T> RTW_HD V3<T> at(const Ray<T>& r, T t) { return r.o + r.d * t; }                     // ray.rs:25-28
+RTW_HD V3<float> at(const Ray<float>& r, float t) { return {fmaf(r.d.x, t, r.o.x), fmaf(r.d.y, t, r.o.y), fmaf(r.d.z, t, r.o.z)}; }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Same constants as curand_philox4x32_x.h.
@@ -219,6 +227,49 @@ template <class T> struct SceneView {
     const Vec4T<T>* lights;        // (cx, cy, cz, r) in the lights list's insertion order
     int32_t n_nodes, n_top, n_spheres, n_planes, n_lights;
 };
+
+// Tag type: every section of the scene (nodes, spheres, materials, lights) sits in SHARED memory, so the
+// accessors below can issue ld.shared.v4 instead of generic loads (ncu/SASS: the generic path compiled to
+// 7 x LD.E.64 per node; this is 4 x LDS.128).
+template <class T> struct SceneViewSh : SceneView<T> {};
+
+RTW_D float4 lds128(const void* p) {
+    float4 v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+RTW_D uint32_t lds32(const void* p) {
+    uint32_t v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+RTW_D void unpack_node(float4 a, float4 b, float4 c, float4 d, Node<float>& nd) {
+    nd.lmin[0] = a.x; nd.lmin[1] = a.y; nd.lmin[2] = a.z; nd.lmax[0] = a.w;
+    nd.lmax[1] = b.x; nd.lmax[2] = b.y; nd.rmin[0] = b.z; nd.rmin[1] = b.w;
+    nd.rmin[2] = c.x; nd.rmax[0] = c.y; nd.rmax[1] = c.z; nd.rmax[2] = c.w;
+    nd.left = __float_as_int(d.x); nd.right = __float_as_int(d.y);
+}
+// accessors: generic (any T) / FP32 vectorised / FP32 shared
+template <class T> RTW_D void load_node(const SceneView<T>& sc, int32_t cur, Node<T>& nd) { nd = cur < sc.n_top ? sc.top_nodes[cur] : sc.nodes[cur]; }
+RTW_D void load_node(const SceneView<float>& sc, int32_t cur, Node<float>& nd) {
+    const float4* p = reinterpret_cast<const float4*>(cur < sc.n_top ? sc.top_nodes + cur : sc.nodes + cur);
+    unpack_node(p[0], p[1], p[2], p[3], nd);
+}
+RTW_D void load_node(const SceneViewSh<float>& sc, int32_t cur, Node<float>& nd) {
+    const char* p = reinterpret_cast<const char*>(sc.top_nodes + cur);
+    unpack_node(lds128(p), lds128(p + 16), lds128(p + 32), lds128(p + 48), nd);
+}
+template <class T> RTW_D Vec4T<T> load_sphere(const SceneView<T>& sc, int32_t i) { return sc.spheres[i]; }
+template <class T> RTW_D Vec4T<T> load_sphere_mat(const SceneView<T>& sc, int32_t i) { return sc.sphere_mat[i]; }
+template <class T> RTW_D uint32_t load_sphere_info(const SceneView<T>& sc, int32_t i) { return sc.sphere_info[i]; }
+template <class T> RTW_D Vec4T<T> load_light(const SceneView<T>& sc, int32_t i) { return sc.lights[i]; }
+RTW_D Vec4T<float> as_vec4(float4 v) { return Vec4T<float>{v.x, v.y, v.z, v.w}; }
+RTW_D Vec4T<float> load_sphere(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.spheres + i)); }
+RTW_D Vec4T<float> load_sphere_mat(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.sphere_mat + i)); }
+RTW_D uint32_t load_sphere_info(const SceneViewSh<float>& sc, int32_t i) { return lds32(sc.sphere_info + i); }
+RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.lights + i)); }
 
 template <class T> struct CameraT {
     V3<T> center, pixel00, du, dv, ddu, ddv, background;

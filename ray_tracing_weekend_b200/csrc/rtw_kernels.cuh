@@ -1,6 +1,7 @@
 // rtw_kernels.cuh — intersection, shading and the render / batch kernels, templated on the
 // arithmetic policy (see rtw_device.cuh).  Included by kernels_f32.cu (fast) and kernels_f64.cu (exact).
 #pragma once
+#include <type_traits>
 #include "rtw_device.cuh"
 
 namespace rtw {
@@ -77,14 +78,14 @@ template <class T> RTW_D bool sphere_root(const Vec4T<T>& s, const Ray<T>& r, T 
 // Root selection and the inclusive range test are the reference's.
 RTW_D bool sphere_root_fast(const Vec4T<float>& s, const Ray<float>& r, float inv_a, float start, float end, float* t_out) {
     float ocx = r.o.x - s.x, ocy = r.o.y - s.y, ocz = r.o.z - s.z;
-    float hb = r.d.x * ocx + r.d.y * ocy + r.d.z * ocz;
+    float hb = fmaf(r.d.x, ocx, fmaf(r.d.y, ocy, r.d.z * ocz));
     float k = hb * inv_a;
     float lx = fmaf(-k, r.d.x, ocx), ly = fmaf(-k, r.d.y, ocy), lz = fmaf(-k, r.d.z, ocz);
     float r2 = s.w * s.w;
-    float dq = r2 - (lx * lx + ly * ly + lz * lz);          // disc / a
+    float dq = fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2)));   // disc / a
     if (!(dq > 0.f)) return false;
     float sq = sqrtf(dq * inv_a);                             // sqrt(disc) / a
-    float c_a = ((ocx * ocx + ocy * ocy + ocz * ocz) - r2) * inv_a;
+    float c_a = fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -r2))) * inv_a;
     float q = -(k + copysignf(sq, k));
     float other = c_a * frcp(q);
     float near_root = k < 0.f ? other : q, far_root = k < 0.f ? q : other;
@@ -97,14 +98,36 @@ RTW_D bool sphere_root_fast(const Vec4T<float>& s, const Ray<float>& r, float in
     return true;
 }
 
+// HitRecord::new (hittable.rs:102-129) for the winning primitive only.
+// best >= 0: sorted sphere index; best <= -2: plane index -2 - best.
+template <class T, bool EXACT, class SC>
+RTW_D void hit_record(const SC& sc, const Ray<T>& r, int32_t best, T best_t, Hit<T>* h) {
+    V3<T> outward;
+    h->t = best_t;
+    h->p = at(r, best_t);
+    if (best >= 0) {
+        Vec4T<T> s = load_sphere(sc, best);
+        if constexpr (EXACT) outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;            // sphere.rs:82-83
+        else outward = (h->p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
+        Vec4T<T> m = load_sphere_mat(sc, best);
+        h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = load_sphere_info(sc, best);
+    } else {
+        const PlaneT<T>& pl = sc.planes[-2 - best];
+        outward = pl.normal;
+        h->albedo = mk<T>(pl.albedo[0], pl.albedo[1], pl.albedo[2]); h->param = pl.param; h->info = pl.info;
+    }
+    h->front_face = dot(r.d, outward) < T(0);
+    h->normal = h->front_face ? outward : -outward;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Closest hit: Hittable::hit of the world (bvh.rs:163-188 + hittable_list.rs:394-406), i.e.
 // argmin-t over planes passing Plane::hit and spheres passing (own AABB test) && Sphere::hit.
 // The reference visits both children with the un-shrunk range and keeps the first minimum; here the
 // range is shrunk to the best t so far and children are visited near-first — the argmin is the same
 // except for exact-t ties and the documented grazing cases.
-template <class T, bool EXACT, bool COUNT>
-RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
     using Mt = M<T, EXACT>;
     bool found = false;
     T best_t = tmax;
@@ -133,7 +156,8 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
     int32_t cur = 0;        // root inner node
     for (;;) {
         while (cur >= 0) {
-            const Node<T>& nd = cur < sc.n_top ? sc.top_nodes[cur] : sc.nodes[cur];
+            Node<T> nd;
+            load_node(sc, cur, nd);
             if (COUNT) tl.node_visits++;
             bool hl, hr; T tl_near = T(0), tr_near = T(0);
             if constexpr (EXACT) {
@@ -163,7 +187,7 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
             uint32_t enc = (uint32_t)~cur;
             uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
-                Vec4T<T> s = sc.spheres[i];
+                Vec4T<T> s = load_sphere(sc, (int32_t)i);
                 if constexpr (EXACT) {
                     // BoundedHittable::bounded_hit (hittable.rs:191-196): the sphere's own box first
                     // (Sphere::new's box, sphere.rs:42-45), with the un-shrunk range like the reference
@@ -182,23 +206,7 @@ RTW_D bool closest_hit(const SceneView<T>& sc, const Ray<T>& r, T tmin, T tmax, 
         cur = stack[sp * stride];
     }
     if (!found) return false;
-    // HitRecord::new (hittable.rs:102-129) for the winner only
-    V3<T> outward;
-    h->t = best_t;
-    h->p = at(r, best_t);
-    if (best >= 0) {
-        Vec4T<T> s = sc.spheres[best];
-        if constexpr (EXACT) outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;            // sphere.rs:82-83
-        else outward = (h->p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
-        Vec4T<T> m = sc.sphere_mat[best];
-        h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = sc.sphere_info[best];
-    } else {
-        const PlaneT<T>& pl = sc.planes[-2 - best];
-        outward = pl.normal;
-        h->albedo = mk<T>(pl.albedo[0], pl.albedo[1], pl.albedo[2]); h->param = pl.param; h->info = pl.info;
-    }
-    h->front_face = dot(r.d, outward) < T(0);
-    h->normal = h->front_face ? outward : -outward;
+    hit_record<T, EXACT, SC>(sc, r, best, best_t, h);
     return true;
 }
 
@@ -212,7 +220,10 @@ template <class T, bool EXACT> struct Onb {
         v = M<T, EXACT>::normalize(cross(w, a));
         u = cross(w, v);
     }
-    RTW_D V3<T> transform(V3<T> a) const { return ((mk<T>(0, 0, 0) + u * a.x) + v * a.y) + w * a.z; }
+    RTW_D V3<T> transform(V3<T> a) const {
+        if constexpr (EXACT) return ((mk<T>(0, 0, 0) + u * a.x) + v * a.y) + w * a.z;
+        else return mk<T>(fmaf(w.x, a.z, fmaf(v.x, a.y, u.x * a.x)), fmaf(w.y, a.z, fmaf(v.y, a.y, u.y * a.x)), fmaf(w.z, a.z, fmaf(v.z, a.y, u.z * a.x)));
+    }
 };
 
 template <class T> RTW_D V3<T> reflect(V3<T> s, V3<T> o) { return s - (o * T(2)) * dot(s, o); }       // vec.rs:103-107
@@ -226,15 +237,15 @@ template <class T, bool EXACT> RTW_D V3<T> refract(V3<T> s, V3<T> o, T eta) {   
 // Sphere::pdf_value (sphere.rs:101-111) summed over the lights list (hittable_list.rs:408-412).
 // Fast path: Sphere::hit(ray, 0..=inf) succeeds iff disc > 0 and the larger root is >= 0, i.e. iff
 // disc > 0 && (hb <= 0 || c <= 0) — no square root or division until a light is actually hit.
-template <class T, bool EXACT, bool COUNT>
-RTW_D T lights_pdf_value(const SceneView<T>& sc, V3<T> origin, V3<T> dir, Tally& tl) {
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
     using Mt = M<T, EXACT>;
     T acc = T(0);
     if constexpr (EXACT) {
         T a = sqlen(dir);
         Ray<T> r{origin, dir};
         for (int i = 0; i < sc.n_lights; ++i) {
-            Vec4T<T> s = sc.lights[i];
+            Vec4T<T> s = load_light(sc, i);
             if (COUNT) tl.light_tests++;
             T t;
             T v = T(0);
@@ -253,14 +264,14 @@ RTW_D T lights_pdf_value(const SceneView<T>& sc, V3<T> origin, V3<T> dir, Tally&
         // hit iff |l|^2 < r^2 and (towards >= 0 or the origin is inside): 13 flop, no division or root on a miss
         V3<T> nd = Mt::normalize(dir);
         for (int i = 0; i < sc.n_lights; ++i) {
-            Vec4T<T> s = sc.lights[i];
+            Vec4T<T> s = load_light(sc, i);
             if (COUNT) tl.light_tests++;
             T cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
-            T towards = nd.x * cx + nd.y * cy + nd.z * cz;
+            T towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
             T lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
             T r2 = s.w * s.w;
-            if (r2 - (lx * lx + ly * ly + lz * lz) > T(0)) {
-                T distance_squared = cx * cx + cy * cy + cz * cz;
+            if (fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2))) > T(0)) {
+                T distance_squared = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
                 if (towards >= T(0) || distance_squared <= r2) {
                     T cos_theta_max = Mt::sqrt_(T(1) - r2 * frcp(distance_squared));
                     T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
@@ -293,8 +304,8 @@ enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE
 
 // Material::scatter (+ the Scatter branch of ray_colour_tail_call, camera.rs:484-521).
 // Returns the vertex kind; on V_SPECULAR / V_DIFFUSE writes the next ray and the factor for `mult`.
-template <class T, bool EXACT, bool COUNT>
-RTW_D uint32_t shade(const SceneView<T>& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
     using Mt = M<T, EXACT>;
     uint32_t kind = h.info & 3u;
     if (kind == LAMBERTIAN) {                                   // material.rs:357-376
@@ -303,7 +314,7 @@ RTW_D uint32_t shade(const SceneView<T>& sc, const Ray<T>& r, const Hit<T>& h, S
         V3<T> dir;
         if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
             uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
-            dir = sphere_random<T, EXACT>(sc.lights[idx], h.p, rng);
+            dir = sphere_random<T, EXACT>(load_light(sc, (int32_t)idx), h.p, rng);
         } else {                                                // CosineWeightedHemisphere, utils.rs:146-161
             T r1 = standard(rng);
             T r2 = standard(rng);
@@ -314,7 +325,7 @@ RTW_D uint32_t shade(const SceneView<T>& sc, const Ray<T>& r, const Hit<T>& h, S
             T z = Mt::sqrt_(T(1) - r2);
             dir = uvw.transform(mk<T>(x, y, z));
         }
-        T light_v = lights_pdf_value<T, EXACT, COUNT>(sc, h.p, dir, tl);
+        T light_v = lights_pdf_value<T, EXACT, COUNT, SC>(sc, h.p, dir, tl);
         V3<T> nd = Mt::normalize(dir);
         T cos_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));   // CosinePdf::value, pdf.rs:46-49
         T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
@@ -390,8 +401,8 @@ template <class T> struct PathState {
     uint32_t depth;
 };
 
-template <class T, bool EXACT, bool COUNT>
-RTW_D bool path_step(const SceneView<T>& sc, const CameraT<T>& cam, uint64_t seed, T tmin, uint32_t pixel, uint32_t sample,
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin, uint32_t pixel, uint32_t sample,
                      PathState<T>& ps, V3<T>* value, int32_t* stack, int stride, uint32_t& nrays, Tally& tl) {
     if (ps.depth == 0) {                                        // camera.rs:470-472
         if (COUNT) tl.depth_out++;
@@ -400,7 +411,7 @@ RTW_D bool path_step(const SceneView<T>& sc, const CameraT<T>& cam, uint64_t see
     }
     nrays++;
     Hit<T> h;
-    if (!closest_hit<T, EXACT, COUNT>(sc, ps.r, tmin, M<T, EXACT>::inf(), &h, stack, stride, tl)) {   // camera.rs:473-475
+    if (!closest_hit<T, EXACT, COUNT, SC>(sc, ps.r, tmin, M<T, EXACT>::inf(), &h, stack, stride, tl)) {   // camera.rs:473-475
         if (COUNT) tl.missed++;
         *value = ps.mult * cam.background + ps.res;
         return true;
@@ -409,7 +420,7 @@ RTW_D bool path_step(const SceneView<T>& sc, const CameraT<T>& cam, uint64_t see
     Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u);
     Ray<T> next;
     V3<T> w;
-    uint32_t kind = shade<T, EXACT, COUNT>(sc, ps.r, h, rng, &next, &w, tl);
+    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl);
     if (kind == V_ABSORB) { *value = ps.mult * emitted + ps.res; return true; }       // camera.rs:484-486
     if (kind == V_DIFFUSE) ps.res = ps.res + ps.mult * emitted;                       // camera.rs:519
     ps.mult = ps.mult * w;
@@ -461,8 +472,9 @@ RTW_D void flush_counters(DeviceCounters* c, uint32_t npaths, uint32_t nrays, co
 // (an atomic counter); each lane owns one pixel and runs its spp paths back to back, regenerating a
 // camera ray as soon as its previous path ends (render_internal + ray_colour_tail_call,
 // camera.rs:315-388, 460-522).  Samples of a pixel are summed in sample order.
-template <class T, bool EXACT, bool COUNT, int BLOCK>
+template <class T, bool EXACT, bool COUNT, int BLOCK, bool SH = false>
 __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
+    static_assert(!(EXACT && SH), "the exact path reads the scene from global memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
     SceneView<T> sc = P.scene;
@@ -502,6 +514,9 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
         }
         __syncthreads();
     }
+    using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
+    SC scv;
+    static_cast<SceneView<T>&>(scv) = sc;
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     int32_t* stack = stack_base + threadIdx.x;
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
             if (!__any_sync(0xffffffffu, alive)) break;
             if (alive) {
                 V3<T> value;
-                if (path_step<T, EXACT, COUNT>(sc, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+                if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
                     if (P.flags & 1u) value = fix_nan(value);
                     acc = acc + value;                          // fold(Colour::default(), +), camera.rs:335
                     alive = false;
@@ -587,7 +602,7 @@ RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
     return __float2ull_rn(v * kFixedScale);                    // negative values clamp to 0
 }
 
-template <bool COUNT, int BLOCK>
+template <bool COUNT, int BLOCK, bool SH>
 __global__ void __launch_bounds__(BLOCK) render_pool_kernel(RenderParams<float> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
@@ -629,6 +644,9 @@ __global__ void __launch_bounds__(BLOCK) render_pool_kernel(RenderParams<float> 
         }
         __syncthreads();
     }
+    using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
+    SC scv;
+    static_cast<SceneView<T>&>(scv) = sc;
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -694,7 +712,7 @@ __global__ void __launch_bounds__(BLOCK) render_pool_kernel(RenderParams<float> 
         }
         if (alive) {
             V3<T> value;
-            if (path_step<T, EXACT, COUNT>(sc, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+            if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
                 alive = false;
                 if (P.flags & 1u) value = fix_nan(value);
                 if (q != acc_q) {
@@ -758,7 +776,7 @@ __global__ void __launch_bounds__(BLOCK) trace_batch_kernel(BatchParams<T> P) {
     Ray<T> r{load3<T>(P.o, idx), load3<T>(P.d, idx)};
     Hit<T> h;
     Tally tl;
-    bool hit = closest_hit<T, EXACT, false>(P.scene, r, P.tmin, P.tmax, &h, stack_s + threadIdx.x, BLOCK, tl);
+    bool hit = closest_hit<T, EXACT, false, SceneView<T>>(P.scene, r, P.tmin, P.tmax, &h, stack_s + threadIdx.x, BLOCK, tl);
     P.prim[idx] = hit ? (int32_t)(h.info >> 2) : -1;
     P.t[idx] = hit ? (double)h.t : __builtin_huge_val();
 }
@@ -772,7 +790,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) 
     Hit<T> h;
     Tally tl;
     V3<T> zero = mk<T>(0, 0, 0);
-    if (!closest_hit<T, EXACT, false>(P.scene, r, P.tmin, M<T, EXACT>::inf(), &h, stack_s + threadIdx.x, BLOCK, tl)) {
+    if (!closest_hit<T, EXACT, false, SceneView<T>>(P.scene, r, P.tmin, M<T, EXACT>::inf(), &h, stack_s + threadIdx.x, BLOCK, tl)) {
         P.prim[idx] = -1; P.t[idx] = __builtin_huge_val(); P.kind[idx] = V_MISS;
         store3(P.p, idx, zero); store3(P.normal, idx, zero); store3(P.dir, idx, zero); store3(P.weight, idx, zero);
         return;
@@ -780,7 +798,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) 
     Stream<EXACT> rng(P.seed, P.a[idx], P.b[idx], P.c[idx]);
     Ray<T> next{zero, zero};
     V3<T> w = zero;
-    uint32_t kind = shade<T, EXACT, false>(P.scene, r, h, rng, &next, &w, tl);
+    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl);
     P.prim[idx] = (int32_t)(h.info >> 2); P.t[idx] = (double)h.t; P.kind[idx] = kind;
     store3(P.p, idx, h.p); store3(P.normal, idx, h.normal);
     store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
@@ -811,7 +829,7 @@ __global__ void __launch_bounds__(BLOCK) path_radiance_kernel(BatchParams<T> P) 
     V3<T> value;
     uint32_t nrays = 0;
     Tally tl;
-    while (!path_step<T, EXACT, false>(P.scene, P.cam, P.seed, P.tmin, pixel, s, ps, &value, stack_s + threadIdx.x, BLOCK, nrays, tl)) {}
+    while (!path_step<T, EXACT, false, SceneView<T>>(P.scene, P.cam, P.seed, P.tmin, pixel, s, ps, &value, stack_s + threadIdx.x, BLOCK, nrays, tl)) {}
     if (P.flags & 1u) value = fix_nan(value);
     store3(P.rgb, idx, value);
 }

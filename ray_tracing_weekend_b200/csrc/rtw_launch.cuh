@@ -10,9 +10,10 @@ constexpr size_t kSmemSceneBudget = 64 * 1024;   // per-CTA budget for staged sc
 
 // decide which scene sections the fast kernels stage in shared memory; returns the dynamic smem size
 template <class T, bool EXACT>
-size_t plan_smem(RenderParams<T>& P, int block) {
+size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr) {
     size_t smem = sizeof(int32_t) * kStackDepth * block;
     P.smem_nodes = P.smem_spheres = P.smem_lights = 0;
+    if (all_shared) *all_shared = false;
     if (!EXACT) {
         size_t budget = kSmemSceneBudget;
         size_t lights = (size_t)P.scene.n_lights * sizeof(Vec4T<T>);
@@ -27,6 +28,8 @@ size_t plan_smem(RenderParams<T>& P, int block) {
             size_t top = std::min(nodes, budget) / sizeof(Node<T>) * sizeof(Node<T>);
             P.smem_nodes = (uint32_t)top;
         }
+        if (all_shared)
+            *all_shared = P.smem_nodes == nodes && (P.smem_spheres || !P.scene.n_spheres) && (P.smem_lights || !P.scene.n_lights);
         smem += P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     }
     return smem;
@@ -45,15 +48,23 @@ cudaError_t persistent_grid(K kernel, int block, size_t smem, int sm_count, int*
     return cudaSuccess;
 }
 
+template <class K, class P>
+cudaError_t launch_persistent(K kernel, const P& params, int block, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    int grid = 0;
+    cudaError_t e = persistent_grid(kernel, block, smem, sm_count, &grid, info);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, block, smem, s>>>(params);
+    return cudaGetLastError();
+}
+
 template <class T, bool EXACT, bool COUNT>
 cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    auto kernel = render_mega_kernel<T, EXACT, COUNT, kRenderBlock>;
-    size_t smem = plan_smem<T, EXACT>(P, kRenderBlock);
-    int grid = 0;
-    cudaError_t e = persistent_grid(kernel, kRenderBlock, smem, sm_count, &grid, info);
-    if (e != cudaSuccess) return e;
-    kernel<<<grid, kRenderBlock, smem, s>>>(P);
-    return cudaGetLastError();
+    bool sh = false;
+    size_t smem = plan_smem<T, EXACT>(P, kRenderBlock, &sh);
+    if constexpr (!EXACT) {
+        if (sh) return launch_persistent(render_mega_kernel<T, EXACT, COUNT, kRenderBlock, true>, P, kRenderBlock, smem, sm_count, s, info);
+    }
+    return launch_persistent(render_mega_kernel<T, EXACT, COUNT, kRenderBlock, false>, P, kRenderBlock, smem, sm_count, s, info);
 }
 
 template <class T, bool EXACT>
@@ -92,23 +103,37 @@ cudaError_t launch_untile_t(const T* tiles, uint32_t width, uint32_t height, uin
     return cudaGetLastError();
 }
 
-template <bool COUNT>
-cudaError_t launch_render_pool_impl(RenderParams<float> P, PoolParams Q, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    auto kernel = render_pool_kernel<COUNT, kRenderBlock>;
-    size_t smem = plan_smem<float, false>(P, kRenderBlock);
+template <bool COUNT, bool SH>
+cudaError_t launch_render_pool_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    auto kernel = render_pool_kernel<COUNT, kRenderBlock, SH>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, kRenderBlock, smem, sm_count, &grid, info);
     if (e != cudaSuccess) return e;
-    uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
-    e = cudaMemsetAsync(Q.accum, 0, (size_t)n_slots * 3 * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(Q.poison, 0, (size_t)n_slots * sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
     kernel<<<grid, kRenderBlock, smem, s>>>(P, Q);
-    e = cudaGetLastError();
+    return cudaGetLastError();
+}
+
+inline cudaError_t pool_clear(const RenderParams<float>& P, const PoolParams& Q, cudaStream_t s) {
+    uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
+    cudaError_t e = cudaMemsetAsync(Q.accum, 0, (size_t)n_slots * 3 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(Q.poison, 0, (size_t)n_slots * sizeof(uint32_t), s);
+}
+inline cudaError_t pool_finalize(const RenderParams<float>& P, const PoolParams& Q, cudaStream_t s) {
+    uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
     pool_finalize_kernel<0><<<(n_slots + 255) / 256, 256, 0, s>>>(Q.accum, Q.poison, P.tiles, n_slots);
     return cudaGetLastError();
+}
+
+template <bool COUNT>
+cudaError_t launch_render_pool_impl(RenderParams<float> P, PoolParams Q, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    bool sh = false;
+    size_t smem = plan_smem<float, false>(P, kRenderBlock, &sh);
+    cudaError_t e = pool_clear(P, Q, s);
+    if (e != cudaSuccess) return e;
+    e = sh ? launch_render_pool_sh<COUNT, true>(P, Q, smem, sm_count, s, info) : launch_render_pool_sh<COUNT, false>(P, Q, smem, sm_count, s, info);
+    if (e != cudaSuccess) return e;
+    return pool_finalize(P, Q, s);
 }
 
 #define RTW_DEFINE_LAUNCHERS(SUFFIX, T, EXACT)                                                                                   \

@@ -260,3 +260,21 @@ def test_furnace_fp32_tracks_reference_acne(rtw, oracle):
     assert abs(vals[(rtw.RTW_F64, rtw.TMIN_REFERENCE)][0] - 0.27) < 0.015
     assert abs(vals[(rtw.RTW_F32, rtw.TMIN_REFERENCE)][0] - vals[(rtw.RTW_F64, rtw.TMIN_REFERENCE)][0]) < 0.02
     assert abs(vals[(rtw.RTW_F32, rtw.TMIN_REFERENCE)][1] - vals[(rtw.RTW_F64, rtw.TMIN_REFERENCE)][1]) < 0.2
+
+
+def test_wavefront_is_bit_identical_to_megakernel(rtw, simple_scene, gscene):
+    """RTW_WAVEFRONT (CTA-local queues in shared memory) traces the same paths with the same arithmetic as the
+    pooled megakernel and accumulates in the same fixed point: the images must match bit for bit."""
+    for (w, h, spp, depth) in ((128, 72, 24, 50), (70, 50, 3, 50), (64, 36, 600, 5), (33, 17, 1, 1)):
+        cam = (simple_scene["cb"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(depth).with_image_width(w).with_image_height(h)
+               .with_samples_per_pixel(spp).build())
+        for flags in (0, rtw.RTW_FLAG_COUNT_EVENTS):
+            a, a8, sa = gscene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, mode=rtw.RTW_MEGAKERNEL, flags=flags))
+            b, b8, sb = gscene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, mode=rtw.RTW_WAVEFRONT, flags=flags))
+            for k in ("paths", "rays", "node_visits", "sphere_tests", "light_tests", "lambertian", "metal", "dielectric", "absorbed", "missed", "depth_out"):
+                assert sa[k] == sb[k], (k, sa[k], sb[k], (w, h, spp, depth))
+            diff = np.abs(np.nan_to_num(a, nan=-1.0) - np.nan_to_num(b, nan=-1.0))
+            assert np.array_equal(a, b, equal_nan=True), ((w, h, spp, depth), float(diff.max()), int((diff > 0).sum()), int(diff.size))
+            assert np.array_equal(a8, b8)
+    with pytest.raises(rtw.RtwError):
+        gscene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64, mode=rtw.RTW_WAVEFRONT))

@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" surface declared in include/rtw.h: scene upload, Camera::render and the
 // per-ray batch operations, on the current CUDA device.  No CPU fallback: every compute entry point
 // fails with RTW_E_NO_DEVICE / RTW_E_CUDA when the GPU path is unavailable.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -193,6 +194,7 @@ int render_tiles_t(rtw_scene* s, SceneDev<T>& d, const rtw_camera* cam, const rt
     P.tiles_total = rtw_tiles_total(cam->image_width, cam->image_height);
     P.n_local_tiles = rtw_tiles_per_rank(cam->image_width, cam->image_height, world);
     P.tiles = tiles; P.work_counter = s->d_work; P.counters = s->d_counters;
+    P.stack_depth = std::min<uint32_t>(kStackDepth, s->bvh.depth + 2);
     CU(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned int), stream));
     CU(cudaMemsetAsync(s->d_counters, 0, sizeof(DeviceCounters), stream));
     CU(launch(P, (o->flags & RTW_FLAG_COUNT_EVENTS) != 0, s->sm_count, stream, &s->last_launch));

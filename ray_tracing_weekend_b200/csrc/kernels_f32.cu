@@ -9,27 +9,28 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
     return count ? launch_render_pool_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_impl<false>(P, Q, sm_count, s, info);
 }
 template <bool COUNT, bool SH>
-cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, uint32_t stack_depth, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
+cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
     constexpr int BLOCK = 256, NP = 768;
     auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, BLOCK, smem, s>>>(P, Q, stack_depth);
+    kernel<<<grid, BLOCK, smem, s>>>(P, Q);
     return cudaGetLastError();
 }
 template <bool COUNT>
 cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
     constexpr int BLOCK = 256, NP = 768;
-    uint32_t stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
+    P.stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
     bool sh = false;
     plan_smem<float, false>(P, BLOCK, &sh);
+    const uint32_t stack_depth = P.stack_depth;
     size_t scene = P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     size_t smem = sizeof(int32_t) * stack_depth * BLOCK + scene + wavefront_state_bytes<BLOCK, NP>();
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
-    e = sh ? launch_render_wavefront_sh<COUNT, true>(P, Q, stack_depth, smem, sm_count, s, info)
-           : launch_render_wavefront_sh<COUNT, false>(P, Q, stack_depth, smem, sm_count, s, info);
+    e = sh ? launch_render_wavefront_sh<COUNT, true>(P, Q, smem, sm_count, s, info)
+           : launch_render_wavefront_sh<COUNT, false>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     return pool_finalize(P, Q, s);
 }

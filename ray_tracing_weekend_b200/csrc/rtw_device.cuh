@@ -131,6 +131,16 @@ RTW_HD float frcp(float x) {
 #endif
 }
 RTW_HD double frcp(double x) { return 1. / x; }
+// approximate square root on the SFU (MUFU.SQRT, ~1 ulp)
+RTW_HD float fsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policies.
@@ -178,7 +188,7 @@ template <> struct M<float, false> {
     static RTW_HD float inf() { return __builtin_huge_valf(); }
     static RTW_HD float max_(float a, float b) { return fmaxf(a, b); }
     static RTW_HD float min_(float a, float b) { return fminf(a, b); }
-    static RTW_HD float sqrt_(float a) { return sqrtf(a); }
+    static RTW_HD float sqrt_(float a) { return fsqrt(a); }
     static RTW_HD V3<float> normalize(V3<float> a) {
 #ifdef __CUDA_ARCH__
         return a * rsqrtf(sqlen(a));

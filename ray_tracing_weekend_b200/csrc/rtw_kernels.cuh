@@ -84,7 +84,7 @@ RTW_D bool sphere_root_fast(const Vec4T<float>& s, const Ray<float>& r, float in
     float r2 = s.w * s.w;
     float dq = fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2)));   // disc / a
     if (!(dq > 0.f)) return false;
-    float sq = sqrtf(dq * inv_a);                             // sqrt(disc) / a
+    float sq = fsqrt(dq * inv_a);                             // sqrt(disc) / a
     float c_a = fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -r2))) * inv_a;
     float q = -(k + copysignf(sq, k));
     float other = c_a * frcp(q);
@@ -137,7 +137,9 @@ RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h,
         const PlaneT<T>& pl = sc.planes[i];
         T denom = dot(r.d, pl.normal);
         if (!(denom > Mt::EPS)) continue;
-        T t = -dot(r.o - pl.point, pl.normal) / denom;
+        T t;
+        if constexpr (EXACT) t = -dot(r.o - pl.point, pl.normal) / denom;
+        else t = -dot(r.o - pl.point, pl.normal) * frcp(denom);
         if (!(tmin <= t && t <= tmax)) continue;
         if (!found || t < best_t) { found = true; best_t = t; best = -2 - i; }
     }
@@ -444,6 +446,7 @@ template <class T> struct RenderParams {
     DeviceCounters* counters;
     // shared-memory staging of the scene (fast path only): bytes of each section, 0 = keep in global
     uint32_t smem_nodes, smem_spheres, smem_lights;
+    uint32_t stack_depth;           // traversal stack entries per thread: BVH depth + 2, at most kStackDepth
 };
 
 RTW_D uint32_t warp_sum(uint32_t v) {
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
     SceneView<T> sc = P.scene;
     if constexpr (!EXACT) {
         // stage the scene in shared memory when the host decided it fits
-        unsigned char* cur = smem_raw + sizeof(int32_t) * kStackDepth * BLOCK;
+        unsigned char* cur = smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK;
         if (P.smem_nodes) {
             uint4* dst = reinterpret_cast<uint4*>(cur);
             const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
@@ -603,14 +606,14 @@ RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
 }
 
 template <bool COUNT, int BLOCK, bool SH>
-__global__ void __launch_bounds__(BLOCK) render_pool_kernel(RenderParams<float> P, PoolParams Q) {
+__global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<float> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
     SceneView<T> sc = P.scene;
     {
-        unsigned char* cur = smem_raw + sizeof(int32_t) * kStackDepth * BLOCK;
+        unsigned char* cur = smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK;
         if (P.smem_nodes) {
             uint4* dst = reinterpret_cast<uint4*>(cur);
             const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);

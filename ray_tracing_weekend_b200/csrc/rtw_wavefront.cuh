@@ -66,7 +66,8 @@ RTW_D V3<float> wf_res(uint32_t dep) {
 }
 
 template <bool COUNT, int BLOCK, int NP, bool SH>
-__global__ void __launch_bounds__(BLOCK) render_wavefront_kernel(RenderParams<float> P, PoolParams Q, uint32_t stack_depth) {
+__global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams<float> P, PoolParams Q) {
+    const uint32_t stack_depth = P.stack_depth;
     using T = float;
     constexpr bool EXACT = false;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(BLOCK) render_wavefront_kernel(RenderParams<fl
                                 const PlaneT<T>& pl = sc.planes[i];
                                 T denom = dot(r.d, pl.normal);
                                 if (!(denom > M<T, EXACT>::EPS)) continue;
-                                T t = -dot(r.o - pl.point, pl.normal) / denom;
+                                T t = -dot(r.o - pl.point, pl.normal) * frcp(denom);
                                 if (!(tmin <= t && t <= tmax)) continue;
                                 if (best == -1 || t < best_t) { best_t = t; best = -2 - i; }
                             }

@@ -139,6 +139,7 @@ def run_cuda(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback (use --impl reference for the CPU baseline)")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     rank, world, local_rank = D.init_from_env()
     if world != args.gpus:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun --nproc-per-node {args.gpus}")
@@ -239,7 +240,7 @@ def run_cuda(args):
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=WORKLOAD, mode=("wavefront (CTA-local queues in shared memory)" if args.mode == "wavefront" else
                               "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
-                        tmin="f64::EPSILON (reference)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
+                        tmin="RTW_TMIN_REFERENCE: machine epsilon of the working precision (the reference uses f64::EPSILON in f64)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
             mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
             kernel_ms_per_step=kern_ms / args.steps,
             roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,

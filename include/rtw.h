@@ -127,6 +127,9 @@ RTW_API uint32_t    rtw_tiles_per_rank(uint32_t width, uint32_t height, uint32_t
 
 /* ---- device management ------------------------------------------------------------------------ */
 RTW_API int rtw_device_count(void);           /* >= 0, or RTW_E_* */
+/* Device buffers of destroyed scenes / finished renders are kept in a process-wide cache (<= 4 GiB) and reused;
+ * this frees them. */
+RTW_API int rtw_release_cached_memory(void);
 
 /* ---- scene ------------------------------------------------------------------------------------ */
 /* Replaces what scenes::simple hands to render: `world` = BoundedVolumeHierarchy::from(HittableList)

@@ -22,7 +22,7 @@ TMIN_REFERENCE = -1.0      # rtw_opts.tmin: machine epsilon of the working preci
 # every symbol include/rtw.h and include/rtw_host.h declare
 RTW_SYMBOLS = (
     "rtw_abi_version", "rtw_last_error", "rtw_camera_build", "rtw_philox4x32_10", "rtw_tiles_total", "rtw_tiles_per_rank",
-    "rtw_device_count", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
+    "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
@@ -104,6 +104,7 @@ def load(build_if_missing: bool = True):
     L.rtw_tiles_total.argtypes = [u32, u32]; L.rtw_tiles_total.restype = u32
     L.rtw_tiles_per_rank.argtypes = [u32, u32, u32]; L.rtw_tiles_per_rank.restype = u32
     L.rtw_device_count.restype = C.c_int
+    L.rtw_release_cached_memory.restype = C.c_int
     L.rtw_scene_create.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, vp, sz, vp]
     L.rtw_scene_destroy.argtypes = [vp]; L.rtw_scene_destroy.restype = None
     L.rtw_scene_info.argtypes = [vp, vp]

@@ -152,12 +152,38 @@ class Scene:
         self.n_spheres, self.n_planes, self.n_lights = ns, npl, nl
         self.upload_bytes = ns * 32 + ns * 4 + npl * 48 + npl * 4 + (ns + npl) * 40 + nl * 32
 
+    @classmethod
+    def from_arrays(cls, spheres, sphere_materials, planes=None, plane_materials=None, lights=None):
+        """Array form of the constructor for large scenes: spheres [n,4] f64 (cx,cy,cz,r), sphere_materials [n,5] f64
+        (kind,r,g,b,param) one row per sphere, planes [m,6], plane_materials [m,5], lights [l,4]."""
+        self = cls.__new__(cls)
+        spheres = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        sm = np.asarray(sphere_materials, dtype=np.float64).reshape(-1, 5)
+        planes = np.ascontiguousarray(planes if planes is not None else np.zeros((0, 6)), dtype=np.float64).reshape(-1, 6)
+        pm = np.asarray(plane_materials if plane_materials is not None else np.zeros((0, 5)), dtype=np.float64).reshape(-1, 5)
+        lights = np.ascontiguousarray(lights if lights is not None else np.zeros((0, 4)), dtype=np.float64).reshape(-1, 4)
+        ns, npl, nl = len(spheres), len(planes), len(lights)
+        mats = np.zeros(ns + npl, dtype=np.dtype([("kind", "<u4"), ("reserved", "<u4"), ("r", "<f8"), ("g", "<f8"), ("b", "<f8"), ("param", "<f8")]))
+        allm = np.concatenate([sm, pm]) if ns + npl else np.zeros((0, 5))
+        mats["kind"] = allm[:, 0].astype(np.uint32); mats["r"] = allm[:, 1]; mats["g"] = allm[:, 2]; mats["b"] = allm[:, 3]; mats["param"] = allm[:, 4]
+        smat = np.arange(ns, dtype=np.uint32); pmat = np.arange(ns, ns + npl, dtype=np.uint32)
+        self._h = C.c_void_p()
+        _lib.check(_lib.load().rtw_scene_create(_p(spheres), _p(smat), ns, _p(planes), _p(pmat), npl, _p(mats), ns + npl, _p(lights), nl,
+                                                C.byref(self._h)))
+        self.n_spheres, self.n_planes, self.n_lights = ns, npl, nl
+        self.upload_bytes = ns * 32 + ns * 4 + npl * 48 + npl * 4 + (ns + npl) * 40 + nl * 32
+        return self
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             _lib.load().rtw_scene_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
 
     def info(self):
         out = np.zeros(5, dtype=np.uint64)

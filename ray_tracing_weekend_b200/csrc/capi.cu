@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,25 +30,63 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                                 \
     } while (0)
 
+constexpr size_t kLightBvhThreshold = 64;   // more lights than this: BVH over the lights (FP32 path)
+
+// Device allocations are recycled through a small process-wide cache: cudaMalloc / cudaFree of the tens of MB
+// of per-render buffers (and cudaFree's implicit device synchronisation) otherwise dominate the end-to-end
+// time of a scene_create -> render -> scene_destroy cycle.  rtw_release_cached_memory() empties it.
+struct DevCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> blocks;
+    size_t bytes = 0;
+    static constexpr size_t kMaxBytes = size_t(4) << 30;
+};
+DevCache& dev_cache() { static DevCache c; return c; }
+size_t round_alloc(size_t n) { return n <= (1u << 20) ? (n + 511) / 512 * 512 : (n + (1u << 20) - 1) / (1u << 20) * (1u << 20); }
+cudaError_t cached_malloc(void** p, size_t n) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    n = round_alloc(n);
+    {
+        DevCache& c = dev_cache();
+        std::lock_guard<std::mutex> g(c.m);
+        auto it = c.blocks.find({dev, n});
+        if (it != c.blocks.end()) { *p = it->second; c.blocks.erase(it); c.bytes -= n; return cudaSuccess; }
+    }
+    return cudaMalloc(p, n);
+}
+void cached_free(void* p, size_t n) {
+    if (!p) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
+    n = round_alloc(n);
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> g(c.m);
+    if (c.bytes + n > DevCache::kMaxBytes) { cudaFree(p); return; }
+    c.blocks.insert({{dev, n}, p});
+    c.bytes += n;
+}
+
 template <class P> struct DevBuf {
     P* p = nullptr; size_t n = 0;
     cudaError_t upload(const std::vector<P>& h) {
         release();
         n = h.size();
         if (!n) return cudaSuccess;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(P));
-        if (e != cudaSuccess) { p = nullptr; return e; }
+        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), n * sizeof(P));
+        if (e != cudaSuccess) { p = nullptr; n = 0; return e; }
         return cudaMemcpy(p, h.data(), n * sizeof(P), cudaMemcpyHostToDevice);
     }
     cudaError_t reserve(size_t count) {
         if (count <= n && p) return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc(&p, count * sizeof(P));
+        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), count * sizeof(P));
         if (e != cudaSuccess) { p = nullptr; return e; }
         n = count;
         return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cached_free(p, n * sizeof(P)); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(P); }
 };
 
@@ -55,22 +95,32 @@ float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nexta
 
 template <class T> void fill_node(Node<T>& n, const host::FlatNode& f);
 template <> void fill_node<double>(Node<double>& n, const host::FlatNode& f) {
-    for (int a = 0; a < 3; ++a) { n.lmin[a] = f.lbox.mn[a]; n.lmax[a] = f.lbox.mx[a]; n.rmin[a] = f.rbox.mn[a]; n.rmax[a] = f.rbox.mx[a]; }
+    for (int a = 0; a < 3; ++a) { n.la[a] = f.lbox.mn[a]; n.lb[a] = f.lbox.mx[a]; n.ra[a] = f.rbox.mn[a]; n.rb[a] = f.rbox.mx[a]; }
 }
 template <> void fill_node<float>(Node<float>& n, const host::FlatNode& f) {
-    // conservative: round outward, then pad by a few ulps so FP32 slab arithmetic cannot cull a
-    // sphere its own FP32 test would accept
-    auto lo = [](double v) { float x = round_down(v); return x - 4e-7f * std::fmax(1.f, std::fabs(x)); };
-    auto hi = [](double v) { float x = round_up(v); return x + 4e-7f * std::fmax(1.f, std::fabs(x)); };
-    for (int a = 0; a < 3; ++a) { n.lmin[a] = lo(f.lbox.mn[a]); n.lmax[a] = hi(f.lbox.mx[a]); n.rmin[a] = lo(f.rbox.mn[a]); n.rmax[a] = hi(f.rbox.mx[a]); }
+    // (centre, half-extent) in FP32, conservative: the half-extent is rounded up from the f64 box around the
+    // ROUNDED centre and padded by ~8 ulp of the box scale so FP32 slab arithmetic cannot cull a sphere its own
+    // FP32 test would accept
+    auto conv = [](const host::Box& b, float* c, float* h) {
+        for (int a = 0; a < 3; ++a) {
+            float cc = (float)(0.5 * (b.mn[a] + b.mx[a]));
+            if (!std::isfinite(cc)) cc = 0.f;
+            double e = std::fmax(b.mx[a] - (double)cc, (double)cc - b.mn[a]);
+            float hh = round_up(e);
+            hh += 1e-6f * std::fmax(1.f, std::fabs(cc) + hh);
+            c[a] = cc; h[a] = hh;
+        }
+    };
+    conv(f.lbox, n.la, n.lb);
+    conv(f.rbox, n.ra, n.rb);
 }
 
 template <class T> struct SceneDev {
-    DevBuf<Node<T>> nodes; DevBuf<Vec4T<T>> spheres, sphere_mat, lights; DevBuf<uint32_t> info; DevBuf<PlaneT<T>> planes;
+    DevBuf<Node<T>> nodes, light_nodes; DevBuf<Vec4T<T>> spheres, sphere_mat, lights; DevBuf<uint32_t> info; DevBuf<PlaneT<T>> planes;
     DevBuf<T> tiles;
     SceneView<T> view{};
-    size_t bytes() const { return nodes.bytes() + spheres.bytes() + sphere_mat.bytes() + lights.bytes() + info.bytes() + planes.bytes(); }
-    void release() { nodes.release(); spheres.release(); sphere_mat.release(); lights.release(); info.release(); planes.release(); tiles.release(); }
+    size_t bytes() const { return light_nodes.bytes() + nodes.bytes() + spheres.bytes() + sphere_mat.bytes() + lights.bytes() + info.bytes() + planes.bytes(); }
+    void release() { light_nodes.release(); nodes.release(); spheres.release(); sphere_mat.release(); lights.release(); info.release(); planes.release(); tiles.release(); }
 };
 
 }  // namespace
@@ -89,6 +139,7 @@ struct rtw_scene {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     LaunchInfo last_launch;
     uint32_t last_launches = 1;
+    uint32_t light_bvh_depth = 0;
 };
 
 namespace {
@@ -115,9 +166,32 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
         mat[k] = Vec4T<T>{(T)m.r, (T)m.g, (T)m.b, (T)m.param};
         info[k] = ((uint32_t)(np + src) << 2) | (m.kind & 3u);
     }
-    for (size_t k = 0; k < s->lights.size(); ++k) {
-        const rtw_sphere& q = s->lights[k];
-        lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
+    // lights: insertion order; on the FP32 path a long list gets its own BVH (leaf order) so that
+    // lights.pdf_value is not O(#lights) per diffuse bounce
+    std::vector<Node<T>> light_nodes;
+    const bool light_bvh = sizeof(T) == 4 && s->lights.size() > kLightBvhThreshold;
+    if (light_bvh) {
+        host::Builder lb;
+        host::Bvh lbvh = lb.build(reinterpret_cast<const double*>(s->lights.data()), s->lights.size(), 4, kMaxTreeDepth);
+        light_nodes.resize(lbvh.nodes.size());
+        for (size_t i = 0; i < lbvh.nodes.size(); ++i) {
+            const host::FlatNode& f = lbvh.nodes[i];
+            Node<T> n{};
+            fill_node<T>(n, f);
+            n.left = f.left >= 0 ? f.left : encode_leaf(f.lfirst, f.lcount);
+            n.right = f.right >= 0 ? f.right : encode_leaf(f.rfirst, f.rcount);
+            light_nodes[i] = n;
+        }
+        for (size_t k = 0; k < s->lights.size(); ++k) {
+            const rtw_sphere& q = s->lights[lbvh.order[k]];
+            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
+        }
+        s->light_bvh_depth = lbvh.depth;
+    } else {
+        for (size_t k = 0; k < s->lights.size(); ++k) {
+            const rtw_sphere& q = s->lights[k];
+            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
+        }
     }
     std::vector<PlaneT<T>> planes(np);
     for (size_t k = 0; k < np; ++k) {
@@ -132,12 +206,13 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
         planes[k] = p;
     }
     CU(d.nodes.upload(nodes)); CU(d.spheres.upload(sph)); CU(d.sphere_mat.upload(mat)); CU(d.info.upload(info));
-    CU(d.lights.upload(lights)); CU(d.planes.upload(planes));
+    CU(d.lights.upload(lights)); CU(d.planes.upload(planes)); CU(d.light_nodes.upload(light_nodes));
     d.view.nodes = d.nodes.p; d.view.top_nodes = d.nodes.p; d.view.n_top = 0;
     d.view.spheres = d.spheres.p; d.view.sphere_mat = d.sphere_mat.p; d.view.sphere_info = d.info.p;
     d.view.planes = d.planes.p; d.view.lights = d.lights.p;
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_spheres = (int32_t)ns; d.view.n_planes = (int32_t)np;
     d.view.n_lights = (int32_t)lights.size();
+    d.view.light_nodes = d.light_nodes.p; d.view.n_light_nodes = (int32_t)light_nodes.size();
     return RTW_OK;
 }
 
@@ -194,7 +269,7 @@ int render_tiles_t(rtw_scene* s, SceneDev<T>& d, const rtw_camera* cam, const rt
     P.tiles_total = rtw_tiles_total(cam->image_width, cam->image_height);
     P.n_local_tiles = rtw_tiles_per_rank(cam->image_width, cam->image_height, world);
     P.tiles = tiles; P.work_counter = s->d_work; P.counters = s->d_counters;
-    P.stack_depth = std::min<uint32_t>(kStackDepth, s->bvh.depth + 2);
+    P.stack_depth = std::min<uint32_t>(kStackDepth, std::max(s->bvh.depth, s->light_bvh_depth) + 2);
     CU(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned int), stream));
     CU(cudaMemsetAsync(s->d_counters, 0, sizeof(DeviceCounters), stream));
     CU(launch(P, (o->flags & RTW_FLAG_COUNT_EVENTS) != 0, s->sm_count, stream, &s->last_launch));
@@ -294,6 +369,14 @@ int rtw_camera_build(const rtw_camera_builder* b, rtw_camera* out) {
     return RTW_OK;
 }
 
+int rtw_release_cached_memory(void) {
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> g(c.m);
+    for (auto& kv : c.blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+    c.blocks.clear(); c.bytes = 0;
+    return RTW_OK;
+}
+
 int rtw_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -340,8 +423,8 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_work, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, sizeof(DeviceCounters));
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int));
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     int rc = upload_scene<float>(s, s->f32);
@@ -354,8 +437,8 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
 void rtw_scene_destroy(rtw_scene* s) {
     if (!s) return;
     s->f32.release(); s->f64.release();
-    if (s->d_work) cudaFree(s->d_work);
-    if (s->d_counters) cudaFree(s->d_counters);
+    cached_free(s->d_work, sizeof(unsigned int));
+    cached_free(s->d_counters, sizeof(DeviceCounters));
     s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release();
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
@@ -392,7 +475,7 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
         const bool wavefront = o->mode == RTW_WAVEFRONT;
         if (wavefront && cam->max_depth > 0xffffu) return fail(RTW_E_UNSUPPORTED, "wavefront mode: max_depth > 65535");
-        const uint32_t bvh_depth = s->bvh.depth;
+        const uint32_t bvh_depth = std::max(s->bvh.depth, s->light_bvh_depth);
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)
                              : launch_render_pool_f32(P, Q, count, sms, str, info);

@@ -216,8 +216,9 @@ template <> struct __align__(16) Vec4T<double> { double x, y, z, w; };
 
 // Inner node with both child boxes.  child >= 0: inner node index; child < 0: leaf, ~child =
 // first_sorted_sphere << 4 | (count - 1), count in 0..16 encoded as (count-1)&15 with a flag for 0
+// Child boxes: (la, lb) / (ra, rb) are (min, max) on the f64 path and (centre, half-extent) on the FP32 path.
 template <class T> struct __align__(16) Node {
-    T lmin[3], lmax[3], rmin[3], rmax[3];
+    T la[3], lb[3], ra[3], rb[3];
     int32_t left, right;
     int32_t pad[2];
 };
@@ -234,8 +235,9 @@ template <class T> struct SceneView {
     const Vec4T<T>* sphere_mat;    // sorted: (albedo r, g, b, param)
     const uint32_t* sphere_info;   // sorted: prim_id << 2 | kind
     const PlaneT<T>* planes;
-    const Vec4T<T>* lights;        // (cx, cy, cz, r) in the lights list's insertion order
-    int32_t n_nodes, n_top, n_spheres, n_planes, n_lights;
+    const Vec4T<T>* lights;        // (cx, cy, cz, r) in the lights list's insertion order (leaf order when light_nodes is set)
+    const Node<T>* light_nodes;    // optional BVH over the lights (fast path, many lights); global memory
+    int32_t n_nodes, n_top, n_spheres, n_planes, n_lights, n_light_nodes;
 };
 
 // Tag type: every section of the scene (nodes, spheres, materials, lights) sits in SHARED memory, so the
@@ -256,9 +258,9 @@ RTW_D uint32_t lds32(const void* p) {
     return v;
 }
 RTW_D void unpack_node(float4 a, float4 b, float4 c, float4 d, Node<float>& nd) {
-    nd.lmin[0] = a.x; nd.lmin[1] = a.y; nd.lmin[2] = a.z; nd.lmax[0] = a.w;
-    nd.lmax[1] = b.x; nd.lmax[2] = b.y; nd.rmin[0] = b.z; nd.rmin[1] = b.w;
-    nd.rmin[2] = c.x; nd.rmax[0] = c.y; nd.rmax[1] = c.z; nd.rmax[2] = c.w;
+    nd.la[0] = a.x; nd.la[1] = a.y; nd.la[2] = a.z; nd.lb[0] = a.w;
+    nd.lb[1] = b.x; nd.lb[2] = b.y; nd.ra[0] = b.z; nd.ra[1] = b.w;
+    nd.ra[2] = c.x; nd.rb[0] = c.y; nd.rb[1] = c.z; nd.rb[2] = c.w;
     nd.left = __float_as_int(d.x); nd.right = __float_as_int(d.y);
 }
 // accessors: generic (any T) / FP32 vectorised / FP32 shared
@@ -279,7 +281,11 @@ RTW_D Vec4T<float> as_vec4(float4 v) { return Vec4T<float>{v.x, v.y, v.z, v.w}; 
 RTW_D Vec4T<float> load_sphere(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.spheres + i)); }
 RTW_D Vec4T<float> load_sphere_mat(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.sphere_mat + i)); }
 RTW_D uint32_t load_sphere_info(const SceneViewSh<float>& sc, int32_t i) { return lds32(sc.sphere_info + i); }
-RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.lights + i)); }
+// with a light BVH the lights stay in global memory (read through L1), otherwise they are staged like the rest
+RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
+    if (sc.n_light_nodes > 0) return as_vec4(__ldg(reinterpret_cast<const float4*>(sc.lights + i)));
+    return as_vec4(lds128(sc.lights + i));
+}
 
 template <class T> struct CameraT {
     V3<T> center, pixel00, du, dv, ddu, ddv, background;

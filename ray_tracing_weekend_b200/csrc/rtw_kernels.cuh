@@ -38,15 +38,24 @@ RTW_D bool box_hit_exact(const double* mn, const double* mx, const Ray<double>& 
     return Md::max_(start, tmin) <= Md::min_(end, tmax);
 }
 
-// Fast: reciprocal-direction slabs, one FMA per plane.  oi = o * inv_d.  NaNs (0 * inf) drop out of
-// fminf/fmaxf, which makes the axis unconstrained — conservative.
-struct RayAux { float ix, iy, iz, ox, oy, oz; };
-RTW_D bool box_hit_fast(const float* mn, const float* mx, const RayAux& a, float tmin, float tmax, float* tnear) {
-    float x0 = fmaf(mn[0], a.ix, -a.ox), x1 = fmaf(mx[0], a.ix, -a.ox);
-    float y0 = fmaf(mn[1], a.iy, -a.oy), y1 = fmaf(mx[1], a.iy, -a.oy);
-    float z0 = fmaf(mn[2], a.iz, -a.oz), z1 = fmaf(mx[2], a.iz, -a.oz);
-    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+// Fast: slabs from the box centre c and half-extent h.  Per axis m = (c - o) / d, e = h / |d|, the slab is
+// [m - e, m + e]: three FMAs and NO per-axis min/max (ncu: the ALU pipe that executes FMNMX was the busiest
+// pipe at 62 %, the FMA pipe at 34 %); entry / exit are one 3-input max / min each (FMNMX3).
+// i = 1/d, oi = o/d, a = |1/d|.  NaNs (0 * inf) drop out of min/max: the axis becomes unconstrained — conservative.
+struct RayAux { float ix, iy, iz, ox, oy, oz, ax, ay, az; };
+RTW_D float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+RTW_D float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+RTW_D void ray_aux(const Ray<float>& r, RayAux& a) {
+    a.ix = frcp(r.d.x); a.iy = frcp(r.d.y); a.iz = frcp(r.d.z);
+    a.ox = r.o.x * a.ix; a.oy = r.o.y * a.iy; a.oz = r.o.z * a.iz;
+    a.ax = fabsf(a.ix); a.ay = fabsf(a.iy); a.az = fabsf(a.iz);
+}
+RTW_D bool box_hit_fast(const float* c, const float* h, const RayAux& a, float tmin, float tmax, float* tnear) {
+    float mx = fmaf(c[0], a.ix, -a.ox), my = fmaf(c[1], a.iy, -a.oy), mz = fmaf(c[2], a.iz, -a.oz);
+    float tn = fmax3(fmaf(-h[0], a.ax, mx), fmaf(-h[1], a.ay, my), fmaf(-h[2], a.az, mz));
+    float tf = fmin3(fmaf(h[0], a.ax, mx), fmaf(h[1], a.ay, my), fmaf(h[2], a.az, mz));
+    tn = fmaxf(tn, tmin);
+    tf = fminf(tf, tmax);
     *tnear = tn;
     return tn <= tf;
 }
@@ -148,8 +157,7 @@ RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h,
     float inv_a = 0.f;
     if constexpr (!EXACT) {
         inv_a = frcp(a);
-        aux.ix = frcp(r.d.x); aux.iy = frcp(r.d.y); aux.iz = frcp(r.d.z);
-        aux.ox = r.o.x * aux.ix; aux.oy = r.o.y * aux.iy; aux.oz = r.o.z * aux.iz;
+        ray_aux(r, aux);
     }
     // while-while traversal: descend inner nodes until a leaf is reached, then test its spheres; a
     // stop code at the bottom of the stack ends the walk.
@@ -163,11 +171,11 @@ RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h,
             if (COUNT) tl.node_visits++;
             bool hl, hr; T tl_near = T(0), tr_near = T(0);
             if constexpr (EXACT) {
-                hl = box_hit_exact(nd.lmin, nd.lmax, r, tmin, best_t);
-                hr = box_hit_exact(nd.rmin, nd.rmax, r, tmin, best_t);
+                hl = box_hit_exact(nd.la, nd.lb, r, tmin, best_t);
+                hr = box_hit_exact(nd.ra, nd.rb, r, tmin, best_t);
             } else {
-                hl = box_hit_fast(nd.lmin, nd.lmax, aux, tmin, best_t, &tl_near);
-                hr = box_hit_fast(nd.rmin, nd.rmax, aux, tmin, best_t, &tr_near);
+                hl = box_hit_fast(nd.la, nd.lb, aux, tmin, best_t, &tl_near);
+                hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, best_t, &tr_near);
             }
             int32_t l = nd.left, rr = nd.right;
             if (hl && hr) {
@@ -240,7 +248,7 @@ template <class T, bool EXACT> RTW_D V3<T> refract(V3<T> s, V3<T> o, T eta) {   
 // Fast path: Sphere::hit(ray, 0..=inf) succeeds iff disc > 0 and the larger root is >= 0, i.e. iff
 // disc > 0 && (hb <= 0 || c <= 0) — no square root or division until a light is actually hit.
 template <class T, bool EXACT, bool COUNT, class SC>
-RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
+RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl, int32_t* stack, int stride) {
     using Mt = M<T, EXACT>;
     T acc = T(0);
     if constexpr (EXACT) {
@@ -265,8 +273,7 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
         // unit direction once; per light: towards = nd.(c - o), perpendicular residual l = (c - o) - towards nd,
         // hit iff |l|^2 < r^2 and (towards >= 0 or the origin is inside): 13 flop, no division or root on a miss
         V3<T> nd = Mt::normalize(dir);
-        for (int i = 0; i < sc.n_lights; ++i) {
-            Vec4T<T> s = load_light(sc, i);
+        auto term = [&](const Vec4T<T>& s) {
             if (COUNT) tl.light_tests++;
             T cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
             T towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
@@ -280,6 +287,40 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
                     acc += frcp(solid_angle);
                 }
             }
+        };
+        if (sc.n_light_nodes > 0) {
+            // many lights (the reference's O(#lights) sum, hittable_list.rs:408-412, made sub-linear): walk a BVH over
+            // the light spheres and evaluate only the lights whose box the ray (t in [0, inf)) crosses.  A light
+            // the ray misses contributes exactly 0 to the sum, so only the summation order changes.
+            RayAux aux;
+            ray_aux(Ray<float>{origin, nd}, aux);
+            stack[0] = kStop;
+            int sp = 1;
+            int32_t cur = 0;
+            for (;;) {
+                while (cur >= 0) {
+                    const float4* p = reinterpret_cast<const float4*>(sc.light_nodes + cur);
+                    Node<float> ln;
+                    unpack_node(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), ln);
+                    float t0, t1;
+                    bool hl = box_hit_fast(ln.la, ln.lb, aux, 0.f, Mt::inf(), &t0);
+                    bool hr = box_hit_fast(ln.ra, ln.rb, aux, 0.f, Mt::inf(), &t1);
+                    if (hl && hr) { stack[sp * stride] = ln.right; sp++; cur = ln.left; }
+                    else if (hl) cur = ln.left;
+                    else if (hr) cur = ln.right;
+                    else { sp--; cur = stack[sp * stride]; }
+                }
+                if (cur == kStop) break;
+                if (cur != kEmptyLeaf) {
+                    uint32_t enc = (uint32_t)~cur;
+                    uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
+                    for (uint32_t i = first; i < first + count; ++i) term(load_light(sc, (int32_t)i));
+                }
+                sp--;
+                cur = stack[sp * stride];
+            }
+        } else {
+            for (int i = 0; i < sc.n_lights; ++i) term(load_light(sc, i));
         }
         return acc * frcp((T)sc.n_lights);
     }
@@ -307,7 +348,8 @@ enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE
 // Material::scatter (+ the Scatter branch of ray_colour_tail_call, camera.rs:484-521).
 // Returns the vertex kind; on V_SPECULAR / V_DIFFUSE writes the next ray and the factor for `mult`.
 template <class T, bool EXACT, bool COUNT, class SC>
-RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
+RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl,
+                     int32_t* stack, int stride) {
     using Mt = M<T, EXACT>;
     uint32_t kind = h.info & 3u;
     if (kind == LAMBERTIAN) {                                   // material.rs:357-376
@@ -327,7 +369,7 @@ RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXAC
             T z = Mt::sqrt_(T(1) - r2);
             dir = uvw.transform(mk<T>(x, y, z));
         }
-        T light_v = lights_pdf_value<T, EXACT, COUNT, SC>(sc, h.p, dir, tl);
+        T light_v = lights_pdf_value<T, EXACT, COUNT, SC>(sc, h.p, dir, tl, stack, stride);
         V3<T> nd = Mt::normalize(dir);
         T cos_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));   // CosinePdf::value, pdf.rs:46-49
         T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
@@ -422,7 +464,7 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
     Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u);
     Ray<T> next;
     V3<T> w;
-    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl);
+    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl, stack, stride);
     if (kind == V_ABSORB) { *value = ps.mult * emitted + ps.res; return true; }       // camera.rs:484-486
     if (kind == V_DIFFUSE) ps.res = ps.res + ps.mult * emitted;                       // camera.rs:519
     ps.mult = ps.mult * w;
@@ -801,7 +843,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) 
     Stream<EXACT> rng(P.seed, P.a[idx], P.b[idx], P.c[idx]);
     Ray<T> next{zero, zero};
     V3<T> w = zero;
-    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl);
+    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
     P.prim[idx] = (int32_t)(h.info >> 2); P.t[idx] = (double)h.t; P.kind[idx] = kind;
     store3(P.p, idx, h.p); store3(P.normal, idx, h.normal);
     store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);

@@ -18,7 +18,7 @@ size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr) {
     if (!EXACT) {
         size_t budget = kSmemSceneBudget;
         size_t lights = (size_t)P.scene.n_lights * sizeof(Vec4T<T>);
-        if (lights && lights <= budget) { P.smem_lights = (uint32_t)lights; budget -= lights; }
+        if (lights && lights <= budget && P.scene.n_light_nodes == 0) { P.smem_lights = (uint32_t)lights; budget -= lights; }
         size_t sph = (size_t)P.scene.n_spheres * sizeof(Vec4T<T>);
         size_t sph_total = 2 * sph + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16;
         size_t nodes = (size_t)P.scene.n_nodes * sizeof(Node<T>);
@@ -30,7 +30,7 @@ size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr) {
             P.smem_nodes = (uint32_t)top;
         }
         if (all_shared)
-            *all_shared = P.smem_nodes == nodes && (P.smem_spheres || !P.scene.n_spheres) && (P.smem_lights || !P.scene.n_lights);
+            *all_shared = P.smem_nodes == nodes && (P.smem_spheres || !P.scene.n_spheres) && (P.smem_lights || !P.scene.n_lights || P.scene.n_light_nodes > 0);
         smem += P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     }
     return smem;

@@ -229,8 +229,7 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
                                 if (best == -1 || t < best_t) { best_t = t; best = -2 - i; }
                             }
                             inv_a = frcp(sqlen(r.d));
-                            aux.ix = frcp(r.d.x); aux.iy = frcp(r.d.y); aux.iz = frcp(r.d.z);
-                            aux.ox = r.o.x * aux.ix; aux.oy = r.o.y * aux.iy; aux.oz = r.o.z * aux.iz;
+                            ray_aux(r, aux);
                             stack[0] = kStop; sp = 1; cur = 0;
                         }
                     }
@@ -242,8 +241,8 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
             load_node(sc, cur, nd);
                         if (COUNT) tl.node_visits++;
                         float tl_near, tr_near;
-                        bool hl = box_hit_fast(nd.lmin, nd.lmax, aux, tmin, best_t, &tl_near);
-                        bool hr = box_hit_fast(nd.rmin, nd.rmax, aux, tmin, best_t, &tr_near);
+                        bool hl = box_hit_fast(nd.la, nd.lb, aux, tmin, best_t, &tl_near);
+                        bool hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, best_t, &tr_near);
                         int32_t l = nd.left, rr = nd.right;
                         if (hl && hr) {
                             bool swap = tr_near < tl_near;
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
                     Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u);
                     Ray<T> next;
                     V3<T> w;
-                    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl);
+                    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
                     V3<T> emitted = mk<T>(0, 0, 0);
                     if (kind == V_ABSORB) {                                     // camera.rs:484-486
                         wf_finish(Q, S.q[slot], mult * emitted + wf_res(dep), P.flags);

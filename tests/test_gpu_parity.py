@@ -278,3 +278,79 @@ def test_wavefront_is_bit_identical_to_megakernel(rtw, simple_scene, gscene):
             assert np.array_equal(a8, b8)
     with pytest.raises(rtw.RtwError):
         gscene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64, mode=rtw.RTW_WAVEFRONT))
+
+
+def _scene_pair(rtw, oracle, seed, n, p_l, p_m, ground=0):
+    """The same generated scene on the GPU (array constructor) and in the oracle."""
+    a = rtw.scenes.simple_arrays(seed, n, p_l, p_m, ground)
+    gs = rtw.Scene.from_arrays(a["spheres"], a["sphere_materials"], a["planes"], a["plane_materials"], a["lights"])
+    desc = oracle.scene_simple(seed, n, p_l, p_m, ground)
+    assert np.array_equal(desc.spheres, a["spheres"]) and np.array_equal(desc.lights, a["lights"])
+    return a, gs, desc, oracle.Scene(desc)
+
+
+def test_scene_larger_than_shared_memory(rtw, oracle):
+    """6 400 spheres do not fit the shared-memory staging: top BVH levels in shared memory, the rest read from
+    global memory, and 320 lights take the light-BVH path.  Same parity bars as the small scene."""
+    a, gs, desc, osc = _scene_pair(rtw, oracle, 77, 40, 0.8, 0.95)
+    assert gs.n_spheres > 6000 and gs.n_lights > 64 and gs.info()["device_bytes"] > 300_000
+    w, h, spp = 96, 54, 6
+    cam = a["cam"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).build()
+    ocam = oracle.camera_for(desc, w, h, spp, 50)
+    rng = np.random.default_rng(2)
+    n = 6000
+    i = rng.integers(0, w, n); j = rng.integers(0, h, n); s = rng.integers(0, spp, n)
+    o, d = oracle.get_rays(ocam, oracle.options(seed=77), i, j, s)
+    p0, t0, _ = osc.trace_batch(o, d)
+    hit = p0 >= 0
+    pts = o[hit] + d[hit] * t0[hit][:, None]
+    o = np.concatenate([o, pts[rng.integers(0, len(pts), n)]]); d = np.concatenate([d, rng.normal(size=(n, 3))])
+    # f64 path: bit-exact ids and t
+    for tmin in (oracle.EPS, 1e-3):
+        pr, tr, _ = osc.trace_batch(o, d, tmin=tmin)
+        pg, tg = gs.trace_batch(o, d, tmin=tmin, precision=rtw.RTW_F64)
+        assert np.array_equal(pr, pg) and np.array_equal(tr, tg)
+    # f32 path: ids
+    o32 = o.astype(np.float32).astype(np.float64); d32 = d.astype(np.float32).astype(np.float64)
+    pr, tr, _ = osc.trace_batch(o32, d32, tmin=1e-3)
+    pg, tg = gs.trace_batch(o32, d32, tmin=1e-3, precision=rtw.RTW_F32)
+    assert (pr == pg).mean() > 0.995
+    # f64 image bit-exact (the exact path's linear light sum over 320 lights in insertion order)
+    ref, _, cnt, _ = osc.render(ocam, oracle.options(seed=77, rng_mode=oracle.W64, math_mode=oracle.PORTABLE))
+    got, _, st = gs.render(cam, rtw.RenderOptions(seed=77, precision=rtw.RTW_F64))
+    assert np.array_equal(ref, got, equal_nan=True) and st["rays"] == cnt["rays"]
+    # f32: megakernel == wavefront bit for bit on the global-memory + light-BVH path, and the image tracks the oracle
+    m, _, sm = gs.render(cam, rtw.RenderOptions(seed=77, precision=rtw.RTW_F32, flags=rtw.RTW_FLAG_FIX_NAN))
+    wv, _, sw = gs.render(cam, rtw.RenderOptions(seed=77, precision=rtw.RTW_F32, mode=rtw.RTW_WAVEFRONT, flags=rtw.RTW_FLAG_FIX_NAN))
+    assert np.array_equal(m, wv) and sm["rays"] == sw["rays"]
+    spp2 = 64
+    cam2 = a["cam"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp2).build()
+    ref2, _, c2, _ = osc.render(oracle.camera_for(desc, w, h, spp2, 50), oracle.options(seed=78, fix_nan=True))
+    got2, _, s2 = gs.render(cam2, rtw.RenderOptions(seed=77, precision=rtw.RTW_F32, flags=rtw.RTW_FLAG_FIX_NAN))
+    assert abs(ref2.mean() - got2.mean()) / spp2 < 0.01
+    assert abs(s2["rays"] / s2["paths"] - c2["rays"] / c2["paths"]) < 0.08 * c2["rays"] / c2["paths"]
+    gs.close()
+
+
+def test_light_bvh_sum_equals_linear_sum(rtw, oracle):
+    """80 % glass (BASELINE C5 recipe): 399 lights -> the FP32 path walks a BVH over the lights instead of the
+    reference's linear sum (hittable_list.rs:408-412).  On cosine-sampled vertices (same direction as the oracle's)
+    the mixture weight must agree, i.e. the BVH sum equals the linear sum."""
+    a, gs, desc, osc = _scene_pair(rtw, oracle, SEED, 11, 0.1, 0.2)
+    assert gs.n_lights > 300
+    cam_o = oracle.camera_for(desc, 200, 112, 4, 50)
+    rng = np.random.default_rng(4)
+    n = 80000
+    i = rng.integers(0, 200, n); j = rng.integers(0, 112, n); s = rng.integers(0, 4, n)
+    o, d = oracle.get_rays(cam_o, oracle.options(seed=SEED), i, j, s)
+    pix = rng.integers(0, 20000, n); smp = rng.integers(0, 64, n); vtx = rng.integers(1, 51, n)
+    ref = osc.scatter_batch(o, d, pix, smp, vtx, oracle.options(seed=SEED, tmin=1e-3, rng_mode=oracle.W32))
+    got = gs.scatter_batch(o, d, pix, smp, vtx, rtw.RenderOptions(seed=SEED, tmin=1e-3, precision=rtw.RTW_F32))
+    diffuse = (ref["kind"] == 3) & (got["kind"] == 3) & (ref["prim"] == got["prim"])
+    same_dir = diffuse & (np.abs(ref["dir"] - got["dir"]).max(axis=1) < 1e-4)       # cosine branch (light branch: other index order)
+    assert same_dir.sum() > 500
+    wr, wg = ref["weight"][same_dir], got["weight"][same_dir]
+    ok = np.isfinite(wr).all(axis=1) & np.isfinite(wg).all(axis=1)
+    rel = np.abs(wr[ok] - wg[ok]) / np.maximum(np.abs(wr[ok]), 1e-3)
+    assert np.quantile(rel, 0.99) < 2e-3 and np.median(rel) < 1e-5, (np.quantile(rel, 0.99), np.median(rel))
+    gs.close()

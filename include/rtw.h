@@ -118,8 +118,9 @@ RTW_API const char* rtw_last_error(void);
 RTW_API int         rtw_camera_build(const rtw_camera_builder* builder, rtw_camera* out);
 /* Philox4x32-10 block function; the device code runs the same rounds (KATs in tests/). */
 RTW_API void        rtw_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* Image partition used by the tile entry points: tiles of RTW_TILE_W x RTW_TILE_H pixels in
- * row-major tile order; tile k belongs to rank k % world and is that rank's local tile k / world. */
+/* Image partition used by the tile entry points: tiles of RTW_TILE_W x RTW_TILE_H pixels; tile (tx, ty) has slot
+ * k = ty * tiles_x + (tx + rot(ty)) % tiles_x with rot(ty) = ((ty * 0x9E3779B1u) >> 15) % tiles_x (rows rotated so no rank
+ * owns whole tile columns); slot k belongs to rank k % world and is that rank's local tile k / world. */
 #define RTW_TILE_W 16
 #define RTW_TILE_H 16
 RTW_API uint32_t    rtw_tiles_total(uint32_t width, uint32_t height);

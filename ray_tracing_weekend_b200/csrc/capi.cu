@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -419,7 +420,9 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     s->planes.assign(planes, planes + n_planes); s->plane_material.assign(plane_material, plane_material + n_planes);
     s->materials.assign(materials, materials + n_materials); s->lights.assign(lights, lights + n_lights);
     host::Builder builder;
-    s->bvh = builder.build(reinterpret_cast<const double*>(s->spheres.data()), n_spheres, 4, kMaxTreeDepth);
+    int max_leaf = 2;                                     // measured best of 1..8 on `simple` (profiles/README.md); tuning knob for experiments: RTW_BVH_MAX_LEAF=1..8
+    if (const char* e = std::getenv("RTW_BVH_MAX_LEAF")) { int v = std::atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }
+    s->bvh = builder.build(reinterpret_cast<const double*>(s->spheres.data()), n_spheres, max_leaf, kMaxTreeDepth);
     auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);

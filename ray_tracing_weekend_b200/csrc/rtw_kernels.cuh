@@ -577,7 +577,9 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
         uint32_t tile = local_tile * P.world + P.rank;
         uint32_t lx = (sub % (kTileW / kWarpTileW)) * kWarpTileW + (lane % kWarpTileW);
         uint32_t ly = (sub / (kTileW / kWarpTileW)) * kWarpTileH + (lane / kWarpTileW);
-        uint32_t i = (tile % P.tiles_x) * kTileW + lx, j = (tile / P.tiles_x) * kTileH + ly;
+        uint32_t ttx, tty;
+        slot_tile(tile, P.tiles_x, &ttx, &tty);
+        uint32_t i = ttx * kTileW + lx, j = tty * kTileH + ly;
         bool valid = tile < P.tiles_total && i < cam.width && j < cam.height;
         uint32_t pixel = j * cam.width + i;
         V3<T> acc = mk<T>(0, 0, 0);
@@ -726,7 +728,9 @@ __global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<floa
                     chunk_end = npx * spp;
                     if (G == 1) {       // skip padding pixels (outside the image / padding tiles) as a whole
                         uint32_t tile = (chunk_q0 >> 8) * P.world + P.rank, in = chunk_q0 & 255u;
-                        uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                        uint32_t ttx, tty;
+                        slot_tile(tile, P.tiles_x, &ttx, &tty);
+                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                         if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) chunk_end = 0;
                     }
                 }
@@ -738,7 +742,9 @@ __global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<floa
                     sample = r - pin * spp;
                     q = chunk_q0 + pin;
                     uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
-                    uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                    uint32_t ttx, tty;
+                        slot_tile(tile, P.tiles_x, &ttx, &tty);
+                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                     if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                         pixel = j * cam.width + i;
                         Stream<EXACT> rng(P.seed, pixel, sample, 0u);
@@ -888,7 +894,7 @@ __global__ void untile_resolve_kernel(const T* tiles, uint32_t width, uint32_t h
                                       uint32_t tiles_x, uint32_t spp, double* rgb_sum, uint8_t* rgb8) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= width || j >= height) return;
-    uint32_t tile = (j / kTileH) * tiles_x + (i / kTileW);
+    uint32_t tile = tile_slot(i / kTileW, j / kTileH, tiles_x);
     uint32_t rank = tile % world, local = tile / world;
     const T* src = tiles + (((size_t)rank * tiles_per_rank + local) * (kTileW * kTileH) + (size_t)(j % kTileH) * kTileW + (i % kTileW)) * 3;
     size_t dst = ((size_t)j * width + i) * 3;

@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
                     L.chunk_next = 0; L.chunk_end = npx * spp;
                     if (G == 1) {       // skip padding pixels as a whole
                         uint32_t tile = (L.chunk_q0 >> 8) * P.world + P.rank, in = L.chunk_q0 & 255u;
-                        uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                        uint32_t ttx, tty;
+                        slot_tile(tile, P.tiles_x, &ttx, &tty);
+                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                         if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) L.chunk_end = 0;
                     }
                     continue;
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
                     uint32_t pin = r / spp, sample = r - pin * spp;
                     uint32_t q = L.seg[s].q0 + pin;
                     uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
-                    uint32_t i = (tile % P.tiles_x) * kTileW + (in & 15u), j = (tile / P.tiles_x) * kTileH + (in >> 4);
+                    uint32_t ttx, tty;
+                        slot_tile(tile, P.tiles_x, &ttx, &tty);
+                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                     if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                         uint32_t pixel = j * cam.width + i;
                         Stream<EXACT> rng(P.seed, pixel, sample, 0u);

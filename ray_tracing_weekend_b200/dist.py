@@ -5,8 +5,9 @@ The reference has no distributed path; its only parallelism is rayon over pixels
 (shared/src/camera.rs:353).  Pixels are independent and the RNG is keyed by the absolute pixel index, so
 the image does not depend on the number of GPUs or on which GPU renders which tile.
 
-Partition (same constants as include/rtw.h): tiles of 16x16 pixels in row-major tile order; global tile k
-is owned by rank k % world and is that rank's local tile k // world.  Every rank holds
+Partition (same constants as include/rtw.h): tiles of 16x16 pixels; tile (tx, ty) has slot
+k = ty * tiles_x + (tx + rot(ty)) % tiles_x (every tile row rotated pseudo-randomly, so that no rank ends up with
+whole tile columns); slot k is owned by rank k % world and is that rank's local tile k // world.  Every rank holds
 tiles_per_rank = ceil(tiles_total / world) local tiles (the tail is padding and stays zero), so the gather
 moves equally sized buffers and needs no size exchange.
 """
@@ -34,20 +35,27 @@ def tiles_per_rank(width: int, height: int, world: int) -> int:
     return (tiles_total(width, height) + world - 1) // world
 
 
-def tile_owner(tile: int, world: int):
-    """(rank, local index) of global tile `tile`."""
-    return tile % world, tile // world
+def tile_row_rotation(ty: int, tiles_x: int) -> int:
+    """csrc/rtw_device.cuh: tile_row_rotation (32-bit arithmetic)."""
+    return (((ty * 0x9E3779B1) & 0xFFFFFFFF) >> 15) % tiles_x
+
+
+def tile_owner(slot: int, world: int):
+    """(rank, local index) of tile slot `slot`."""
+    return slot % world, slot // world
 
 
 def local_tile_ids(width: int, height: int, rank: int, world: int):
-    """Global tile ids of this rank's local tiles, in local order (padding slots excluded)."""
+    """Tile slots of this rank's local tiles, in local order (padding slots excluded)."""
     return list(range(rank, tiles_total(width, height), world))
 
 
-def tile_rect(tile: int, width: int, height: int):
-    """Pixel rectangle (i0, j0, i1, j1) of a tile, clipped to the image; j = 0 is the bottom row."""
-    tx, _ = tiles_xy(width, height)
-    i0, j0 = (tile % tx) * TILE_W, (tile // tx) * TILE_H
+def tile_rect(slot: int, width: int, height: int):
+    """Pixel rectangle (i0, j0, i1, j1) of the tile in slot `slot`, clipped to the image; j = 0 is the bottom row."""
+    tiles_x, _ = tiles_xy(width, height)
+    ty, c = divmod(slot, tiles_x)
+    tx = (c - tile_row_rotation(ty, tiles_x)) % tiles_x
+    i0, j0 = tx * TILE_W, ty * TILE_H
     return i0, j0, min(i0 + TILE_W, width), min(j0 + TILE_H, height)
 
 

@@ -3,6 +3,12 @@
 #include <algorithm>
 #include "rtw_launch.cuh"
 #include "rtw_wavefront.cuh"
+
+namespace rtw {
+// wavefront launch shape: ONE CTA per SM (its warps never synchronise after the scene is staged), 24 warps,
+// 96 path slots per warp -> ~216 KB of shared memory for `simple`
+constexpr int kWfBlock = 768, kWfSlotsPerWarp = 96;
+}
 namespace rtw {
 RTW_DEFINE_LAUNCHERS(f32, float, false)
 cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
@@ -10,7 +16,7 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 }
 template <bool COUNT, bool SH>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    constexpr int BLOCK = 256, NP = 768;
+    constexpr int BLOCK = kWfBlock, NP = kWfSlotsPerWarp;
     auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
@@ -20,13 +26,16 @@ cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size
 }
 template <bool COUNT>
 cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    constexpr int BLOCK = 256, NP = 768;
+    constexpr int BLOCK = kWfBlock, NP = kWfSlotsPerWarp;
     P.stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
+    // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene
+    const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
+    const size_t limit = 227 * 1024;
+    if (fixed + 1024 > limit) return cudaErrorInvalidConfiguration;
     bool sh = false;
-    plan_smem<float, false>(P, BLOCK, &sh);
-    const uint32_t stack_depth = P.stack_depth;
+    plan_smem<float, false>(P, BLOCK, &sh, std::min<size_t>(kSmemSceneBudget, (limit - fixed) / 64 * 64));
     size_t scene = P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
-    size_t smem = sizeof(int32_t) * stack_depth * BLOCK + scene + wavefront_state_bytes<BLOCK, NP>();
+    size_t smem = fixed + scene;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
     e = sh ? launch_render_wavefront_sh<COUNT, true>(P, Q, smem, sm_count, s, info)

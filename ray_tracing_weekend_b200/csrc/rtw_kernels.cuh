@@ -136,7 +136,7 @@ RTW_D void hit_record(const SC& sc, const Ray<T>& r, int32_t best, T best_t, Hit
 // range is shrunk to the best t so far and children are visited near-first — the argmin is the same
 // except for exact-t ties and the documented grazing cases.
 template <class T, bool EXACT, bool COUNT, class SC>
-RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* best_out, T* t_out, int32_t* stack, int stride, Tally& tl) {
     using Mt = M<T, EXACT>;
     bool found = false;
     T best_t = tmax;
@@ -215,7 +215,16 @@ RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h,
         sp--;
         cur = stack[sp * stride];
     }
-    if (!found) return false;
+    *best_out = best;
+    *t_out = best_t;
+    return found;
+}
+
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+    int32_t best;
+    T best_t;
+    if (!closest_prim<T, EXACT, COUNT, SC>(sc, r, tmin, tmax, &best, &best_t, stack, stride, tl)) return false;
     hit_record<T, EXACT, SC>(sc, r, best, best_t, h);
     return true;
 }

@@ -10,13 +10,13 @@ constexpr size_t kSmemSceneBudget = 64 * 1024;   // per-CTA budget for staged sc
 
 // decide which scene sections the fast kernels stage in shared memory; returns the dynamic smem size
 template <class T, bool EXACT>
-size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr) {
+size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr, size_t scene_budget = kSmemSceneBudget) {
     if (P.stack_depth == 0 || P.stack_depth > (uint32_t)kStackDepth) P.stack_depth = kStackDepth;
     size_t smem = sizeof(int32_t) * P.stack_depth * block;
     P.smem_nodes = P.smem_spheres = P.smem_lights = 0;
     if (all_shared) *all_shared = false;
     if (!EXACT) {
-        size_t budget = kSmemSceneBudget;
+        size_t budget = scene_budget;
         size_t lights = (size_t)P.scene.n_lights * sizeof(Vec4T<T>);
         if (lights && lights <= budget && P.scene.n_light_nodes == 0) { P.smem_lights = (uint32_t)lights; budget -= lights; }
         size_t sph = (size_t)P.scene.n_spheres * sizeof(Vec4T<T>);

@@ -1,63 +1,45 @@
 // rtw_wavefront.cuh — the wavefront renderer (RTW_WAVEFRONT, fast path only).
 //
-// generate / extend / shade queues, compacted with warp ballots and sorted by material — but CTA-local:
-// every persistent CTA keeps NP paths in flight in SHARED memory (SoA path state + index lists per
-// stage) and steps all of them one bounce per iteration:
+// generate / extend / shade queues sorted by material and compacted with warp ballots — held in SHARED
+// memory and private to each WARP:
 //
-//   GENERATE  free slots take the next paths of the CTA's chunk of the pixel-major path stream
-//             (Camera::get_ray, camera.rs:274-293)                                   -> extend list
-//   EXTEND    closest hit (bvh.rs:163-188): every lane pulls rays from the extend list one by one, so
-//             a lane whose traversal ends early starts the next ray instead of idling
-//             miss -> the path ends (camera.rs:473-475); hit -> list of its material
-//   SHADE     one list per material (Lambertian + light-pdf loop / Metal / Dialectric), so a warp runs
-//             one Material::scatter (material.rs:357-488)                             -> extend list
+//   every warp keeps NPW (96) paths in flight in its own slice of shared memory (SoA path state + one index
+//   list per stage) and repeatedly runs the stage whose list is longest on up to 32 of its paths, one per lane:
+//     GENERATE  free slots take the next paths of the warp's chunk of the pixel-major path stream
+//               (Camera::get_ray, camera.rs:274-293)                                       -> extend list
+//     EXTEND    closest hit (bvh.rs:163-188); miss -> the path ends (camera.rs:473-475), hit -> list of its material
+//     SHADE     one list per material (Lambertian + light-pdf loop / Metal / Dialectric): all lanes run the same
+//               Material::scatter (material.rs:357-488)                                    -> extend list
 //
-// Why CTA-local: a global-memory wavefront writes and re-reads ~130 B of path state per bounce
-// (~380 GB per 1080p/500spp frame) and needs thousands of launches; the same queues in the 227 KB of
-// shared memory cost neither.  The megakernel runs these stages per lane in lock step and leaves
-// ~60 % of the lanes idle (ncu: 12.6 of 32 threads active); here lanes only ever execute a stage
-// together with lanes that need the same stage.
-// The paths, their RNG streams and the arithmetic are exactly the pooled megakernel's, and radiance is
-// accumulated in the same 64-bit fixed point, so both renderers produce bit-identical images.
+// Why: the megakernel runs trace + every material branch in lock step per lane; ncu shows 12.9 of 32 threads
+// active, the expensive Lambertian branch (29-light pdf loop) executing with ~1/3 of the lanes.  Here a stage
+// only runs when (nearly) 32 paths want it: with 96 slots per warp a simulation of the measured stage mix gives
+// > 31 busy lanes per batch (64 slots: 26).
+// Why warp-private and in shared memory: a global-memory wavefront moves ~130 B of path state per bounce through
+// L2 / HBM (~350 GB per 1080p / 500 spp frame) and needs thousands of launches; a CTA-wide version of these queues
+// (first attempt, profiles/) spent 21 % of its time in bar.sync and ran at 16 warps / SM.  Warp-private lists need
+// no barrier and no atomics: every list operation is a ballot + popcount prefix, counts live in registers.
+// The paths, their RNG streams and the arithmetic are exactly the pooled megakernel's and radiance is accumulated
+// in the same 64-bit fixed point, so both renderers produce bit-identical images (tests/test_gpu_parity.py).
 #pragma once
 #include "rtw_kernels.cuh"
 
 namespace rtw {
 
-struct WfSegment { uint32_t q0, start, count, offset; };
+enum WfStage : int { WF_FREE = 0, WF_EXT = 1, WF_LAMB = 2, WF_METAL = 3, WF_DIEL = 4, WF_STAGES = 5 };
 
-template <int NP> struct WfLists {
-    uint16_t free_[2][NP], ext[2][NP], lamb[NP], metal[NP], diel[NP];
-    uint32_t n_free[2], n_ext[2], n_lamb, n_metal, n_diel, cursor;
-    // path stream
-    uint32_t chunk_next, chunk_end, chunk_q0, exhausted, n_gen, n_seg, done;
-    WfSegment seg[4];
+template <int NPW> struct WfWarp {
+    float ox[NPW], oy[NPW], oz[NPW], dx[NPW], dy[NPW], dz[NPW], mx[NPW], my[NPW], mz[NPW], ht[NPW];
+    uint32_t q[NPW], pix[NPW], smp[NPW], dep[NPW];  // dep = depth | res-is-NaN bits << 16
+    int32_t hp[NPW];                                 // hit primitive: >= 0 sorted sphere, <= -2 plane
+    uint8_t list[WF_STAGES][NPW];
 };
 
-template <int NP> struct WfPaths {
-    float ox[NP], oy[NP], oz[NP], dx[NP], dy[NP], dz[NP], mx[NP], my[NP], mz[NP], ht[NP];
-    uint32_t q[NP], pix[NP], smp[NP], dep[NP];      // dep = depth | res-is-NaN bits << 16
-    int32_t hp[NP];                                  // hit primitive: >= 0 sorted sphere, <= -2 plane
-};
-
-// warp-aggregated push of `idx` onto a shared-memory list by the lanes with pred set
-RTW_D void wf_push(bool pred, uint16_t* list, uint32_t* count, uint32_t idx) {
-    uint32_t m = __ballot_sync(__activemask(), pred);
-    if (!pred) return;
-    uint32_t lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
-}
-
-// a finished path: add its radiance to the pixel's fixed-point accumulators
-RTW_D void wf_finish(const PoolParams& Q, uint32_t q, V3<float> value, uint32_t flags) {
-    if (flags & 1u) value = fix_nan(value);
-    uint32_t bad = 0;
-    unsigned long long a0 = pool_fixed(value.x, 0, bad), a1 = pool_fixed(value.y, 1, bad), a2 = pool_fixed(value.z, 2, bad);
-    pool_flush(Q, q, a0, a1, a2);
-    if (bad) atomicOr(Q.poison + q, bad);
+// warp-synchronous push: every lane of the warp calls it; lanes with pred append `slot`
+RTW_D void wf_push(uint8_t* list, uint32_t& count, bool pred, uint32_t slot, uint32_t lt_mask) {
+    uint32_t m = __ballot_sync(0xffffffffu, pred);
+    if (pred) list[count + __popc(m & lt_mask)] = (uint8_t)slot;
+    count += __popc(m);
 }
 
 RTW_D V3<float> wf_res(uint32_t dep) {
@@ -65,13 +47,36 @@ RTW_D V3<float> wf_res(uint32_t dep) {
     return mk<float>((dep >> 16) & 1u ? qnan : 0.f, (dep >> 17) & 1u ? qnan : 0.f, (dep >> 18) & 1u ? qnan : 0.f);
 }
 
-template <bool COUNT, int BLOCK, int NP, bool SH>
-__global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams<float> P, PoolParams Q) {
-    const uint32_t stack_depth = P.stack_depth;
+// lane-private partial sums of the pixel the lane last finished a path of (same scheme as the pooled megakernel)
+struct WfAcc {
+    uint32_t q = 0xffffffffu, bad = 0;
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+};
+RTW_D void wf_acc_flush(const PoolParams& Q, WfAcc& A) {
+    if (A.q != 0xffffffffu) {
+        pool_flush(Q, A.q, A.a0, A.a1, A.a2);
+        if (A.bad) atomicOr(Q.poison + A.q, A.bad);
+    }
+}
+RTW_D void wf_finish(const PoolParams& Q, WfAcc& A, uint32_t q, V3<float> value, uint32_t flags) {
+    if (flags & 1u) value = fix_nan(value);
+    if (q != A.q) {
+        wf_acc_flush(Q, A);
+        A.q = q; A.a0 = A.a1 = A.a2 = 0ull; A.bad = 0;
+    }
+    A.a0 += pool_fixed(value.x, 0, A.bad);
+    A.a1 += pool_fixed(value.y, 1, A.bad);
+    A.a2 += pool_fixed(value.z, 2, A.bad);
+}
+
+template <bool COUNT, int BLOCK, int NPW, bool SH>
+__global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
+    static_assert(NPW <= 255 && NPW >= 32, "slot indices are stored in one byte");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [stack][scene sections][paths][lists]
+    // layout: [stack][scene sections][one WfWarp per warp]
+    const uint32_t stack_depth = P.stack_depth;
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);
     SceneView<T> sc0 = P.scene;
     unsigned char* cur_p = smem_raw + sizeof(int32_t) * stack_depth * BLOCK;
@@ -108,245 +113,169 @@ __global__ void __launch_bounds__(BLOCK, 2) render_wavefront_kernel(RenderParams
             sc0.lights = reinterpret_cast<const Vec4T<T>*>(cur_p);
             cur_p += P.smem_lights;
         }
+        __syncthreads();                                  // the only block-wide barrier of the kernel
     }
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC sc;
     static_cast<SceneView<T>&>(sc) = sc0;
-    WfPaths<NP>& S = *reinterpret_cast<WfPaths<NP>*>(cur_p);
-    WfLists<NP>& L = *reinterpret_cast<WfLists<NP>*>(cur_p + sizeof(WfPaths<NP>));
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt_mask = (1u << lane) - 1u;
+    WfWarp<NPW>& S = reinterpret_cast<WfWarp<NPW>*>(cur_p)[warp];
 
     const CameraT<T>& cam = P.cam;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, lt_mask = (1u << lane) - 1u;
     int32_t* stack = stack_base + tid;
     const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
     const uint32_t spp = cam.spp, G = Q.pixels_per_chunk;
     uint32_t npaths = 0, nrays = 0;
     Tally tl;
+    WfAcc acc;
 
-    for (uint32_t i = tid; i < NP; i += BLOCK) L.free_[0][i] = (uint16_t)i;
-    if (tid == 0) {
-        L.n_free[0] = NP; L.n_free[1] = 0; L.n_ext[0] = L.n_ext[1] = 0; L.n_lamb = L.n_metal = L.n_diel = 0; L.cursor = 0;
-        L.chunk_next = L.chunk_end = L.chunk_q0 = 0; L.exhausted = (spp == 0 || cam.max_depth == 0) ? 1u : 0u; L.done = 0;
-    }
-    // max_depth == 0: every path returns 0 (camera.rs:470-472) — the accumulators are already zero
-    uint32_t cb = 0;                                      // parity of the current list buffers
+    // warp-uniform state (registers): list lengths and the cursor into the path stream
+    uint32_t n_free = NPW, n_ext = 0, n_lamb = 0, n_metal = 0, n_diel = 0;
+    uint32_t chunk_next = 0, chunk_end = 0, chunk_q0 = 0;
+    bool exhausted = (spp == 0 || cam.max_depth == 0);       // max_depth == 0: every path returns 0 (camera.rs:470-472)
+    for (uint32_t i = lane; i < NPW; i += 32) S.list[WF_FREE][i] = (uint8_t)i;
+
     for (;;) {
-        __syncthreads();
-        // ---- plan GENERATE: thread 0 maps the free slots onto segments of the path stream -----------------
-        if (tid == 0) {
-            uint32_t need = L.n_free[cb], nseg = 0, off = 0;
-            while (need > 0 && nseg < 4) {
-                if (L.chunk_next == L.chunk_end) {
-                    if (L.exhausted) break;
-                    uint32_t c = atomicAdd(P.work_counter, 1u);
-                    if (c >= Q.n_chunks) { L.exhausted = 1; break; }
-                    L.chunk_q0 = c * G;
-                    uint32_t npx = min(G, n_slots - L.chunk_q0);
-                    L.chunk_next = 0; L.chunk_end = npx * spp;
-                    if (G == 1) {       // skip padding pixels as a whole
-                        uint32_t tile = (L.chunk_q0 >> 8) * P.world + P.rank, in = L.chunk_q0 & 255u;
-                        uint32_t ttx, tty;
-                        slot_tile(tile, P.tiles_x, &ttx, &tty);
-                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
-                        if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) L.chunk_end = 0;
-                    }
-                    continue;
-                }
-                uint32_t take = min(need, L.chunk_end - L.chunk_next);
-                L.seg[nseg].q0 = L.chunk_q0; L.seg[nseg].start = L.chunk_next; L.seg[nseg].count = take; L.seg[nseg].offset = off;
-                nseg++; off += take; L.chunk_next += take; need -= take;
-            }
-            L.n_seg = nseg; L.n_gen = off;
-            L.cursor = 0;
-        }
-        __syncthreads();
-        // ---- GENERATE ---------------------------------------------------------------------------------------
-        {
-            const uint32_t nfree = L.n_free[cb], ngen = L.n_gen, nseg = L.n_seg;
-            for (uint32_t k0 = 0; k0 < nfree; k0 += BLOCK) {
-                uint32_t k = k0 + tid;
-                bool in_range = k < nfree;
-                uint32_t slot = in_range ? L.free_[cb][k] : 0;
-                bool started = false;
-                if (in_range && k < ngen) {
-                    uint32_t s = 0;
-                    while (s + 1 < nseg && k >= L.seg[s + 1].offset) s++;
-                    uint32_t r = L.seg[s].start + (k - L.seg[s].offset);
-                    uint32_t pin = r / spp, sample = r - pin * spp;
-                    uint32_t q = L.seg[s].q0 + pin;
-                    uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
+        __syncwarp();
+        // ---- pick the stage with the longest list (free slots only count while the stream has paths left) ----
+        uint32_t nf = (exhausted && chunk_next == chunk_end) ? 0u : n_free;
+        int stage = WF_FREE;
+        uint32_t best = nf;
+        if (n_ext > best) { best = n_ext; stage = WF_EXT; }
+        if (n_lamb > best) { best = n_lamb; stage = WF_LAMB; }
+        if (n_metal > best) { best = n_metal; stage = WF_METAL; }
+        if (n_diel > best) { best = n_diel; stage = WF_DIEL; }
+        if (best == 0) break;                                 // nothing in flight and the stream is dry
+
+        if (stage == WF_FREE) {
+            // ---- GENERATE ----------------------------------------------------------------------------------
+            if (chunk_next == chunk_end) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(P.work_counter, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= Q.n_chunks) { exhausted = true; continue; }
+                chunk_q0 = c * G;
+                uint32_t npx = min(G, n_slots - chunk_q0);
+                chunk_next = 0; chunk_end = npx * spp;
+                if (G == 1) {       // skip padding pixels (outside the image / padding tiles) as a whole
+                    uint32_t tile = (chunk_q0 >> 8) * P.world + P.rank, in = chunk_q0 & 255u;
                     uint32_t ttx, tty;
-                        slot_tile(tile, P.tiles_x, &ttx, &tty);
-                        uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
-                    if (tile < P.tiles_total && i < cam.width && j < cam.height) {
-                        uint32_t pixel = j * cam.width + i;
-                        Stream<EXACT> rng(P.seed, pixel, sample, 0u);
-                        Ray<T> ray = get_ray<T, EXACT>(cam, i, j, rng);
-                        S.ox[slot] = ray.o.x; S.oy[slot] = ray.o.y; S.oz[slot] = ray.o.z;
-                        S.dx[slot] = ray.d.x; S.dy[slot] = ray.d.y; S.dz[slot] = ray.d.z;
-                        S.mx[slot] = 1.f; S.my[slot] = 1.f; S.mz[slot] = 1.f;
-                        S.q[slot] = q; S.pix[slot] = pixel; S.smp[slot] = sample; S.dep[slot] = cam.max_depth;
-                        started = true;
-                        npaths++;
-                    }
+                    slot_tile(tile, P.tiles_x, &ttx, &tty);
+                    uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
+                    if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) chunk_end = 0;
                 }
-                wf_push(started, L.ext[cb], &L.n_ext[cb], slot);
-                wf_push(in_range && !started, L.free_[cb ^ 1], &L.n_free[cb ^ 1], slot);
+                if (chunk_next == chunk_end) continue;
             }
-        }
-        __syncthreads();
-        if (L.n_ext[cb] == 0 && L.exhausted) break;      // nothing in flight and the stream is dry (uniform)
-        // ---- EXTEND -----------------------------------------------------------------------------------------
-        {
-            const uint32_t n = L.n_ext[cb];
-            const uint16_t* list = L.ext[cb];
-            bool have = false;
-            uint32_t slot = 0;
-            Ray<T> r;
-            RayAux aux;
-            float inv_a = 0.f, best_t = 0.f;
-            int32_t best = -1, cur = kStop;
-            int sp = 0;
-            const float tmin = P.tmin, tmax = M<T, EXACT>::inf();
-            for (;;) {
-                uint32_t want = __ballot_sync(0xffffffffu, !have);
-                if (want) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&L.cursor, (uint32_t)__popc(want));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (!have) {
-                        uint32_t k = base + __popc(want & lt_mask);
-                        if (k < n) {
-                            slot = list[k];
-                            r.o = mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]);
-                            r.d = mk<T>(S.dx[slot], S.dy[slot], S.dz[slot]);
-                            have = true;
-                            nrays++;
-                            best = -1; best_t = tmax;
-                            // planes: Plane::hit (entities/plane.rs:61-76), one-sided
-                            for (int i = 0; i < sc.n_planes; ++i) {
-                                const PlaneT<T>& pl = sc.planes[i];
-                                T denom = dot(r.d, pl.normal);
-                                if (!(denom > M<T, EXACT>::EPS)) continue;
-                                T t = -dot(r.o - pl.point, pl.normal) * frcp(denom);
-                                if (!(tmin <= t && t <= tmax)) continue;
-                                if (best == -1 || t < best_t) { best_t = t; best = -2 - i; }
-                            }
-                            inv_a = frcp(sqlen(r.d));
-                            ray_aux(r, aux);
-                            stack[0] = kStop; sp = 1; cur = 0;
-                        }
-                    }
-                }
-                if (!__any_sync(0xffffffffu, have)) break;
-                if (have) {
-                    while (cur >= 0) {
-                        Node<T> nd;
-            load_node(sc, cur, nd);
-                        if (COUNT) tl.node_visits++;
-                        float tl_near, tr_near;
-                        bool hl = box_hit_fast(nd.la, nd.lb, aux, tmin, best_t, &tl_near);
-                        bool hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, best_t, &tr_near);
-                        int32_t l = nd.left, rr = nd.right;
-                        if (hl && hr) {
-                            bool swap = tr_near < tl_near;
-                            stack[sp * BLOCK] = swap ? l : rr; sp++;
-                            cur = swap ? rr : l;
-                        } else if (hl) cur = l;
-                        else if (hr) cur = rr;
-                        else { sp--; cur = stack[sp * BLOCK]; }
-                    }
-                    if (cur == kStop) {
-                        // traversal finished: miss ends the path (camera.rs:473-475), a hit is queued by material
-                        have = false;
-                        if (best == -1) {
-                            if (COUNT) tl.missed++;
-                            V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                            wf_finish(Q, S.q[slot], mult * cam.background + wf_res(S.dep[slot]), P.flags);
-                            uint32_t pos = atomicAdd(&L.n_free[cb ^ 1], 1u);
-                            L.free_[cb ^ 1][pos] = (uint16_t)slot;
-                        } else {
-                            S.ht[slot] = best_t; S.hp[slot] = best;
-                            uint32_t kind = best >= 0 ? (load_sphere_info(sc, best) & 3u) : (sc.planes[-2 - best].info & 3u);
-                            uint16_t* dst = kind == LAMBERTIAN ? L.lamb : (kind == METAL ? L.metal : L.diel);
-                            uint32_t* cnt = kind == LAMBERTIAN ? &L.n_lamb : (kind == METAL ? &L.n_metal : &L.n_diel);
-                            uint32_t pos = atomicAdd(cnt, 1u);
-                            dst[pos] = (uint16_t)slot;
-                        }
-                    } else {
-                        if (cur != kEmptyLeaf) {
-                            uint32_t enc = (uint32_t)~cur;
-                            uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
-                            for (uint32_t i = first; i < first + count; ++i) {
-                                Vec4T<T> s = load_sphere(sc, (int32_t)i);
-                                if (COUNT) tl.sphere_tests++;
-                                T t;
-                                if (sphere_root_fast(s, r, inv_a, tmin, tmax, &t) && (best == -1 || t < best_t)) { best_t = t; best = (int32_t)i; }
-                            }
-                        }
-                        sp--;
-                        cur = stack[sp * BLOCK];
-                    }
+            const uint32_t take = min(min(32u, n_free), chunk_end - chunk_next);
+            n_free -= take;                                   // pop `take` slots from the end of the free list
+            const bool active = lane < take;
+            uint32_t slot = active ? S.list[WF_FREE][n_free + lane] : 0u;
+            bool started = false;
+            if (active) {
+                uint32_t r = chunk_next + lane;
+                uint32_t pin = r / spp, sample = r - pin * spp;
+                uint32_t q = chunk_q0 + pin;
+                uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
+                uint32_t ttx, tty;
+                slot_tile(tile, P.tiles_x, &ttx, &tty);
+                uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
+                if (tile < P.tiles_total && i < cam.width && j < cam.height) {
+                    uint32_t pixel = j * cam.width + i;
+                    Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                    Ray<T> ray = get_ray<T, EXACT>(cam, i, j, rng);
+                    S.ox[slot] = ray.o.x; S.oy[slot] = ray.o.y; S.oz[slot] = ray.o.z;
+                    S.dx[slot] = ray.d.x; S.dy[slot] = ray.d.y; S.dz[slot] = ray.d.z;
+                    S.mx[slot] = 1.f; S.my[slot] = 1.f; S.mz[slot] = 1.f;
+                    S.q[slot] = q; S.pix[slot] = pixel; S.smp[slot] = sample; S.dep[slot] = cam.max_depth;
+                    started = true;
+                    npaths++;
                 }
             }
-        }
-        __syncthreads();
-        // ---- SHADE: one list per material -------------------------------------------------------------------
-#pragma unroll 1
-        for (int m = 0; m < 3; ++m) {
-            const uint16_t* list = m == 0 ? L.lamb : (m == 1 ? L.metal : L.diel);
-            const uint32_t n = m == 0 ? L.n_lamb : (m == 1 ? L.n_metal : L.n_diel);
-            for (uint32_t k0 = 0; k0 < n; k0 += BLOCK) {
-                uint32_t k = k0 + tid;
-                bool in_range = k < n;
-                uint32_t slot = in_range ? list[k] : 0;
-                bool to_ext = false, to_free = false;
-                if (in_range) {
-                    Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
-                    Hit<T> h;
-                    hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
-                    uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
+            chunk_next += take;
+            __syncwarp();
+            wf_push(S.list[WF_EXT], n_ext, started, slot, lt_mask);
+            wf_push(S.list[WF_FREE], n_free, active && !started, slot, lt_mask);
+        } else if (stage == WF_EXT) {
+            // ---- EXTEND ------------------------------------------------------------------------------------
+            const uint32_t n = min(32u, n_ext);
+            n_ext -= n;
+            const bool active = lane < n;
+            uint32_t slot = active ? S.list[WF_EXT][n_ext + lane] : 0u;
+            uint32_t kind = 0xffu;                            // 0..2 material list, 3 = miss (slot becomes free)
+            if (active) {
+                Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
+                nrays++;
+                // closest hit without the hit record: the winner's id and t are stored, SHADE builds the record
+                T best_t; int32_t bestp;
+                if (closest_prim<T, EXACT, COUNT, SC>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &best_t, stack, BLOCK, tl)) {
+                    S.ht[slot] = best_t; S.hp[slot] = bestp;
+                    uint32_t k = bestp >= 0 ? (load_sphere_info(sc, bestp) & 3u) : (sc.planes[-2 - bestp].info & 3u);
+                    kind = k == LAMBERTIAN ? 0u : (k == METAL ? 1u : 2u);
+                } else {
+                    if (COUNT) tl.missed++;
                     V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                    Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u);
-                    Ray<T> next;
-                    V3<T> w;
-                    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
-                    V3<T> emitted = mk<T>(0, 0, 0);
-                    if (kind == V_ABSORB) {                                     // camera.rs:484-486
-                        wf_finish(Q, S.q[slot], mult * emitted + wf_res(dep), P.flags);
+                    wf_finish(Q, acc, S.q[slot], mult * cam.background + wf_res(S.dep[slot]), P.flags);   // camera.rs:473-475
+                    kind = 3u;
+                }
+            }
+            __syncwarp();
+            wf_push(S.list[WF_LAMB], n_lamb, kind == 0u, slot, lt_mask);
+            wf_push(S.list[WF_METAL], n_metal, kind == 1u, slot, lt_mask);
+            wf_push(S.list[WF_DIEL], n_diel, kind == 2u, slot, lt_mask);
+            wf_push(S.list[WF_FREE], n_free, kind == 3u, slot, lt_mask);
+        } else {
+            // ---- SHADE: all lanes run the same material -------------------------------------------------------
+            uint32_t cnt = stage == WF_LAMB ? n_lamb : (stage == WF_METAL ? n_metal : n_diel);
+            const uint32_t n = min(32u, cnt);
+            cnt -= n;
+            if (stage == WF_LAMB) n_lamb = cnt; else if (stage == WF_METAL) n_metal = cnt; else n_diel = cnt;
+            const bool active = lane < n;
+            uint32_t slot = active ? S.list[stage][cnt + lane] : 0u;
+            bool to_ext = false, to_free = false;
+            if (active) {
+                Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
+                Hit<T> h;
+                hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
+                uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
+                V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
+                Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u);
+                Ray<T> next;
+                V3<T> w;
+                uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
+                V3<T> emitted = mk<T>(0, 0, 0);
+                if (kind == V_ABSORB) {                                     // camera.rs:484-486
+                    wf_finish(Q, acc, S.q[slot], mult * emitted + wf_res(dep), P.flags);
+                    to_free = true;
+                } else {
+                    if (kind == V_DIFFUSE) {                                // res + mult * emitted (camera.rs:519): 0 or NaN per channel
+                        V3<T> rs = wf_res(dep) + mult * emitted;
+                        dep |= (rs.x != rs.x ? 1u << 16 : 0u) | (rs.y != rs.y ? 1u << 17 : 0u) | (rs.z != rs.z ? 1u << 18 : 0u);
+                    }
+                    mult = mult * w;
+                    depth -= 1;
+                    dep = (dep & 0xffff0000u) | depth;
+                    if (depth == 0) {                                       // camera.rs:470-472
+                        if (COUNT) tl.depth_out++;
+                        wf_finish(Q, acc, S.q[slot], mk<T>(0, 0, 0) + wf_res(dep), P.flags);
                         to_free = true;
                     } else {
-                        if (kind == V_DIFFUSE) {                                // res + mult * emitted (camera.rs:519): 0 or NaN per channel
-                            V3<T> rs = wf_res(dep) + mult * emitted;
-                            dep |= (rs.x != rs.x ? 1u << 16 : 0u) | (rs.y != rs.y ? 1u << 17 : 0u) | (rs.z != rs.z ? 1u << 18 : 0u);
-                        }
-                        mult = mult * w;
-                        depth -= 1;
-                        dep = (dep & 0xffff0000u) | depth;
-                        if (depth == 0) {                                       // camera.rs:470-472
-                            if (COUNT) tl.depth_out++;
-                            wf_finish(Q, S.q[slot], mk<T>(0, 0, 0) + wf_res(dep), P.flags);
-                            to_free = true;
-                        } else {
-                            S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
-                            S.dx[slot] = next.d.x; S.dy[slot] = next.d.y; S.dz[slot] = next.d.z;
-                            S.mx[slot] = mult.x; S.my[slot] = mult.y; S.mz[slot] = mult.z;
-                            S.dep[slot] = dep;
-                            to_ext = true;
-                        }
+                        S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
+                        S.dx[slot] = next.d.x; S.dy[slot] = next.d.y; S.dz[slot] = next.d.z;
+                        S.mx[slot] = mult.x; S.my[slot] = mult.y; S.mz[slot] = mult.z;
+                        S.dep[slot] = dep;
+                        to_ext = true;
                     }
                 }
-                wf_push(to_ext, L.ext[cb ^ 1], &L.n_ext[cb ^ 1], slot);
-                wf_push(to_free, L.free_[cb ^ 1], &L.n_free[cb ^ 1], slot);
             }
+            __syncwarp();
+            wf_push(S.list[WF_EXT], n_ext, to_ext, slot, lt_mask);
+            wf_push(S.list[WF_FREE], n_free, to_free, slot, lt_mask);
         }
-        __syncthreads();
-        if (tid == 0) { L.n_free[cb] = 0; L.n_ext[cb] = 0; L.n_lamb = L.n_metal = L.n_diel = 0; }
-        cb ^= 1;
     }
+    wf_acc_flush(Q, acc);
     flush_counters<COUNT>(P.counters, npaths, nrays, tl);
 }
 
-template <int BLOCK, int NP> size_t wavefront_state_bytes() { return sizeof(WfPaths<NP>) + sizeof(WfLists<NP>); }
+template <int BLOCK, int NPW> size_t wavefront_state_bytes() { return sizeof(WfWarp<NPW>) * (BLOCK / 32); }
 
 }  // namespace rtw

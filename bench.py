@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """bench.py — Mrays/s / Mpaths/s of the CUDA render path on BASELINE config C2:
-random-spheres (scenes::simple, seeded) 1920x1080, 500 spp, depth 50, megakernel, N B200s.
+random-spheres (scenes::simple, seeded) 1920x1080, 500 spp, depth 50, N B200s; the wavefront renderer is timed
+(the faster of the two FP32 renderers), the megakernel is measured beside it outside the timed region.
 
 A step is one full render of that frame: rtw_render_tiles_device on every rank (tiles interleaved across
 ranks), one NCCL gather of the tile buffers on rank 0, untile + resolve there.  Contract: see the task
@@ -223,6 +224,25 @@ def run_cuda(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
 
+    # the other renderer on the same frame, outside the timed region (same image bit for bit)
+    other = None
+    if not args.lane_per_pixel:
+        omode = R.RTW_MEGAKERNEL if mode == R.RTW_WAVEFRONT else R.RTW_WAVEFRONT
+        oopts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=omode)
+        scene.render_tiles_device(cam, oopts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+        barrier()
+        oev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        oev[0].record()
+        for _ in range(2):
+            scene.render_tiles_device(cam, oopts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+        oev[1].record()
+        barrier()
+        ot = torch.tensor([oev[0].elapsed_time(oev[1]) / 2], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ot, op=dist.ReduceOp.MAX)
+        other = dict(mode="megakernel (pooled path stream)" if omode == R.RTW_MEGAKERNEL else "wavefront", kernel_ms_per_step=float(ot.item()),
+                     mrays_per_s=total["rays"] / float(ot.item()) * 1e-3)
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
@@ -230,28 +250,30 @@ def run_cuda(args):
         secs = step_ms * 1e-3
         mrays = total["rays"] * args.steps / secs * 1e-6
         achieved = local_flops / (kern_ms / args.steps * 1e-3) / 1e12        # this rank's kernel: flop / its duration
+        kernel_name = "render_wavefront_kernel" if args.mode == "wavefront" else ("render_mega_kernel<float>" if args.lane_per_pixel else "render_pool_kernel")
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and SPP == 500 and world == 1:           # the capture is of the default single-GPU workload
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                traffic = json.load(f).get(kernel_name, {}).get("dram_bytes_per_launch")
         line = dict(
             metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload=WORKLOAD, mode=("wavefront (CTA-local queues in shared memory)" if args.mode == "wavefront" else
+            config=dict(workload=WORKLOAD, mode=("wavefront (warp-private queues in shared memory)" if args.mode == "wavefront" else
                               "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
                         tmin="RTW_TMIN_REFERENCE: machine epsilon of the working precision (the reference uses f64::EPSILON in f64)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
             mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
             kernel_ms_per_step=kern_ms / args.steps,
             roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,
                           peak_source=f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json); no FP32 figure is in that file",
-                          kernel="render_wavefront_kernel" if args.mode == "wavefront" else ("render_mega_kernel<float>" if args.lane_per_pixel else "render_pool_kernel"), flop_per_launch=local_flops,
+                          kernel=kernel_name, flop_per_launch=local_flops,
                           frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None),
             e2e=dict(value=total["rays"] * e2e_steps / e2e_s * 1e-6, unit="Mrays/s", h2d_bytes_per_step=scene.upload_bytes * world,
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
-            gpu_launches=args.steps * ((1 if args.lane_per_pixel else 2) * world + 1),
+            gpu_launches=args.steps * ((1 if (args.lane_per_pixel and args.mode == "megakernel") else 2) * world + 1),
             clocks=clocks,
             events_per_step={k: total[k] for k in keys},
+            other_renderer=other,
         )
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -280,7 +302,7 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
-    ap.add_argument("--mode", default="megakernel", choices=["megakernel", "wavefront"])
+    ap.add_argument("--mode", default="wavefront", choices=["megakernel", "wavefront"])
     args = ap.parse_args()
     if args.spp != SPP:
         SPP = args.spp

@@ -90,7 +90,8 @@ typedef struct {
                              depends on how this compares with the rounding noise of hit points (self-intersection),
                              which is a relation in ulps, not in absolute terms. */
     uint32_t precision;   /* RTW_F32 | RTW_F64                                                      */
-    uint32_t mode;        /* RTW_MEGAKERNEL | RTW_WAVEFRONT                                         */
+    uint32_t mode;        /* RTW_MEGAKERNEL | RTW_WAVEFRONT: which FP32 renderer (same image bit for bit; the
+                             wavefront is the faster one).  Ignored by RTW_F64, which has a single renderer.    */
     uint32_t flags;
     uint32_t reserved;
 } rtw_opts;

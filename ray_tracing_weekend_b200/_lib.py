@@ -89,7 +89,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if build_if_missing and os.environ.get("RTW_NO_BUILD") != "1":
+    if os.environ.get("RTW_LIBRARY"):                      # tuning builds (scripts/): another build of the same library
+        path = os.environ["RTW_LIBRARY"]
+    elif build_if_missing and os.environ.get("RTW_NO_BUILD") != "1":
         path = _build.build_library()
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -m ray_tracing_weekend_b200.build` (needs nvcc). "

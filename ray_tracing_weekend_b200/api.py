@@ -116,7 +116,7 @@ class RenderOptions:
     seed: int = 20261018
     tmin: float = TMIN_REFERENCE               # camera.rs:473: EPSILON of the working precision
     precision: int = RTW_F32
-    mode: int = RTW_MEGAKERNEL
+    mode: int = RTW_WAVEFRONT                   # the faster FP32 renderer; RTW_MEGAKERNEL gives the same image
     flags: int = 0
 
     def pod(self) -> rtw_opts:

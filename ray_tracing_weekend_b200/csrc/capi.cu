@@ -249,7 +249,6 @@ int check_opts(const rtw_opts* o) {
     if (!o) return fail(RTW_E_INVALID, "opts is NULL");
     if (o->precision != RTW_F32 && o->precision != RTW_F64) return fail(RTW_E_INVALID, "opts.precision");
     if (o->mode != RTW_MEGAKERNEL && o->mode != RTW_WAVEFRONT) return fail(RTW_E_INVALID, "opts.mode");
-    if (o->mode == RTW_WAVEFRONT && o->precision != RTW_F32) return fail(RTW_E_UNSUPPORTED, "wavefront mode exists on the RTW_F32 path only");
     if (o->tmin != o->tmin) return fail(RTW_E_INVALID, "opts.tmin is NaN");
     return RTW_OK;
 }
@@ -464,6 +463,7 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
     if (world == 0 || rank >= world) return fail(RTW_E_INVALID, "rank/world");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t launches = 1;
+    // RTW_F64 has one renderer (lane per pixel, samples summed in order); `mode` only selects among the FP32 renderers
     bool pooled = o->precision == RTW_F32 && (o->mode == RTW_WAVEFRONT || !(o->flags & RTW_FLAG_LANE_PER_PIXEL));
     if (pooled) {
         size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;

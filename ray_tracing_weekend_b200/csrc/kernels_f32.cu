@@ -1,6 +1,7 @@
 // kernels_f32.cu — the fast (FP32) instantiation of every kernel.  Compiled with -fmad=false: fused
 // multiply-adds are written explicitly (fmaf) in the hot code so that all kernels round identically.
 #include <algorithm>
+#include <cstdlib>
 #include "rtw_launch.cuh"
 #include "rtw_wavefront.cuh"
 
@@ -14,9 +15,8 @@ RTW_DEFINE_LAUNCHERS(f32, float, false)
 cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_pool_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_impl<false>(P, Q, sm_count, s, info);
 }
-template <bool COUNT, bool SH>
+template <bool COUNT, bool SH, int BLOCK, int NP>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    constexpr int BLOCK = kWfBlock, NP = kWfSlotsPerWarp;
     auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
@@ -24,9 +24,8 @@ cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size
     kernel<<<grid, BLOCK, smem, s>>>(P, Q);
     return cudaGetLastError();
 }
-template <bool COUNT>
-cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    constexpr int BLOCK = kWfBlock, NP = kWfSlotsPerWarp;
+template <bool COUNT, int BLOCK, int NP>
+cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
     P.stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
     // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene
     const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
@@ -38,10 +37,24 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
     size_t smem = fixed + scene;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
-    e = sh ? launch_render_wavefront_sh<COUNT, true>(P, Q, smem, sm_count, s, info)
-           : launch_render_wavefront_sh<COUNT, false>(P, Q, smem, sm_count, s, info);
+    e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP>(P, Q, smem, sm_count, s, info)
+           : launch_render_wavefront_sh<COUNT, false, BLOCK, NP>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     return pool_finalize(P, Q, s);
+}
+template <bool COUNT>
+cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
+#ifdef RTW_WF_SWEEP
+    // tuning build only (nvcc -DRTW_WF_SWEEP): launch shape from the environment
+    const char* e = std::getenv("RTW_WF_SHAPE");
+    int shape = e ? std::atoi(e) : 0;
+    if (shape == 1) return launch_render_wavefront_shape<COUNT, 896, 64>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 2) return launch_render_wavefront_shape<COUNT, 832, 80>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 3) return launch_render_wavefront_shape<COUNT, 640, 112>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 4) return launch_render_wavefront_shape<COUNT, 704, 96>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 5) return launch_render_wavefront_shape<COUNT, 768, 88>(P, Q, bvh_depth, sm_count, s, info);
+#endif
+    return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
 }
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_wavefront_impl<true>(P, Q, bvh_depth, sm_count, s, info)

@@ -255,17 +255,26 @@ template <class T> struct SceneView {
 // Tag type: every section of the scene (nodes, spheres, materials, lights) sits in SHARED memory, so the
 // accessors below can issue ld.shared.v4 instead of generic loads (ncu/SASS: the generic path compiled to
 // 7 x LD.E.64 per node; this is 4 x LDS.128).
-template <class T> struct SceneViewSh : SceneView<T> {};
+template <class T> struct SceneViewSh : SceneView<T> {
+    uint32_t s_nodes = 0, s_spheres = 0, s_mat = 0, s_info = 0, s_lights = 0;   // 32-bit shared-window addresses
+    RTW_D void bind() {
+        s_nodes = (uint32_t)__cvta_generic_to_shared(this->top_nodes);
+        s_spheres = (uint32_t)__cvta_generic_to_shared(this->spheres);
+        s_mat = (uint32_t)__cvta_generic_to_shared(this->sphere_mat);
+        s_info = (uint32_t)__cvta_generic_to_shared(this->sphere_info);
+        s_lights = (uint32_t)__cvta_generic_to_shared(this->lights);
+    }
+};
+template <class T> RTW_D void bind_scene(SceneView<T>&) {}
+template <class T> RTW_D void bind_scene(SceneViewSh<T>& sc) { sc.bind(); }
 
-RTW_D float4 lds128(const void* p) {
+RTW_D float4 lds128(uint32_t a) {
     float4 v;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-RTW_D uint32_t lds32(const void* p) {
+RTW_D uint32_t lds32(uint32_t a) {
     uint32_t v;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
@@ -282,7 +291,7 @@ RTW_D void load_node(const SceneView<float>& sc, int32_t cur, Node<float>& nd) {
     unpack_node(p[0], p[1], p[2], p[3], nd);
 }
 RTW_D void load_node(const SceneViewSh<float>& sc, int32_t cur, Node<float>& nd) {
-    const char* p = reinterpret_cast<const char*>(sc.top_nodes + cur);
+    uint32_t p = sc.s_nodes + (uint32_t)cur * 64u;
     unpack_node(lds128(p), lds128(p + 16), lds128(p + 32), lds128(p + 48), nd);
 }
 template <class T> RTW_D Vec4T<T> load_sphere(const SceneView<T>& sc, int32_t i) { return sc.spheres[i]; }
@@ -290,13 +299,13 @@ template <class T> RTW_D Vec4T<T> load_sphere_mat(const SceneView<T>& sc, int32_
 template <class T> RTW_D uint32_t load_sphere_info(const SceneView<T>& sc, int32_t i) { return sc.sphere_info[i]; }
 template <class T> RTW_D Vec4T<T> load_light(const SceneView<T>& sc, int32_t i) { return sc.lights[i]; }
 RTW_D Vec4T<float> as_vec4(float4 v) { return Vec4T<float>{v.x, v.y, v.z, v.w}; }
-RTW_D Vec4T<float> load_sphere(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.spheres + i)); }
-RTW_D Vec4T<float> load_sphere_mat(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.sphere_mat + i)); }
-RTW_D uint32_t load_sphere_info(const SceneViewSh<float>& sc, int32_t i) { return lds32(sc.sphere_info + i); }
+RTW_D Vec4T<float> load_sphere(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.s_spheres + (uint32_t)i * 16u)); }
+RTW_D Vec4T<float> load_sphere_mat(const SceneViewSh<float>& sc, int32_t i) { return as_vec4(lds128(sc.s_mat + (uint32_t)i * 16u)); }
+RTW_D uint32_t load_sphere_info(const SceneViewSh<float>& sc, int32_t i) { return lds32(sc.s_info + (uint32_t)i * 4u); }
 // with a light BVH the lights stay in global memory (read through L1), otherwise they are staged like the rest
 RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
     if (sc.n_light_nodes > 0) return as_vec4(__ldg(reinterpret_cast<const float4*>(sc.lights + i)));
-    return as_vec4(lds128(sc.lights + i));
+    return as_vec4(lds128(sc.s_lights + (uint32_t)i * 16u));
 }
 
 template <class T> struct CameraT {

@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC scv;
     static_cast<SceneView<T>&>(scv) = sc;
+    bind_scene(scv);
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     int32_t* stack = stack_base + threadIdx.x;
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<floa
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC scv;
     static_cast<SceneView<T>&>(scv) = sc;
+    bind_scene(scv);
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC sc;
     static_cast<SceneView<T>&>(sc) = sc0;
+    bind_scene(sc);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt_mask = (1u << lane) - 1u;
     WfWarp<NPW>& S = reinterpret_cast<WfWarp<NPW>*>(cur_p)[warp];
 

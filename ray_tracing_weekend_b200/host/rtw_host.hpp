@@ -106,7 +106,7 @@ struct RenderOptions {
     uint64_t seed = 20261018;
     double tmin = RTW_TMIN_REFERENCE;               // camera.rs:473: machine epsilon of the working precision
     Precision precision = Precision::F32;
-    uint32_t mode = RTW_MEGAKERNEL, flags = 0;
+    uint32_t mode = RTW_WAVEFRONT, flags = 0;       // the faster FP32 renderer; RTW_MEGAKERNEL renders the same image
 };
 
 class Camera;

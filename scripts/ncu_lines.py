@@ -77,6 +77,35 @@ def main():
     tinst = sum(a[1] for a in agg.values()) or 1
     tthr = sum(a[2] for a in agg.values())
     print(f"total samples {ts}, warp instructions {tinst}, thread instructions {tthr}, avg threads/inst {tthr / tinst:.2f}")
+    # per-function roll-up: a source line belongs to the last function header above it
+    funcs = {}
+    def func_of(fn, ln):
+        for base in ("ray_tracing_weekend_b200/csrc",):
+            path = os.path.join(base, fn)
+            if os.path.exists(path):
+                if path not in funcs:
+                    heads = []
+                    for i, t in enumerate(open(path, errors="replace").read().splitlines(), 1):
+                        m = re.match(r"^(?:template.*>\s*)?(?:RTW_D|RTW_HD|__global__|static RTW_HD|inline)\b.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", t.strip())
+                        if m and not t.strip().startswith("//"):
+                            heads.append((i, m.group(1)))
+                    funcs[path] = heads
+                name = "?"
+                for i, nme in funcs[path]:
+                    if i <= ln:
+                        name = nme
+                    else:
+                        break
+                return f"{fn}:{name}"
+        return fn
+    roll = defaultdict(lambda: [0, 0, 0])
+    for key, a in agg.items():
+        f = func_of(*key)
+        roll[f][0] += a[0]; roll[f][1] += a[1]; roll[f][2] += a[2]
+    print("-- by function (samples%, warp-inst%, threads/inst) --")
+    for f, a in sorted(roll.items(), key=lambda kv: -kv[1][0])[:22]:
+        print(f"{a[0] / ts * 100:8.2f} {a[1] / tinst * 100:6.2f} {a[2] / max(a[1], 1):8.1f}  {f}")
+    print("-- by source line --")
     print(f"{'samples%':>8} {'inst%':>6} {'thr/inst':>8}  top stalls | source line")
     src_cache = {}
     for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:

@@ -27,6 +27,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) {                                                                          \
             int code_ = (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? RTW_E_NO_DEVICE  \
                         : (e_ == cudaErrorMemoryAllocation ? RTW_E_NOMEM : RTW_E_CUDA);                   \
+            cudaGetLastError(); /* clear the non-sticky error so it cannot surface in a later call */      \
             return fail(code_, std::string(#expr) + ": " + cudaGetErrorString(e_));                       \
         }                                                                                                 \
     } while (0)
@@ -91,7 +92,6 @@ template <class P> struct DevBuf {
     size_t bytes() const { return n * sizeof(P); }
 };
 
-float round_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
 float round_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
 
 template <class T> void fill_node(Node<T>& n, const host::FlatNode& f);

@@ -29,7 +29,7 @@ cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, u
     P.stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
     // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene
     const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
-    const size_t limit = 227 * 1024;
+    const size_t limit = 226 * 1024;                      // 227 KB per CTA minus the static shared memory (mbarrier) and slack
     if (fixed + 1024 > limit) return cudaErrorInvalidConfiguration;
     bool sh = false;
     plan_smem<float, false>(P, BLOCK, &sh, std::min<size_t>(kSmemSceneBudget, (limit - fixed) / 64 * 64));

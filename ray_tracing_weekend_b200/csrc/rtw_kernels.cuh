@@ -522,6 +522,55 @@ RTW_D void flush_counters(DeviceCounters* c, uint32_t npaths, uint32_t nrays, co
     }
 }
 
+// Scene staging: the sections the host chose (plan_smem) are copied global -> shared by the TMA engine
+// (cp.async.bulk, SASS UBLKCP) while the CTA waits on one mbarrier; afterwards `sc` points into shared memory.
+RTW_D void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), m = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(gmem_src), "r"(bytes), "r"(m) : "memory");
+}
+RTW_D void stage_scene(const RenderParams<float>& P, unsigned char* cur, SceneView<float>& sc) {
+    __shared__ __align__(8) uint64_t mbar;
+    const uint32_t info_bytes = ((uint32_t)P.scene.n_spheres * 4u + 15u) / 16u * 16u;
+    unsigned char* p_nodes = cur;        cur += P.smem_nodes;
+    unsigned char* p_spheres = cur;      cur += P.smem_spheres;
+    unsigned char* p_mat = cur;          cur += P.smem_spheres;
+    unsigned char* p_info = cur;         cur += P.smem_spheres ? info_bytes : 0u;
+    unsigned char* p_lights = cur;
+    const uint32_t total = P.smem_nodes + (P.smem_spheres ? 2u * P.smem_spheres + info_bytes : 0u) + P.smem_lights;
+    if (total) {
+        const uint32_t m = (uint32_t)__cvta_generic_to_shared(&mbar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(m) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(total) : "memory");
+            if (P.smem_nodes) tma_load_1d(p_nodes, P.scene.nodes, P.smem_nodes, &mbar);
+            if (P.smem_spheres) {
+                tma_load_1d(p_spheres, P.scene.spheres, P.smem_spheres, &mbar);
+                tma_load_1d(p_mat, P.scene.sphere_mat, P.smem_spheres, &mbar);
+                tma_load_1d(p_info, P.scene.sphere_info, info_bytes, &mbar);      // the allocation is padded to 512 B
+            }
+            if (P.smem_lights) tma_load_1d(p_lights, P.scene.lights, P.smem_lights, &mbar);
+        }
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(m) : "memory");
+        if (!done) __trap();                                   // never hang the GPU on a staging bug
+    }
+    if (P.smem_nodes) { sc.top_nodes = reinterpret_cast<const Node<float>*>(p_nodes); sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<float>)); }
+    if (P.smem_spheres) {
+        sc.spheres = reinterpret_cast<const Vec4T<float>*>(p_spheres);
+        sc.sphere_mat = reinterpret_cast<const Vec4T<float>*>(p_mat);
+        sc.sphere_info = reinterpret_cast<const uint32_t*>(p_info);
+    }
+    if (P.smem_lights) sc.lights = reinterpret_cast<const Vec4T<float>*>(p_lights);
+}
+template <class T> RTW_D void stage_scene(const RenderParams<T>&, unsigned char*, SceneView<T>&) {}   // exact path: global memory
+
 // Megakernel: persistent CTAs; each warp pulls 8x4-pixel warp tiles from this GPU's work queue
 // (an atomic counter); each lane owns one pixel and runs its spp paths back to back, regenerating a
 // camera ray as soon as its previous path ends (render_internal + ray_colour_tail_call,
@@ -532,42 +581,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
     SceneView<T> sc = P.scene;
-    if constexpr (!EXACT) {
-        // stage the scene in shared memory when the host decided it fits
-        unsigned char* cur = smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK;
-        if (P.smem_nodes) {
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
-            for (uint32_t i = threadIdx.x; i < P.smem_nodes / 16; i += BLOCK) dst[i] = src[i];
-            sc.top_nodes = reinterpret_cast<const Node<T>*>(cur);
-            sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<T>));
-            cur += P.smem_nodes;
-        }
-        if (P.smem_spheres) {
-            uint32_t n16 = P.smem_spheres / 16;       // one float4 per sphere, twice (geometry + material) + info
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.spheres);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc.spheres = reinterpret_cast<const Vec4T<T>*>(cur);
-            cur += P.smem_spheres;
-            dst = reinterpret_cast<uint4*>(cur);
-            src = reinterpret_cast<const uint4*>(P.scene.sphere_mat);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc.sphere_mat = reinterpret_cast<const Vec4T<T>*>(cur);
-            cur += P.smem_spheres;
-            uint32_t* dsti = reinterpret_cast<uint32_t*>(cur);
-            for (uint32_t i = threadIdx.x; i < (uint32_t)P.scene.n_spheres; i += BLOCK) dsti[i] = P.scene.sphere_info[i];
-            sc.sphere_info = dsti;
-            cur += (P.scene.n_spheres * 4 + 15) / 16 * 16;
-        }
-        if (P.smem_lights) {
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.lights);
-            for (uint32_t i = threadIdx.x; i < P.smem_lights / 16; i += BLOCK) dst[i] = src[i];
-            sc.lights = reinterpret_cast<const Vec4T<T>*>(cur);
-        }
-        __syncthreads();
-    }
+    if constexpr (!EXACT) stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC scv;
     static_cast<SceneView<T>&>(scv) = sc;
@@ -666,41 +680,7 @@ __global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<floa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
     SceneView<T> sc = P.scene;
-    {
-        unsigned char* cur = smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK;
-        if (P.smem_nodes) {
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
-            for (uint32_t i = threadIdx.x; i < P.smem_nodes / 16; i += BLOCK) dst[i] = src[i];
-            sc.top_nodes = reinterpret_cast<const Node<T>*>(cur);
-            sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<T>));
-            cur += P.smem_nodes;
-        }
-        if (P.smem_spheres) {
-            uint32_t n16 = P.smem_spheres / 16;
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.spheres);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc.spheres = reinterpret_cast<const Vec4T<T>*>(cur);
-            cur += P.smem_spheres;
-            dst = reinterpret_cast<uint4*>(cur);
-            src = reinterpret_cast<const uint4*>(P.scene.sphere_mat);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc.sphere_mat = reinterpret_cast<const Vec4T<T>*>(cur);
-            cur += P.smem_spheres;
-            uint32_t* dsti = reinterpret_cast<uint32_t*>(cur);
-            for (uint32_t i = threadIdx.x; i < (uint32_t)P.scene.n_spheres; i += BLOCK) dsti[i] = P.scene.sphere_info[i];
-            sc.sphere_info = dsti;
-            cur += (P.scene.n_spheres * 4 + 15) / 16 * 16;
-        }
-        if (P.smem_lights) {
-            uint4* dst = reinterpret_cast<uint4*>(cur);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.lights);
-            for (uint32_t i = threadIdx.x; i < P.smem_lights / 16; i += BLOCK) dst[i] = src[i];
-            sc.lights = reinterpret_cast<const Vec4T<T>*>(cur);
-        }
-        __syncthreads();
-    }
+    stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC scv;
     static_cast<SceneView<T>&>(scv) = sc;

@@ -80,41 +80,8 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);
     SceneView<T> sc0 = P.scene;
     unsigned char* cur_p = smem_raw + sizeof(int32_t) * stack_depth * BLOCK;
-    {
-        if (P.smem_nodes) {
-            uint4* dst = reinterpret_cast<uint4*>(cur_p);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.nodes);
-            for (uint32_t i = threadIdx.x; i < P.smem_nodes / 16; i += BLOCK) dst[i] = src[i];
-            sc0.top_nodes = reinterpret_cast<const Node<T>*>(cur_p);
-            sc0.n_top = (int32_t)(P.smem_nodes / sizeof(Node<T>));
-            cur_p += P.smem_nodes;
-        }
-        if (P.smem_spheres) {
-            uint32_t n16 = P.smem_spheres / 16;
-            uint4* dst = reinterpret_cast<uint4*>(cur_p);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.spheres);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc0.spheres = reinterpret_cast<const Vec4T<T>*>(cur_p);
-            cur_p += P.smem_spheres;
-            dst = reinterpret_cast<uint4*>(cur_p);
-            src = reinterpret_cast<const uint4*>(P.scene.sphere_mat);
-            for (uint32_t i = threadIdx.x; i < n16; i += BLOCK) dst[i] = src[i];
-            sc0.sphere_mat = reinterpret_cast<const Vec4T<T>*>(cur_p);
-            cur_p += P.smem_spheres;
-            uint32_t* dsti = reinterpret_cast<uint32_t*>(cur_p);
-            for (uint32_t i = threadIdx.x; i < (uint32_t)P.scene.n_spheres; i += BLOCK) dsti[i] = P.scene.sphere_info[i];
-            sc0.sphere_info = dsti;
-            cur_p += (P.scene.n_spheres * 4 + 15) / 16 * 16;
-        }
-        if (P.smem_lights) {
-            uint4* dst = reinterpret_cast<uint4*>(cur_p);
-            const uint4* src = reinterpret_cast<const uint4*>(P.scene.lights);
-            for (uint32_t i = threadIdx.x; i < P.smem_lights / 16; i += BLOCK) dst[i] = src[i];
-            sc0.lights = reinterpret_cast<const Vec4T<T>*>(cur_p);
-            cur_p += P.smem_lights;
-        }
-        __syncthreads();                                  // the only block-wide barrier of the kernel
-    }
+    stage_scene(P, cur_p, sc0);                           // TMA bulk copies; the only block-wide wait of the kernel
+    cur_p += P.smem_nodes + (P.smem_spheres ? 2u * P.smem_spheres + ((uint32_t)P.scene.n_spheres * 4u + 15u) / 16u * 16u : 0u) + P.smem_lights;
     using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
     SC sc;
     static_cast<SceneView<T>&>(sc) = sc0;

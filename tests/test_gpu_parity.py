@@ -356,3 +356,46 @@ def test_light_bvh_sum_equals_linear_sum(rtw, oracle):
     rel = np.abs(wr[ok] - wg[ok]) / np.maximum(np.abs(wr[ok]), 1e-3)
     assert np.quantile(rel, 0.99) < 2e-3 and np.median(rel) < 1e-5, (np.quantile(rel, 0.99), np.median(rel))
     gs.close()
+
+
+def test_edge_cases(rtw, oracle):
+    """Empty world, metal-only world without lights, defocus camera (UnitDisk rejection loop), depth 1, 1 spp,
+    image sizes that are not multiples of the 16x16 tile — f64 path bit-exact against the oracle, FP32 renderers
+    bit-identical to each other."""
+    # (a) empty world: every path misses -> spp * background
+    sc = rtw.Scene(rtw.HittableList(), rtw.HittableList())
+    cam = rtw.CameraBuilder().with_image_width(37).with_image_height(19).with_samples_per_pixel(3).with_max_depth(5).with_background((0.25, 0.5, 1.0)).build()
+    for prec in (rtw.RTW_F32, rtw.RTW_F64):
+        img, rgb8, st = sc.render(cam, rtw.RenderOptions(seed=1, precision=prec))
+        assert np.array_equal(img, np.broadcast_to(np.array([0.75, 1.5, 3.0]), img.shape)) and st["rays"] == st["paths"] == 37 * 19 * 3
+        assert np.array_equal(rgb8[0, 0], [128, 181, 255])
+    sc.close()
+    # (b) metal + glass only, no lights list needed; defocus camera
+    mats = oracle.make_materials([(oracle.METAL, 0.8, 0.7, 0.6, 0.3), (oracle.DIELECTRIC, 1, 1, 1, 1.5), (oracle.METAL, 0.9, 0.9, 0.9, 0.0)])
+    spheres = np.array([[0, 0, 0, 1.0], [2.2, 0, 0, 1.0], [0, -101, 0, 100.0], [-2.2, 0.3, 0.5, 0.7]])
+    smat = np.array([0, 1, 2, 0], dtype=np.uint32)
+    desc = oracle.SceneDesc(spheres, smat, mats, np.zeros((0, 6)), [], np.zeros((0, 4)))
+    osc = oracle.Scene(desc)
+    rows = desc.materials_array()[smat]
+    gs = rtw.Scene.from_arrays(spheres, rows)
+    for (w, h, spp, depth, defocus) in ((50, 35, 5, 50, 0.6), (17, 33, 1, 1, 0.0), (64, 48, 2, 3, 0.2)):
+        cb = (rtw.CameraBuilder().with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).with_max_depth(depth)
+              .with_background((0.7, 0.8, 1.0)).with_vfov(35).with_lookfrom((3, 2, 7)).with_lookat((0, 0, 0)).with_vup((0, 1, 0))
+              .with_focus_dist(7.5).with_defocus_angle(defocus))
+        cam = cb.build()
+        ocb = oracle.CameraBuilder.from_buffer_copy(cb.pod)       # same POD layout
+        ocam = oracle.camera_build(ocb)
+        assert list(ocam.pixel00) == list(cam.pod.pixel00_loc) and list(ocam.ddu) == list(cam.pod.defocus_disk_u)
+        ii, jj = np.meshgrid(np.arange(w), np.arange(h))
+        ss = (ii + jj) % spp
+        o_o, d_o = oracle.get_rays(ocam, oracle.options(seed=9, rng_mode=oracle.W64), ii.ravel(), jj.ravel(), ss.ravel())
+        o_g, d_g = cam.get_rays(ii.ravel(), jj.ravel(), ss.ravel(), rtw.RenderOptions(seed=9, precision=rtw.RTW_F64))
+        assert np.array_equal(o_o, o_g) and np.array_equal(d_o, d_g)
+        ref, _, cnt, _ = osc.render(ocam, oracle.options(seed=9, rng_mode=oracle.W64, math_mode=oracle.PORTABLE))
+        got, _, st = gs.render(cam, rtw.RenderOptions(seed=9, precision=rtw.RTW_F64))
+        assert np.array_equal(ref, got, equal_nan=True) and st["rays"] == cnt["rays"], (w, h, spp, depth)
+        a, a8, sa = gs.render(cam, rtw.RenderOptions(seed=9, precision=rtw.RTW_F32, mode=rtw.RTW_WAVEFRONT))
+        b, b8, sb = gs.render(cam, rtw.RenderOptions(seed=9, precision=rtw.RTW_F32, mode=rtw.RTW_MEGAKERNEL))
+        assert np.array_equal(a, b, equal_nan=True) and sa["rays"] == sb["rays"]
+        assert abs(a.mean() - ref.mean()) < 0.05 * spp
+    gs.close()

@@ -22,13 +22,33 @@ V_MISS, V_ABSORB, V_SPECULAR, V_DIFFUSE = 0, 1, 2, 3
 EPS = 2.220446049250313e-16
 
 
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("rtw_oracle.hpp", "oracle_capi.cpp", "oracle_cli.cpp", "Makefile"):
+        with open(os.path.join(_HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """Compile the restatement with g++ (make); returns the .so path."""
-    srcs = [os.path.join(_HERE, f) for f in ("rtw_oracle.hpp", "oracle_capi.cpp", "oracle_cli.cpp", "Makefile")]
-    stale = force or not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
-    if stale:
-        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    """Compile the restatement with g++ (make); returns the .so path.  Staleness is decided by source content
+    (the built library travels inside repo snapshots whose mtimes mean nothing)."""
+    import fcntl
+    stamp = os.path.join(_HERE, "_build", ".source_hash")
+    def stale():
+        if not os.path.exists(_LIB_PATH) or not os.path.exists(stamp):
+            return True
+        with open(stamp) as f:
+            return f.read().strip() != _source_hash()
+    if force or stale():
+        os.makedirs(os.path.join(_HERE, "_build"), exist_ok=True)
+        with open(os.path.join(_HERE, "_build", ".build_lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():
+                subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+                with open(stamp, "w") as f:
+                    f.write(_source_hash())
     return _LIB_PATH
 
 

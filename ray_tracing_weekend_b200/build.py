@@ -6,6 +6,8 @@ Three translation units: kernels_f32.cu (fast path, FMA on), kernels_f64.cu (ref
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -44,11 +46,26 @@ def _sources():
     return out
 
 
+HASH_PATH = os.path.join(LIB_DIR, ".source_hash")
+
+
+def source_hash() -> str:
+    """Content hash of every source and of the build recipe.  Staleness is decided by content, not by mtime:
+    the built library travels to the GPU box inside a repo snapshot whose mtimes mean nothing, and N torchrun
+    ranks importing the package at once must not all decide to rebuild."""
+    h = hashlib.sha256()
+    for p in sorted(_sources()):
+        h.update(os.path.relpath(p, HERE).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -56,6 +73,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time (torchrun ranks, pytest-xdist workers); the others wait and then find it fresh
+    with open(os.path.join(LIB_DIR, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -83,6 +109,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("rtw_bin build failed: " + " ".join(cli) + "\n" + r.stdout)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

@@ -476,8 +476,8 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
         uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
-        const bool wavefront = o->mode == RTW_WAVEFRONT;
-        if (wavefront && cam->max_depth > 0xffffu) return fail(RTW_E_UNSUPPORTED, "wavefront mode: max_depth > 65535");
+        // the wavefront packs the remaining depth into 16 bits; deeper paths take the (bit-identical) megakernel
+        const bool wavefront = o->mode == RTW_WAVEFRONT && cam->max_depth <= 0xffffu;
         const uint32_t bvh_depth = std::max(s->bvh.depth, s->light_bvh_depth);
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)

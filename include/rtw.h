@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 1
+#define RTW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -42,18 +42,58 @@ enum {
 /* DynMaterial flattened (shared/src/material.rs:251-325).  Textures: SolidColour only
  * (shared/src/texture.rs:15-22). */
 enum {
-    RTW_LAMBERTIAN = 0, /* Lambertian{SolidColour(r,g,b)}        material.rs:327-376 */
+    RTW_LAMBERTIAN = 0, /* Lambertian{texture}                   material.rs:327-376 */
     RTW_METAL = 1,      /* Metal{albedo=(r,g,b), fuzz=param}     material.rs:378-421 */
     RTW_DIELECTRIC = 2, /* Dialectric{index_of_refraction=param} material.rs:423-488 */
-    RTW_INVISIBLE = 3   /* Invisible: never scatters, emits 0    material.rs:319-325 */
+    RTW_INVISIBLE = 3,  /* Invisible: never scatters, emits 0    material.rs:319-325 */
+    RTW_DIFFUSE_LIGHT = 4, /* DiffuseLight{texture}: emits, never scatters   material.rs:490-514   [general scenes only] */
+    RTW_ISOTROPIC = 5      /* Isotropic{texture}: SpherePdf scatter          material.rs:516-554   [general scenes only] */
 };
-typedef struct { uint32_t kind; uint32_t reserved; double r, g, b, param; } rtw_material;
+/* texture: 0 = SolidColour(r,g,b) (texture.rs:15-22); k > 0 = rtw_scene_desc.textures[k-1] (general scenes only). */
+typedef struct { uint32_t kind; uint32_t texture; double r, g, b, param; } rtw_material;
 
 /* Sphere{center, radius} (shared/src/entities/sphere.rs:25-30) */
 typedef struct { double cx, cy, cz, r; } rtw_sphere;
 /* Plane{point, normal}; normal is normalised by the library like Plane::new (entities/plane.rs:27-39).
  * One-sided: only rays with dir.normal > EPSILON hit (plane.rs:62-63). */
 typedef struct { double px, py, pz, nx, ny, nz; } rtw_plane;
+
+/* ---- general scenes: the other entities, Transformed<T>, emissive materials, NoiseTexture ---- */
+/* Quad::new(q, u, v) (entities/quadrilateral.rs:36-56) and Triangle::new(q, u, v) (entities/triangles.rs:34-54). */
+typedef struct { double q[3], u[3], v[3]; } rtw_quad;
+/* Cuboid::new(p, q): six Quads (entities/cuboid.rs:26-50). */
+typedef struct { double p[3], q[3]; } rtw_cuboid;
+/* Transformation{rotation (row-major Matrix3), translation} of the default (non-euclid) build
+ * (geometry/src/transformations.rs:96-100).  A Transformed<T> hits with the reference's arithmetic, including
+ * transform_vector3d adding the translation to the ray DIRECTION (:123-126) and the normal staying in instance space
+ * (entities/transformations.rs:14-29). */
+typedef struct { double rotation[9]; double translation[3]; } rtw_transform;
+enum { RTW_PRIM_SPHERE = 0, RTW_PRIM_PLANE = 1, RTW_PRIM_QUAD = 2, RTW_PRIM_TRIANGLE = 3, RTW_PRIM_CUBOID = 4 };
+/* One entry of a HittableList: entity `index` of the array its kind names (quads[] for QUAD and TRIANGLE), material,
+ * and transform = -1 or an index into transforms[] (the entry is then a Transformed<T>). */
+typedef struct { uint32_t kind, index, material; int32_t transform; } rtw_prim;
+enum { RTW_TEX_NOISE = 1 }; /* NoiseTexture{noise: perlins[perlin], scale} (texture.rs:57-102) */
+typedef struct { uint32_t kind, perlin; double scale; double reserved[3]; } rtw_texture;
+/* Perlin's tables (perlin.rs:13-19): rand_vec = 256 UnitSphere samples, three permutations of 0..255. */
+typedef struct { double rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; } rtw_perlin;
+/* world / lights of any scene of scenes/src/lib.rs: two HittableLists over shared entity arrays.
+ * world_is_bvh / lights_is_bvh record whether the reference wraps the list in BoundedVolumeHierarchy::from: for `world`
+ * it does not change the result (argmin-t either way); for `lights` it changes the f64 rounding of pdf_value
+ * (bvh.rs:67-76, 191-194) and is supported for at most 5 lights (one Leaf) — beyond that the reference's
+ * aux_random (bvh.rs:78-93) indexes out of range. */
+typedef struct {
+    const rtw_sphere* spheres;       uint64_t n_spheres;
+    const rtw_plane* planes;         uint64_t n_planes;
+    const rtw_quad* quads;           uint64_t n_quads;
+    const rtw_cuboid* cuboids;       uint64_t n_cuboids;
+    const rtw_transform* transforms; uint64_t n_transforms;
+    const rtw_material* materials;   uint64_t n_materials;
+    const rtw_texture* textures;     uint64_t n_textures;
+    const rtw_perlin* perlins;       uint64_t n_perlins;
+    const rtw_prim* world;           uint64_t n_world;
+    const rtw_prim* lights;          uint64_t n_lights;
+    uint32_t world_is_bvh, lights_is_bvh;
+} rtw_scene_desc;
 
 /* The fields of Camera the render loop reads (shared/src/camera.rs:231-260). */
 typedef struct {
@@ -127,6 +167,16 @@ RTW_API void        rtw_philox4x32_10(const uint32_t ctr[4], const uint32_t key[
 RTW_API uint32_t    rtw_tiles_total(uint32_t width, uint32_t height);
 RTW_API uint32_t    rtw_tiles_per_rank(uint32_t width, uint32_t height, uint32_t world); /* padded: same on every rank */
 
+/* Transformation::then (geometry/src/transformations.rs:104-116): out = a.then(b), i.e. a applied first.  */
+RTW_API void        rtw_transform_then(const rtw_transform* a, const rtw_transform* b, rtw_transform* out);
+/* Transformation::inverse (:128-136 + matrix3.rs:12-30); returns 0 when the determinant is not a normal number. */
+RTW_API int         rtw_transform_inverse(const rtw_transform* a, rtw_transform* out);
+/* rotation(angle_degrees, axis 0|1|2) (:38-64). */
+RTW_API void        rtw_rotation(double angle_degrees, int axis, rtw_transform* out);
+/* Perlin::new (perlin.rs:46-57) with the tables drawn from Philox stream (seed; 0x9E71A000 + index, 0, 0) instead of
+ * thread_rng. */
+RTW_API void        rtw_perlin_generate(uint64_t seed, uint32_t index, rtw_perlin* out);
+
 /* ---- device management ------------------------------------------------------------------------ */
 RTW_API int rtw_device_count(void);           /* >= 0, or RTW_E_* */
 /* Device buffers of destroyed scenes / finished renders are kept in a process-wide cache (<= 4 GiB) and reused;
@@ -145,6 +195,12 @@ RTW_API int  rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_
                       const rtw_material* materials, size_t n_materials,
                       const rtw_sphere* lights, size_t n_lights,
                       rtw_scene** out);
+/* General scenes: any world / lights pair the reference's scenes build from Sphere, Plane, Quad, Triangle, Cuboid,
+ * Transformed<T>, with DiffuseLight / Isotropic materials and NoiseTexture (cornell_box, simple_light, debug,
+ * simple_transform, perlin_spheres: scenes/src/lib.rs:40-89, 235-653).  Rendered by the general kernels (both
+ * precisions; `mode` is ignored).  Primitive ids reported by the batch calls are indices into desc->world.
+ * Transformed planes are RTW_E_UNSUPPORTED (their reference AABB is non-finite). */
+RTW_API int  rtw_scene_create_general(const rtw_scene_desc* desc, rtw_scene** out);
 RTW_API void rtw_scene_destroy(rtw_scene* scene);
 /* nodes, leaves, depth, max leaf size, bytes resident on the device */
 RTW_API int  rtw_scene_info(const rtw_scene* scene, uint64_t out[5]);

@@ -25,7 +25,7 @@ EPS = 2.220446049250313e-16
 def _source_hash() -> str:
     import hashlib
     h = hashlib.sha256()
-    for f in ("rtw_oracle.hpp", "oracle_capi.cpp", "oracle_cli.cpp", "Makefile"):
+    for f in ("rtw_oracle.hpp", "rtw_oracle_general.hpp", "oracle_capi.cpp", "oracle_general_capi.cpp", "oracle_cli.cpp", "Makefile"):
         with open(os.path.join(_HERE, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -121,6 +121,25 @@ def lib():
         L.orc_resolve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
         L.orc_hardware_threads.restype = C.c_uint32
         L.orc_camera_build.argtypes = [C.c_void_p, C.c_void_p]
+        # general scenes (rtw_oracle_general.hpp)
+        L.orc_gscene_create.restype = C.c_void_p
+        L.orc_gscene_create.argtypes = [C.c_void_p]
+        L.orc_gscene_destroy.argtypes = [C.c_void_p]
+        L.orc_gtrace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, C.c_double] + [C.c_void_p] * 4
+        L.orc_gscatter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 13
+        L.orc_gpath_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+        L.orc_grender.restype = C.c_double
+        L.orc_grender.argtypes = [C.c_void_p] * 6
+        L.orc_perlin_generate.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
+        L.orc_perlin_turb.restype = C.c_double
+        L.orc_perlin_turb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.orc_sin_portable.restype = C.c_double
+        L.orc_sin_portable.argtypes = [C.c_double]
+        L.orc_transform_then.argtypes = [C.c_void_p] * 3
+        L.orc_transform_inverse.restype = C.c_int32
+        L.orc_transform_inverse.argtypes = [C.c_void_p] * 2
+        L.orc_rotation.argtypes = [C.c_double, C.c_int32, C.c_void_p]
+        L.orc_gprim_box.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -282,3 +301,103 @@ def options(seed=20261018, tmin=EPS, rng_mode=W64, math_mode=LIBM, faithful_bvh=
 
 def hardware_threads():
     return int(lib().orc_hardware_threads())
+
+
+# ---- general scenes (rtw_oracle_general.hpp) --------------------------------------------------------------------
+DIFFUSE_LIGHT, ISOTROPIC = 4, 5
+
+
+class GTransform(C.Structure):
+    _fields_ = [("rotation", C.c_double * 9), ("translation", C.c_double * 3)]
+
+
+class GPerlin(C.Structure):
+    _fields_ = [("rand_vec", (C.c_double * 3) * 256), ("perm_x", C.c_uint8 * 256), ("perm_y", C.c_uint8 * 256), ("perm_z", C.c_uint8 * 256)]
+
+
+def transform(rotation=(1, 0, 0, 0, 1, 0, 0, 0, 1), translation=(0, 0, 0)) -> GTransform:
+    t = GTransform()
+    t.rotation[:] = [float(x) for x in rotation]
+    t.translation[:] = [float(x) for x in translation]
+    return t
+
+
+def transform_then(a: GTransform, b: GTransform) -> GTransform:
+    out = GTransform()
+    lib().orc_transform_then(C.byref(a), C.byref(b), C.byref(out))
+    return out
+
+
+def transform_inverse(a: GTransform):
+    out = GTransform()
+    return out if lib().orc_transform_inverse(C.byref(a), C.byref(out)) else None
+
+
+def rotation(angle_degrees, axis) -> GTransform:
+    out = GTransform()
+    lib().orc_rotation(float(angle_degrees), int(axis), C.byref(out))
+    return out
+
+
+def perlin_generate(seed, index=0) -> GPerlin:
+    out = GPerlin()
+    lib().orc_perlin_generate(seed, index, C.byref(out))
+    return out
+
+
+def perlin_turb(tables: GPerlin, p, depth=7) -> float:
+    """depth <= 0: Perlin::noise; else Perlin::turb."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    return lib().orc_perlin_turb(C.byref(tables), _p(p), depth)
+
+
+def sin_portable(x: float) -> float:
+    return lib().orc_sin_portable(float(x))
+
+
+class GScene:
+    """General-scene oracle built from a scene description with the layout of rtw_scene_desc (include/rtw.h); `desc_pod` is
+    any ctypes structure of that layout (the caller keeps the arrays it points into alive)."""
+
+    def __init__(self, desc_pod, keepalive=None):
+        self._keep = (desc_pod, keepalive)
+        self.h = lib().orc_gscene_create(C.cast(C.pointer(desc_pod), C.c_void_p))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_gscene_destroy(self.h)
+            self.h = None
+
+    def prim_box(self, index, lights=False):
+        out = np.zeros(6)
+        lib().orc_gprim_box(self.h, int(lights), index, _p(out))
+        return out
+
+    def trace_batch(self, o, d, tmin=EPS, tmax=float("inf")):
+        o = np.ascontiguousarray(o, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+        n = o.shape[0]
+        prim = np.zeros(n, dtype=np.int32); t = np.zeros(n); p = np.zeros((n, 3)); normal = np.zeros((n, 3))
+        lib().orc_gtrace_batch(self.h, n, _p(o), _p(d), tmin, tmax, _p(prim), _p(t), _p(p), _p(normal))
+        return prim, t, p, normal
+
+    def scatter_batch(self, o, d, pixel, sample, vertex, opts: Options):
+        o = np.ascontiguousarray(o, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+        n = o.shape[0]
+        pixel, sample, vertex = (np.ascontiguousarray(a, dtype=np.uint32) for a in (pixel, sample, vertex))
+        prim = np.zeros(n, dtype=np.int32); t = np.zeros(n); kind = np.zeros(n, dtype=np.uint32)
+        p, normal, dr, w, e = (np.zeros((n, 3)) for _ in range(5))
+        lib().orc_gscatter_batch(self.h, C.byref(opts), n, _p(o), _p(d), _p(pixel), _p(sample), _p(vertex), _p(prim), _p(t),
+                                 _p(kind), _p(p), _p(normal), _p(dr), _p(w), _p(e))
+        return dict(prim=prim, t=t, kind=kind, p=p, normal=normal, dir=dr, weight=w, emitted=e)
+
+    def path_radiance(self, cam: Camera, opts: Options, i, j, sample):
+        i, j, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (i, j, sample))
+        out = np.zeros((len(i), 3))
+        lib().orc_gpath_radiance(self.h, C.byref(cam), C.byref(opts), len(i), _p(i), _p(j), _p(sample), _p(out))
+        return out
+
+    def render(self, cam: Camera, opts: Options):
+        img = np.zeros((cam.height, cam.width, 3))
+        cnt = Counters(); pan = C.c_uint32(0)
+        sec = lib().orc_grender(self.h, C.byref(cam), C.byref(opts), _p(img), C.byref(cnt), C.byref(pan))
+        return img, sec, cnt.as_dict(), bool(pan.value)

@@ -11,7 +11,9 @@ import os
 from . import build as _build
 
 RTW_OK, RTW_E_INVALID, RTW_E_CUDA, RTW_E_NO_DEVICE, RTW_E_UNSUPPORTED, RTW_E_NOMEM = 0, -1, -2, -3, -4, -5
-RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC, RTW_INVISIBLE = 0, 1, 2, 3
+RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC, RTW_INVISIBLE, RTW_DIFFUSE_LIGHT, RTW_ISOTROPIC = 0, 1, 2, 3, 4, 5
+RTW_PRIM_SPHERE, RTW_PRIM_PLANE, RTW_PRIM_QUAD, RTW_PRIM_TRIANGLE, RTW_PRIM_CUBOID = 0, 1, 2, 3, 4
+RTW_TEX_NOISE = 1
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
 RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL = 1, 2, 4
@@ -24,6 +26,7 @@ RTW_SYMBOLS = (
     "rtw_abi_version", "rtw_last_error", "rtw_camera_build", "rtw_philox4x32_10", "rtw_tiles_total", "rtw_tiles_per_rank",
     "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
+    "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
 
@@ -35,8 +38,41 @@ class RtwError(RuntimeError):
 
 
 class rtw_material(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("reserved", C.c_uint32), ("r", C.c_double), ("g", C.c_double), ("b", C.c_double),
+    _fields_ = [("kind", C.c_uint32), ("texture", C.c_uint32), ("r", C.c_double), ("g", C.c_double), ("b", C.c_double),
                 ("param", C.c_double)]
+
+
+class rtw_quad(C.Structure):
+    _fields_ = [("q", C.c_double * 3), ("u", C.c_double * 3), ("v", C.c_double * 3)]
+
+
+class rtw_cuboid(C.Structure):
+    _fields_ = [("p", C.c_double * 3), ("q", C.c_double * 3)]
+
+
+class rtw_transform(C.Structure):
+    _fields_ = [("rotation", C.c_double * 9), ("translation", C.c_double * 3)]
+
+
+class rtw_prim(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32), ("material", C.c_uint32), ("transform", C.c_int32)]
+
+
+class rtw_texture(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("perlin", C.c_uint32), ("scale", C.c_double), ("reserved", C.c_double * 3)]
+
+
+class rtw_perlin(C.Structure):
+    _fields_ = [("rand_vec", (C.c_double * 3) * 256), ("perm_x", C.c_uint8 * 256), ("perm_y", C.c_uint8 * 256), ("perm_z", C.c_uint8 * 256)]
+
+
+class rtw_scene_desc(C.Structure):
+    _fields_ = [("spheres", C.c_void_p), ("n_spheres", C.c_uint64), ("planes", C.c_void_p), ("n_planes", C.c_uint64),
+                ("quads", C.c_void_p), ("n_quads", C.c_uint64), ("cuboids", C.c_void_p), ("n_cuboids", C.c_uint64),
+                ("transforms", C.c_void_p), ("n_transforms", C.c_uint64), ("materials", C.c_void_p), ("n_materials", C.c_uint64),
+                ("textures", C.c_void_p), ("n_textures", C.c_uint64), ("perlins", C.c_void_p), ("n_perlins", C.c_uint64),
+                ("world", C.c_void_p), ("n_world", C.c_uint64), ("lights", C.c_void_p), ("n_lights", C.c_uint64),
+                ("world_is_bvh", C.c_uint32), ("lights_is_bvh", C.c_uint32)]
 
 
 class rtw_sphere(C.Structure):
@@ -117,6 +153,11 @@ def load(build_if_missing: bool = True):
     L.rtw_scatter_batch.argtypes = [vp, vp, vp, vp, sz] + [vp] * 10
     L.rtw_get_rays.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
     L.rtw_path_radiance.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
+    L.rtw_scene_create_general.argtypes = [vp, vp]
+    L.rtw_transform_then.argtypes = [vp, vp, vp]; L.rtw_transform_then.restype = None
+    L.rtw_transform_inverse.argtypes = [vp, vp]; L.rtw_transform_inverse.restype = C.c_int
+    L.rtw_rotation.argtypes = [dbl, C.c_int, vp]; L.rtw_rotation.restype = None
+    L.rtw_perlin_generate.argtypes = [u64, u32, vp]; L.rtw_perlin_generate.restype = None
     L.rtwh_scene_simple.argtypes = [u64, C.c_int32, dbl, dbl, C.c_int32]; L.rtwh_scene_simple.restype = vp
     L.rtwh_scene_desc_destroy.argtypes = [vp]; L.rtwh_scene_desc_destroy.restype = None
     L.rtwh_scene_desc_counts.argtypes = [vp, vp]; L.rtwh_scene_desc_counts.restype = None

@@ -17,13 +17,29 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (EPSILON, TMIN_REFERENCE, RTW_DIELECTRIC, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN, RTW_INVISIBLE,
-                   RTW_LAMBERTIAN, RTW_MEGAKERNEL, RTW_METAL, RTW_WAVEFRONT, RtwError, rtw_camera, rtw_camera_builder,
-                   rtw_material, rtw_opts, rtw_plane, rtw_sphere, rtw_stats)
+from ._lib import (EPSILON, TMIN_REFERENCE, RTW_DIELECTRIC, RTW_DIFFUSE_LIGHT, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN,
+                   RTW_INVISIBLE, RTW_ISOTROPIC, RTW_LAMBERTIAN, RTW_MEGAKERNEL, RTW_METAL, RTW_PRIM_CUBOID, RTW_PRIM_PLANE,
+                   RTW_PRIM_QUAD, RTW_PRIM_SPHERE, RTW_PRIM_TRIANGLE, RTW_TEX_NOISE, RTW_WAVEFRONT, RtwError, rtw_camera,
+                   rtw_camera_builder, rtw_cuboid, rtw_material, rtw_opts, rtw_perlin, rtw_plane, rtw_prim, rtw_quad,
+                   rtw_scene_desc, rtw_sphere, rtw_stats, rtw_texture, rtw_transform)
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---- textures (shared/src/texture.rs) ------------------------------------------------------------------
+@dataclass(frozen=True)
+class NoiseTexture:                             # NoiseTexture::new(scale), texture.rs:57-102
+    """Perlin tables are drawn from Philox stream (seed; 0x9E71A000 + index) — the reference uses the unseeded thread_rng."""
+    scale: float
+    seed: int = 20261018
+    index: int = 0
+
+    def perlin(self) -> rtw_perlin:
+        out = rtw_perlin()
+        _lib.load().rtw_perlin_generate(self.seed, self.index, C.byref(out))
+        return out
 
 
 # ---- materials (shared/src/material.rs) --------------------------------------------------------------
@@ -32,13 +48,20 @@ class Material:
     kind: int
     colour: tuple = (0.0, 0.0, 0.0)
     param: float = 0.0
+    texture: Optional[NoiseTexture] = None      # None = SolidColour(colour)
 
-    def pod(self) -> rtw_material:
-        return rtw_material(self.kind, 0, float(self.colour[0]), float(self.colour[1]), float(self.colour[2]), float(self.param))
+    def pod(self, texture_index: int = 0) -> rtw_material:
+        return rtw_material(self.kind, texture_index, float(self.colour[0]), float(self.colour[1]), float(self.colour[2]), float(self.param))
 
 
-def Lambertian(colour) -> Material:            # Lambertian::new_with_colour, material.rs:349-351
-    return Material(RTW_LAMBERTIAN, tuple(colour), 0.0)
+def _colour_or_texture(kind, arg):
+    if isinstance(arg, NoiseTexture):
+        return Material(kind, (0.0, 0.0, 0.0), 0.0, arg)
+    return Material(kind, tuple(arg), 0.0)
+
+
+def Lambertian(colour_or_texture) -> Material:     # Lambertian::new / new_with_colour, material.rs:331-351
+    return _colour_or_texture(RTW_LAMBERTIAN, colour_or_texture)
 
 
 def Metal(albedo, fuzz) -> Material:           # Metal::new, material.rs:401-405
@@ -49,12 +72,65 @@ def Dialectric(index_of_refraction) -> Material:   # Dialectric::new, material.r
     return Material(RTW_DIELECTRIC, (1.0, 1.0, 1.0), float(index_of_refraction))
 
 
+def DiffuseLight(colour_or_texture) -> Material:   # DiffuseLight::new / new_with_colour, material.rs:498-504
+    return _colour_or_texture(RTW_DIFFUSE_LIGHT, colour_or_texture)
+
+
+def Isotropic(colour_or_texture) -> Material:      # Isotropic::new / new_with_colour, material.rs:521-527
+    return _colour_or_texture(RTW_ISOTROPIC, colour_or_texture)
+
+
 INVISIBLE = Material(RTW_INVISIBLE)             # INVISIBLE_PTR, material.rs:319-322
 
 
-# ---- entities -------------------------------------------------------------------------------------------
+# ---- transformations (geometry/src/transformations.rs, default non-euclid build) ---------------------------
+class Axis:
+    X, Y, Z = 0, 1, 2
+
+
 @dataclass(frozen=True)
-class Sphere:                                   # entities/sphere.rs:25-47
+class Transformation:                           # transformations.rs:96-136
+    rotation: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)     # row-major Matrix3
+    translation: tuple = (0.0, 0.0, 0.0)
+
+    def pod(self) -> rtw_transform:
+        t = rtw_transform()
+        t.rotation[:] = [float(x) for x in self.rotation]
+        t.translation[:] = [float(x) for x in self.translation]
+        return t
+
+    @staticmethod
+    def _from_pod(t: rtw_transform) -> "Transformation":
+        return Transformation(tuple(t.rotation), tuple(t.translation))
+
+    def then(self, other: "Transformation") -> "Transformation":
+        a, b, out = self.pod(), other.pod(), rtw_transform()
+        _lib.load().rtw_transform_then(C.byref(a), C.byref(b), C.byref(out))
+        return Transformation._from_pod(out)
+
+    def inverse(self) -> Optional["Transformation"]:
+        a, out = self.pod(), rtw_transform()
+        return Transformation._from_pod(out) if _lib.load().rtw_transform_inverse(C.byref(a), C.byref(out)) else None
+
+
+def Translation3(x, y, z) -> Transformation:    # Translation3 = Vec3; From<Vec3> for Transformation, transformations.rs:87-94
+    return Transformation(translation=(float(x), float(y), float(z)))
+
+
+def rotation(angle_degrees, axis) -> Transformation:   # transformations.rs:38-64
+    out = rtw_transform()
+    _lib.load().rtw_rotation(float(angle_degrees), int(axis), C.byref(out))
+    return Transformation._from_pod(out)
+
+
+# ---- entities -------------------------------------------------------------------------------------------
+class _Transformable:                           # Transformable::transform, transformations.rs:193-222
+    def transform(self, t: Transformation) -> "Transformed":
+        return Transformed(self, Transformation().then(t))
+
+
+@dataclass(frozen=True)
+class Sphere(_Transformable):                   # entities/sphere.rs:25-47
     center: tuple
     radius: float
     material: Material
@@ -67,21 +143,73 @@ class Plane:                                    # entities/plane.rs:21-39
     material: Material
 
 
+@dataclass(frozen=True)
+class Quad(_Transformable):                     # entities/quadrilateral.rs:23-56
+    q: tuple
+    u: tuple
+    v: tuple
+    material: Material
+
+
+@dataclass(frozen=True)
+class Triangle(_Transformable):                 # entities/triangles.rs:23-54
+    q: tuple
+    u: tuple
+    v: tuple
+    material: Material
+
+
+@dataclass(frozen=True)
+class Cuboid(_Transformable):                   # entities/cuboid.rs:21-50
+    p: tuple
+    q: tuple
+    material: Material
+
+
+@dataclass(frozen=True)
+class Transformed:                              # Transformed<T>, transformations.rs:168-222
+    instance: object
+    transformation: Transformation
+
+    def transform(self, t: Transformation) -> "Transformed":
+        return Transformed(self.instance, self.transformation.then(t))
+
+    @property
+    def material(self):
+        return self.instance.material
+
+
+_ENTITY_KIND = {Sphere: RTW_PRIM_SPHERE, Plane: RTW_PRIM_PLANE, Quad: RTW_PRIM_QUAD, Triangle: RTW_PRIM_TRIANGLE, Cuboid: RTW_PRIM_CUBOID}
+
+
 class HittableList:                             # hittable_collections/hittable_list.rs:247-294
     def __init__(self):
-        self.spheres: List[Sphere] = []
-        self.planes: List[Plane] = []
+        self.items: List[object] = []
 
     def add(self, obj):
-        if isinstance(obj, Sphere):
-            self.spheres.append(obj)
-        elif isinstance(obj, Plane):
-            self.planes.append(obj)
-        else:
-            raise TypeError(f"{type(obj).__name__} is outside the CUDA backend's scope (Sphere, Plane)")
+        inst = obj.instance if isinstance(obj, Transformed) else obj
+        if type(inst) not in _ENTITY_KIND:
+            raise TypeError(f"{type(obj).__name__} is outside the CUDA backend's scope (Sphere, Plane, Quad, Triangle, Cuboid, Transformed)")
+        self.items.append(obj)
+
+    def extend(self, objs):
+        for o in objs:
+            self.add(o)
+
+    @property
+    def spheres(self):
+        return [o for o in self.items if isinstance(o, Sphere)]
+
+    @property
+    def planes(self):
+        return [o for o in self.items if isinstance(o, Plane)]
+
+    def is_simple(self) -> bool:
+        """Spheres and planes with SolidColour Lambertian / Metal / Dialectric / Invisible materials only: the fast sphere path."""
+        return all(isinstance(o, (Sphere, Plane)) and o.material.kind <= RTW_INVISIBLE and o.material.texture is None for o in self.items)
 
     def len(self):
-        return len(self.spheres) + len(self.planes)
+        return len(self.items)
 
     __len__ = len
 
@@ -101,6 +229,71 @@ class BoundedVolumeHierarchy:                   # hittable_collections/bvh.rs:10
 
     def len(self):
         return self.list.len()
+
+
+class SceneDescription:
+    """rtw_scene_desc plus the ctypes arrays it points into (kept alive here)."""
+
+    def __init__(self, world, lights):
+        w, l = _as_list(world), _as_list(lights)
+        spheres, planes, quads, cuboids, transforms, materials, textures, perlins = [], [], [], [], [], [], [], []
+        mat_index, tex_index = {}, {}
+
+        def material_id(m: Material) -> int:
+            if m not in mat_index:
+                t = 0
+                if m.texture is not None:
+                    if m.texture not in tex_index:
+                        perlins.append(m.texture.perlin())
+                        tx = rtw_texture(RTW_TEX_NOISE, len(perlins) - 1, float(m.texture.scale))
+                        textures.append(tx)
+                        tex_index[m.texture] = len(textures)
+                    t = tex_index[m.texture]
+                materials.append(m.pod(t))
+                mat_index[m] = len(materials) - 1
+            return mat_index[m]
+
+        def entry(obj) -> rtw_prim:
+            tr = -1
+            if isinstance(obj, Transformed):
+                transforms.append(obj.transformation.pod())
+                tr = len(transforms) - 1
+                obj = obj.instance
+            kind = _ENTITY_KIND[type(obj)]
+            f3 = lambda v: (C.c_double * 3)(*map(float, v))
+            if kind == RTW_PRIM_SPHERE:
+                spheres.append(rtw_sphere(*map(float, obj.center), float(obj.radius))); idx = len(spheres) - 1
+            elif kind == RTW_PRIM_PLANE:
+                planes.append(rtw_plane(*map(float, obj.point), *map(float, obj.normal))); idx = len(planes) - 1
+            elif kind == RTW_PRIM_CUBOID:
+                cuboids.append(rtw_cuboid(f3(obj.p), f3(obj.q))); idx = len(cuboids) - 1
+            else:
+                quads.append(rtw_quad(f3(obj.q), f3(obj.u), f3(obj.v))); idx = len(quads) - 1
+            return rtw_prim(kind, idx, material_id(obj.material), tr)
+
+        wl = [entry(o) for o in w.items]
+        ll = [entry(o) for o in l.items]
+
+        def arr(ctype, items):
+            a = (ctype * max(1, len(items)))()
+            for i, x in enumerate(items):
+                a[i] = x
+            return a
+
+        self._keep = dict(spheres=arr(rtw_sphere, spheres), planes=arr(rtw_plane, planes), quads=arr(rtw_quad, quads),
+                          cuboids=arr(rtw_cuboid, cuboids), transforms=arr(rtw_transform, transforms),
+                          materials=arr(rtw_material, materials), textures=arr(rtw_texture, textures),
+                          perlins=arr(rtw_perlin, perlins), world=arr(rtw_prim, wl), lights=arr(rtw_prim, ll))
+        d = rtw_scene_desc()
+        for name, items in (("spheres", spheres), ("planes", planes), ("quads", quads), ("cuboids", cuboids), ("transforms", transforms),
+                            ("materials", materials), ("textures", textures), ("perlins", perlins), ("world", wl), ("lights", ll)):
+            setattr(d, name, C.cast(self._keep[name], C.c_void_p))
+            setattr(d, "n_" + name, len(items))
+        d.world_is_bvh = 1 if isinstance(world, BoundedVolumeHierarchy) else 0
+        d.lights_is_bvh = 1 if isinstance(lights, BoundedVolumeHierarchy) else 0
+        self.pod = d
+        self.upload_bytes = sum(C.sizeof(a) for a in self._keep.values())
+        self.n_world, self.n_lights = len(wl), len(ll)
 
 
 def _as_list(world) -> HittableList:
@@ -126,10 +319,21 @@ class RenderOptions:
 class Scene:
     """rtw_scene handle: world (planes + spheres) and lights uploaded to the current CUDA device."""
 
-    def __init__(self, world, lights):
+    def __init__(self, world, lights, general: Optional[bool] = None):
+        """general=None picks the sphere path (rtw_scene_create) when the scene allows it, else rtw_scene_create_general;
+        True forces the general path."""
         w, l = _as_list(world), _as_list(lights)
-        if l.planes:
-            raise RtwError(_lib.RTW_E_UNSUPPORTED, "lights: only spheres are supported")
+        simple = w.is_simple() and all(isinstance(o, Sphere) for o in l.items) and not isinstance(lights, BoundedVolumeHierarchy)
+        if general is None:
+            general = not simple
+        self.general = bool(general)
+        if self.general:
+            self.desc = SceneDescription(world, lights)
+            self._h = C.c_void_p()
+            _lib.check(_lib.load().rtw_scene_create_general(C.byref(self.desc.pod), C.byref(self._h)))
+            self.n_spheres, self.n_planes, self.n_lights = len(w.spheres), len(w.planes), len(l.items)
+            self.upload_bytes = self.desc.upload_bytes
+            return
         ns, npl, nl = len(w.spheres), len(w.planes), len(l.spheres)
         mats = (rtw_material * max(1, ns + npl))()
         sph = (rtw_sphere * max(1, ns))()

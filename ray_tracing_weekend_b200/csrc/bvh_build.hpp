@@ -53,7 +53,24 @@ public:
             for (int a = 0; a < 3; ++a) { boxes_[i].mn[a] = s[a] - s[3]; boxes_[i].mx[a] = s[a] + s[3]; cent_[3 * i + a] = s[a]; }
             idx_[i] = (uint32_t)i;
         }
+        return finish();
+    }
+    // general primitives: n boxes (world-space Bounded::get_aabbox of each entry), centroid = box centre
+    Bvh build_boxes(const Box* boxes, size_t n, int max_leaf = 4, int max_depth = 31) {
+        n_ = n; max_leaf_ = std::max(1, std::min(max_leaf, 16)); max_depth_ = max_depth;
+        boxes_.assign(boxes, boxes + n); cent_.resize(3 * n); idx_.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            for (int a = 0; a < 3; ++a) cent_[3 * i + a] = 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
+            idx_[i] = (uint32_t)i;
+        }
+        return finish();
+    }
+
+private:
+    Bvh finish() {
+        const size_t n = n_;
         tmp_.clear();
+        depth_seen_ = 0;
         Bvh out;
         if (n == 0) {
             FlatNode f{}; f.lbox.reset(); f.rbox.reset(); f.left = f.right = -1; f.lfirst = f.lcount = f.rfirst = f.rcount = 0;
@@ -97,7 +114,6 @@ public:
         return out;
     }
 
-private:
     struct TNode { Box box; int left, right; uint32_t first, count; };
     size_t n_ = 0; int max_leaf_ = 4, max_depth_ = 31; uint32_t depth_seen_ = 0;
     std::vector<Box> boxes_; std::vector<double> cent_; std::vector<uint32_t> idx_; std::vector<TNode> tmp_;

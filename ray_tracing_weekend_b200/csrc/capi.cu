@@ -13,6 +13,7 @@
 
 #include "../../include/rtw.h"
 #include "bvh_build.hpp"
+#include "general_host.hpp"
 #include "rtw_launch.hpp"
 
 using namespace rtw;
@@ -124,9 +125,34 @@ template <class T> struct SceneDev {
     void release() { light_nodes.release(); nodes.release(); spheres.release(); sphere_mat.release(); lights.release(); info.release(); planes.release(); tiles.release(); }
 };
 
+template <class T> struct SceneDevG {
+    DevBuf<Node<T>> nodes; DevBuf<GPrim<T>> prims, unbounded, lights; DevBuf<Vec4T<T>> spheres; DevBuf<GPlane<T>> plane_geo;
+    DevBuf<GQuad<T>> quads; DevBuf<GXform<T>> xforms; DevBuf<GMat<T>> mats; DevBuf<GPerlin<T>> perlins;
+    SceneViewG<T> view{};
+    size_t bytes() const {
+        return nodes.bytes() + prims.bytes() + unbounded.bytes() + lights.bytes() + spheres.bytes() + plane_geo.bytes() + quads.bytes() +
+               xforms.bytes() + mats.bytes() + perlins.bytes();
+    }
+    void release() {
+        nodes.release(); prims.release(); unbounded.release(); lights.release(); spheres.release(); plane_geo.release(); quads.release();
+        xforms.release(); mats.release(); perlins.release();
+    }
+};
+
+// host copy of a general scene description (rtw_scene_desc owns nothing)
+struct GeneralDesc {
+    std::vector<rtw_sphere> spheres; std::vector<rtw_plane> planes; std::vector<rtw_quad> quads; std::vector<rtw_cuboid> cuboids;
+    std::vector<rtw_transform> transforms; std::vector<rtw_material> materials; std::vector<rtw_texture> textures;
+    std::vector<rtw_perlin> perlins; std::vector<rtw_prim> world, lights;
+    bool lights_is_bvh = false;
+};
+
 }  // namespace
 
 struct rtw_scene {
+    bool general = false;
+    GeneralDesc gdesc;
+    SceneDevG<float> g32; SceneDevG<double> g64;
     std::vector<rtw_sphere> spheres; std::vector<uint32_t> sphere_material;
     std::vector<rtw_plane> planes; std::vector<uint32_t> plane_material;
     std::vector<rtw_material> materials; std::vector<rtw_sphere> lights;
@@ -217,6 +243,129 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
     return RTW_OK;
 }
 
+// ---- general scenes ------------------------------------------------------------------------------------------
+// iteration order of a HittableList: buckets by TypeId (hittable_list.rs:270-294) — compiler-chosen in the reference,
+// fixed here as [Plane, Sphere, Quad, Triangle, Cuboid, then the Transformed<...> of each]
+uint32_t bucket_of(const rtw_prim& e) {
+    uint32_t k = e.kind == RTW_PRIM_PLANE ? 0u : e.kind == RTW_PRIM_SPHERE ? 1u : e.kind;
+    return k + (e.transform >= 0 ? 5u : 0u);
+}
+
+template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
+    const GeneralDesc& g = s->gdesc;
+    auto v3 = [](host::D3 a) { return V3<T>{(T)a.x, (T)a.y, (T)a.z}; };
+    std::vector<Vec4T<T>> spheres(g.spheres.size());
+    for (size_t i = 0; i < g.spheres.size(); ++i) spheres[i] = Vec4T<T>{(T)g.spheres[i].cx, (T)g.spheres[i].cy, (T)g.spheres[i].cz, (T)g.spheres[i].r};
+    std::vector<GPlane<T>> plane_geo(g.planes.size());
+    for (size_t i = 0; i < g.planes.size(); ++i) {
+        const rtw_plane& q = g.planes[i];
+        double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);       // Plane::new normalises (plane.rs:35)
+        plane_geo[i] = GPlane<T>{V3<T>{(T)q.px, (T)q.py, (T)q.pz}, V3<T>{(T)(q.nx / len), (T)(q.ny / len), (T)(q.nz / len)}};
+    }
+    std::vector<GXform<T>> xforms(g.transforms.size());
+    std::vector<char> invertible(g.transforms.size(), 0);
+    for (size_t i = 0; i < g.transforms.size(); ++i) {
+        rtw_transform inv{};
+        invertible[i] = host::transform_inverse(g.transforms[i], &inv) ? 1 : 0;
+        GXform<T> x{};
+        for (int k = 0; k < 9; ++k) { x.fwd[k] = (T)g.transforms[i].rotation[k]; x.inv[k] = (T)inv.rotation[k]; }
+        for (int k = 0; k < 3; ++k) { x.ft[k] = (T)g.transforms[i].translation[k]; x.it[k] = (T)inv.translation[k]; }
+        xforms[i] = x;
+    }
+    std::vector<GMat<T>> mats(g.materials.size());
+    for (size_t i = 0; i < g.materials.size(); ++i) {
+        const rtw_material& m = g.materials[i];
+        GMat<T> o{};
+        o.albedo[0] = (T)m.r; o.albedo[1] = (T)m.g; o.albedo[2] = (T)m.b; o.param = (T)m.param; o.kind = m.kind;
+        if (m.texture) { const rtw_texture& t = g.textures[m.texture - 1]; o.texture = t.kind; o.perlin = t.perlin; o.scale = (T)t.scale; }
+        mats[i] = o;
+    }
+    std::vector<GPerlin<T>> perlins(g.perlins.size());
+    for (size_t i = 0; i < g.perlins.size(); ++i) {
+        for (int k = 0; k < 256; ++k) for (int a = 0; a < 3; ++a) perlins[i].rand_vec[k][a] = (T)g.perlins[i].rand_vec[k][a];
+        std::memcpy(perlins[i].perm_x, g.perlins[i].perm_x, 256); std::memcpy(perlins[i].perm_y, g.perlins[i].perm_y, 256);
+        std::memcpy(perlins[i].perm_z, g.perlins[i].perm_z, 256);
+    }
+    std::vector<GQuad<T>> quads;
+    auto push_quad = [&](const host::QuadH& q) {
+        GQuad<T> o{v3(q.q), v3(q.u), v3(q.v), v3(q.w), v3(q.normal), (T)q.area};
+        quads.push_back(o);
+    };
+    // one list entry -> device record + its world-space box (Bounded::get_aabbox)
+    auto make_entry = [&](const rtw_prim& e, uint32_t id, GPrim<T>* out, host::Box* box, bool* bounded) {
+        GPrim<T> p{};
+        p.kind = e.kind; p.mat = e.material; p.id = id; p.xform = e.transform;
+        host::Box ib{};
+        *bounded = true;
+        switch (e.kind) {
+        case RTW_PRIM_SPHERE: {
+            const rtw_sphere& q = g.spheres[e.index];
+            p.first = e.index;
+            ib.mn[0] = q.cx - q.r; ib.mn[1] = q.cy - q.r; ib.mn[2] = q.cz - q.r; ib.mx[0] = q.cx + q.r; ib.mx[1] = q.cy + q.r; ib.mx[2] = q.cz + q.r;
+            break;
+        }
+        case RTW_PRIM_PLANE: p.first = e.index; *bounded = false; break;
+        case RTW_PRIM_CUBOID: {
+            host::QuadH f[6];
+            host::make_cuboid(host::ld3(g.cuboids[e.index].p), host::ld3(g.cuboids[e.index].q), f, &ib);
+            p.first = (uint32_t)quads.size();
+            for (auto& q : f) push_quad(q);
+            break;
+        }
+        default: {
+            const rtw_quad& q = g.quads[e.index];
+            host::QuadH h = host::make_quad(host::ld3(q.q), host::ld3(q.u), host::ld3(q.v), e.kind == RTW_PRIM_TRIANGLE);
+            p.first = (uint32_t)quads.size();
+            push_quad(h);
+            ib = h.box;
+        }
+        }
+        if (*bounded && e.transform >= 0) ib = host::transformed_box(ib, g.transforms[e.transform]);
+        *box = ib;
+        for (int a = 0; a < 3; ++a) { p.box[a] = (T)ib.mn[a]; p.box[3 + a] = (T)ib.mx[a]; }
+        *out = p;
+    };
+    std::vector<GPrim<T>> bounded, unbounded;
+    std::vector<host::Box> boxes;
+    for (size_t i = 0; i < g.world.size(); ++i) {
+        const rtw_prim& e = g.world[i];
+        GPrim<T> p; host::Box b; bool bd;
+        make_entry(e, (uint32_t)i, &p, &b, &bd);
+        if (e.transform >= 0 && !invertible[e.transform]) continue;     // "if there's no inverse just say it's not hit" (entities/transformations.rs:15-16)
+        if (bd) { bounded.push_back(p); boxes.push_back(b); } else unbounded.push_back(p);
+    }
+    host::Builder builder;
+    s->bvh = builder.build_boxes(boxes.data(), boxes.size(), 2, kMaxTreeDepth);
+    std::vector<Node<T>> nodes(s->bvh.nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const host::FlatNode& f = s->bvh.nodes[i];
+        Node<T> n{};
+        fill_node<T>(n, f);
+        n.left = f.left >= 0 ? f.left : encode_leaf(f.lfirst, f.lcount);
+        n.right = f.right >= 0 ? f.right : encode_leaf(f.rfirst, f.rcount);
+        nodes[i] = n;
+    }
+    std::vector<GPrim<T>> prims(bounded.size());
+    for (size_t k = 0; k < bounded.size(); ++k) prims[k] = bounded[s->bvh.order[k]];
+    std::vector<size_t> lorder(g.lights.size());
+    for (size_t i = 0; i < lorder.size(); ++i) lorder[i] = i;
+    std::stable_sort(lorder.begin(), lorder.end(), [&](size_t a, size_t b) { return bucket_of(g.lights[a]) < bucket_of(g.lights[b]); });
+    std::vector<GPrim<T>> lights(g.lights.size());
+    for (size_t k = 0; k < lorder.size(); ++k) {
+        host::Box b; bool bd;
+        make_entry(g.lights[lorder[k]], (uint32_t)lorder[k], &lights[k], &b, &bd);
+    }
+    CU(d.nodes.upload(nodes)); CU(d.prims.upload(prims)); CU(d.unbounded.upload(unbounded)); CU(d.lights.upload(lights));
+    CU(d.spheres.upload(spheres)); CU(d.plane_geo.upload(plane_geo)); CU(d.quads.upload(quads)); CU(d.xforms.upload(xforms));
+    CU(d.mats.upload(mats)); CU(d.perlins.upload(perlins));
+    d.view.nodes = d.nodes.p; d.view.prims = d.prims.p; d.view.unbounded = d.unbounded.p; d.view.lights = d.lights.p;
+    d.view.spheres = d.spheres.p; d.view.plane_geo = d.plane_geo.p; d.view.quads = d.quads.p; d.view.xforms = d.xforms.p;
+    d.view.mats = d.mats.p; d.view.perlins = d.perlins.p;
+    d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
+    d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
+    return RTW_OK;
+}
+
 // opts.tmin < 0 (RTW_TMIN_REFERENCE): machine epsilon of the working precision, the reference's f64::EPSILON analogue
 template <class T> static inline T resolve_tmin(double tmin) {
     if (tmin < 0.) return sizeof(T) == 8 ? (T)2.220446049250313e-16 : (T)1.1920928955078125e-07;
@@ -259,10 +408,10 @@ void read_stats(const DeviceCounters& c, rtw_stats* st) {
     st->absorbed = c.absorbed; st->missed = c.missed; st->depth_out = c.depth_out;
 }
 
-template <class T, class Launch>
-int render_tiles_t(rtw_scene* s, SceneDev<T>& d, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, T* tiles,
+template <class T, class DEV, class Launch>
+int render_tiles_t(rtw_scene* s, DEV& d, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, T* tiles,
                    cudaStream_t stream, Launch launch) {
-    RenderParams<T> P{};
+    RenderParams<T, decltype(d.view)> P{};
     P.scene = d.view; P.cam = to_camera<T>(cam); P.seed = o->seed; P.tmin = resolve_tmin<T>(o->tmin); P.flags = o->flags;
     P.rank = rank; P.world = world;
     P.tiles_x = (cam->image_width + kTileW - 1) / kTileW;
@@ -279,8 +428,8 @@ int render_tiles_t(rtw_scene* s, SceneDev<T>& d, const rtw_camera* cam, const rt
 }  // namespace
 
 namespace {
-template <class T> BatchParams<T> batch_params(rtw_scene* s, SceneDev<T>& d, size_t n) {
-    BatchParams<T> P{};
+template <class T, class DEV> BatchParams<T, decltype(DEV::view)> batch_params(rtw_scene* s, DEV& d, size_t n) {
+    BatchParams<T, decltype(DEV::view)> P{};
     P.scene = d.view; P.n = n;
     P.o = s->d_in0.p; P.d = s->d_in1.p; P.a = s->d_u0.p; P.b = s->d_u1.p; P.c = s->d_u2.p;
     P.prim = s->d_prim.p; P.t = s->d_out0.p; P.kind = s->d_k.p;
@@ -436,9 +585,87 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     return RTW_OK;
 }
 
+void rtw_transform_then(const rtw_transform* a, const rtw_transform* b, rtw_transform* out) { host::transform_then(*a, *b, out); }
+int rtw_transform_inverse(const rtw_transform* a, rtw_transform* out) { return host::transform_inverse(*a, out) ? 1 : 0; }
+void rtw_rotation(double angle_degrees, int axis, rtw_transform* out) { host::make_rotation(angle_degrees, axis, out); }
+void rtw_perlin_generate(uint64_t seed, uint32_t index, rtw_perlin* out) { host::perlin_generate(seed, index, out); }
+
+int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
+    if (!out) return fail(RTW_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!d) return fail(RTW_E_INVALID, "desc is NULL");
+    if ((d->n_spheres && !d->spheres) || (d->n_planes && !d->planes) || (d->n_quads && !d->quads) || (d->n_cuboids && !d->cuboids) ||
+        (d->n_transforms && !d->transforms) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures) ||
+        (d->n_perlins && !d->perlins) || (d->n_world && !d->world) || (d->n_lights && !d->lights))
+        return fail(RTW_E_INVALID, "NULL array with non-zero count");
+    if (d->n_world >= (1u << 28) || d->n_lights >= (1u << 28)) return fail(RTW_E_UNSUPPORTED, "too many primitives");
+    for (uint64_t i = 0; i < d->n_materials; ++i) {
+        const rtw_material& m = d->materials[i];
+        if (m.kind > RTW_ISOTROPIC) return fail(RTW_E_UNSUPPORTED, "unknown material kind");
+        if (m.texture > d->n_textures) return fail(RTW_E_INVALID, "material texture index out of range");
+        if (m.texture && m.kind != RTW_LAMBERTIAN && m.kind != RTW_DIFFUSE_LIGHT && m.kind != RTW_ISOTROPIC)
+            return fail(RTW_E_INVALID, "only Lambertian, DiffuseLight and Isotropic carry a texture");
+    }
+    for (uint64_t i = 0; i < d->n_textures; ++i) {
+        if (d->textures[i].kind != RTW_TEX_NOISE) return fail(RTW_E_UNSUPPORTED, "texture kind (NoiseTexture only; SolidColour is texture 0)");
+        if (d->textures[i].perlin >= d->n_perlins) return fail(RTW_E_INVALID, "texture perlin index out of range");
+    }
+    bool needs_lights = false;
+    auto check = [&](const rtw_prim* list, uint64_t n, bool world) -> const char* {
+        for (uint64_t i = 0; i < n; ++i) {
+            const rtw_prim& e = list[i];
+            uint64_t limit = e.kind == RTW_PRIM_SPHERE ? d->n_spheres : e.kind == RTW_PRIM_PLANE ? d->n_planes
+                             : (e.kind == RTW_PRIM_QUAD || e.kind == RTW_PRIM_TRIANGLE) ? d->n_quads : e.kind == RTW_PRIM_CUBOID ? d->n_cuboids : 0;
+            if (e.kind > RTW_PRIM_CUBOID) return "unknown primitive kind";
+            if (e.index >= limit) return "primitive index out of range";
+            if (e.material >= d->n_materials) return "primitive material index out of range";
+            if (e.transform >= 0 && (uint64_t)e.transform >= d->n_transforms) return "primitive transform index out of range";
+            if (e.transform < -1) return "primitive transform index out of range";
+            if (e.kind == RTW_PRIM_PLANE && e.transform >= 0) return "transformed planes are not supported";
+            if (e.kind == RTW_PRIM_SPHERE) {
+                const rtw_sphere& q = d->spheres[e.index];
+                if (!(q.r > 0.) || !std::isfinite(q.cx + q.cy + q.cz + q.r)) return "sphere with non-finite centre or non-positive radius";
+            }
+            if (world && (d->materials[e.material].kind == RTW_LAMBERTIAN || d->materials[e.material].kind == RTW_ISOTROPIC)) needs_lights = true;
+        }
+        return nullptr;
+    };
+    if (const char* msg = check(d->world, d->n_world, true)) return fail(std::strstr(msg, "not supported") ? RTW_E_UNSUPPORTED : RTW_E_INVALID, msg);
+    if (const char* msg = check(d->lights, d->n_lights, false)) return fail(std::strstr(msg, "not supported") ? RTW_E_UNSUPPORTED : RTW_E_INVALID, msg);
+    if (needs_lights && d->n_lights == 0)
+        return fail(RTW_E_INVALID, "scattering material with an empty lights list (the reference panics: HittableList shouldn't be empty)");
+    if (d->lights_is_bvh && d->n_lights > 5)
+        return fail(RTW_E_UNSUPPORTED, "a BoundedVolumeHierarchy of more than 5 lights (the reference's aux_random indexes out of range, bvh.rs:78-93)");
+    int ndev = rtw_device_count();
+    if (ndev < 0) return ndev;
+    if (ndev == 0) return fail(RTW_E_NO_DEVICE, "no CUDA device: this backend has no CPU fallback");
+
+    rtw_scene* s = new rtw_scene();
+    s->general = true;
+    GeneralDesc& g = s->gdesc;
+    g.spheres.assign(d->spheres, d->spheres + d->n_spheres); g.planes.assign(d->planes, d->planes + d->n_planes);
+    g.quads.assign(d->quads, d->quads + d->n_quads); g.cuboids.assign(d->cuboids, d->cuboids + d->n_cuboids);
+    g.transforms.assign(d->transforms, d->transforms + d->n_transforms); g.materials.assign(d->materials, d->materials + d->n_materials);
+    g.textures.assign(d->textures, d->textures + d->n_textures); g.perlins.assign(d->perlins, d->perlins + d->n_perlins);
+    g.world.assign(d->world, d->world + d->n_world); g.lights.assign(d->lights, d->lights + d->n_lights);
+    g.lights_is_bvh = d->lights_is_bvh != 0;
+    auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int));
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+    if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
+    int rc = upload_general<float>(s, s->g32);
+    if (rc == RTW_OK) rc = upload_general<double>(s, s->g64);
+    if (rc != RTW_OK) return bail(rc);
+    *out = s;
+    return RTW_OK;
+}
+
 void rtw_scene_destroy(rtw_scene* s) {
     if (!s) return;
-    s->f32.release(); s->f64.release();
+    s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release();
     cached_free(s->d_work, sizeof(unsigned int));
     cached_free(s->d_counters, sizeof(DeviceCounters));
     s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release();
@@ -451,7 +678,7 @@ void rtw_scene_destroy(rtw_scene* s) {
 int rtw_scene_info(const rtw_scene* s, uint64_t out[5]) {
     if (!s || !out) return fail(RTW_E_INVALID, "NULL argument");
     out[0] = s->bvh.nodes.size(); out[1] = s->bvh.leaves; out[2] = s->bvh.depth; out[3] = s->bvh.max_leaf;
-    out[4] = s->f32.bytes() + s->f64.bytes();
+    out[4] = s->f32.bytes() + s->f64.bytes() + s->g32.bytes() + s->g64.bytes();
     return RTW_OK;
 }
 
@@ -469,8 +696,12 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         CU(s->d_accum.reserve(n_slots * 3)); CU(s->d_poison.reserve(n_slots));
     }
+    if (s->general) pooled = false;
     CU(cudaEventRecord(s->ev[0], st));
-    if (pooled) {
+    if (s->general) {
+        if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch_render_general_f32);
+        else rc = render_tiles_t<double>(s, s->g64, cam, o, rank, world, (double*)d_tiles, st, launch_render_general_f64);
+    } else if (pooled) {
         PoolParams Q{};
         Q.accum = s->d_accum.p; Q.poison = s->d_poison.p;
         Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
@@ -562,7 +793,15 @@ int rtw_trace_batch(rtw_scene* s, const double* o, const double* d, size_t n, do
     int rc = reserve_batch(s, n); if (rc) return rc;
     CU(cudaMemcpy(s->d_in0.p, o, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_in1.p, d, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
-    if (precision == RTW_F32) {
+    if (s->general && precision == RTW_F32) {
+        auto P = batch_params<float>(s, s->g32, n);
+        P.tmin = (float)tmin; P.tmax = (float)tmax;
+        CU(launch_trace_general_f32(P, 0));
+    } else if (s->general) {
+        auto P = batch_params<double>(s, s->g64, n);
+        P.tmin = tmin; P.tmax = tmax;
+        CU(launch_trace_general_f64(P, 0));
+    } else if (precision == RTW_F32) {
         BatchParams<float> P = batch_params<float>(s, s->f32, n);
         P.tmin = (float)tmin; P.tmax = (float)tmax;
         CU(launch_trace_f32(P, 0));
@@ -589,7 +828,15 @@ int rtw_scatter_batch(rtw_scene* s, const rtw_opts* opts, const double* o, const
     CU(cudaMemcpy(s->d_u0.p, pixel, n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_u1.p, sample, n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_u2.p, vertex, n * 4, cudaMemcpyHostToDevice));
-    if (opts->precision == RTW_F32) {
+    if (s->general && opts->precision == RTW_F32) {
+        auto P = batch_params<float>(s, s->g32, n);
+        P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
+        CU(launch_scatter_general_f32(P, 0));
+    } else if (s->general) {
+        auto P = batch_params<double>(s, s->g64, n);
+        P.seed = opts->seed; P.tmin = resolve_tmin<double>(opts->tmin); P.flags = opts->flags;
+        CU(launch_scatter_general_f64(P, 0));
+    } else if (opts->precision == RTW_F32) {
         BatchParams<float> P = batch_params<float>(s, s->f32, n);
         P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
         CU(launch_scatter_f32(P, 0));
@@ -645,7 +892,15 @@ int rtw_path_radiance(rtw_scene* s, const rtw_camera* cam, const rtw_opts* opts,
     CU(cudaMemcpy(s->d_u0.p, i, n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_u1.p, j, n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_u2.p, sample, n * 4, cudaMemcpyHostToDevice));
-    if (opts->precision == RTW_F32) {
+    if (s->general && opts->precision == RTW_F32) {
+        auto P = batch_params<float>(s, s->g32, n);
+        P.cam = to_camera<float>(cam); P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
+        CU(launch_path_radiance_general_f32(P, 0));
+    } else if (s->general) {
+        auto P = batch_params<double>(s, s->g64, n);
+        P.cam = to_camera<double>(cam); P.seed = opts->seed; P.tmin = resolve_tmin<double>(opts->tmin); P.flags = opts->flags;
+        CU(launch_path_radiance_general_f64(P, 0));
+    } else if (opts->precision == RTW_F32) {
         BatchParams<float> P = batch_params<float>(s, s->f32, n);
         P.cam = to_camera<float>(cam); P.seed = opts->seed; P.tmin = resolve_tmin<float>(opts->tmin); P.flags = opts->flags;
         CU(launch_path_radiance_f32(P, 0));

@@ -308,6 +308,35 @@ RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
     return as_vec4(lds128(sc.s_lights + (uint32_t)i * 16u));
 }
 
+// ---------------------------------------------------------------------------------------------
+// General scenes (rtw_general.cuh): one table of list entries (entity kind + index + optional Transformed<T>) under one BVH.
+enum PrimKind : uint32_t { P_SPHERE = 0, P_PLANE = 1, P_QUAD = 2, P_TRIANGLE = 3, P_CUBOID = 4 };
+enum MatKindG : uint32_t { DIFFUSE_LIGHT = 4, ISOTROPIC = 5 };
+template <class T> struct GQuad { V3<T> q, u, v, w, normal; T area; };       // Quad / Triangle / one Cuboid face (quadrilateral.rs:23-32)
+template <class T> struct GPlane { V3<T> point, normal; };
+template <class T> struct GXform { T fwd[9], ft[3], inv[9], it[3]; };         // Transformation and its inverse (transformations.rs:96-136)
+template <class T> struct GPrim {
+    T box[6];                // the entry's own world-space box (min, max): bounded_hit's test on the exact path
+    uint32_t kind, first;    // entity kind; index into spheres / plane_geo / quads (cuboid: first of its six quads)
+    uint32_t mat, id;        // material index; position in the world list (the primitive id the batch calls report)
+    int32_t xform;           // -1, or index into xforms: the entry is a Transformed<T>
+    uint32_t pad;
+};
+template <class T> struct GMat { T albedo[3], param, scale; uint32_t kind, texture, perlin; };   // texture: 0 solid, 1 noise
+template <class T> struct GPerlin { T rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; };
+template <class T> struct SceneViewG {
+    const Node<T>* nodes;          // BVH over `prims` (leaf ranges index it)
+    const GPrim<T>* prims;         // bounded entries in BVH leaf order
+    const GPrim<T>* unbounded;     // planes (infinite box): tested linearly
+    const GPrim<T>* lights;        // the lights list in iteration order
+    const Vec4T<T>* spheres; const GPlane<T>* plane_geo; const GQuad<T>* quads; const GXform<T>* xforms;
+    const GMat<T>* mats; const GPerlin<T>* perlins;
+    int32_t n_nodes, n_prims, n_unbounded, n_lights;
+    uint32_t lights_is_bvh;
+};
+template <class SC> struct is_general { static constexpr bool value = false; };
+template <class T> struct is_general<SceneViewG<T>> { static constexpr bool value = true; };
+
 template <class T> struct CameraT {
     V3<T> center, pixel00, du, dv, ddu, ddv, background;
     T defocus_angle, jitter_scale;

@@ -1,0 +1,323 @@
+// rtw_general.cuh — general scenes: Quad, Triangle, Cuboid, Transformed<T>, Plane and Sphere
+// entries in one primitive table under one BVH, DiffuseLight / Isotropic materials, NoiseTexture (Perlin), lights
+// lists that hold quads.  Included at the end of rtw_kernels.cuh; the render / batch kernels there are generic over
+// the scene view and pick these functions up through closest_hit / shade / emitted_of.
+// The sphere-only SceneView path (scenes::simple, the headline workload) does not go through this file.
+#pragma once
+
+namespace rtw {
+
+// ---- Transformed<T> (entities/transformations.rs:14-29, geometry/src/transformations.rs:118-126) ----------------
+template <class T> RTW_D V3<T> g_mat_vec(const T* m, V3<T> v) {                      // matrix3.rs:88-100: row . v
+    return mk<T>(dot(mk<T>(m[0], m[1], m[2]), v), dot(mk<T>(m[3], m[4], m[5]), v), dot(mk<T>(m[6], m[7], m[8]), v));
+}
+template <class T> RTW_D Ray<T> g_instance_ray(const GXform<T>& X, const Ray<T>& r) {
+    V3<T> it = mk<T>(X.it[0], X.it[1], X.it[2]);
+    return Ray<T>{g_mat_vec<T>(X.inv, r.o) + it, g_mat_vec<T>(X.inv, r.d) + it};       // transform_vector3d adds the translation too
+}
+
+// ---- Quad::hit / Triangle::hit (quadrilateral.rs:79-98, triangles.rs:74-92) --------------------------------------
+template <class T, bool EXACT>
+RTW_D bool g_quad_hit(const GQuad<T>& Q, bool tri, const Ray<T>& r, T tmin, T tmax, T* t_out) {
+    T denom = dot(r.d, Q.normal);
+    if (!(fabs(denom) > M<T, EXACT>::EPS)) return false;
+    T t = -(dot(r.o - Q.q, Q.normal) / denom);
+    if (!(tmin <= t && t <= tmax)) return false;
+    V3<T> pq = at(r, t) - Q.q;
+    T a = dot(cross(pq, Q.v), Q.w), b = dot(cross(Q.u, pq), Q.w);                   // get_quad_uv
+    bool inside = tri ? (T(0) <= a + b && a + b <= T(1)) : (T(0) <= a && a <= T(1) && T(0) <= b && b <= T(1));
+    if (!inside) return false;
+    *t_out = t;
+    return true;
+}
+
+// Hittable::hit of one list entry in the entity's own space; *sub = the quad that was hit (cuboid face)
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>& r, T tmin, T tmax, T* t_out, uint32_t* sub, Tally& tl) {
+    Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
+    *sub = pr.first;
+    switch (pr.kind) {
+    case P_SPHERE: {
+        if (COUNT) tl.sphere_tests++;
+        T a = sqlen(rr.d);
+        if constexpr (EXACT) return sphere_root<T>(sc.spheres[pr.first], rr, a, tmin, tmax, t_out);
+        else return sphere_root_fast(sc.spheres[pr.first], rr, frcp(a), tmin, tmax, t_out);
+    }
+    case P_PLANE: {                                                                     // plane.rs:61-76, one-sided
+        const GPlane<T>& pl = sc.plane_geo[pr.first];
+        T denom = dot(rr.d, pl.normal);
+        if (!(denom > M<T, EXACT>::EPS)) return false;
+        T t = -dot(rr.o - pl.point, pl.normal) / denom;
+        if (!(tmin <= t && t <= tmax)) return false;
+        *t_out = t;
+        return true;
+    }
+    case P_CUBOID: {                                                                    // cuboid.rs:53-60: first minimum of the six faces
+        bool any = false; T best = T(0);
+        for (uint32_t f = 0; f < 6u; ++f) {
+            T t;
+            if (g_quad_hit<T, EXACT>(sc.quads[pr.first + f], false, rr, tmin, tmax, &t) && (!any || t < best)) { any = true; best = t; *sub = pr.first + f; }
+        }
+        *t_out = best;
+        return any;
+    }
+    default:
+        return g_quad_hit<T, EXACT>(sc.quads[pr.first], pr.kind == P_TRIANGLE, rr, tmin, tmax, t_out);
+    }
+}
+
+// sin of a moderate argument as a fixed IEEE sequence (oracle: sin_portable) / FP32: sinf
+RTW_D double g_sin(double x) {
+    const double two_over_pi = 6.36619772367581382433e-01;
+    const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    double fn = floor(x * two_over_pi + 0.5);
+    int n = (int)fn;
+    double y = (x - fn * pio2_1) - fn * pio2_1t;
+    double z = y * y;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double ps = S1 + z * (S2 + z * (S3 + z * (S4 + z * (S5 + z * S6))));
+    double pc = C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6))));
+    double sy = y + (y * z) * ps;
+    double cy = (1. - 0.5 * z) + (z * z) * pc;
+    switch (n & 3) { case 0: return sy; case 1: return cy; case 2: return -sy; default: return -cy; }
+}
+RTW_D float g_sin(float x) { return sinf(x); }
+
+// Perlin::noise / turb (perlin.rs:59-110)
+template <class T> RTW_D int g_wrap256(T f) { T r = fmod(f, T(256)); if (r < T(0)) r += T(256); return (int)r; }
+template <class T> RTW_D T g_noise(const GPerlin<T>& pn, V3<T> p) {
+    T fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
+    T u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    T acc = T(0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                int idx = pn.perm_x[g_wrap256(fx + (T)i)] ^ pn.perm_y[g_wrap256(fy + (T)j)] ^ pn.perm_z[g_wrap256(fz + (T)k)];
+                V3<T> c = mk<T>(pn.rand_vec[idx][0], pn.rand_vec[idx][1], pn.rand_vec[idx][2]);
+                T di = (T)i, dj = (T)j, dk = (T)k;
+                V3<T> weight_v = mk<T>(u - di, v - dj, w - dk);
+                T term = (di * u + (T(1) - di) * (T(1) - u)) * (dj * v + (T(1) - dj) * (T(1) - v)) * (dk * w + (T(1) - dk) * (T(1) - w)) * dot(c, weight_v);
+                acc = acc + term;
+            }
+    return acc;
+}
+template <class T> RTW_D T g_turb(const GPerlin<T>& pn, V3<T> p, int depth) {
+    T accum = T(0), weight = T(1);
+    V3<T> tp = p;
+    for (int i = 0; i < depth; ++i) { accum += weight * g_noise<T>(pn, tp); tp = tp * T(2); weight *= T(0.5); }
+    return accum;
+}
+// Texture::get_colour (texture.rs:15-22, 90-102)
+template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, V3<T> point) {
+    if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+    T arg = m.scale * point.z + g_turb<T>(sc.perlins[m.perlin], point, 7) * T(10);
+    return mk<T>(T(0.5), T(0.5), T(0.5)) * (g_sin(arg) + T(1));
+}
+
+// ---- closest hit over the planes + the BVH of bounded entries ----------------------------------------------------
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+    bool found = false;
+    T best_t = tmax;
+    const GPrim<T>* best = nullptr;
+    uint32_t best_sub = 0;
+    for (int i = 0; i < sc.n_unbounded; ++i) {
+        T t; uint32_t sub;
+        if (g_prim_hit<T, EXACT, COUNT>(sc, sc.unbounded[i], r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
+            found = true; best_t = t; best = sc.unbounded + i; best_sub = sub;
+        }
+    }
+    RayAux aux;
+    if constexpr (!EXACT) ray_aux(r, aux);
+    stack[0] = kStop;
+    int sp = 1;
+    int32_t cur = sc.n_prims > 0 ? 0 : kStop;
+    for (;;) {
+        while (cur >= 0) {
+            Node<T> nd = sc.nodes[cur];
+            if (COUNT) tl.node_visits++;
+            bool hl, hr; T tl_near = T(0), tr_near = T(0);
+            if constexpr (EXACT) {
+                hl = box_hit_exact(nd.la, nd.lb, r, tmin, best_t);
+                hr = box_hit_exact(nd.ra, nd.rb, r, tmin, best_t);
+            } else {
+                hl = box_hit_fast(nd.la, nd.lb, aux, tmin, best_t, &tl_near);
+                hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, best_t, &tr_near);
+            }
+            int32_t l = nd.left, rr = nd.right;
+            if (hl && hr) {
+                bool swap = !EXACT && tr_near < tl_near;
+                stack[sp * stride] = swap ? l : rr; sp++;
+                cur = swap ? rr : l;
+            } else if (hl) cur = l;
+            else if (hr) cur = rr;
+            else { sp--; cur = stack[sp * stride]; }
+        }
+        if (cur == kStop) break;
+        if (cur != kEmptyLeaf) {
+            uint32_t enc = (uint32_t)~cur;
+            uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                const GPrim<T>& pr = sc.prims[i];
+                if constexpr (EXACT) {                             // bounded_hit (hittable.rs:191-196): the entry's own box, un-shrunk range
+                    if (!box_hit_exact(pr.box, pr.box + 3, r, tmin, tmax)) continue;
+                } else if (pr.xform >= 0) {
+                    // a Transformed<T> is hit with a DIFFERENT ray than its box (the instance ray's direction carries the
+                    // translation), so its own world-space box is part of the result, not only a culling aid
+                    float c[3], hh[3], tn;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { c[a] = 0.5f * (pr.box[a] + pr.box[3 + a]); hh[a] = 0.5f * (pr.box[3 + a] - pr.box[a]); }
+                    if (!box_hit_fast(c, hh, aux, tmin, tmax, &tn)) continue;
+                }
+                T t; uint32_t sub;
+                if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
+                    found = true; best_t = t; best = &pr; best_sub = sub;
+                }
+            }
+        }
+        sp--;
+        cur = stack[sp * stride];
+    }
+    if (!found) return false;
+    // HitRecord::new (hittable.rs:102-129) in the entity's space, then p back to world space (transformations.rs:21-27)
+    const GPrim<T>& pr = *best;
+    Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
+    h->t = best_t;
+    V3<T> p = at(rr, best_t);
+    V3<T> outward;
+    if (pr.kind == P_SPHERE) {
+        Vec4T<T> s = sc.spheres[pr.first];
+        if constexpr (EXACT) outward = (p - mk<T>(s.x, s.y, s.z)) / s.w;
+        else outward = (p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
+    } else if (pr.kind == P_PLANE) outward = sc.plane_geo[pr.first].normal;
+    else outward = sc.quads[best_sub].normal;
+    h->front_face = dot(rr.d, outward) < T(0);
+    h->normal = h->front_face ? outward : -outward;
+    if (pr.xform >= 0) {
+        const GXform<T>& X = sc.xforms[pr.xform];
+        p = g_mat_vec<T>(X.fwd, p) + mk<T>(X.ft[0], X.ft[1], X.ft[2]);
+    }
+    h->p = p;
+    const GMat<T>& m = sc.mats[pr.mat];
+    h->gkind = m.kind;
+    h->info = (pr.id << 2) | (m.kind & 3u);
+    h->param = m.param;
+    // Metal reads its own albedo; Lambertian / Isotropic / DiffuseLight read their texture at the hit point
+    h->albedo = (m.kind == LAMBERTIAN || m.kind >= DIFFUSE_LIGHT) ? g_texture<T>(sc, m, p) : mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+    return true;
+}
+
+// ---- lights: HittableList::{pdf_value, random} (hittable_list.rs:408-420) over spheres, quads, triangles ---------
+template <class T, bool EXACT, bool COUNT>
+RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    T acc = T(0);
+    Ray<T> r{origin, dir};
+    T a = sqlen(dir);
+    for (int i = 0; i < sc.n_lights; ++i) {
+        const GPrim<T>& pr = sc.lights[i];
+        T v = T(0);
+        if (pr.xform < 0) {                                        // Transformed<T>, Cuboid, Plane: Hittable default 0 (hittable.rs:175-177)
+            if (pr.kind == P_SPHERE) {                             // sphere.rs:101-111
+                if (COUNT) tl.light_tests++;
+                Vec4T<T> s = sc.spheres[pr.first];
+                T t;
+                bool hit;
+                if constexpr (EXACT) hit = sphere_root<T>(s, r, a, T(0), Mt::inf(), &t);
+                else hit = sphere_root_fast(s, r, frcp(a), T(0), Mt::inf(), &t);
+                if (hit) {
+                    T distance_squared = sqlen(mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z));
+                    T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
+                    v = T(1) / (T(2) * Mt::PI * (T(1) - cos_theta_max));
+                }
+            } else if (pr.kind == P_QUAD || pr.kind == P_TRIANGLE) {   // quadrilateral.rs:100-112
+                if (COUNT) tl.light_tests++;
+                const GQuad<T>& Q = sc.quads[pr.first];
+                T t;
+                if (g_quad_hit<T, EXACT>(Q, pr.kind == P_TRIANGLE, r, T(0), Mt::inf(), &t)) {
+                    T distance_squared = t * t * a;
+                    V3<T> n = dot(dir, Q.normal) < T(0) ? Q.normal : -Q.normal;
+                    T cosine = fabs(dot(dir, n) / Mt::sqrt_(a));
+                    v = distance_squared / (cosine * Q.area);
+                }
+            }
+        }
+        acc = acc + v;
+    }
+    T len = (T)sc.n_lights;
+    if (sc.lights_is_bvh) return ((acc / len) * len) / len;       // bvh.rs:67-76, 191-194 over one Leaf
+    return acc / len;
+}
+template <class T, bool EXACT>
+RTW_D V3<T> g_lights_random(const SceneViewG<T>& sc, V3<T> origin, Stream<EXACT>& rng) {
+    const GPrim<T>& pr = sc.lights[uindex(rng, (uint32_t)sc.n_lights)];
+    if (pr.xform < 0) {
+        if (pr.kind == P_SPHERE) return sphere_random<T, EXACT>(sc.spheres[pr.first], origin, rng);
+        if (pr.kind == P_QUAD || pr.kind == P_TRIANGLE) {         // quadrilateral.rs:114-118, triangles.rs:108-117
+            const GQuad<T>& Q = sc.quads[pr.first];
+            T r1 = open01(rng), r2 = open01(rng);
+            if (pr.kind == P_TRIANGLE && r1 + r2 > T(1)) { r1 = T(1) - r1; r2 = T(1) - r2; }
+            return ((Q.q + Q.u * r1) + Q.v * r2) - origin;
+        }
+    }
+    return mk<T>(1, 0, 0);                                        // Hittable::random default, hittable.rs:179-181
+}
+
+template <class T> RTW_D V3<T> g_emitted(const Hit<T>& h) {       // DiffuseLight::emitted (material.rs:506-514); others 0
+    return h.gkind == DIFFUSE_LIGHT ? h.albedo : mk<T>(0, 0, 0);
+}
+
+// Material::scatter + the Scatter branch of ray_colour_tail_call (camera.rs:484-521)
+template <class T, bool EXACT, bool COUNT>
+RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    const uint32_t kind = h.gkind;
+    if (kind == LAMBERTIAN || kind == ISOTROPIC) {
+        const bool cosine = kind == LAMBERTIAN;
+        if (COUNT && cosine) tl.lambertian++;
+        Onb<T, EXACT> uvw(h.normal);
+        V3<T> dir;
+        if (standard(rng) < T(0.5)) dir = g_lights_random<T, EXACT>(sc, h.p, rng);      // MixturePdf::generate (pdf1 = lights)
+        else if (cosine) {                                                              // CosineWeightedHemisphere, utils.rs:146-161
+            T r1 = standard(rng), r2 = standard(rng);
+            T sn, cs;
+            Mt::sincos_2pi(r1, &sn, &cs);
+            dir = uvw.transform(mk<T>(cs * Mt::sqrt_(r2), sn * Mt::sqrt_(r2), Mt::sqrt_(T(1) - r2)));
+        } else {                                                                        // SpherePdf::generate = UnitSphere (pdf.rs:21-31)
+            for (;;) {
+                T a = T(2) * standard(rng) - T(1), b = T(2) * standard(rng) - T(1), c = T(2) * standard(rng) - T(1);
+                dir = mk<T>(a, b, c);
+                if (sqlen(dir) < T(1)) break;
+            }
+        }
+        T light_v = g_lights_pdf_value<T, EXACT, COUNT>(sc, h.p, dir, tl);
+        T own_v, scattering_pdf;
+        if (cosine) {
+            V3<T> nd = Mt::normalize(dir);
+            own_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));
+            scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));
+        } else {
+            own_v = T(1) / (T(4) * Mt::PI);
+            scattering_pdf = T(1) / (T(4) * Mt::PI);
+        }
+        T pdf_value = light_v * T(0.5) + own_v * T(0.5);
+        *next = Ray<T>{h.p, dir};
+        *weight = (h.albedo * scattering_pdf) / pdf_value;
+        return V_DIFFUSE;
+    }
+    if (kind == METAL || kind == DIELECTRIC) {
+        // same code as the sphere-only scenes: shade() never touches the scene for these two kinds
+        SceneView<T> none{};
+        return shade<T, EXACT, COUNT, SceneView<T>>(none, r, h, rng, next, weight, tl, nullptr, 0);
+    }
+    if (COUNT) tl.absorbed++;                                      // DiffuseLight, Invisible: Material::scatter default None
+    return V_ABSORB;
+}
+
+}  // namespace rtw

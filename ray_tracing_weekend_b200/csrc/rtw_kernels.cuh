@@ -13,12 +13,20 @@ template <class T> struct Hit {
     uint32_t info;         // prim_id << 2 | kind
     V3<T> albedo;
     T param;
+    uint32_t gkind;        // general scenes only: the full material kind (DiffuseLight, Isotropic do not fit 2 bits)
 };
 
 struct Tally {             // per-thread event counters (only live when COUNT)
     uint32_t node_visits = 0, sphere_tests = 0, light_tests = 0, lambertian = 0, metal = 0, dielectric = 0,
              absorbed = 0, missed = 0, depth_out = 0;
 };
+
+// general scenes (rtw_general.cuh, included at the end of this file)
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl);
+template <class T, bool EXACT, bool COUNT>
+RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl);
+template <class T> RTW_D V3<T> g_emitted(const Hit<T>& h);
 
 // ---------------------------------------------------------------------------------------------
 // Ray / box.  Exact: AABoxHit for AABBox::hit (shared/src/hittable.rs:38-87) verbatim.
@@ -222,11 +230,14 @@ RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* 
 
 template <class T, bool EXACT, bool COUNT, class SC>
 RTW_D bool closest_hit(const SC& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+    if constexpr (is_general<SC>::value) return g_closest_hit<T, EXACT, COUNT>(sc, r, tmin, tmax, h, stack, stride, tl);
+    else {
     int32_t best;
     T best_t;
     if (!closest_prim<T, EXACT, COUNT, SC>(sc, r, tmin, tmax, &best, &best_t, stack, stride, tl)) return false;
     hit_record<T, EXACT, SC>(sc, r, best, best_t, h);
     return true;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,6 +371,8 @@ template <class T, bool EXACT, bool COUNT, class SC>
 RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl,
                      int32_t* stack, int stride) {
     using Mt = M<T, EXACT>;
+    if constexpr (is_general<SC>::value) return g_shade<T, EXACT, COUNT>(sc, r, h, rng, next, weight, tl);
+    else {
     uint32_t kind = h.info & 3u;
     if (kind == LAMBERTIAN) {                                   // material.rs:357-376
         if (COUNT) tl.lambertian++;
@@ -425,6 +438,7 @@ RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXAC
     }
     if (COUNT) tl.absorbed++;                                   // Invisible: Material defaults, material.rs:32-49
     return V_ABSORB;
+    }
 }
 
 // Camera::get_ray (camera.rs:274-293)
@@ -470,6 +484,7 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
         return true;
     }
     V3<T> emitted = mk<T>(0, 0, 0);                             // Material::emitted default, material.rs:42-44
+    if constexpr (is_general<SC>::value) emitted = g_emitted<T>(h);
     Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u);
     Ray<T> next;
     V3<T> w;
@@ -485,8 +500,8 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
 template <class T> RTW_D V3<T> fix_nan(V3<T> v) { return mk<T>(v.x != v.x ? T(0) : v.x, v.y != v.y ? T(0) : v.y, v.z != v.z ? T(0) : v.z); }
 
 // ---------------------------------------------------------------------------------------------
-template <class T> struct RenderParams {
-    SceneView<T> scene;
+template <class T, class SCENE = SceneView<T>> struct RenderParams {
+    SCENE scene;
     CameraT<T> cam;
     uint64_t seed;
     T tmin;
@@ -575,17 +590,21 @@ template <class T> RTW_D void stage_scene(const RenderParams<T>&, unsigned char*
 // (an atomic counter); each lane owns one pixel and runs its spp paths back to back, regenerating a
 // camera ray as soon as its previous path ends (render_internal + ray_colour_tail_call,
 // camera.rs:315-388, 460-522).  Samples of a pixel are summed in sample order.
-template <class T, bool EXACT, bool COUNT, int BLOCK, bool SH = false>
-__global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T> P) {
+template <class T, bool EXACT, bool COUNT, int BLOCK, bool SH = false, class SCENE = SceneView<T>>
+__global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCENE> P) {
     static_assert(!(EXACT && SH), "the exact path reads the scene from global memory");
+    static_assert(!(is_general<SCENE>::value && SH), "general scenes are read from global memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
-    SceneView<T> sc = P.scene;
-    if constexpr (!EXACT) stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
-    using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
+    using SC = typename std::conditional<SH, SceneViewSh<T>, SCENE>::type;
     SC scv;
-    static_cast<SceneView<T>&>(scv) = sc;
-    bind_scene(scv);
+    if constexpr (is_general<SCENE>::value) scv = P.scene;
+    else {
+        SceneView<T> sc = P.scene;
+        if constexpr (!EXACT) stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
+        static_cast<SceneView<T>&>(scv) = sc;
+        bind_scene(scv);
+    }
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     int32_t* stack = stack_base + threadIdx.x;
@@ -794,8 +813,8 @@ __global__ void pool_finalize_kernel(const unsigned long long* accum, const uint
 
 // ---------------------------------------------------------------------------------------------
 // Batch kernels (one thread per ray) — the parity surface.
-template <class T> struct BatchParams {
-    SceneView<T> scene;
+template <class T, class SCENE = SceneView<T>> struct BatchParams {
+    SCENE scene;
     CameraT<T> cam;
     uint64_t seed;
     T tmin, tmax;
@@ -810,21 +829,21 @@ template <class T> struct BatchParams {
 template <class T> RTW_D V3<T> load3(const double* p, size_t i) { return mk<T>((T)p[3 * i], (T)p[3 * i + 1], (T)p[3 * i + 2]); }
 template <class T> RTW_D void store3(double* p, size_t i, V3<T> v) { p[3 * i] = (double)v.x; p[3 * i + 1] = (double)v.y; p[3 * i + 2] = (double)v.z; }
 
-template <class T, bool EXACT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) trace_batch_kernel(BatchParams<T> P) {
+template <class T, bool EXACT, int BLOCK, class SCENE = SceneView<T>>
+__global__ void __launch_bounds__(BLOCK) trace_batch_kernel(BatchParams<T, SCENE> P) {
     __shared__ int32_t stack_s[kStackDepth * BLOCK];
     size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (idx >= P.n) return;
     Ray<T> r{load3<T>(P.o, idx), load3<T>(P.d, idx)};
     Hit<T> h;
     Tally tl;
-    bool hit = closest_hit<T, EXACT, false, SceneView<T>>(P.scene, r, P.tmin, P.tmax, &h, stack_s + threadIdx.x, BLOCK, tl);
+    bool hit = closest_hit<T, EXACT, false, SCENE>(P.scene, r, P.tmin, P.tmax, &h, stack_s + threadIdx.x, BLOCK, tl);
     P.prim[idx] = hit ? (int32_t)(h.info >> 2) : -1;
     P.t[idx] = hit ? (double)h.t : __builtin_huge_val();
 }
 
-template <class T, bool EXACT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) {
+template <class T, bool EXACT, int BLOCK, class SCENE = SceneView<T>>
+__global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T, SCENE> P) {
     __shared__ int32_t stack_s[kStackDepth * BLOCK];
     size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (idx >= P.n) return;
@@ -832,7 +851,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) 
     Hit<T> h;
     Tally tl;
     V3<T> zero = mk<T>(0, 0, 0);
-    if (!closest_hit<T, EXACT, false, SceneView<T>>(P.scene, r, P.tmin, M<T, EXACT>::inf(), &h, stack_s + threadIdx.x, BLOCK, tl)) {
+    if (!closest_hit<T, EXACT, false, SCENE>(P.scene, r, P.tmin, M<T, EXACT>::inf(), &h, stack_s + threadIdx.x, BLOCK, tl)) {
         P.prim[idx] = -1; P.t[idx] = __builtin_huge_val(); P.kind[idx] = V_MISS;
         store3(P.p, idx, zero); store3(P.normal, idx, zero); store3(P.dir, idx, zero); store3(P.weight, idx, zero);
         return;
@@ -840,7 +859,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T> P) 
     Stream<EXACT> rng(P.seed, P.a[idx], P.b[idx], P.c[idx]);
     Ray<T> next{zero, zero};
     V3<T> w = zero;
-    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
+    uint32_t kind = shade<T, EXACT, false, SCENE>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
     P.prim[idx] = (int32_t)(h.info >> 2); P.t[idx] = (double)h.t; P.kind[idx] = kind;
     store3(P.p, idx, h.p); store3(P.normal, idx, h.normal);
     store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
@@ -857,8 +876,8 @@ __global__ void __launch_bounds__(BLOCK) get_rays_kernel(BatchParams<T> P, doubl
     store3(o, idx, r.o); store3(d, idx, r.d);
 }
 
-template <class T, bool EXACT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) path_radiance_kernel(BatchParams<T> P) {
+template <class T, bool EXACT, int BLOCK, class SCENE = SceneView<T>>
+__global__ void __launch_bounds__(BLOCK) path_radiance_kernel(BatchParams<T, SCENE> P) {
     __shared__ int32_t stack_s[kStackDepth * BLOCK];
     size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (idx >= P.n) return;
@@ -871,7 +890,7 @@ __global__ void __launch_bounds__(BLOCK) path_radiance_kernel(BatchParams<T> P) 
     V3<T> value;
     uint32_t nrays = 0;
     Tally tl;
-    while (!path_step<T, EXACT, false, SceneView<T>>(P.scene, P.cam, P.seed, P.tmin, pixel, s, ps, &value, stack_s + threadIdx.x, BLOCK, nrays, tl)) {}
+    while (!path_step<T, EXACT, false, SCENE>(P.scene, P.cam, P.seed, P.tmin, pixel, s, ps, &value, stack_s + threadIdx.x, BLOCK, nrays, tl)) {}
     if (P.flags & 1u) value = fix_nan(value);
     store3(P.rgb, idx, value);
 }
@@ -906,3 +925,5 @@ __global__ void untile_resolve_kernel(const T* tiles, uint32_t width, uint32_t h
 }
 
 }  // namespace rtw
+
+#include "rtw_general.cuh"

@@ -68,6 +68,30 @@ cudaError_t launch_render_impl(RenderParams<T> P, int sm_count, cudaStream_t s, 
     return launch_persistent(render_mega_kernel<T, EXACT, COUNT, kRenderBlock, false>, P, kRenderBlock, smem, sm_count, s, info);
 }
 
+// general scenes: lane-per-pixel megakernel, scene in global memory (small tables: L1-resident)
+template <class T, bool EXACT>
+cudaError_t launch_render_general_t(RenderParams<T, SceneViewG<T>> P, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    if (P.stack_depth == 0 || P.stack_depth > (uint32_t)kStackDepth) P.stack_depth = kStackDepth;
+    size_t smem = sizeof(int32_t) * P.stack_depth * kRenderBlock;
+    if (count) return launch_persistent(render_mega_kernel<T, EXACT, true, kRenderBlock, false, SceneViewG<T>>, P, kRenderBlock, smem, sm_count, s, info);
+    return launch_persistent(render_mega_kernel<T, EXACT, false, kRenderBlock, false, SceneViewG<T>>, P, kRenderBlock, smem, sm_count, s, info);
+}
+template <class T, bool EXACT> cudaError_t launch_trace_general_t(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    trace_batch_kernel<T, EXACT, kBatchBlock, SceneViewG<T>><<<(int)((P.n + kBatchBlock - 1) / kBatchBlock), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template <class T, bool EXACT> cudaError_t launch_scatter_general_t(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    scatter_batch_kernel<T, EXACT, kBatchBlock, SceneViewG<T>><<<(int)((P.n + kBatchBlock - 1) / kBatchBlock), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template <class T, bool EXACT> cudaError_t launch_path_radiance_general_t(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    path_radiance_kernel<T, EXACT, kBatchBlock, SceneViewG<T>><<<(int)((P.n + kBatchBlock - 1) / kBatchBlock), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
 template <class T, bool EXACT>
 cudaError_t launch_render_t(RenderParams<T> P, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_impl<T, EXACT, true>(P, sm_count, s, info) : launch_render_impl<T, EXACT, false>(P, sm_count, s, info);
@@ -147,6 +171,12 @@ cudaError_t launch_render_pool_impl(RenderParams<float> P, PoolParams Q, int sm_
         return launch_get_rays_t<T, EXACT>(P, o, d, s);                                                                           \
     }                                                                                                                            \
     cudaError_t launch_path_radiance_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_path_radiance_t<T, EXACT>(P, s); } \
+    cudaError_t launch_render_general_##SUFFIX(RenderParams<T, SceneViewG<T>> P, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) { \
+        return launch_render_general_t<T, EXACT>(P, count, sm_count, s, info);                                                    \
+    }                                                                                                                            \
+    cudaError_t launch_trace_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) { return launch_trace_general_t<T, EXACT>(P, s); } \
+    cudaError_t launch_scatter_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) { return launch_scatter_general_t<T, EXACT>(P, s); } \
+    cudaError_t launch_path_radiance_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s) { return launch_path_radiance_general_t<T, EXACT>(P, s); } \
     cudaError_t launch_untile_##SUFFIX(const T* tiles, uint32_t width, uint32_t height, uint32_t world, uint32_t tiles_per_rank,  \
                                        uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {                            \
         return launch_untile_t<T>(tiles, width, height, world, tiles_per_rank, spp, rgb_sum, rgb8, s);                            \

@@ -12,6 +12,10 @@ struct LaunchInfo { int grid = 0, block = 0; size_t smem = 0; int blocks_per_sm 
     cudaError_t launch_scatter_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                                 \
     cudaError_t launch_get_rays_##SUFFIX(const BatchParams<T>& P, double* o, double* d, cudaStream_t s);          \
     cudaError_t launch_path_radiance_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                           \
+    cudaError_t launch_render_general_##SUFFIX(RenderParams<T, SceneViewG<T>> P, bool count, int sm_count, cudaStream_t s, LaunchInfo*); \
+    cudaError_t launch_trace_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s);            \
+    cudaError_t launch_scatter_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s);          \
+    cudaError_t launch_path_radiance_general_##SUFFIX(const BatchParams<T, SceneViewG<T>>& P, cudaStream_t s);    \
     cudaError_t launch_untile_##SUFFIX(const T* tiles, uint32_t width, uint32_t height, uint32_t world,           \
                                        uint32_t tiles_per_rank, uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
 

@@ -1,0 +1,41 @@
+"""Golden fixture of the GENERAL-scene oracle (oracle/rtw_oracle_general.hpp) on the reference's scenes cornell_box, simple_light,
+debugging_scene and simple_transform (scenes/src/lib.rs:235-653).  Run from the repo root:
+`python tests/golden/make_golden_general.py`.  The reference cannot run here (no Rust toolchain) and has no golden vectors
+for this path, so this pins the ORACLE (and through it the CUDA path) against drift.  Scene descriptions come from the
+product's host mirror (ray_tracing_weekend_b200.scenes, no GPU involved); all arithmetic is the oracle's, in PORTABLE
+math mode (fixed IEEE sequences instead of libm sin/cos) so that the numbers do not depend on the libm build."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEED = 20261018
+
+
+def compute(O, R):
+    out = {}
+    for name in ("cornell_box", "simple_light", "debugging_scene", "simple_transform"):
+        gen = getattr(R.scenes, name)
+        world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
+        d = R.SceneDescription(world, lights)
+        g = O.GScene(d.pod, d)
+        cam = cb.with_vfov(40.).with_aspect_ratio(1.0).with_image_width(24).with_image_height(24).with_samples_per_pixel(4).with_max_depth(12).build()
+        img, _, cnt, _ = g.render(O.Camera.from_buffer_copy(cam.pod), O.options(seed=SEED, math_mode=O.PORTABLE, threads=1))
+        out[name] = dict(n_world=d.n_world, n_lights=d.n_lights, rays=cnt["rays"], paths=cnt["paths"],
+                         image_sum=np.nan_to_num(img, nan=-1.0).reshape(-1)[::7].tolist())
+    return out
+
+
+if __name__ == "__main__":
+    from oracle import pyoracle as O
+    import ray_tracing_weekend_b200 as R
+    g = compute(O, R)
+    with open(os.path.join(HERE, "general_oracle.json"), "w") as f:
+        json.dump(g, f)
+    print({k: (v["rays"], v["paths"]) for k, v in g.items()})

@@ -1,0 +1,183 @@
+"""GPU parity tests of the general-scene path (Quad, Triangle, Cuboid, Transformed<T>, DiffuseLight,
+Isotropic, NoiseTexture, quad lights) through the C ABI (rtw_scene_create_general + the same render / batch entry points)
+against the general oracle on the same scene description and the same Philox streams.
+
+f64 path: bit-exact (hits, vertices, path radiance, whole images).  f32 path: statistically (mean radiance, PSNR)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261018
+SCENES = ("cornell_box", "simple_light", "debugging_scene", "simple_transform")
+
+
+def _build(rtw, oracle, name):
+    gen = getattr(rtw.scenes, name)
+    world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
+    scene = rtw.Scene(world, lights)
+    assert scene.general
+    return scene, oracle.GScene(scene.desc.pod, scene.desc), cb
+
+
+def _random_scene(rtw, rng, n=160):
+    """A mixed bag: every entity kind, half of them Transformed, every material kind, a NoiseTexture."""
+    noise = rtw.NoiseTexture(3.0, SEED, 2)
+    mats = [rtw.Lambertian((0.7, 0.6, 0.5)), rtw.Metal((0.8, 0.8, 0.9), 0.1), rtw.Dialectric(1.5), rtw.DiffuseLight((2., 2., 2.)),
+            rtw.Isotropic((0.4, 0.5, 0.6)), rtw.Lambertian(noise), rtw.INVISIBLE]
+    world, lights = rtw.HittableList(), rtw.HittableList()
+    world.add(rtw.Plane((0., -6., 0.), (0., -1., 0.), mats[0]))
+    for k in range(n):
+        c = rng.uniform(-5, 5, 3)
+        m = mats[int(rng.integers(0, len(mats)))]
+        kind = k % 4
+        if kind == 0:
+            e = rtw.Sphere(tuple(c), float(rng.uniform(0.2, 0.8)), m)
+        elif kind == 1:
+            e = rtw.Quad(tuple(c), tuple(rng.normal(size=3)), tuple(rng.normal(size=3)), m)
+        elif kind == 2:
+            e = rtw.Triangle(tuple(c), tuple(rng.normal(size=3)), tuple(rng.normal(size=3)), m)
+        else:
+            e = rtw.Cuboid(tuple(c), tuple(c + rng.uniform(0.2, 1.2, 3)), m)
+        if rng.random() < 0.5:
+            # rotations only or rotation + tiny translation: a large translation sends the instance ray far away (the
+            # reference adds it to the direction), which would leave nothing to compare
+            e = e.transform(rtw.rotation(float(rng.uniform(-90, 90)), int(rng.integers(0, 3))))
+            if rng.random() < 0.5:
+                e = e.transform(rtw.Translation3(*rng.normal(size=3) * 0.05))
+        world.add(e)
+    lights.add(rtw.Quad((-1., 7., -1.), (2., 0., 0.), (0., 0., 2.), mats[3]))
+    lights.add(rtw.Sphere((3., 6., 0.), 0.7, mats[3]))
+    lights.add(rtw.Triangle((-4., 6., 2.), (1.5, 0., 0.), (0., 0., 1.5), mats[3]))
+    lights.add(rtw.Cuboid((0., 0., 0.), (1., 1., 1.), mats[3]).transform(rtw.Translation3(0., 8., 0.)))
+    for l in lights.items[:3]:
+        world.add(l)
+    return world, lights
+
+
+def _rays(oracle, og, cam_pod, n, seed):
+    rng = np.random.default_rng(seed)
+    ocam = oracle.Camera.from_buffer_copy(cam_pod)
+    i = rng.integers(0, ocam.width, n); j = rng.integers(0, ocam.height, n); s = rng.integers(0, 4, n)
+    o, d = oracle.get_rays(ocam, oracle.options(seed=SEED), i, j, s)
+    prim, t, p, _ = og.trace_batch(o, d)
+    hit = prim >= 0
+    if hit.sum() > 0:
+        k = rng.integers(0, hit.sum(), n)
+        o = np.concatenate([o, p[hit][k]]); d = np.concatenate([d, rng.normal(size=(n, 3))])
+    return o, d
+
+
+def _cam(cb, w=48, h=48, spp=4, depth=12):
+    return cb.with_vfov(40.).with_aspect_ratio(w / h).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).with_max_depth(depth).build()
+
+
+@pytest.mark.parametrize("name", SCENES + ("random",))
+def test_general_hits_and_vertices_f64_bit_exact(rtw, oracle, name):
+    if name == "random":
+        world, lights = _random_scene(rtw, np.random.default_rng(11))
+        scene = rtw.Scene(world, lights)
+        og = oracle.GScene(scene.desc.pod, scene.desc)
+        cb = rtw.CameraBuilder().with_lookfrom((0., 2., 16.)).with_lookat((0., 0., 0.)).with_focus_dist(16.)
+    else:
+        scene, og, cb = _build(rtw, oracle, name)
+    try:
+        cam = _cam(cb)
+        o, d = _rays(oracle, og, cam.pod, 3000, 7)
+        for tmin in (oracle.EPS, 1e-3):
+            prim_o, t_o, _, _ = og.trace_batch(o, d, tmin=tmin)
+            prim_g, t_g = scene.trace_batch(o, d, tmin=tmin, precision=rtw.RTW_F64)
+            assert np.array_equal(prim_o, prim_g), f"{(prim_o != prim_g).sum()} id mismatches"
+            assert np.array_equal(t_o, t_g)
+        assert (prim_o >= 0).sum() > 200
+        if name == "random":
+            assert len(set(prim_o[prim_o >= 0])) > 60                 # many different entries are actually hit
+        rng = np.random.default_rng(9)
+        pixel = rng.integers(0, 90000, len(o)); sample = rng.integers(0, 100, len(o)); vertex = rng.integers(1, 51, len(o))
+        ref = og.scatter_batch(o, d, pixel, sample, vertex, oracle.options(seed=SEED, math_mode=oracle.PORTABLE))
+        got = scene.scatter_batch(o, d, pixel, sample, vertex, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64))
+        assert np.array_equal(ref["prim"], got["prim"]) and np.array_equal(ref["kind"], got["kind"])
+        for k in ("t", "p", "normal", "dir", "weight"):
+            assert np.array_equal(ref[k], got[k], equal_nan=True), k
+    finally:
+        scene.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_general_image_f64_bit_exact(rtw, oracle, name):
+    scene, og, cb = _build(rtw, oracle, name)
+    try:
+        cam = _cam(cb, 40, 30, 6, 20)
+        ocam = oracle.Camera.from_buffer_copy(cam.pod)
+        opts = oracle.options(seed=SEED, math_mode=oracle.PORTABLE)
+        ref, _, cnt, _ = og.render(ocam, opts)
+        got, rgb8, st = scene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64, flags=rtw.RTW_FLAG_COUNT_EVENTS))
+        assert np.array_equal(ref, got, equal_nan=True), f"{name}: {(~np.isclose(ref, got, equal_nan=True)).sum()} values differ"
+        assert st["rays"] == cnt["rays"] and st["paths"] == cnt["paths"] == 40 * 30 * 6
+        assert np.array_equal(rgb8, oracle.resolve(ref, 6))
+        rng = np.random.default_rng(2)
+        i = rng.integers(0, 40, 500); j = rng.integers(0, 30, 500); s = rng.integers(0, 6, 500)
+        assert np.array_equal(og.path_radiance(ocam, opts, i, j, s),
+                              scene.path_radiance(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64), i, j, s), equal_nan=True)
+    finally:
+        scene.close()
+
+
+def test_general_path_equals_sphere_path_on_simple(rtw, oracle, simple_scene):
+    """scenes::simple through rtw_scene_create_general == through rtw_scene_create (f64: bit-identical image)."""
+    cam = (simple_scene["cb"].with_vfov(40.).with_aspect_ratio(16 / 9).with_image_width(64).with_image_height(36).with_samples_per_pixel(4)
+           .with_max_depth(50).build())
+    a = rtw.Scene(simple_scene["world"], simple_scene["lights"])
+    b = rtw.Scene(simple_scene["world"], simple_scene["lights"], general=True)
+    try:
+        assert not a.general and b.general
+        opts = rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64)
+        ia, _, sa = a.render(cam, opts)
+        ib, _, sb = b.render(cam, opts)
+        assert np.array_equal(ia, ib, equal_nan=True) and sa["rays"] == sb["rays"]
+    finally:
+        a.close(); b.close()
+
+
+def test_cornell_box_f32_image_statistics(rtw, oracle):
+    """FP32 general path vs the f64 oracle with independent noise: same mean radiance, images agree to render noise."""
+    scene, og, cb = _build(rtw, oracle, "cornell_box")
+    try:
+        w = h = 64
+        spp = 128
+        cam = _cam(cb, w, h, spp, 50)
+        ocam = oracle.Camera.from_buffer_copy(cam.pod)
+        ref, _, cnt, _ = og.render(ocam, oracle.options(seed=SEED + 1, math_mode=oracle.PORTABLE))
+        got, _, st = scene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32))
+        ref64b, _, _ = scene.render(cam, rtw.RenderOptions(seed=SEED + 2, precision=rtw.RTW_F64))
+        a, b, c = ref / spp, got / spp, ref64b / spp
+        ok = np.isfinite(a).all(axis=2) & np.isfinite(b).all(axis=2) & np.isfinite(c).all(axis=2)
+        assert ok.mean() > 0.9
+        # fireflies (15x light through the glass sphere) dominate the raw mean: compare clamped radiance
+        ca, cb_, cc = np.clip(a[ok], 0, 2), np.clip(b[ok], 0, 2), np.clip(c[ok], 0, 2)
+        assert abs(cb_.mean() - ca.mean()) < 0.04 * ca.mean(), (ca.mean(), cb_.mean())
+        mse_noise = ((ca - cc) ** 2).mean()            # two f64 renders with different seeds
+        mse_f32 = ((ca - cb_) ** 2).mean()
+        assert mse_f32 < 1.5 * mse_noise + 1e-4, (mse_f32, mse_noise)
+        assert abs(st["rays"] / st["paths"] - cnt["rays"] / cnt["paths"]) < 0.05 * cnt["rays"] / cnt["paths"]
+    finally:
+        scene.close()
+
+
+def test_general_scene_validation(rtw):
+    from ray_tracing_weekend_b200 import _lib
+    white = rtw.Lambertian((0.5, 0.5, 0.5))
+    world = rtw.HittableList(); world.add(rtw.Quad((0., 0., 0.), (1., 0., 0.), (0., 1., 0.), white))
+    with pytest.raises(rtw.RtwError) as e:                          # Lambertian + empty lights: the reference panics
+        rtw.Scene(world, rtw.HittableList())
+    assert e.value.code == _lib.RTW_E_INVALID
+    lights = rtw.HittableList(); lights.extend(rtw.Sphere((float(k), 5., 0.), 0.3, rtw.INVISIBLE) for k in range(6))
+    with pytest.raises(rtw.RtwError) as e:                          # a BVH of > 5 lights: aux_random is broken in the reference
+        rtw.Scene(world, rtw.BoundedVolumeHierarchy.from_list(lights))
+    assert e.value.code == _lib.RTW_E_UNSUPPORTED
+    # an empty world renders the background
+    empty = rtw.Scene(rtw.HittableList(), lights, general=True)
+    cam = rtw.CameraBuilder().with_image_width(5).with_image_height(3).with_samples_per_pixel(2).with_background((0.25, 0.5, 1.)).build()
+    img, _, st = empty.render(cam, rtw.RenderOptions(seed=1, precision=rtw.RTW_F64))
+    assert np.array_equal(img, np.broadcast_to(np.array([0.5, 1., 2.]), (3, 5, 3))) and st["rays"] == 30
+    empty.close()

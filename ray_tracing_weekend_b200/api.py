@@ -206,7 +206,12 @@ class HittableList:                             # hittable_collections/hittable_
 
     def is_simple(self) -> bool:
         """Spheres and planes with SolidColour Lambertian / Metal / Dialectric / Invisible materials only: the fast sphere path."""
-        return all(isinstance(o, (Sphere, Plane)) and o.material.kind <= RTW_INVISIBLE and o.material.texture is None for o in self.items)
+        def plane_ok(o):        # Plane::get_aabbox puts an axis-aligned plane's box through the origin (plane.rs:78-107)
+            n = np.asarray(o.normal, dtype=np.float64)
+            n = n / np.sqrt((n * n).sum())
+            return not any(abs(n[(a + 1) % 3]) < EPSILON and abs(n[(a + 2) % 3]) < EPSILON and o.point[a] != 0.0 for a in range(3))
+        return all(isinstance(o, (Sphere, Plane)) and o.material.kind <= RTW_INVISIBLE and o.material.texture is None
+                   and (isinstance(o, Sphere) or plane_ok(o)) for o in self.items)
 
     def len(self):
         return len(self.items)

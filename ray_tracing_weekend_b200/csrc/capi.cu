@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <string>
@@ -304,7 +305,18 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
             ib.mn[0] = q.cx - q.r; ib.mn[1] = q.cy - q.r; ib.mn[2] = q.cz - q.r; ib.mx[0] = q.cx + q.r; ib.mx[1] = q.cy + q.r; ib.mx[2] = q.cz + q.r;
             break;
         }
-        case RTW_PRIM_PLANE: p.first = e.index; *bounded = false; break;
+        case RTW_PRIM_PLANE: {                                          // Plane::get_aabbox (plane.rs:78-107)
+            p.first = e.index; *bounded = false;
+            const rtw_plane& q = g.planes[e.index];
+            double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);
+            double n[3] = {q.nx / len, q.ny / len, q.nz / len};
+            const double eps = 2.220446049250313e-16, inf = std::numeric_limits<double>::infinity();
+            for (int a = 0; a < 3; ++a) {
+                bool flat = std::fabs(n[(a + 1) % 3]) < eps && std::fabs(n[(a + 2) % 3]) < eps;
+                ib.mn[a] = flat ? 0. : -inf; ib.mx[a] = flat ? 0. : inf;
+            }
+            break;
+        }
         case RTW_PRIM_CUBOID: {
             host::QuadH f[6];
             host::make_cuboid(host::ld3(g.cuboids[e.index].p), host::ld3(g.cuboids[e.index].q), f, &ib);
@@ -363,6 +375,8 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     d.view.mats = d.mats.p; d.view.perlins = d.perlins.p;
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
     d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
+    d.view.has_xforms = 0;
+    for (const GPrim<T>& p : prims) if (p.xform >= 0) d.view.has_xforms = 1;
     return RTW_OK;
 }
 
@@ -553,6 +567,17 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     }
     for (size_t i = 0; i < n_planes; ++i) {
         if (plane_material[i] >= n_materials) return fail(RTW_E_INVALID, "plane material index out of range");
+        // Plane::get_aabbox (plane.rs:78-107) is the slab {axis = 0} for an axis-aligned normal whatever the plane's offset, and
+        // bounded_hit tests it first: for a plane through the origin that equals Plane::hit's own range test (this path), for
+        // an offset one it hides most of the plane (the general path applies the box)
+        {
+            const rtw_plane& q = planes[i];
+            double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);
+            double n[3] = {q.nx / len, q.ny / len, q.nz / len}, pt[3] = {q.px, q.py, q.pz};
+            for (int a = 0; a < 3; ++a)
+                if (std::fabs(n[(a + 1) % 3]) < 2.220446049250313e-16 && std::fabs(n[(a + 2) % 3]) < 2.220446049250313e-16 && pt[a] != 0.)
+                    return fail(RTW_E_UNSUPPORTED, "axis-aligned plane that does not pass through the origin: use rtw_scene_create_general");
+        }
         any_lambertian |= materials[plane_material[i]].kind == RTW_LAMBERTIAN;
     }
     for (size_t i = 0; i < n_materials; ++i)

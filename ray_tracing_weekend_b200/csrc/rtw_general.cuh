@@ -16,14 +16,39 @@ template <class T> RTW_D Ray<T> g_instance_ray(const GXform<T>& X, const Ray<T>&
     return Ray<T>{g_mat_vec<T>(X.inv, r.o) + it, g_mat_vec<T>(X.inv, r.d) + it};       // transform_vector3d adds the translation too
 }
 
+// Flat entities are where self-intersection ("acne") is decided: a ray leaving a quad re-hits it iff the rounding noise of
+// dot(p - q, n) has the right sign and exceeds tmin * |denom|.  Those statistics depend on WHERE roundings happen, so the
+// plane equation and the hit point are evaluated with the reference's unfused operation sequence in both precisions
+// (dot = (x*x + y*y) + z*z, p = o + d*t) — the translation units are compiled with -fmad=false.
+template <class T> RTW_D T g_dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class T> RTW_D V3<T> g_at(const Ray<T>& r, T t) { return mk<T>(r.o.x + r.d.x * t, r.o.y + r.d.y * t, r.o.z + r.d.z * t); }
+
+// AABBox::hit (hittable.rs:38-87) in the working precision, min / max form (handles the infinite slabs of a Plane's box)
+template <class T, bool EXACT>
+RTW_D bool g_box_hit(const T* mn, const T* mx, const Ray<T>& r, T start, T end) {
+    using Mt = M<T, EXACT>;
+    T x0 = (mn[0] - r.o.x) / r.d.x, x1 = (mx[0] - r.o.x) / r.d.x;
+    if (signbit(r.d.x)) { T s = x0; x0 = x1; x1 = s; }
+    T tmin = x0, tmax = x1;
+    T y0 = (mn[1] - r.o.y) / r.d.y, y1 = (mx[1] - r.o.y) / r.d.y;
+    if (signbit(r.d.y)) { T s = y0; y0 = y1; y1 = s; }
+    if (tmax < y0 || tmin > y1) return false;
+    tmin = Mt::max_(tmin, y0); tmax = Mt::min_(tmax, y1);
+    T z0 = (mn[2] - r.o.z) / r.d.z, z1 = (mx[2] - r.o.z) / r.d.z;
+    if (signbit(r.d.z)) { T s = z0; z0 = z1; z1 = s; }
+    if (tmax < z0 || tmin > z1) return false;
+    tmin = Mt::max_(tmin, z0); tmax = Mt::min_(tmax, z1);
+    return Mt::max_(start, tmin) <= Mt::min_(end, tmax);
+}
+
 // ---- Quad::hit / Triangle::hit (quadrilateral.rs:79-98, triangles.rs:74-92) --------------------------------------
 template <class T, bool EXACT>
 RTW_D bool g_quad_hit(const GQuad<T>& Q, bool tri, const Ray<T>& r, T tmin, T tmax, T* t_out) {
-    T denom = dot(r.d, Q.normal);
+    T denom = g_dot(r.d, Q.normal);
     if (!(fabs(denom) > M<T, EXACT>::EPS)) return false;
-    T t = -(dot(r.o - Q.q, Q.normal) / denom);
+    T t = -(g_dot(r.o - Q.q, Q.normal) / denom);
     if (!(tmin <= t && t <= tmax)) return false;
-    V3<T> pq = at(r, t) - Q.q;
+    V3<T> pq = g_at(r, t) - Q.q;
     T a = dot(cross(pq, Q.v), Q.w), b = dot(cross(Q.u, pq), Q.w);                   // get_quad_uv
     bool inside = tri ? (T(0) <= a + b && a + b <= T(1)) : (T(0) <= a && a <= T(1) && T(0) <= b && b <= T(1));
     if (!inside) return false;
@@ -45,9 +70,9 @@ RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>&
     }
     case P_PLANE: {                                                                     // plane.rs:61-76, one-sided
         const GPlane<T>& pl = sc.plane_geo[pr.first];
-        T denom = dot(rr.d, pl.normal);
+        T denom = g_dot(rr.d, pl.normal);
         if (!(denom > M<T, EXACT>::EPS)) return false;
-        T t = -dot(rr.o - pl.point, pl.normal) / denom;
+        T t = -g_dot(rr.o - pl.point, pl.normal) / denom;
         if (!(tmin <= t && t <= tmax)) return false;
         *t_out = t;
         return true;
@@ -129,6 +154,9 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
     uint32_t best_sub = 0;
     for (int i = 0; i < sc.n_unbounded; ++i) {
         T t; uint32_t sub;
+        // bounded_hit (hittable.rs:191-196) with Plane::get_aabbox (plane.rs:78-107): an axis-aligned plane's box is the
+        // slab {axis = 0} whatever the plane's offset — part of the result, so tested in both precisions
+        if (!g_box_hit<T, EXACT>(sc.unbounded[i].box, sc.unbounded[i].box + 3, r, tmin, tmax)) continue;
         if (g_prim_hit<T, EXACT, COUNT>(sc, sc.unbounded[i], r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
             found = true; best_t = t; best = sc.unbounded + i; best_sub = sub;
         }
@@ -143,12 +171,16 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
             Node<T> nd = sc.nodes[cur];
             if (COUNT) tl.node_visits++;
             bool hl, hr; T tl_near = T(0), tr_near = T(0);
+            // A Transformed<T> reports t along its INSTANCE ray, whose direction carries the inverse translation
+            // (transformations.rs:123-126): that t says nothing about where the world ray meets the entry's box, so with
+            // transforms in the scene the best t so far must not cull nodes (the reference never shrinks the range).
+            const T far_limit = sc.has_xforms ? tmax : best_t;
             if constexpr (EXACT) {
-                hl = box_hit_exact(nd.la, nd.lb, r, tmin, best_t);
-                hr = box_hit_exact(nd.ra, nd.rb, r, tmin, best_t);
+                hl = box_hit_exact(nd.la, nd.lb, r, tmin, far_limit);
+                hr = box_hit_exact(nd.ra, nd.rb, r, tmin, far_limit);
             } else {
-                hl = box_hit_fast(nd.la, nd.lb, aux, tmin, best_t, &tl_near);
-                hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, best_t, &tr_near);
+                hl = box_hit_fast(nd.la, nd.lb, aux, tmin, far_limit, &tl_near);
+                hr = box_hit_fast(nd.ra, nd.rb, aux, tmin, far_limit, &tr_near);
             }
             int32_t l = nd.left, rr = nd.right;
             if (hl && hr) {
@@ -170,10 +202,7 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
                 } else if (pr.xform >= 0) {
                     // a Transformed<T> is hit with a DIFFERENT ray than its box (the instance ray's direction carries the
                     // translation), so its own world-space box is part of the result, not only a culling aid
-                    float c[3], hh[3], tn;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) { c[a] = 0.5f * (pr.box[a] + pr.box[3 + a]); hh[a] = 0.5f * (pr.box[3 + a] - pr.box[a]); }
-                    if (!box_hit_fast(c, hh, aux, tmin, tmax, &tn)) continue;
+                    if (!g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax)) continue;
                 }
                 T t; uint32_t sub;
                 if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
@@ -189,7 +218,7 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
     const GPrim<T>& pr = *best;
     Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
     h->t = best_t;
-    V3<T> p = at(rr, best_t);
+    V3<T> p = pr.kind == P_SPHERE ? at(rr, best_t) : g_at(rr, best_t);
     V3<T> outward;
     if (pr.kind == P_SPHERE) {
         Vec4T<T> s = sc.spheres[pr.first];

@@ -34,6 +34,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                                 \
     } while (0)
 
+constexpr size_t kFlatListLimit = 24;       // general scenes with at most this many bounded entries skip the BVH (linear, kind-sorted walk)
 constexpr size_t kLightBvhThreshold = 64;   // more lights than this: BVH over the lights (FP32 path)
 
 // Device allocations are recycled through a small process-wide cache: cudaMalloc / cudaFree of the tens of MB
@@ -358,7 +359,15 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
         nodes[i] = n;
     }
     std::vector<GPrim<T>> prims(bounded.size());
-    for (size_t k = 0; k < bounded.size(); ++k) prims[k] = bounded[s->bvh.order[k]];
+    const bool flat = bounded.size() <= kFlatListLimit;
+    if (flat) {
+        prims = bounded;
+        std::stable_sort(prims.begin(), prims.end(), [](const GPrim<T>& a, const GPrim<T>& b) {
+            return std::make_pair(a.kind, a.xform >= 0) < std::make_pair(b.kind, b.xform >= 0);
+        });
+    } else {
+        for (size_t k = 0; k < bounded.size(); ++k) prims[k] = bounded[s->bvh.order[k]];
+    }
     std::vector<size_t> lorder(g.lights.size());
     for (size_t i = 0; i < lorder.size(); ++i) lorder[i] = i;
     std::stable_sort(lorder.begin(), lorder.end(), [&](size_t a, size_t b) { return bucket_of(g.lights[a]) < bucket_of(g.lights[b]); });
@@ -375,6 +384,7 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     d.view.mats = d.mats.p; d.view.perlins = d.perlins.p;
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
     d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
+    d.view.flat = flat ? 1u : 0u;
     d.view.has_xforms = 0;
     for (const GPrim<T>& p : prims) if (p.xform >= 0) d.view.has_xforms = 1;
     return RTW_OK;
@@ -721,10 +731,22 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         CU(s->d_accum.reserve(n_slots * 3)); CU(s->d_poison.reserve(n_slots));
     }
-    if (s->general) pooled = false;
+    if (s->general && (o->flags & RTW_FLAG_LANE_PER_PIXEL)) pooled = false;      // `mode` does not apply to general scenes
     CU(cudaEventRecord(s->ev[0], st));
     if (s->general) {
-        if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch_render_general_f32);
+        // general scenes: FP32 = pooled path stream (or lane per pixel with RTW_FLAG_LANE_PER_PIXEL), f64 = lane per pixel
+        if (pooled) {
+            PoolParams Q{};
+            Q.accum = s->d_accum.p; Q.poison = s->d_poison.p;
+            Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
+            uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
+            Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+            auto launch = [&](RenderParams<float, SceneViewG<float>> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
+                return launch_render_pool_general_f32(P, Q, count, sms, str, info);
+            };
+            rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch);
+            launches = 2;
+        } else if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch_render_general_f32);
         else rc = render_tiles_t<double>(s, s->g64, cam, o, rank, world, (double*)d_tiles, st, launch_render_general_f64);
     } else if (pooled) {
         PoolParams Q{};

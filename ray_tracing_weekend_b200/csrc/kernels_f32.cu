@@ -15,6 +15,9 @@ RTW_DEFINE_LAUNCHERS(f32, float, false)
 cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_pool_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_impl<false>(P, Q, sm_count, s, info);
 }
+cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    return count ? launch_render_pool_general_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_general_impl<false>(P, Q, sm_count, s, info);
+}
 template <bool COUNT, bool SH, int BLOCK, int NP>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
     auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH>;

@@ -332,7 +332,7 @@ template <class T> struct SceneViewG {
     const Vec4T<T>* spheres; const GPlane<T>* plane_geo; const GQuad<T>* quads; const GXform<T>* xforms;
     const GMat<T>* mats; const GPerlin<T>* perlins;
     int32_t n_nodes, n_prims, n_unbounded, n_lights;
-    uint32_t lights_is_bvh, has_xforms;
+    uint32_t lights_is_bvh, has_xforms, flat;   // flat: few entries, walked linearly (sorted by kind) instead of through the BVH
 };
 template <class SC> struct is_general { static constexpr bool value = false; };
 template <class T> struct is_general<SceneViewG<T>> { static constexpr bool value = true; };

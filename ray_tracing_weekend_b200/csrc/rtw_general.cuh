@@ -161,11 +161,32 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
             found = true; best_t = t; best = sc.unbounded + i; best_sub = sub;
         }
     }
+    // one list entry against the ray: the entry's own box where it is part of the result, then Hittable::hit
+    auto test_entry = [&](const GPrim<T>& pr) {
+        if constexpr (EXACT) {                             // bounded_hit (hittable.rs:191-196): the entry's own box, un-shrunk range
+            if (!box_hit_exact(pr.box, pr.box + 3, r, tmin, tmax)) return;
+        } else if (pr.xform >= 0) {
+            // a Transformed<T> is hit with a DIFFERENT ray than its box (the instance ray's direction carries the
+            // translation), so its own world-space box is part of the result, not only a culling aid
+            if (!g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax)) return;
+        }
+        T t; uint32_t sub;
+        if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
+            found = true; best_t = t; best = &pr; best_sub = sub;
+        }
+    };
     RayAux aux;
     if constexpr (!EXACT) ray_aux(r, aux);
     stack[0] = kStop;
     int sp = 1;
     int32_t cur = sc.n_prims > 0 ? 0 : kStop;
+    if (sc.flat) {
+        // a handful of entries (cornell_box: 8): every lane walks the whole list, sorted by kind on the host, in lockstep —
+        // no tree, no per-lane leaf order, the kind switch is warp-uniform (ncu on the BVH version of this scene: leaf tests
+        // ran at 2-7 active threads per warp)
+        for (int i = 0; i < sc.n_prims; ++i) test_entry(sc.prims[i]);
+        cur = kStop;
+    }
     for (;;) {
         while (cur >= 0) {
             Node<T> nd = sc.nodes[cur];
@@ -195,20 +216,7 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
         if (cur != kEmptyLeaf) {
             uint32_t enc = (uint32_t)~cur;
             uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
-            for (uint32_t i = first; i < first + count; ++i) {
-                const GPrim<T>& pr = sc.prims[i];
-                if constexpr (EXACT) {                             // bounded_hit (hittable.rs:191-196): the entry's own box, un-shrunk range
-                    if (!box_hit_exact(pr.box, pr.box + 3, r, tmin, tmax)) continue;
-                } else if (pr.xform >= 0) {
-                    // a Transformed<T> is hit with a DIFFERENT ray than its box (the instance ray's direction carries the
-                    // translation), so its own world-space box is part of the result, not only a culling aid
-                    if (!g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax)) continue;
-                }
-                T t; uint32_t sub;
-                if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
-                    found = true; best_t = t; best = &pr; best_sub = sub;
-                }
-            }
+            for (uint32_t i = first; i < first + count; ++i) test_entry(sc.prims[i]);
         }
         sp--;
         cur = stack[sp * stride];

@@ -692,18 +692,22 @@ RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
     return __float2ull_rn(v * kFixedScale);                    // negative values clamp to 0
 }
 
-template <bool COUNT, int BLOCK, bool SH>
-__global__ void __launch_bounds__(BLOCK, 4) render_pool_kernel(RenderParams<float> P, PoolParams Q) {
+template <bool COUNT, int BLOCK, bool SH, class SCENE = SceneView<float>>
+__global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) render_pool_kernel(RenderParams<float, SCENE> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
+    static_assert(!(is_general<SCENE>::value && SH), "general scenes are read from global memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);                  // [kStackDepth][BLOCK]
-    SceneView<T> sc = P.scene;
-    stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
-    using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
+    using SC = typename std::conditional<SH, SceneViewSh<T>, SCENE>::type;
     SC scv;
-    static_cast<SceneView<T>&>(scv) = sc;
-    bind_scene(scv);
+    if constexpr (is_general<SCENE>::value) scv = P.scene;
+    else {
+        SceneView<T> sc = P.scene;
+        stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
+        static_cast<SceneView<T>&>(scv) = sc;
+        bind_scene(scv);
+    }
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;

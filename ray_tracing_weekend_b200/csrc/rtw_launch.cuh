@@ -138,13 +138,13 @@ cudaError_t launch_render_pool_sh(RenderParams<float> P, PoolParams Q, size_t sm
     return cudaGetLastError();
 }
 
-inline cudaError_t pool_clear(const RenderParams<float>& P, const PoolParams& Q, cudaStream_t s) {
+template <class PARAMS> inline cudaError_t pool_clear(const PARAMS& P, const PoolParams& Q, cudaStream_t s) {
     uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
     cudaError_t e = cudaMemsetAsync(Q.accum, 0, (size_t)n_slots * 3 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     return cudaMemsetAsync(Q.poison, 0, (size_t)n_slots * sizeof(uint32_t), s);
 }
-inline cudaError_t pool_finalize(const RenderParams<float>& P, const PoolParams& Q, cudaStream_t s) {
+template <class PARAMS> inline cudaError_t pool_finalize(const PARAMS& P, const PoolParams& Q, cudaStream_t s) {
     uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
     pool_finalize_kernel<0><<<(n_slots + 255) / 256, 256, 0, s>>>(Q.accum, Q.poison, P.tiles, n_slots);
     return cudaGetLastError();
@@ -157,6 +157,23 @@ cudaError_t launch_render_pool_impl(RenderParams<float> P, PoolParams Q, int sm_
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
     e = sh ? launch_render_pool_sh<COUNT, true>(P, Q, smem, sm_count, s, info) : launch_render_pool_sh<COUNT, false>(P, Q, smem, sm_count, s, info);
+    if (e != cudaSuccess) return e;
+    return pool_finalize(P, Q, s);
+}
+
+// general scenes, FP32: the pooled path stream (fixed-point accumulation: the image does not depend on scheduling)
+template <bool COUNT>
+cudaError_t launch_render_pool_general_impl(RenderParams<float, SceneViewG<float>> P, PoolParams Q, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    if (P.stack_depth == 0 || P.stack_depth > (uint32_t)kStackDepth) P.stack_depth = kStackDepth;
+    size_t smem = sizeof(int32_t) * P.stack_depth * kRenderBlock;
+    cudaError_t e = pool_clear(P, Q, s);
+    if (e != cudaSuccess) return e;
+    auto kernel = render_pool_kernel<COUNT, kRenderBlock, false, SceneViewG<float>>;
+    int grid = 0;
+    e = persistent_grid(kernel, kRenderBlock, smem, sm_count, &grid, info);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kRenderBlock, smem, s>>>(P, Q);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return pool_finalize(P, Q, s);
 }

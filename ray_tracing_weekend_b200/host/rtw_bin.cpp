@@ -1,5 +1,5 @@
 // rtw_bin.cpp — the reference's `bin` (bin/src/main.rs:54-105) with the CUDA backend behind
-// Camera::render:   rtw_bin simple [--backend cuda] [--width W --height H --spp S --depth D]
+// Camera::render:   rtw_bin <simple|simple-light|cornell-box|debug|simple-transform> [--backend cuda] [--width W --height H --spp S --depth D]
 //                           [--seed N] [--precision f32|f64] [--tmin X] [--out image.ppm]
 // Config.toml parsing is replaced by flags (defaults = the reference's Config.toml:7-11).
 // Writes ASCII P3 with rows reversed exactly like main.rs:89-104.
@@ -32,15 +32,30 @@ int main(int argc, char** argv) {
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (backend != "cuda") { std::fprintf(stderr, "this binary only carries the CUDA backend (--backend cuda); the CPU renderer is the reference's own\n"); return 2; }
-    if (scene != "simple") { std::fprintf(stderr, "scene '%s' is outside the CUDA backend's scope (spheres + plane + lambertian/metal/dielectric): use simple\n", scene.c_str()); return 2; }
     try {
-        scenes::Output sc = scenes::simple(opt.seed);
+        scenes::Output simple_sc;
+        scenes::GeneralOutput general_sc;
+        bool general = true;
+        CameraBuilder cb;
+        if (scene == "simple") { simple_sc = scenes::simple(opt.seed); cb = simple_sc.cam; general = false; }
+        else if (scene == "simple-light" || scene == "simple_light") general_sc = scenes::simple_light(opt.seed);
+        else if (scene == "cornell-box" || scene == "cornell_box") general_sc = scenes::cornell_box();
+        else if (scene == "debug") general_sc = scenes::debugging_scene(opt.seed);
+        else if (scene == "simple-transform" || scene == "simple_transform") general_sc = scenes::simple_transform(opt.seed);
+        else {
+            // perlin-spheres, checkered-spheres and plane pair Lambertian surfaces with an EMPTY lights list: the reference panics
+            // on the first light sample (hittable_list.rs:414-419)
+            std::fprintf(stderr, "scene '%s' is not provided (simple, simple-light, cornell-box, debug, simple-transform)\n", scene.c_str());
+            return 2;
+        }
+        if (general) cb = general_sc.cam;
         // main.rs:72-79
-        Camera cam = sc.cam.with_vfov(40.).with_aspect_ratio((double)width / (double)height).with_max_depth(depth)
+        Camera cam = cb.with_vfov(40.).with_aspect_ratio((double)width / (double)height).with_max_depth(depth)
                          .with_image_width(width).with_image_height(height).with_samples_per_pixel((uint16_t)spp).build();
         rtw_stats st{};
         auto t0 = std::chrono::steady_clock::now();
-        auto img = cam.render(sc.world, sc.lights, opt, &st);
+        auto img = general ? cam.render(general_sc.world_ref(), general_sc.lights_ref(), opt, &st)
+                           : cam.render(simple_sc.world, simple_sc.lights, opt, &st);
         double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::fprintf(stderr, "rendered %ux%u spp %u in %.3f s (kernel %.3f ms): %.1f Mpaths/s, %.1f Mrays/s\n", width, height, spp, sec,
                      st.kernel_ms, st.paths / st.kernel_ms * 1e-3, st.rays / st.kernel_ms * 1e-3);

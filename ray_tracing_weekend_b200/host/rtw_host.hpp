@@ -12,6 +12,13 @@
 //   hittable_collections::bvh::BoundedVolumeHierarchy  rtw_host::BoundedVolumeHierarchy::from(list)
 //   shared::camera::{CameraBuilder, Camera}            rtw_host::CameraBuilder (with_*, build), Camera::render
 //   scenes::simple                                     rtw_host::scenes::simple(seed)   (seeded: the reference's is not)
+//   shared::entities::{Quad, Triangle, Cuboid}         rtw_host::Quad / Triangle / Cuboid
+//   geometry::transformations::{Transformation,        rtw_host::Transformation, rotation(), Translation3, entity.transform(t)
+//     Transformed<T>, rotation}, vec3::Translation3       -> Transformed<T>
+//   shared::material::{DiffuseLight, Isotropic}        rtw_host::DiffuseLight / Isotropic
+//   shared::texture::NoiseTexture                      rtw_host::NoiseTexture (Perlin tables seeded)
+//   scenes::{simple_light, cornell_box,                rtw_host::scenes::{simple_light, cornell_box, debugging_scene, simple_transform}
+//     debugging_scene, simple_transform}
 //
 // Where the reference panics (unwrap / expect), this layer throws std::runtime_error.
 #pragma once
@@ -22,6 +29,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rtw.h"
@@ -50,37 +58,115 @@ struct SampledColour {
     std::string to_string() const { return std::to_string(rgb[0]) + " " + std::to_string(rgb[1]) + " " + std::to_string(rgb[2]); }
 };
 
+// ---- textures (shared/src/texture.rs) ------------------------------------------------------------------
+struct NoiseTexture {                               // texture.rs:57-102; Perlin tables from Philox stream (seed; 0x9E71A000 + index)
+    double scale = 1.; uint64_t seed = 20261018; uint32_t index = 0;
+    static std::shared_ptr<const NoiseTexture> new_(double scale, uint64_t seed = 20261018, uint32_t index = 0) {
+        auto t = std::make_shared<NoiseTexture>(); t->scale = scale; t->seed = seed; t->index = index; return t;
+    }
+};
+using TexturePtr = std::shared_ptr<const NoiseTexture>;
+
 // ---- materials (shared/src/material.rs) -----------------------------------------------------------
-struct Material { rtw_material pod{}; };
+struct Material { rtw_material pod{}; TexturePtr texture; };       // texture == nullptr: SolidColour(pod.r, pod.g, pod.b)
 using MaterialPtr = std::shared_ptr<const Material>;
-inline MaterialPtr make_material(uint32_t kind, Colour c, double param) {
+inline MaterialPtr make_material(uint32_t kind, Colour c, double param, TexturePtr tex = nullptr) {
     auto m = std::make_shared<Material>();
-    m->pod.kind = kind; m->pod.r = c.v.x; m->pod.g = c.v.y; m->pod.b = c.v.z; m->pod.param = param;
+    m->pod.kind = kind; m->pod.r = c.v.x; m->pod.g = c.v.y; m->pod.b = c.v.z; m->pod.param = param; m->texture = std::move(tex);
     return m;
 }
-struct Lambertian { static MaterialPtr new_with_colour(Colour c) { return make_material(RTW_LAMBERTIAN, c, 0.); } };   // material.rs:345-355
+struct Lambertian {                                                                                                     // material.rs:331-355
+    static MaterialPtr new_with_colour(Colour c) { return make_material(RTW_LAMBERTIAN, c, 0.); }
+    static MaterialPtr new_(TexturePtr t) { return make_material(RTW_LAMBERTIAN, Colour(), 0., std::move(t)); }
+};
 struct Metal { static MaterialPtr new_(Colour albedo, double fuzz) { return make_material(RTW_METAL, albedo, fuzz); } }; // material.rs:401-405
 struct Dialectric { static MaterialPtr new_(double ior) { return make_material(RTW_DIELECTRIC, Colour(1., 1., 1.), ior); } }; // material.rs:443-448
+struct DiffuseLight {                                                                                                   // material.rs:498-504
+    static MaterialPtr new_with_colour(Colour c) { return make_material(RTW_DIFFUSE_LIGHT, c, 0.); }
+    static MaterialPtr new_(TexturePtr t) { return make_material(RTW_DIFFUSE_LIGHT, Colour(), 0., std::move(t)); }
+};
+struct Isotropic {                                                                                                      // material.rs:521-527
+    static MaterialPtr new_with_colour(Colour c) { return make_material(RTW_ISOTROPIC, c, 0.); }
+    static MaterialPtr new_(TexturePtr t) { return make_material(RTW_ISOTROPIC, Colour(), 0., std::move(t)); }
+};
 inline MaterialPtr invisible() { static MaterialPtr p = make_material(RTW_INVISIBLE, Colour(0., 0., 0.), 0.); return p; }  // material.rs:319-322
 
+// ---- transformations (geometry/src/transformations.rs, the default non-euclid build) --------------------
+enum class Axis : int { X = 0, Y = 1, Z = 2 };
+struct Transformation {                             // :96-136; arithmetic in the library so every host language agrees bit for bit
+    rtw_transform pod{{1., 0., 0., 0., 1., 0., 0., 0., 1.}, {0., 0., 0.}};
+    Transformation then(const Transformation& t) const { Transformation o; rtw_transform_then(&pod, &t.pod, &o.pod); return o; }
+    std::optional<Transformation> inverse() const { Transformation o; if (!rtw_transform_inverse(&pod, &o.pod)) return std::nullopt; return o; }
+};
+inline Transformation Translation3(double x, double y, double z) { Transformation t; t.pod.translation[0] = x; t.pod.translation[1] = y; t.pod.translation[2] = z; return t; }
+inline Transformation rotation(double angle_degrees, Axis axis) { Transformation t; rtw_rotation(angle_degrees, (int)axis, &t.pod); return t; }
+
+template <class T> struct Transformed {             // :168-222
+    T instance; Transformation transformation;
+    Transformed transform(const Transformation& t) const { return Transformed{instance, transformation.then(t)}; }
+};
+template <class Self> struct Transformable {        // Transformable::transform, :193-222
+    Transformed<Self> transform(const Transformation& t) const { return Transformed<Self>{static_cast<const Self&>(*this), Transformation().then(t)}; }
+};
+
 // ---- entities --------------------------------------------------------------------------------------
-struct Sphere { Point3 center; double radius; MaterialPtr mat;                       // entities/sphere.rs:25-47
-    static Sphere new_(Point3 c, double r, MaterialPtr m) { return Sphere{c, r, std::move(m)}; } };
+struct Sphere : Transformable<Sphere> { Point3 center; double radius = 0.; MaterialPtr mat;      // entities/sphere.rs:25-47
+    static Sphere new_(Point3 c, double r, MaterialPtr m) { Sphere s; s.center = c; s.radius = r; s.mat = std::move(m); return s; } };
 struct Plane { Point3 point; Vec3 normal; MaterialPtr mat;                           // entities/plane.rs:21-39
     static Plane new_(Point3 p, Vec3 n, MaterialPtr m) { return Plane{p, n, std::move(m)}; } };
+struct Quad : Transformable<Quad> { Point3 q; Vec3 u, v; MaterialPtr mat;            // entities/quadrilateral.rs:23-56
+    static Quad new_(Point3 q, Vec3 u, Vec3 v, MaterialPtr m) { Quad s; s.q = q; s.u = u; s.v = v; s.mat = std::move(m); return s; } };
+struct Triangle : Transformable<Triangle> { Point3 q; Vec3 u, v; MaterialPtr mat;    // entities/triangles.rs:23-54
+    static Triangle new_(Point3 q, Vec3 u, Vec3 v, MaterialPtr m) { Triangle s; s.q = q; s.u = u; s.v = v; s.mat = std::move(m); return s; } };
+struct Cuboid : Transformable<Cuboid> { Point3 p, q; MaterialPtr mat;                // entities/cuboid.rs:21-50
+    static Cuboid new_(Point3 p, Point3 q, MaterialPtr m) { Cuboid s; s.p = p; s.q = q; s.mat = std::move(m); return s; } };
 
-// hittable_collections/hittable_list.rs:247-294 — objects keep insertion order per type
+// One HittableList entry in insertion order (what rtw_prim + the entity arrays of rtw_scene_desc are filled from).
+struct Entry {
+    uint32_t kind = RTW_PRIM_SPHERE;
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, c[3] = {0, 0, 0}; double r = 0.;     // sphere: a = centre, r; plane: a = point, b = normal;
+    MaterialPtr mat;                                                                 // quad / triangle: a = q, b = u, c = v; cuboid: a = p, b = q
+    std::optional<Transformation> transform;
+};
+
+// hittable_collections/hittable_list.rs:247-294
 class HittableList {
 public:
-    void add(const Sphere& s) { spheres_.push_back(s); }
-    void add(const Plane& p) { planes_.push_back(p); }
-    size_t len() const { return spheres_.size() + planes_.size(); }
+    void add(const Sphere& s) { spheres_.push_back(s); push(RTW_PRIM_SPHERE, s.center, Vec3(), Vec3(), s.radius, s.mat, std::nullopt); }
+    void add(const Plane& p) { planes_.push_back(p); push(RTW_PRIM_PLANE, p.point, p.normal, Vec3(), 0., p.mat, std::nullopt); }
+    void add(const Quad& q) { push(RTW_PRIM_QUAD, q.q, q.u, q.v, 0., q.mat, std::nullopt); }
+    void add(const Triangle& q) { push(RTW_PRIM_TRIANGLE, q.q, q.u, q.v, 0., q.mat, std::nullopt); }
+    void add(const Cuboid& c) { push(RTW_PRIM_CUBOID, c.p, c.q, Vec3(), 0., c.mat, std::nullopt); }
+    void add(const Transformed<Sphere>& t) { push(RTW_PRIM_SPHERE, t.instance.center, Vec3(), Vec3(), t.instance.radius, t.instance.mat, t.transformation); }
+    void add(const Transformed<Quad>& t) { push(RTW_PRIM_QUAD, t.instance.q, t.instance.u, t.instance.v, 0., t.instance.mat, t.transformation); }
+    void add(const Transformed<Triangle>& t) { push(RTW_PRIM_TRIANGLE, t.instance.q, t.instance.u, t.instance.v, 0., t.instance.mat, t.transformation); }
+    void add(const Transformed<Cuboid>& t) { push(RTW_PRIM_CUBOID, t.instance.p, t.instance.q, Vec3(), 0., t.instance.mat, t.transformation); }
+    size_t len() const { return entries_.size(); }
     bool is_empty() const { return len() == 0; }
     const std::vector<Sphere>& spheres() const { return spheres_; }
     const std::vector<Plane>& planes() const { return planes_; }
+    const std::vector<Entry>& entries() const { return entries_; }
+    // spheres + planes through the origin with SolidColour Lambertian / Metal / Dialectric / Invisible: the fast sphere path
+    bool is_simple() const {
+        for (const Entry& e : entries_) {
+            if (e.kind > RTW_PRIM_PLANE || e.transform || !e.mat || e.mat->pod.kind > RTW_INVISIBLE || e.mat->texture) return false;
+            if (e.kind == RTW_PRIM_PLANE) {
+                double len = std::sqrt(e.b[0] * e.b[0] + e.b[1] * e.b[1] + e.b[2] * e.b[2]);
+                for (int k = 0; k < 3; ++k)
+                    if (std::fabs(e.b[(k + 1) % 3] / len) < 2.220446049250313e-16 && std::fabs(e.b[(k + 2) % 3] / len) < 2.220446049250313e-16 && e.a[k] != 0.) return false;
+            }
+        }
+        return true;
+    }
 private:
+    void push(uint32_t kind, Vec3 a, Vec3 b, Vec3 c, double r, MaterialPtr m, std::optional<Transformation> t) {
+        Entry e; e.kind = kind; e.a[0] = a.x; e.a[1] = a.y; e.a[2] = a.z; e.b[0] = b.x; e.b[1] = b.y; e.b[2] = b.z; e.c[0] = c.x; e.c[1] = c.y; e.c[2] = c.z;
+        e.r = r; e.mat = std::move(m); e.transform = std::move(t);
+        entries_.push_back(std::move(e));
+    }
     std::vector<Sphere> spheres_;
     std::vector<Plane> planes_;
+    std::vector<Entry> entries_;
 };
 
 // hittable_collections/bvh.rs:106-143.  The host object only carries the primitives; the device BVH is
@@ -97,8 +183,59 @@ private:
 // What Camera::render receives as `world` / `lights` (&dyn Hittable in the reference, camera.rs:295).
 struct World {
     const HittableList* list;
-    World(const HittableList& l) : list(&l) {}
-    World(const BoundedVolumeHierarchy& b) : list(&b.list()) {}
+    bool is_bvh;
+    World(const HittableList& l) : list(&l), is_bvh(false) {}
+    World(const BoundedVolumeHierarchy& b) : list(&b.list()), is_bvh(true) {}
+};
+
+// rtw_scene_desc + the arrays it points into, built from two lists (same layout rules as the Python mirror)
+struct SceneDescription {
+    std::vector<rtw_sphere> spheres; std::vector<rtw_plane> planes; std::vector<rtw_quad> quads; std::vector<rtw_cuboid> cuboids;
+    std::vector<rtw_transform> transforms; std::vector<rtw_material> materials; std::vector<rtw_texture> textures;
+    std::vector<rtw_perlin> perlins; std::vector<rtw_prim> world, lights;
+    rtw_scene_desc pod{};
+    SceneDescription(World w, World l) {
+        std::vector<const Material*> seen_m; std::vector<const NoiseTexture*> seen_t;
+        auto material_id = [&](const MaterialPtr& m) -> uint32_t {
+            if (!m) throw std::runtime_error("primitive without material");
+            for (size_t i = 0; i < seen_m.size(); ++i) if (seen_m[i] == m.get()) return (uint32_t)i;
+            rtw_material pod = m->pod;
+            pod.texture = 0;
+            if (m->texture) {
+                size_t t = 0;
+                while (t < seen_t.size() && seen_t[t] != m->texture.get()) ++t;
+                if (t == seen_t.size()) {
+                    rtw_perlin pn; rtw_perlin_generate(m->texture->seed, m->texture->index, &pn); perlins.push_back(pn);
+                    rtw_texture tx{}; tx.kind = RTW_TEX_NOISE; tx.perlin = (uint32_t)perlins.size() - 1; tx.scale = m->texture->scale;
+                    textures.push_back(tx); seen_t.push_back(m->texture.get());
+                }
+                pod.texture = (uint32_t)t + 1;
+            }
+            materials.push_back(pod); seen_m.push_back(m.get());
+            return (uint32_t)materials.size() - 1;
+        };
+        auto entry = [&](const Entry& e) {
+            rtw_prim p{}; p.kind = e.kind; p.transform = -1; p.material = material_id(e.mat);
+            if (e.transform) { transforms.push_back(e.transform->pod); p.transform = (int32_t)transforms.size() - 1; }
+            switch (e.kind) {
+                case RTW_PRIM_SPHERE: spheres.push_back({e.a[0], e.a[1], e.a[2], e.r}); p.index = (uint32_t)spheres.size() - 1; break;
+                case RTW_PRIM_PLANE: planes.push_back({e.a[0], e.a[1], e.a[2], e.b[0], e.b[1], e.b[2]}); p.index = (uint32_t)planes.size() - 1; break;
+                case RTW_PRIM_CUBOID: { rtw_cuboid c{{e.a[0], e.a[1], e.a[2]}, {e.b[0], e.b[1], e.b[2]}}; cuboids.push_back(c); p.index = (uint32_t)cuboids.size() - 1; break; }
+                default: { rtw_quad q{{e.a[0], e.a[1], e.a[2]}, {e.b[0], e.b[1], e.b[2]}, {e.c[0], e.c[1], e.c[2]}}; quads.push_back(q); p.index = (uint32_t)quads.size() - 1; }
+            }
+            return p;
+        };
+        for (const Entry& e : w.list->entries()) world.push_back(entry(e));
+        for (const Entry& e : l.list->entries()) lights.push_back(entry(e));
+        pod.spheres = spheres.data(); pod.n_spheres = spheres.size(); pod.planes = planes.data(); pod.n_planes = planes.size();
+        pod.quads = quads.data(); pod.n_quads = quads.size(); pod.cuboids = cuboids.data(); pod.n_cuboids = cuboids.size();
+        pod.transforms = transforms.data(); pod.n_transforms = transforms.size(); pod.materials = materials.data(); pod.n_materials = materials.size();
+        pod.textures = textures.data(); pod.n_textures = textures.size(); pod.perlins = perlins.data(); pod.n_perlins = perlins.size();
+        pod.world = world.data(); pod.n_world = world.size(); pod.lights = lights.data(); pod.n_lights = lights.size();
+        pod.world_is_bvh = w.is_bvh ? 1u : 0u; pod.lights_is_bvh = l.is_bvh ? 1u : 0u;
+    }
+    SceneDescription(const SceneDescription&) = delete;
+    SceneDescription& operator=(const SceneDescription&) = delete;
 };
 
 enum class Precision : uint32_t { F32 = RTW_F32, F64 = RTW_F64 };
@@ -145,21 +282,28 @@ public:
     // Camera::render (camera.rs:295-297): out[j][i], j = 0 is the bottom row.
     std::vector<std::vector<SampledColour>> render(World world, World lights, const RenderOptions& opt = RenderOptions(),
                                                    rtw_stats* stats = nullptr) const {
-        std::vector<rtw_sphere> spheres; std::vector<uint32_t> smat; std::vector<rtw_plane> planes; std::vector<uint32_t> pmat;
-        std::vector<rtw_material> mats; std::vector<rtw_sphere> ls;
-        auto mat_id = [&](const MaterialPtr& m) {
-            if (!m) throw std::runtime_error("primitive without material");
-            mats.push_back(m->pod);
-            return (uint32_t)mats.size() - 1;
-        };
-        for (const Plane& p : world.list->planes()) { planes.push_back({p.point.x, p.point.y, p.point.z, p.normal.x, p.normal.y, p.normal.z}); pmat.push_back(mat_id(p.mat)); }
-        for (const Sphere& s : world.list->spheres()) { spheres.push_back({s.center.x, s.center.y, s.center.z, s.radius}); smat.push_back(mat_id(s.mat)); }
-        if (!lights.list->planes().empty()) throw std::runtime_error("lights: only spheres are supported by the CUDA backend");
-        for (const Sphere& s : lights.list->spheres()) ls.push_back({s.center.x, s.center.y, s.center.z, s.radius});
         rtw_scene* scene = nullptr;
-        int rc = rtw_scene_create(spheres.data(), smat.data(), spheres.size(), planes.data(), pmat.data(), planes.size(), mats.data(),
-                                  mats.size(), ls.data(), ls.size(), &scene);
-        if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_scene_create: ") + rtw_last_error());
+        bool simple = world.list->is_simple() && !lights.is_bvh && lights.list->spheres().size() == lights.list->len();
+        if (simple) {
+            std::vector<rtw_sphere> spheres; std::vector<uint32_t> smat; std::vector<rtw_plane> planes; std::vector<uint32_t> pmat;
+            std::vector<rtw_material> mats; std::vector<rtw_sphere> ls;
+            auto mat_id = [&](const MaterialPtr& m) {
+                if (!m) throw std::runtime_error("primitive without material");
+                mats.push_back(m->pod);
+                return (uint32_t)mats.size() - 1;
+            };
+            for (const Plane& p : world.list->planes()) { planes.push_back({p.point.x, p.point.y, p.point.z, p.normal.x, p.normal.y, p.normal.z}); pmat.push_back(mat_id(p.mat)); }
+            for (const Sphere& s : world.list->spheres()) { spheres.push_back({s.center.x, s.center.y, s.center.z, s.radius}); smat.push_back(mat_id(s.mat)); }
+            for (const Sphere& s : lights.list->spheres()) ls.push_back({s.center.x, s.center.y, s.center.z, s.radius});
+            int rc = rtw_scene_create(spheres.data(), smat.data(), spheres.size(), planes.data(), pmat.data(), planes.size(), mats.data(),
+                                      mats.size(), ls.data(), ls.size(), &scene);
+            if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_scene_create: ") + rtw_last_error());
+        } else {
+            SceneDescription d(world, lights);
+            int rc = rtw_scene_create_general(&d.pod, &scene);
+            if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_scene_create_general: ") + rtw_last_error());
+        }
+        int rc;
         rtw_opts o{}; o.seed = opt.seed; o.tmin = opt.tmin; o.precision = (uint32_t)opt.precision; o.mode = opt.mode; o.flags = opt.flags;
         size_t npx = (size_t)c_.image_width * c_.image_height;
         std::vector<double> sum(npx * 3); std::vector<uint8_t> q(npx * 3);
@@ -211,6 +355,18 @@ private:
 };
 
 struct Output { BoundedVolumeHierarchy world; HittableList lights; CameraBuilder cam; };
+// the general scenes return either plain lists or BoundedVolumeHierarchy wrappers, like the reference's generators
+struct GeneralOutput {
+    HittableList world, lights; bool world_is_bvh = false, lights_is_bvh = false; CameraBuilder cam;
+    BoundedVolumeHierarchy world_bvh, lights_bvh;
+    World world_ref() const { return world_is_bvh ? World(world_bvh) : World(world); }
+    World lights_ref() const { return lights_is_bvh ? World(lights_bvh) : World(lights); }
+    void wrap(bool w, bool l) {
+        world_is_bvh = w; lights_is_bvh = l;
+        if (w) world_bvh = BoundedVolumeHierarchy::from(world);
+        if (l) lights_bvh = BoundedVolumeHierarchy::from(lights);
+    }
+};
 
 // scenes::simple (scenes/src/lib.rs:155-233) with an explicit seed, generalised by the grid half-size n,
 // the material thresholds and the ground variant so the BASELINE stress configs share the recipe.
@@ -260,6 +416,83 @@ inline Output simple(uint64_t seed, int n = 11, double p_lambertian = 0.8, doubl
     CameraBuilder cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_focus_dist((lookfrom - lookat).length())
                             .with_vfov(40.).with_background(Colour(1., 1., 1.));
     return Output{BoundedVolumeHierarchy::from(std::move(world)), std::move(lights), cam};
+}
+
+// scenes::simple_light (scenes/src/lib.rs:235-290)
+inline GeneralOutput simple_light(uint64_t seed) {
+    GeneralOutput o;
+    MaterialPtr pertext = Lambertian::new_(NoiseTexture::new_(4., seed));
+    MaterialPtr difflight = DiffuseLight::new_with_colour(Colour(4., 4., 4.));
+    o.world.add(Plane::new_(Point3(0., 0., 0.), Vec3(0., 1., 0.), pertext));
+    o.world.add(Sphere::new_(Point3(0., 2., 0.), 2., pertext));
+    o.world.add(Quad::new_(Point3(3., 1., -2.), Vec3(2., 0., 0.), Vec3(0., 2., 0.), difflight));
+    o.lights.add(Quad::new_(Point3(3., 1., -2.), Vec3(2., 0., 0.), Vec3(0., 2., 0.), difflight));
+    Point3 lookfrom(26., 3., 6.), lookat(0., 2., 0.);
+    o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_focus_dist((lookfrom - lookat).length()).with_vfov(40.);
+    return o;
+}
+
+// scenes::cornell_box (scenes/src/lib.rs:292-380)
+inline GeneralOutput cornell_box() {
+    GeneralOutput o;
+    MaterialPtr red = Lambertian::new_with_colour(Colour(0.65, 0.05, 0.05)), white = Lambertian::new_with_colour(Colour(0.73, 0.73, 0.73)),
+                green = Lambertian::new_with_colour(Colour(0.12, 0.45, 0.15)), light = DiffuseLight::new_with_colour(Colour(15., 15., 15.)),
+                glass = Dialectric::new_(1.5);
+    o.world.add(Quad::new_(Point3(555., 0., 0.), Vec3(0., 555., 0.), Vec3(0., 0., 555.), green));
+    o.world.add(Quad::new_(Point3(0., 0., 0.), Vec3(0., 555., 0.), Vec3(0., 0., 555.), red));
+    o.world.add(Quad::new_(Point3(0., 0., 0.), Vec3(555., 0., 0.), Vec3(0., 0., 555.), white));
+    o.world.add(Quad::new_(Point3(0., 555., 0.), Vec3(555., 0., 0.), Vec3(0., 0., 555.), white));
+    o.world.add(Quad::new_(Point3(0., 0., 555.), Vec3(0., 555., 0.), Vec3(555., 0., 0.), white));
+    o.world.add(Cuboid::new_(Point3(), Point3(165., 330., 165.), white).transform(Translation3(265., 0., 295.)).transform(rotation(15., Axis::Y)));
+    o.world.add(Sphere::new_(Point3(190., 90., 190.), 90., glass));
+    o.world.add(Quad::new_(Point3(343., 554., 332.), Vec3(-130., 0., 0.), Vec3(0., 0., -105.), light));
+    o.lights.add(Quad::new_(Point3(343., 554., 332.), Vec3(-130., 0., 0.), Vec3(0., 0., -105.), light));
+    o.lights.add(Sphere::new_(Point3(190., 90., 190.), 90., glass));
+    Point3 lookfrom(277.5, 277.5, -800.), lookat(277.5, 277.5, 0.);
+    o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_vfov(40.).with_defocus_angle(0.).with_focus_dist((lookfrom - lookat).length());
+    return o;
+}
+
+inline void corner_walls(HittableList& world, const MaterialPtr& white) {       // the eight quads of lib.rs:403-448 / 527-572
+    const double c[8][9] = {{6, 0, 6, 0, 2, 0, -2, 0, 0}, {6, 0, 6, 0, 2, 0, 0, 0, -2}, {-6, 0, 6, 0, 2, 0, 2, 0, 0}, {-6, 0, 6, 0, 2, 0, 0, 0, -2},
+                            {-6, 0, -6, 0, 2, 0, 2, 0, 0}, {-6, 0, -6, 0, 2, 0, 0, 0, 2}, {6, 0, -6, 0, 2, 0, -2, 0, 0}, {6, 0, -6, 0, 2, 0, 0, 0, 2}};
+    for (const auto& k : c) world.add(Quad::new_(Point3(k[0], k[1], k[2]), Vec3(k[3], k[4], k[5]), Vec3(k[6], k[7], k[8]), white));
+}
+inline CameraBuilder debug_camera() {
+    return CameraBuilder().with_image_width(3).with_image_height(2).with_samples_per_pixel(10).with_max_depth(5)
+        .with_lookfrom(Point3(0., 20., 0.)).with_lookat(Point3(0., 0., 0.)).with_focus_dist(4.);
+}
+
+// scenes::debugging_scene (scenes/src/lib.rs:382-505)
+inline GeneralOutput debugging_scene(uint64_t seed) {
+    GeneralOutput o;
+    MaterialPtr pertext = Lambertian::new_(NoiseTexture::new_(4., seed));
+    o.world.add(Plane::new_(Point3(0., 0., 0.), Vec3(0., 1., 0.), pertext));
+    o.world.add(Sphere::new_(Point3(0., 2., 0.), 2., pertext));
+    corner_walls(o.world, Lambertian::new_with_colour(Colour(0.75, 0.75, 0.75)));
+    const double g[4][6] = {{5, 1, 5, 0.5, 0, 0.5}, {-5, 1, 5, 1, 0, 0}, {-5, 1, -5, 0, 1, 0}, {5, 1, -5, 0, 0, 1}};
+    std::vector<Sphere> glow;
+    for (const auto& k : g) glow.push_back(Sphere::new_(Point3(k[0], k[1], k[2]), 1., DiffuseLight::new_with_colour(Colour(k[3], k[4], k[5]))));
+    for (const Sphere& s : glow) o.world.add(s);
+    for (const Sphere& s : glow) o.lights.add(s);
+    o.cam = debug_camera();
+    o.wrap(true, true);
+    return o;
+}
+
+// scenes::simple_transform (scenes/src/lib.rs:507-653)
+inline GeneralOutput simple_transform(uint64_t seed) {
+    GeneralOutput o;
+    o.world.add(Plane::new_(Point3(0., 0., 0.), Vec3(0., 1., 0.), Lambertian::new_(NoiseTexture::new_(4., seed))));
+    corner_walls(o.world, Lambertian::new_with_colour(Colour(0.75, 0.75, 0.75)));
+    Cuboid original = Cuboid::new_(Point3(), Point3(1., 1., 1.), DiffuseLight::new_with_colour(Colour(1., 0., 0.)));
+    Transformed<Cuboid> cubes[3] = {original.transform(Translation3(-0.5, 0., -0.5)), original.transform(Translation3(2., 0., 2.)),
+                                    original.transform(Translation3(-3., 0., -3.)).transform(rotation(45., Axis::Y))};
+    for (const auto& c : cubes) o.world.add(c);
+    for (const auto& c : cubes) o.lights.add(c);
+    o.cam = debug_camera();
+    o.wrap(true, true);
+    return o;
 }
 
 }  // namespace scenes

@@ -10,7 +10,7 @@ pub mod philox;
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
 
-#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwMaterial { pub kind: u32, pub reserved: u32, pub r: f64, pub g: f64, pub b: f64, pub param: f64 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwMaterial { pub kind: u32, pub texture: u32, pub r: f64, pub g: f64, pub b: f64, pub param: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwSphere { pub cx: f64, pub cy: f64, pub cz: f64, pub r: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwPlane { pub px: f64, pub py: f64, pub pz: f64, pub nx: f64, pub ny: f64, pub nz: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -31,6 +31,34 @@ pub const RTW_F32: u32 = 0; pub const RTW_F64: u32 = 1;
 pub const RTW_MEGAKERNEL: u32 = 0; pub const RTW_WAVEFRONT: u32 = 1;
 pub const RTW_TMIN_REFERENCE: f64 = -1.0;
 pub const RTW_LAMBERTIAN: u32 = 0; pub const RTW_METAL: u32 = 1; pub const RTW_DIELECTRIC: u32 = 2; pub const RTW_INVISIBLE: u32 = 3;
+pub const RTW_DIFFUSE_LIGHT: u32 = 4; pub const RTW_ISOTROPIC: u32 = 5;
+
+// ---- general scenes (ABI version 2): Quad, Triangle, Cuboid, Transformed<T>, NoiseTexture -----------------------
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwQuad { pub q: [f64; 3], pub u: [f64; 3], pub v: [f64; 3] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwCuboid { pub p: [f64; 3], pub q: [f64; 3] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct RtwTransform { pub rotation: [f64; 9], pub translation: [f64; 3] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwPrim { pub kind: u32, pub index: u32, pub material: u32, pub transform: i32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwTexture { pub kind: u32, pub perlin: u32, pub scale: f64, pub reserved: [f64; 3] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct RtwPerlin { pub rand_vec: [[f64; 3]; 256], pub perm_x: [u8; 256], pub perm_y: [u8; 256], pub perm_z: [u8; 256] }
+pub const RTW_PRIM_SPHERE: u32 = 0; pub const RTW_PRIM_PLANE: u32 = 1; pub const RTW_PRIM_QUAD: u32 = 2; pub const RTW_PRIM_TRIANGLE: u32 = 3;
+pub const RTW_PRIM_CUBOID: u32 = 4; pub const RTW_TEX_NOISE: u32 = 1;
+#[repr(C)]
+pub struct RtwSceneDesc {
+    pub spheres: *const RtwSphere, pub n_spheres: u64, pub planes: *const RtwPlane, pub n_planes: u64,
+    pub quads: *const RtwQuad, pub n_quads: u64, pub cuboids: *const RtwCuboid, pub n_cuboids: u64,
+    pub transforms: *const RtwTransform, pub n_transforms: u64, pub materials: *const RtwMaterial, pub n_materials: u64,
+    pub textures: *const RtwTexture, pub n_textures: u64, pub perlins: *const RtwPerlin, pub n_perlins: u64,
+    pub world: *const RtwPrim, pub n_world: u64, pub lights: *const RtwPrim, pub n_lights: u64,
+    pub world_is_bvh: u32, pub lights_is_bvh: u32,
+}
+#[link(name = "rtw_cuda")]
+unsafe extern "C" {
+    pub fn rtw_scene_create_general(desc: *const RtwSceneDesc, out: *mut *mut c_void) -> c_int;
+    pub fn rtw_transform_then(a: *const RtwTransform, b: *const RtwTransform, out: *mut RtwTransform);
+    pub fn rtw_transform_inverse(a: *const RtwTransform, out: *mut RtwTransform) -> c_int;
+    pub fn rtw_rotation(angle_degrees: f64, axis: c_int, out: *mut RtwTransform);
+    pub fn rtw_perlin_generate(seed: u64, index: u32, out: *mut RtwPerlin);
+}
 
 #[link(name = "rtw_cuda")]
 unsafe extern "C" {

@@ -201,6 +201,15 @@ RTW_API int  rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_
  * precisions; `mode` is ignored).  Primitive ids reported by the batch calls are indices into desc->world.
  * Transformed planes are RTW_E_UNSUPPORTED (their reference AABB is non-finite). */
 RTW_API int  rtw_scene_create_general(const rtw_scene_desc* desc, rtw_scene** out);
+/* Which builder makes the world BVH of the scenes created AFTER this call (process-wide).  The result of Hittable::hit does not
+ * depend on the tree, so images are bit-identical either way; the builders trade build time against traversal cost.
+ *   RTW_BVH_HOST_SAH:    binned SAH on one host thread (best trees; 1.0 s for 1 M spheres)
+ *   RTW_BVH_DEVICE_LBVH: Morton codes + radix sort + Karras' radix tree + bottom-up fit, all on the GPU (rtw_scene_create only)
+ *   RTW_BVH_AUTO:        device LBVH from 200 000 spheres, host SAH below (default)
+ * A device-built tree deeper than the traversal stack allows (30 levels) silently falls back to the host builder. */
+enum { RTW_BVH_AUTO = 0, RTW_BVH_HOST_SAH = 1, RTW_BVH_DEVICE_LBVH = 2 };
+RTW_API int  rtw_set_bvh_builder(int mode);
+RTW_API int  rtw_scene_bvh_builder(const rtw_scene* scene);   /* RTW_BVH_HOST_SAH or RTW_BVH_DEVICE_LBVH: the builder that made this scene's tree */
 RTW_API void rtw_scene_destroy(rtw_scene* scene);
 /* nodes, leaves, depth, max leaf size, bytes resident on the device */
 RTW_API int  rtw_scene_info(const rtw_scene* scene, uint64_t out[5]);

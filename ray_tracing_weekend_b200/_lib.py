@@ -14,6 +14,7 @@ RTW_OK, RTW_E_INVALID, RTW_E_CUDA, RTW_E_NO_DEVICE, RTW_E_UNSUPPORTED, RTW_E_NOM
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC, RTW_INVISIBLE, RTW_DIFFUSE_LIGHT, RTW_ISOTROPIC = 0, 1, 2, 3, 4, 5
 RTW_PRIM_SPHERE, RTW_PRIM_PLANE, RTW_PRIM_QUAD, RTW_PRIM_TRIANGLE, RTW_PRIM_CUBOID = 0, 1, 2, 3, 4
 RTW_TEX_NOISE = 1
+RTW_BVH_AUTO, RTW_BVH_HOST_SAH, RTW_BVH_DEVICE_LBVH = 0, 1, 2
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
 RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL = 1, 2, 4
@@ -26,7 +27,7 @@ RTW_SYMBOLS = (
     "rtw_abi_version", "rtw_last_error", "rtw_camera_build", "rtw_philox4x32_10", "rtw_tiles_total", "rtw_tiles_per_rank",
     "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
-    "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
+    "rtw_set_bvh_builder", "rtw_scene_bvh_builder", "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
 
@@ -154,6 +155,8 @@ def load(build_if_missing: bool = True):
     L.rtw_get_rays.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
     L.rtw_path_radiance.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
     L.rtw_scene_create_general.argtypes = [vp, vp]
+    L.rtw_set_bvh_builder.argtypes = [C.c_int]
+    L.rtw_scene_bvh_builder.argtypes = [vp]
     L.rtw_transform_then.argtypes = [vp, vp, vp]; L.rtw_transform_then.restype = None
     L.rtw_transform_inverse.argtypes = [vp, vp]; L.rtw_transform_inverse.restype = C.c_int
     L.rtw_rotation.argtypes = [dbl, C.c_int, vp]; L.rtw_rotation.restype = None

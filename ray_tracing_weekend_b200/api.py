@@ -397,7 +397,8 @@ class Scene:
     def info(self):
         out = np.zeros(5, dtype=np.uint64)
         _lib.check(_lib.load().rtw_scene_info(self._h, _p(out)))
-        return dict(nodes=int(out[0]), leaves=int(out[1]), depth=int(out[2]), max_leaf=int(out[3]), device_bytes=int(out[4]))
+        return dict(nodes=int(out[0]), leaves=int(out[1]), depth=int(out[2]), max_leaf=int(out[3]), device_bytes=int(out[4]),
+                    builder={1: "host-sah", 2: "device-lbvh"}.get(int(_lib.load().rtw_scene_bvh_builder(self._h)), "?"))
 
     # Hittable::hit for a batch (hittable.rs:173)
     def trace_batch(self, o, d, tmin=EPSILON, tmax=float("inf"), precision=RTW_F32):
@@ -536,6 +537,11 @@ def philox4x32_10(ctr: Sequence[int], key: Sequence[int]) -> np.ndarray:
     out = np.zeros(4, dtype=np.uint32)
     _lib.load().rtw_philox4x32_10(_p(ctr), _p(key), _p(out))
     return out
+
+
+def set_bvh_builder(mode: int):
+    """rtw_set_bvh_builder: RTW_BVH_AUTO | RTW_BVH_HOST_SAH | RTW_BVH_DEVICE_LBVH for the scenes created afterwards."""
+    _lib.check(_lib.load().rtw_set_bvh_builder(int(mode)))
 
 
 def device_count() -> int:

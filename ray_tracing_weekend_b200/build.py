@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("kernels_f32.cu", ["-fmad=false"]),    # FMAs are explicit (fmaf) so every kernel rounds alike
     ("kernels_f64.cu", ["-fmad=false"]),
+    ("bvh_device.cu", ["-fmad=false"]),     # device-side LBVH construction (CUB radix sort + hand-written tree kernels)
     ("capi.cu", []),
     ("../host/rtw_host_capi.cpp", []),
 ]

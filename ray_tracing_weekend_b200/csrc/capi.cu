@@ -14,6 +14,7 @@
 
 #include "../../include/rtw.h"
 #include "bvh_build.hpp"
+#include "bvh_device.hpp"
 #include "general_host.hpp"
 #include "rtw_launch.hpp"
 
@@ -169,14 +170,16 @@ struct rtw_scene {
     LaunchInfo last_launch;
     uint32_t last_launches = 1;
     uint32_t light_bvh_depth = 0;
+    int bvh_builder = RTW_BVH_HOST_SAH;          // which builder made the world BVH
+    DeviceBvhInfo device_bvh;
 };
 
 namespace {
 
-template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
+template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_device = false) {
     const host::Bvh& b = s->bvh;
-    std::vector<Node<T>> nodes(b.nodes.size());
-    for (size_t i = 0; i < b.nodes.size(); ++i) {
+    std::vector<Node<T>> nodes(world_on_device ? 0 : b.nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
         const host::FlatNode& f = b.nodes[i];
         Node<T> n{};
         fill_node<T>(n, f);
@@ -185,9 +188,10 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
         nodes[i] = n;
     }
     size_t ns = s->spheres.size(), np = s->planes.size();
-    std::vector<Vec4T<T>> sph(ns), mat(ns), lights(s->lights.size());
-    std::vector<uint32_t> info(ns);
-    for (size_t k = 0; k < ns; ++k) {
+    const size_t ns_host = world_on_device ? 0 : ns;       // device-built: nodes and sorted sphere arrays are already in place
+    std::vector<Vec4T<T>> sph(ns_host), mat(ns_host), lights(s->lights.size());
+    std::vector<uint32_t> info(ns_host);
+    for (size_t k = 0; k < ns_host; ++k) {
         uint32_t src = b.order[k];
         const rtw_sphere& q = s->spheres[src];
         const rtw_material& m = s->materials[s->sphere_material[src]];
@@ -234,12 +238,12 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d) {
         p.albedo[0] = (T)m.r; p.albedo[1] = (T)m.g; p.albedo[2] = (T)m.b; p.param = (T)m.param;
         planes[k] = p;
     }
-    CU(d.nodes.upload(nodes)); CU(d.spheres.upload(sph)); CU(d.sphere_mat.upload(mat)); CU(d.info.upload(info));
+    if (!world_on_device) { CU(d.nodes.upload(nodes)); CU(d.spheres.upload(sph)); CU(d.sphere_mat.upload(mat)); CU(d.info.upload(info)); }
     CU(d.lights.upload(lights)); CU(d.planes.upload(planes)); CU(d.light_nodes.upload(light_nodes));
     d.view.nodes = d.nodes.p; d.view.top_nodes = d.nodes.p; d.view.n_top = 0;
     d.view.spheres = d.spheres.p; d.view.sphere_mat = d.sphere_mat.p; d.view.sphere_info = d.info.p;
     d.view.planes = d.planes.p; d.view.lights = d.lights.p;
-    d.view.n_nodes = (int32_t)nodes.size(); d.view.n_spheres = (int32_t)ns; d.view.n_planes = (int32_t)np;
+    d.view.n_nodes = (int32_t)(world_on_device ? s->device_bvh.node_slots : nodes.size()); d.view.n_spheres = (int32_t)ns; d.view.n_planes = (int32_t)np;
     d.view.n_lights = (int32_t)lights.size();
     d.view.light_nodes = d.light_nodes.p; d.view.n_light_nodes = (int32_t)light_nodes.size();
     return RTW_OK;
@@ -387,6 +391,53 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     d.view.flat = flat ? 1u : 0u;
     d.view.has_xforms = 0;
     for (const GPrim<T>& p : prims) if (p.xform >= 0) d.view.has_xforms = 1;
+    return RTW_OK;
+}
+
+// ---- device-side BVH construction (bvh_device.cu) ---------------------------------------------------------------
+int g_bvh_builder = RTW_BVH_AUTO;
+constexpr size_t kDeviceBuildThreshold = 200000;    // RTW_BVH_AUTO: spheres from which the LBVH's build time wins over the SAH tree's quality
+
+// returns RTW_OK with *built = false when the tree came out deeper than the traversal stack allows (caller falls back to the host builder)
+int build_world_on_device(rtw_scene* s, int max_leaf, bool* built) {
+    *built = false;
+    const size_t ns = s->spheres.size(), np = s->planes.size();
+    std::vector<double> mats(4 * ns);
+    std::vector<uint32_t> info(ns);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t k = 0; k < ns; ++k) {
+        const rtw_sphere& q = s->spheres[k];
+        const rtw_material& m = s->materials[s->sphere_material[k]];
+        mats[4 * k] = m.r; mats[4 * k + 1] = m.g; mats[4 * k + 2] = m.b; mats[4 * k + 3] = m.param;
+        info[k] = ((uint32_t)(np + k) << 2) | (m.kind & 3u);
+        const double c[3] = {q.cx, q.cy, q.cz};
+        for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], c[a]); hi[a] = std::fmax(hi[a], c[a]); }
+    }
+    DevBuf<double> d_sph, d_mat; DevBuf<uint32_t> d_info;
+    auto cleanup = [&]() { d_sph.release(); d_mat.release(); d_info.release(); };
+    cudaError_t e = d_sph.reserve(4 * ns);
+    if (e == cudaSuccess) e = cudaMemcpy(d_sph.p, s->spheres.data(), ns * sizeof(rtw_sphere), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = d_mat.upload(mats);
+    if (e == cudaSuccess) e = d_info.upload(info);
+    if (e == cudaSuccess) e = s->f64.nodes.reserve(ns - 1);
+    if (e == cudaSuccess) e = s->f32.nodes.reserve(ns - 1);
+    if (e == cudaSuccess) e = s->f64.spheres.reserve(ns);
+    if (e == cudaSuccess) e = s->f64.sphere_mat.reserve(ns);
+    if (e == cudaSuccess) e = s->f32.spheres.reserve(ns);
+    if (e == cudaSuccess) e = s->f32.sphere_mat.reserve(ns);
+    if (e == cudaSuccess) e = s->f32.info.reserve(ns + 128);       // the staging copy reads the info section in 16-byte units
+    if (e == cudaSuccess) e = s->f64.info.reserve(ns + 128);
+    if (e == cudaSuccess)
+        e = build_lbvh_device(d_sph.p, d_mat.p, d_info.p, ns, lo, hi, max_leaf, s->f64.nodes.p, s->f32.nodes.p, s->f64.spheres.p, s->f64.sphere_mat.p,
+                              s->f32.spheres.p, s->f32.sphere_mat.p, s->f32.info.p, &s->device_bvh, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(s->f64.info.p, s->f32.info.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToDevice);
+    cleanup();
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? RTW_E_NOMEM : RTW_E_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e)); }
+    if (s->device_bvh.depth + 2 > (uint32_t)kStackDepth) return RTW_OK;      // too deep for the traversal stack
+    s->bvh = host::Bvh();
+    s->bvh.depth = s->device_bvh.depth; s->bvh.leaves = s->device_bvh.leaves; s->bvh.max_leaf = (uint32_t)max_leaf;
+    s->bvh_builder = RTW_BVH_DEVICE_LBVH;
+    *built = true;
     return RTW_OK;
 }
 
@@ -605,7 +656,7 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     host::Builder builder;
     int max_leaf = 2;                                     // measured best of 1..8 on `simple` (profiles/README.md); tuning knob for experiments: RTW_BVH_MAX_LEAF=1..8
     if (const char* e = std::getenv("RTW_BVH_MAX_LEAF")) { int v = std::atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }
-    s->bvh = builder.build(reinterpret_cast<const double*>(s->spheres.data()), n_spheres, max_leaf, kMaxTreeDepth);
+    const bool want_device = g_bvh_builder == RTW_BVH_DEVICE_LBVH || (g_bvh_builder == RTW_BVH_AUTO && n_spheres >= kDeviceBuildThreshold);
     auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
@@ -613,12 +664,24 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
-    int rc = upload_scene<float>(s, s->f32);
-    if (rc == RTW_OK) rc = upload_scene<double>(s, s->f64);
+    bool on_device = false;
+    int rc = RTW_OK;
+    if (want_device && n_spheres >= 2) rc = build_world_on_device(s, max_leaf, &on_device);
+    if (rc != RTW_OK) return bail(rc);
+    if (!on_device) s->bvh = builder.build(reinterpret_cast<const double*>(s->spheres.data()), n_spheres, max_leaf, kMaxTreeDepth);
+    rc = upload_scene<float>(s, s->f32, on_device);
+    if (rc == RTW_OK) rc = upload_scene<double>(s, s->f64, on_device);
     if (rc != RTW_OK) return bail(rc);
     *out = s;
     return RTW_OK;
 }
+
+int rtw_set_bvh_builder(int mode) {
+    if (mode != RTW_BVH_AUTO && mode != RTW_BVH_HOST_SAH && mode != RTW_BVH_DEVICE_LBVH) return fail(RTW_E_INVALID, "bvh builder mode");
+    g_bvh_builder = mode;
+    return RTW_OK;
+}
+int rtw_scene_bvh_builder(const rtw_scene* s) { return s ? s->bvh_builder : fail(RTW_E_INVALID, "scene is NULL"); }
 
 void rtw_transform_then(const rtw_transform* a, const rtw_transform* b, rtw_transform* out) { host::transform_then(*a, *b, out); }
 int rtw_transform_inverse(const rtw_transform* a, rtw_transform* out) { return host::transform_inverse(*a, out) ? 1 : 0; }
@@ -712,7 +775,7 @@ void rtw_scene_destroy(rtw_scene* s) {
 
 int rtw_scene_info(const rtw_scene* s, uint64_t out[5]) {
     if (!s || !out) return fail(RTW_E_INVALID, "NULL argument");
-    out[0] = s->bvh.nodes.size(); out[1] = s->bvh.leaves; out[2] = s->bvh.depth; out[3] = s->bvh.max_leaf;
+    out[0] = s->bvh_builder == RTW_BVH_DEVICE_LBVH ? s->device_bvh.inner_nodes : s->bvh.nodes.size(); out[1] = s->bvh.leaves; out[2] = s->bvh.depth; out[3] = s->bvh.max_leaf;
     out[4] = s->f32.bytes() + s->f64.bytes() + s->g32.bytes() + s->g64.bytes();
     return RTW_OK;
 }
@@ -755,8 +818,9 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
         // the wavefront packs the remaining depth into 16 bits; deeper paths take the (bit-identical) megakernel
-        const bool wavefront = o->mode == RTW_WAVEFRONT && cam->max_depth <= 0xffffu;
+        // ... and a tree too deep for the wavefront's shared-memory stacks (a device-built LBVH can be) does too
         const uint32_t bvh_depth = std::max(s->bvh.depth, s->light_bvh_depth);
+        const bool wavefront = o->mode == RTW_WAVEFRONT && cam->max_depth <= 0xffffu && bvh_depth <= wavefront_max_bvh_depth();
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)
                              : launch_render_pool_f32(P, Q, count, sms, str, info);

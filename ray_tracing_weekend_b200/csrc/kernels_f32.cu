@@ -29,11 +29,14 @@ cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size
 }
 template <bool COUNT, int BLOCK, int NP>
 cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    P.stack_depth = std::min<uint32_t>(kStackDepth, bvh_depth + 2);
-    // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene
-    const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
+    // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene.
+    // A walk pushes at most one entry per inner level below the stop code, so `bvh_depth` entries always suffice; two spare
+    // entries are kept unless the tree is so deep that the stacks would not fit next to the path slots.
     const size_t limit = 226 * 1024;                      // 227 KB per CTA minus the static shared memory (mbarrier) and slack
-    if (fixed + 1024 > limit) return cudaErrorInvalidConfiguration;
+    const size_t max_entries = (limit - 1024 - wavefront_state_bytes<BLOCK, NP>()) / (sizeof(int32_t) * BLOCK);
+    P.stack_depth = (uint32_t)std::min<size_t>(std::min<uint32_t>(kStackDepth, bvh_depth + 2), max_entries);
+    if (P.stack_depth < bvh_depth) return cudaErrorInvalidConfiguration;
+    const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
     bool sh = false;
     plan_smem<float, false>(P, BLOCK, &sh, std::min<size_t>(kSmemSceneBudget, (limit - fixed) / 64 * 64));
     size_t scene = P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
@@ -58,6 +61,12 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
     if (shape == 5) return launch_render_wavefront_shape<COUNT, 768, 88>(P, Q, bvh_depth, sm_count, s, info);
 #endif
     return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
+}
+// deepest BVH the default wavefront shape can traverse: its per-thread stacks share the CTA's shared memory with the path slots
+uint32_t wavefront_max_bvh_depth() {
+    const size_t limit = 226 * 1024, state = wavefront_state_bytes<kWfBlock, kWfSlotsPerWarp>();
+    size_t entries = (limit - 1024 - state) / (sizeof(int32_t) * kWfBlock);
+    return (uint32_t)std::min<size_t>(entries, kStackDepth - 2);
 }
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_wavefront_impl<true>(P, Q, bvh_depth, sm_count, s, info)

@@ -24,6 +24,7 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 uint32_t pool_pixels_per_chunk(uint32_t spp);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
+uint32_t wavefront_max_bvh_depth();
 RTW_DECLARE_LAUNCHERS(f64, double)
 
 }  // namespace rtw

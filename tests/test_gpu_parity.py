@@ -422,3 +422,55 @@ def test_cpp_host_mirror_cli_matches_python(rtw, simple_scene, tmp_path):
     assert out.read_text() == ref.read_text()
     lines = out.read_text().splitlines()
     assert lines[:3] == ["P3", f"{w} {h}", "255"] and len(lines) == 3 + w * h
+
+
+def test_device_built_bvh_renders_the_same_image(rtw, oracle, simple_scene):
+    """the world BVH built on the GPU (Morton codes + radix sort + Karras radix tree + bottom-up fit) instead
+    of by the host SAH builder.  Hittable::hit does not depend on the tree: f64 hits are bit-exact against the oracle and the
+    f64 image is bit-identical to the one rendered with the host-built tree."""
+    cam, ocam = _camera(rtw, oracle, simple_scene, 64, 36, 4, 50)
+    o, d = _ray_batch(rtw, oracle, simple_scene, 2000, 2000)
+    prim_o, t_o, _ = simple_scene["oscene"].trace_batch(o, d)
+    host = rtw.Scene(simple_scene["world"], simple_scene["lights"])
+    rtw.set_bvh_builder(rtw.RTW_BVH_DEVICE_LBVH)
+    try:
+        dev = rtw.Scene(simple_scene["world"], simple_scene["lights"])
+    finally:
+        rtw.set_bvh_builder(rtw.RTW_BVH_AUTO)
+    try:
+        ih, idv = host.info(), dev.info()
+        assert ih["builder"] == "host-sah" and idv["builder"] == "device-lbvh"
+        assert idv["leaves"] >= 484 // 2 and 8 <= idv["depth"] <= 30 and idv["nodes"] + 1 == idv["leaves"]
+        prim_g, t_g = dev.trace_batch(o, d, precision=rtw.RTW_F64)
+        assert np.array_equal(prim_o, prim_g) and np.array_equal(t_o, t_g)
+        opts = rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64)
+        a, _, sa = host.render(cam, opts)
+        b, _, sb = dev.render(cam, opts)
+        assert np.array_equal(a, b, equal_nan=True) and sa["rays"] == sb["rays"]
+        # FP32: the renderers read a different (conservative) set of boxes, grazing rays may differ; the image is the same to noise
+        for mode in (rtw.RTW_WAVEFRONT, rtw.RTW_MEGAKERNEL):
+            a32, _, _ = host.render(cam, rtw.RenderOptions(seed=SEED, mode=mode))
+            b32, _, _ = dev.render(cam, rtw.RenderOptions(seed=SEED, mode=mode))
+            same = np.isclose(a32, b32, rtol=1e-6, atol=1e-6, equal_nan=True).all(axis=2)
+            assert same.mean() > 0.995, same.mean()
+    finally:
+        host.close(); dev.close()
+    # a larger scene (6 400 spheres, deeper tree, duplicates in the coarse Morton bits)
+    arrays = rtw.scenes.simple_arrays(SEED, 40)
+    desc = oracle.scene_simple(SEED, 40)
+    osc = oracle.Scene(desc)
+    rtw.set_bvh_builder(rtw.RTW_BVH_DEVICE_LBVH)
+    try:
+        big = rtw.Scene.from_arrays(arrays["spheres"], arrays["sphere_materials"], arrays["planes"], arrays["plane_materials"], arrays["lights"])
+    finally:
+        rtw.set_bvh_builder(rtw.RTW_BVH_AUTO)
+    try:
+        assert big.info()["builder"] == "device-lbvh"
+        rng = np.random.default_rng(4)
+        oo = rng.uniform(-30, 30, (4000, 3)); oo[:, 1] = rng.uniform(0.05, 8, 4000)
+        dd = rng.normal(size=(4000, 3))
+        p_o, tt_o, _ = osc.trace_batch(oo, dd)
+        p_g, tt_g = big.trace_batch(oo, dd, precision=rtw.RTW_F64)
+        assert np.array_equal(p_o, p_g) and np.array_equal(tt_o, tt_g) and (p_o >= 1).sum() > 300
+    finally:
+        big.close()

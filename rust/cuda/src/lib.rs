@@ -58,6 +58,8 @@ unsafe extern "C" {
     pub fn rtw_transform_inverse(a: *const RtwTransform, out: *mut RtwTransform) -> c_int;
     pub fn rtw_rotation(angle_degrees: f64, axis: c_int, out: *mut RtwTransform);
     pub fn rtw_perlin_generate(seed: u64, index: u32, out: *mut RtwPerlin);
+    pub fn rtw_set_bvh_builder(mode: c_int) -> c_int;           // 0 auto, 1 host SAH, 2 device LBVH
+    pub fn rtw_scene_bvh_builder(scene: *const c_void) -> c_int;
 }
 
 #[link(name = "rtw_cuda")]

@@ -44,7 +44,7 @@ for name in which:
     # CPU port of the reference on the host cores, bounded sample: same scene / camera at reduced size
     from oracle import pyoracle as O
     og = O.GScene(sc.desc.pod, sc.desc)
-    ws, hs, ss = w // 8, h // 8, 16
+    ws, hs, ss = w // 2, h // 2, 32             # bounded sample: a quarter of the pixels, 32 spp (seconds of CPU work)
     cams = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(ws).with_image_height(hs).with_samples_per_pixel(ss).build()
     _, sec, cnt, _ = og.render(O.Camera.from_buffer_copy(cams.pod), O.options(seed=SEED))
     print(json.dumps(dict(scene=name, precision="cpu-oracle-f64", cores=O.hardware_threads(), sample=f"{ws}x{hs}, {ss} spp", seconds=round(sec, 3),

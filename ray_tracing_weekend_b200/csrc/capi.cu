@@ -35,7 +35,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                                 \
     } while (0)
 
-constexpr size_t kFlatListLimit = 24;       // general scenes with at most this many bounded entries skip the BVH (linear, kind-sorted walk)
+constexpr size_t kFlatListLimit = 8;        // general scenes with at most this many bounded entries skip the BVH (linear, kind-sorted walk)
 constexpr size_t kLightBvhThreshold = 64;   // more lights than this: BVH over the lights (FP32 path)
 
 // Device allocations are recycled through a small process-wide cache: cudaMalloc / cudaFree of the tens of MB

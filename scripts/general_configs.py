@@ -19,6 +19,8 @@ for name in which:
     world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
     sc = R.Scene(world, lights)
     cam = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).build()
+    if once and os.environ.get("RTW_GENERAL_SMALL"):
+        cam = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w // 2).with_image_height(h // 2).with_samples_per_pixel(64).build()
     if once:
         _, _, st = sc.render(cam, R.RenderOptions(seed=SEED, precision=R.RTW_F32), want_sum=False, want_rgb8=True)
         print(json.dumps(dict(scene=name, kernel_ms=st["kernel_ms"], rays=st["rays"])))

@@ -72,8 +72,12 @@ enum { RTW_PRIM_SPHERE = 0, RTW_PRIM_PLANE = 1, RTW_PRIM_QUAD = 2, RTW_PRIM_TRIA
 /* One entry of a HittableList: entity `index` of the array its kind names (quads[] for QUAD and TRIANGLE), material,
  * and transform = -1 or an index into transforms[] (the entry is then a Transformed<T>). */
 typedef struct { uint32_t kind, index, material; int32_t transform; } rtw_prim;
-enum { RTW_TEX_NOISE = 1 }; /* NoiseTexture{noise: perlins[perlin], scale} (texture.rs:57-102) */
-typedef struct { uint32_t kind, perlin; double scale; double reserved[3]; } rtw_texture;
+enum { RTW_TEX_NOISE = 1,   /* NoiseTexture{noise: perlins[perlin], scale} (texture.rs:57-102) */
+       RTW_TEX_CHECKER = 2 };/* CheckerTexture{inv_scale = 1 / scale, even, odd} (texture.rs:24-55): even / odd are 0 = SolidColour(even_colour /
+                               odd_colour) or k > 0 = textures[k-1], which must be a NoiseTexture.  Reads the hit's (u, v): Quad / Triangle /
+                               Cuboid-face coordinates, Sphere::get_sphere_uv (sphere.rs:49-54), (x, z) on a Plane whose normal is +y
+                               (plane.rs:41-47; other plane orientations are RTW_E_UNSUPPORTED with a checker). */
+typedef struct { uint32_t kind, perlin; double scale; uint32_t even, odd; double even_colour[3], odd_colour[3]; } rtw_texture;
 /* Perlin's tables (perlin.rs:13-19): rand_vec = 256 UnitSphere samples, three permutations of 0..255. */
 typedef struct { double rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; } rtw_perlin;
 /* world / lights of any scene of scenes/src/lib.rs: two HittableLists over shared entity arrays.

@@ -14,7 +14,7 @@ struct orc_gquad { double q[3], u[3], v[3]; };
 struct orc_gcuboid { double p[3], q[3]; };
 struct orc_gtransform { double rotation[9], translation[3]; };
 struct orc_gprim { uint32_t kind, index, material; int32_t transform; };
-struct orc_gtexture { uint32_t kind, perlin; double scale; double reserved[3]; };
+struct orc_gtexture { uint32_t kind, perlin; double scale; uint32_t even, odd; double even_colour[3], odd_colour[3]; };
 struct orc_gperlin { double rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; };
 struct orc_gdesc {
     const double* spheres; uint64_t n_spheres;          // [n][4]
@@ -88,7 +88,10 @@ GScene* orc_gscene_create(const orc_gdesc* d) {
         const orc_gmaterial& m = d->materials[i];
         s->materials.push_back(GMaterial{m.kind, m.texture, {m.r, m.g, m.b}, m.param});
     }
-    for (uint64_t i = 0; i < d->n_textures; ++i) s->textures.push_back(Texture{d->textures[i].kind, d->textures[i].perlin, d->textures[i].scale});
+    for (uint64_t i = 0; i < d->n_textures; ++i) {
+        const orc_gtexture& t = d->textures[i];
+        s->textures.push_back(Texture{t.kind, t.perlin, t.scale, t.even, t.odd, gv3(t.even_colour), gv3(t.odd_colour)});
+    }
     for (uint64_t i = 0; i < d->n_perlins; ++i) {
         Perlin p;
         std::memcpy(p.rand_vec, d->perlins[i].rand_vec, sizeof(p.rand_vec));
@@ -186,6 +189,8 @@ double orc_perlin_turb(const orc_gperlin* t, const double* p, int32_t depth) {
     return depth <= 0 ? pn.noise(gv3(p)) : pn.turb(gv3(p), depth);
 }
 double orc_sin_portable(double x) { return sin_portable(x); }
+double orc_atan2_msun(double y, double x) { return atan2_msun(y, x); }
+double orc_acos_msun(double x) { return acos_msun(x); }
 // Transformation::{apply, inverse} and rotation(): out = a.then(b); returns 0 if not invertible
 void orc_transform_then(const orc_gtransform* a, const orc_gtransform* b, orc_gtransform* out) { g_put_transform(g_transform(*a).then(g_transform(*b)), out); }
 int32_t orc_transform_inverse(const orc_gtransform* a, orc_gtransform* out) {

@@ -135,6 +135,10 @@ def lib():
         L.orc_perlin_turb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_sin_portable.restype = C.c_double
         L.orc_sin_portable.argtypes = [C.c_double]
+        L.orc_atan2_msun.restype = C.c_double
+        L.orc_atan2_msun.argtypes = [C.c_double, C.c_double]
+        L.orc_acos_msun.restype = C.c_double
+        L.orc_acos_msun.argtypes = [C.c_double]
         L.orc_transform_then.argtypes = [C.c_void_p] * 3
         L.orc_transform_inverse.restype = C.c_int32
         L.orc_transform_inverse.argtypes = [C.c_void_p] * 2
@@ -353,6 +357,14 @@ def perlin_turb(tables: GPerlin, p, depth=7) -> float:
 
 def sin_portable(x: float) -> float:
     return lib().orc_sin_portable(float(x))
+
+
+def atan2_msun(y: float, x: float) -> float:
+    return lib().orc_atan2_msun(float(y), float(x))
+
+
+def acos_msun(x: float) -> float:
+    return lib().orc_acos_msun(float(x))
 
 
 class GScene:

@@ -12,9 +12,10 @@
 //     Transformed<...> of each].  It matters for exact-t ties, for the f64 summation order of
 //     lights.pdf_value and for which list position a light index denotes.
 //   * Perlin tables come from the unseeded thread_rng (perlin.rs:37-56); here from a Philox stream.
-//   * NoiseTexture's f64::sin and Sphere uv's atan2 / acos are libm calls whose bits differ between
-//     platforms; MathMode PORTABLE replaces sin by a fixed IEEE sequence (sin_portable below).  Sphere
-//     uv is not evaluated: no texture in scope reads it (NoiseTexture reads the hit point only).
+//   * NoiseTexture's f64::sin and Sphere uv's f64::acos are platform-libm calls whose bits are not pinned;
+//     MathMode PORTABLE replaces them by fixed IEEE sequences (sin_portable, acos_msun).  Sphere uv's
+//     atan2 is libm::atan2 (the `libm` crate, a port of musl / msun) in the reference and is restated
+//     exactly (atan2_msun).  uv is evaluated only where a CheckerTexture reads it.
 #pragma once
 #include "rtw_oracle.hpp"
 
@@ -104,6 +105,93 @@ inline double sin_portable(double x) {
     switch (n & 3) { case 0: return sy; case 1: return cy; case 2: return -sy; default: return -cy; }
 }
 
+// atan2 as the `libm` crate evaluates it (Sphere::get_sphere_uv calls libm::atan2, sphere.rs:49-54; libm 0.2 is a port of
+// musl's atan2.c / atan.c, i.e. FreeBSD msun's e_atan2.c / s_atan.c): a fixed sequence of IEEE operations.
+inline uint32_t hi_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (uint32_t)(b >> 32); }
+inline uint32_t lo_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (uint32_t)b; }
+inline double atan_msun(double x) {
+    static const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    static const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    static const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,
+                                  9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,
+                                  4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    uint32_t ix = hi_word(x);
+    const bool sign = (ix >> 31) != 0;
+    ix &= 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) {                       // |x| >= 2^66
+        if (x != x) return x;
+        double z = atanhi[3] + 0x1p-120;
+        return sign ? -z : z;
+    }
+    if (ix < 0x3fdc0000u) {                        // |x| < 0.4375
+        if (ix < 0x3e400000u) return x;            // |x| < 2^-27
+        id = -1;
+    } else {
+        x = std::fabs(x);
+        if (ix < 0x3ff30000u) {                    // |x| < 1.1875
+            if (ix < 0x3fe60000u) { id = 0; x = (2.0 * x - 1.0) / (2.0 + x); }
+            else { id = 1; x = (x - 1.0) / (x + 1.0); }
+        } else {
+            if (ix < 0x40038000u) { id = 2; x = (x - 1.5) / (1.0 + 1.5 * x); }
+            else { id = 3; x = -1.0 / x; }
+        }
+    }
+    double z = x * x, w = z * z;
+    double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    z = atanhi[id] - (x * (s1 + s2) - atanlo[id] - x);
+    return sign ? -z : z;
+}
+inline double atan2_msun(double y, double x) {
+    const double pi = 3.1415926535897931160E+00, pi_lo = 1.2246467991473531772E-16;
+    if (x != x || y != y) return x + y;
+    uint32_t ix = hi_word(x), lx = lo_word(x), iy = hi_word(y), ly = lo_word(y);
+    if (((ix - 0x3ff00000u) | lx) == 0) return atan_msun(y);       // x = 1.0
+    uint32_t m = ((iy >> 31) & 1u) | ((ix >> 30) & 2u);            // 2 * sign(x) + sign(y)
+    ix &= 0x7fffffffu; iy &= 0x7fffffffu;
+    if ((iy | ly) == 0) { switch (m) { case 0: case 1: return y; case 2: return pi; default: return -pi; } }
+    if ((ix | lx) == 0) return (m & 1u) ? -pi / 2 : pi / 2;
+    if (ix == 0x7ff00000u) {
+        if (iy == 0x7ff00000u) { switch (m) { case 0: return pi / 4; case 1: return -pi / 4; case 2: return 3 * pi / 4; default: return -3 * pi / 4; } }
+        switch (m) { case 0: return 0.0; case 1: return -0.0; case 2: return pi; default: return -pi; }
+    }
+    if (ix + (64u << 20) < iy || iy == 0x7ff00000u) return (m & 1u) ? -pi / 2 : pi / 2;      // |y / x| > 2^64
+    double z = ((m & 2u) && iy + (64u << 20) < ix) ? 0.0 : atan_msun(std::fabs(y / x));
+    switch (m) { case 0: return z; case 1: return -z; case 2: return pi - (z - pi_lo); default: return (z - pi_lo) - pi; }
+}
+// f64::acos is the platform libm's acos in the reference; PORTABLE replaces it by msun's e_acos.c sequence
+inline double acos_msun(double x) {
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+                 pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    auto R = [&](double z) {
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        return p / q;
+    };
+    uint32_t hx = hi_word(x), ix = hx & 0x7fffffffu;
+    if (ix >= 0x3ff00000u) {                       // |x| >= 1 or NaN
+        if (((ix - 0x3ff00000u) | lo_word(x)) == 0) return (hx >> 31) ? 2 * pio2_hi + 0x1p-120 : 0.0;
+        return 0.0 / (x - x);
+    }
+    if (ix < 0x3fe00000u) {                        // |x| < 0.5
+        if (ix <= 0x3c600000u) return pio2_hi + 0x1p-120;
+        return pio2_hi - (x - (pio2_lo - x * R(x * x)));
+    }
+    if (hx >> 31) {                                // x < -0.5
+        double z = (1.0 + x) * 0.5, sq = std::sqrt(z), w = R(z) * sq - pio2_lo;
+        return 2 * (pio2_hi - (sq + w));
+    }
+    double z = (1.0 - x) * 0.5, sq = std::sqrt(z);
+    uint64_t b; std::memcpy(&b, &sq, 8); b &= 0xffffffff00000000ull;
+    double df; std::memcpy(&df, &b, 8);
+    double c = (z - df * df) / (sq + df), w = R(z) * sq + c;
+    return 2 * (df + w);
+}
+
 // shared/src/perlin.rs
 struct Perlin {
     double rand_vec[256][3];
@@ -149,14 +237,18 @@ struct Perlin {
     }
 };
 
-enum TexKind : uint32_t { TEX_SOLID = 0, TEX_NOISE = 1 };
-struct Texture { uint32_t kind = TEX_SOLID; uint32_t perlin = 0; double scale = 1.; };
+enum TexKind : uint32_t { TEX_SOLID = 0, TEX_NOISE = 1, TEX_CHECKER = 2 };
+// NoiseTexture{noise: perlins[perlin], scale} or CheckerTexture{inv_scale = 1 / scale, even, odd}: even / odd are texture
+// references (0 = SolidColour(even_colour / odd_colour), k = textures[k-1]); texture.rs:24-55
+struct Texture { uint32_t kind = TEX_SOLID; uint32_t perlin = 0; double scale = 1.; uint32_t even = 0, odd = 0; V3 even_colour, odd_colour; };
 enum GMatKind : uint32_t { DIFFUSE_LIGHT = 4, ISOTROPIC = 5 };
 struct GMaterial { uint32_t kind = LAMBERTIAN; uint32_t texture = 0; V3 albedo; double param = 0.; };   // texture: 0 = SolidColour(albedo), k = textures[k-1]
 
 // ------------------------------------------------------------------------------------------------
 struct GHit {
     V3 p, normal;
+    V3 sphere_outward;        // spheres: the outward normal get_sphere_uv is evaluated on (sphere.rs:83-84); uv is computed on demand
+    bool sphere_uv = false;
     double t = 0., u = 0., v = 0.;
     bool front_face = false;
     int32_t prim = -1;
@@ -164,6 +256,7 @@ struct GHit {
 };
 inline GHit make_ghit(const Ray& r, double t, V3 outward, double u, double v, uint32_t mat) {   // hittable.rs:102-129
     GHit h;
+    h.sphere_uv = false;
     h.p = r.at(t);
     h.front_face = dot(r.d, outward) < 0.;
     h.normal = h.front_face ? outward : -outward;
@@ -284,12 +377,26 @@ struct Prim {
                 HitRecord h;
                 if (!sphere.hit(r, start, end, &h)) return false;
                 out->p = h.p; out->normal = h.normal; out->t = h.t; out->u = 0.; out->v = 0.; out->front_face = h.front_face; out->mat = h.mat;
+                out->sphere_outward = (h.p - sphere.center) / sphere.radius; out->sphere_uv = true;
                 return true;
             }
             case P_PLANE: {
                 HitRecord h;
                 if (!plane.hit(r, start, end, &h, panicked)) return false;
-                out->p = h.p; out->normal = h.normal; out->t = h.t; out->u = 0.; out->v = 0.; out->front_face = h.front_face; out->mat = h.mat;
+                out->p = h.p; out->normal = h.normal; out->t = h.t; out->front_face = h.front_face; out->mat = h.mat; out->sphere_uv = false;
+                // get_plane_uv (plane.rs:41-55): theta = angle between the normal and +y; (x, z) of the point when it is 0
+                {
+                    V3 V{0., 1., 0.};
+                    double theta = std::atan2(length(cross(plane.normal, V)), dot(plane.normal, V));
+                    if (theta <= EPS) { out->u = h.p.x; out->v = h.p.z; }
+                    else {
+                        V3 k = normalize(cross(plane.normal, V));
+                        V3 w = h.p - plane.point;
+                        V3 rot = (w * std::cos(theta) + cross(k, w) * std::sin(theta)) + (k * dot(k, w)) * (1. - std::cos(theta));
+                        double ip;
+                        out->u = std::modf(rot.x, &ip); out->v = std::modf(rot.z, &ip);
+                    }
+                }
                 return true;
             }
             case P_CUBOID: return cuboid.hit(r, start, end, out);
@@ -447,13 +554,28 @@ struct GScene {
         }
         return V3{1., 0., 0.};                                                            // Hittable::random default, hittable.rs:179-181
     }
-    V3 texture_colour(const GMaterial& m, V3 point, uint32_t math) const {
-        if (m.texture == 0) return m.albedo;                                              // SolidColour, texture.rs:15-22
-        const Texture& t = textures[m.texture - 1];
-        const Perlin& pn = perlins[t.perlin];                                             // NoiseTexture::get_colour, texture.rs:90-102
+    V3 noise_colour(const Texture& t, V3 point, uint32_t math) const {                    // NoiseTexture::get_colour, texture.rs:90-102
+        const Perlin& pn = perlins[t.perlin];
         double arg = t.scale * point.z + pn.turb(point, 7) * 10.;
         double s = math == LIBM ? std::sin(arg) : sin_portable(arg);
         return V3{0.5, 0.5, 0.5} * (s + 1.);
+    }
+    V3 texture_colour(const GMaterial& m, const GHit& rec, uint32_t math) const {
+        if (m.texture == 0) return m.albedo;                                              // SolidColour, texture.rs:15-22
+        const Texture& t = textures[m.texture - 1];
+        if (t.kind == TEX_NOISE) return noise_colour(t, rec.p, math);
+        double u = rec.u, v = rec.v;                                                      // CheckerTexture::get_colour, texture.rs:46-55
+        if (rec.sphere_uv) {                                                              // Sphere::get_sphere_uv, sphere.rs:49-54
+            const double TAU = 6.28318530717958647692528676655900577;
+            V3 n = rec.sphere_outward;
+            u = atan2_msun(-n.z, n.x) / TAU;
+            v = (math == LIBM ? std::acos(n.y) : acos_msun(n.y)) / PI;
+        }
+        double inv_scale = 1. / t.scale;
+        bool is_even = std::fmod(std::floor(u * inv_scale) + std::floor(v * inv_scale), 2.) == 0.;
+        uint32_t ref = is_even ? t.even : t.odd;
+        if (ref == 0) return is_even ? t.even_colour : t.odd_colour;
+        return noise_colour(textures[ref - 1], rec.p, math);
     }
 };
 
@@ -487,10 +609,10 @@ inline void gshade(const GScene& sc, const Options& opt, const Ray& r, const GHi
         vx->weight = (attenuation * scattering_pdf) / pdf_value;
     };
     switch (m.kind) {
-    case LAMBERTIAN: if (c) c->lambertian++; diffuse(sc.texture_colour(m, rec.p, opt.math_mode), true); return;     // material.rs:357-376
-    case ISOTROPIC: diffuse(sc.texture_colour(m, rec.p, opt.math_mode), false); return;                               // material.rs:529-554
+    case LAMBERTIAN: if (c) c->lambertian++; diffuse(sc.texture_colour(m, rec, opt.math_mode), true); return;     // material.rs:357-376
+    case ISOTROPIC: diffuse(sc.texture_colour(m, rec, opt.math_mode), false); return;                               // material.rs:529-554
     case DIFFUSE_LIGHT:                                                                                               // material.rs:506-514
-        vx->emitted = sc.texture_colour(m, rec.p, opt.math_mode);
+        vx->emitted = sc.texture_colour(m, rec, opt.math_mode);
         vx->kind = V_ABSORB; vx->weight = V3{0., 0., 0.};
         return;
     case METAL: case DIELECTRIC: {

@@ -13,7 +13,7 @@ from . import build as _build
 RTW_OK, RTW_E_INVALID, RTW_E_CUDA, RTW_E_NO_DEVICE, RTW_E_UNSUPPORTED, RTW_E_NOMEM = 0, -1, -2, -3, -4, -5
 RTW_LAMBERTIAN, RTW_METAL, RTW_DIELECTRIC, RTW_INVISIBLE, RTW_DIFFUSE_LIGHT, RTW_ISOTROPIC = 0, 1, 2, 3, 4, 5
 RTW_PRIM_SPHERE, RTW_PRIM_PLANE, RTW_PRIM_QUAD, RTW_PRIM_TRIANGLE, RTW_PRIM_CUBOID = 0, 1, 2, 3, 4
-RTW_TEX_NOISE = 1
+RTW_TEX_NOISE, RTW_TEX_CHECKER = 1, 2
 RTW_BVH_AUTO, RTW_BVH_HOST_SAH, RTW_BVH_DEVICE_LBVH = 0, 1, 2
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
@@ -60,7 +60,8 @@ class rtw_prim(C.Structure):
 
 
 class rtw_texture(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("perlin", C.c_uint32), ("scale", C.c_double), ("reserved", C.c_double * 3)]
+    _fields_ = [("kind", C.c_uint32), ("perlin", C.c_uint32), ("scale", C.c_double), ("even", C.c_uint32), ("odd", C.c_uint32),
+                ("even_colour", C.c_double * 3), ("odd_colour", C.c_double * 3)]
 
 
 class rtw_perlin(C.Structure):

@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 from ._lib import (EPSILON, TMIN_REFERENCE, RTW_DIELECTRIC, RTW_DIFFUSE_LIGHT, RTW_F32, RTW_F64, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_FIX_NAN,
                    RTW_INVISIBLE, RTW_ISOTROPIC, RTW_LAMBERTIAN, RTW_MEGAKERNEL, RTW_METAL, RTW_PRIM_CUBOID, RTW_PRIM_PLANE,
-                   RTW_PRIM_QUAD, RTW_PRIM_SPHERE, RTW_PRIM_TRIANGLE, RTW_TEX_NOISE, RTW_WAVEFRONT, RtwError, rtw_camera,
+                   RTW_PRIM_QUAD, RTW_PRIM_SPHERE, RTW_PRIM_TRIANGLE, RTW_TEX_CHECKER, RTW_TEX_NOISE, RTW_WAVEFRONT, RtwError, rtw_camera,
                    rtw_camera_builder, rtw_cuboid, rtw_material, rtw_opts, rtw_perlin, rtw_plane, rtw_prim, rtw_quad,
                    rtw_scene_desc, rtw_sphere, rtw_stats, rtw_texture, rtw_transform)
 
@@ -42,20 +42,32 @@ class NoiseTexture:                             # NoiseTexture::new(scale), text
         return out
 
 
+@dataclass(frozen=True)
+class CheckerTexture:                           # CheckerTexture::new / new_with_colours, texture.rs:24-55
+    """even / odd: a colour triple (SolidColour) or a NoiseTexture."""
+    even: object
+    odd: object
+    scale: float
+
+    @staticmethod
+    def new_with_colours(even, odd, scale) -> "CheckerTexture":
+        return CheckerTexture(tuple(even), tuple(odd), float(scale))
+
+
 # ---- materials (shared/src/material.rs) --------------------------------------------------------------
 @dataclass(frozen=True)
 class Material:
     kind: int
     colour: tuple = (0.0, 0.0, 0.0)
     param: float = 0.0
-    texture: Optional[NoiseTexture] = None      # None = SolidColour(colour)
+    texture: Optional[object] = None            # None = SolidColour(colour); NoiseTexture | CheckerTexture
 
     def pod(self, texture_index: int = 0) -> rtw_material:
         return rtw_material(self.kind, texture_index, float(self.colour[0]), float(self.colour[1]), float(self.colour[2]), float(self.param))
 
 
 def _colour_or_texture(kind, arg):
-    if isinstance(arg, NoiseTexture):
+    if isinstance(arg, (NoiseTexture, CheckerTexture)):
         return Material(kind, (0.0, 0.0, 0.0), 0.0, arg)
     return Material(kind, tuple(arg), 0.0)
 
@@ -244,16 +256,28 @@ class SceneDescription:
         spheres, planes, quads, cuboids, transforms, materials, textures, perlins = [], [], [], [], [], [], [], []
         mat_index, tex_index = {}, {}
 
+        def texture_ref(t) -> int:                 # 1-based index into textures[]
+            if t not in tex_index:
+                tx = rtw_texture()
+                if isinstance(t, NoiseTexture):
+                    perlins.append(t.perlin())
+                    tx.kind, tx.perlin, tx.scale = RTW_TEX_NOISE, len(perlins) - 1, float(t.scale)
+                else:
+                    tx.kind, tx.scale = RTW_TEX_CHECKER, float(t.scale)
+                    for name, sub in (("even", t.even), ("odd", t.odd)):
+                        if isinstance(sub, NoiseTexture):
+                            setattr(tx, name, texture_ref(sub))
+                        elif isinstance(sub, CheckerTexture):
+                            raise RtwError(_lib.RTW_E_UNSUPPORTED, "nested CheckerTexture")
+                        else:
+                            getattr(tx, name + "_colour")[:] = [float(x) for x in sub]
+                textures.append(tx)
+                tex_index[t] = len(textures)
+            return tex_index[t]
+
         def material_id(m: Material) -> int:
             if m not in mat_index:
-                t = 0
-                if m.texture is not None:
-                    if m.texture not in tex_index:
-                        perlins.append(m.texture.perlin())
-                        tx = rtw_texture(RTW_TEX_NOISE, len(perlins) - 1, float(m.texture.scale))
-                        textures.append(tx)
-                        tex_index[m.texture] = len(textures)
-                    t = tex_index[m.texture]
+                t = texture_ref(m.texture) if m.texture is not None else 0
                 materials.append(m.pod(t))
                 mat_index[m] = len(materials) - 1
             return mat_index[m]

@@ -130,15 +130,15 @@ template <class T> struct SceneDev {
 
 template <class T> struct SceneDevG {
     DevBuf<Node<T>> nodes; DevBuf<GPrim<T>> prims, unbounded, lights; DevBuf<Vec4T<T>> spheres; DevBuf<GPlane<T>> plane_geo;
-    DevBuf<GQuad<T>> quads; DevBuf<GXform<T>> xforms; DevBuf<GMat<T>> mats; DevBuf<GPerlin<T>> perlins;
+    DevBuf<GQuad<T>> quads; DevBuf<GXform<T>> xforms; DevBuf<GMat<T>> mats; DevBuf<GTex<T>> textures; DevBuf<GPerlin<T>> perlins;
     SceneViewG<T> view{};
     size_t bytes() const {
         return nodes.bytes() + prims.bytes() + unbounded.bytes() + lights.bytes() + spheres.bytes() + plane_geo.bytes() + quads.bytes() +
-               xforms.bytes() + mats.bytes() + perlins.bytes();
+               xforms.bytes() + mats.bytes() + textures.bytes() + perlins.bytes();
     }
     void release() {
         nodes.release(); prims.release(); unbounded.release(); lights.release(); spheres.release(); plane_geo.release(); quads.release();
-        xforms.release(); mats.release(); perlins.release();
+        xforms.release(); mats.release(); textures.release(); perlins.release();
     }
 };
 
@@ -282,9 +282,16 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     for (size_t i = 0; i < g.materials.size(); ++i) {
         const rtw_material& m = g.materials[i];
         GMat<T> o{};
-        o.albedo[0] = (T)m.r; o.albedo[1] = (T)m.g; o.albedo[2] = (T)m.b; o.param = (T)m.param; o.kind = m.kind;
-        if (m.texture) { const rtw_texture& t = g.textures[m.texture - 1]; o.texture = t.kind; o.perlin = t.perlin; o.scale = (T)t.scale; }
+        o.albedo[0] = (T)m.r; o.albedo[1] = (T)m.g; o.albedo[2] = (T)m.b; o.param = (T)m.param; o.kind = m.kind; o.texture = m.texture;
         mats[i] = o;
+    }
+    std::vector<GTex<T>> textures(g.textures.size());
+    for (size_t i = 0; i < g.textures.size(); ++i) {
+        const rtw_texture& t = g.textures[i];
+        GTex<T> o{};
+        o.kind = t.kind; o.perlin = t.perlin; o.even = t.even; o.odd = t.odd; o.scale = (T)t.scale;
+        for (int a = 0; a < 3; ++a) { o.even_c[a] = (T)t.even_colour[a]; o.odd_c[a] = (T)t.odd_colour[a]; }
+        textures[i] = o;
     }
     std::vector<GPerlin<T>> perlins(g.perlins.size());
     for (size_t i = 0; i < g.perlins.size(); ++i) {
@@ -382,10 +389,10 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     }
     CU(d.nodes.upload(nodes)); CU(d.prims.upload(prims)); CU(d.unbounded.upload(unbounded)); CU(d.lights.upload(lights));
     CU(d.spheres.upload(spheres)); CU(d.plane_geo.upload(plane_geo)); CU(d.quads.upload(quads)); CU(d.xforms.upload(xforms));
-    CU(d.mats.upload(mats)); CU(d.perlins.upload(perlins));
+    CU(d.mats.upload(mats)); CU(d.textures.upload(textures)); CU(d.perlins.upload(perlins));
     d.view.nodes = d.nodes.p; d.view.prims = d.prims.p; d.view.unbounded = d.unbounded.p; d.view.lights = d.lights.p;
     d.view.spheres = d.spheres.p; d.view.plane_geo = d.plane_geo.p; d.view.quads = d.quads.p; d.view.xforms = d.xforms.p;
-    d.view.mats = d.mats.p; d.view.perlins = d.perlins.p;
+    d.view.mats = d.mats.p; d.view.textures = d.textures.p; d.view.perlins = d.perlins.p;
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
     d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
     d.view.flat = flat ? 1u : 0u;
@@ -705,8 +712,16 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
             return fail(RTW_E_INVALID, "only Lambertian, DiffuseLight and Isotropic carry a texture");
     }
     for (uint64_t i = 0; i < d->n_textures; ++i) {
-        if (d->textures[i].kind != RTW_TEX_NOISE) return fail(RTW_E_UNSUPPORTED, "texture kind (NoiseTexture only; SolidColour is texture 0)");
-        if (d->textures[i].perlin >= d->n_perlins) return fail(RTW_E_INVALID, "texture perlin index out of range");
+        const rtw_texture& t = d->textures[i];
+        if (t.kind == RTW_TEX_NOISE) {
+            if (t.perlin >= d->n_perlins) return fail(RTW_E_INVALID, "texture perlin index out of range");
+        } else if (t.kind == RTW_TEX_CHECKER) {
+            for (uint32_t ref : {t.even, t.odd}) {
+                if (ref > d->n_textures) return fail(RTW_E_INVALID, "checker sub-texture index out of range");
+                if (ref && d->textures[ref - 1].kind != RTW_TEX_NOISE) return fail(RTW_E_UNSUPPORTED, "a CheckerTexture's even / odd must be SolidColour or NoiseTexture");
+            }
+            if (!(t.scale != 0.)) return fail(RTW_E_INVALID, "checker scale is zero");
+        } else return fail(RTW_E_UNSUPPORTED, "texture kind (NoiseTexture, CheckerTexture; SolidColour is texture 0)");
     }
     bool needs_lights = false;
     auto check = [&](const rtw_prim* list, uint64_t n, bool world) -> const char* {
@@ -720,6 +735,12 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
             if (e.transform >= 0 && (uint64_t)e.transform >= d->n_transforms) return "primitive transform index out of range";
             if (e.transform < -1) return "primitive transform index out of range";
             if (e.kind == RTW_PRIM_PLANE && e.transform >= 0) return "transformed planes are not supported";
+            if (e.kind == RTW_PRIM_PLANE && d->materials[e.material].texture && d->textures[d->materials[e.material].texture - 1].kind == RTW_TEX_CHECKER) {
+                const rtw_plane& q = d->planes[e.index];       // get_plane_uv (plane.rs:41-55) is (x, z) only when the normal is +y
+                double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);
+                double s2 = (q.nx / len) * (q.nx / len) + (q.nz / len) * (q.nz / len);          // |n x (0,1,0)|^2
+                if (!(std::atan2(std::sqrt(s2), q.ny / len) <= 2.220446049250313e-16)) return "a CheckerTexture on a plane whose normal is not +y is not supported";
+            }
             if (e.kind == RTW_PRIM_SPHERE) {
                 const rtw_sphere& q = d->spheres[e.index];
                 if (!(q.r > 0.) || !std::isfinite(q.cx + q.cy + q.cz + q.r)) return "sphere with non-finite centre or non-positive radius";

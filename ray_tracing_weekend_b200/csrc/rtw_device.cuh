@@ -322,7 +322,9 @@ template <class T> struct GPrim {
     int32_t xform;           // -1, or index into xforms: the entry is a Transformed<T>
     uint32_t pad;
 };
-template <class T> struct GMat { T albedo[3], param, scale; uint32_t kind, texture, perlin; };   // texture: 0 solid, 1 noise
+template <class T> struct GMat { T albedo[3], param; uint32_t kind, texture; };                 // texture: 0 = SolidColour(albedo), k = textures[k-1]
+enum TexKind : uint32_t { TEX_NOISE = 1, TEX_CHECKER = 2 };
+template <class T> struct GTex { uint32_t kind, perlin, even, odd; T scale, even_c[3], odd_c[3]; };   // texture.rs:24-102
 template <class T> struct GPerlin { T rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; };
 template <class T> struct SceneViewG {
     const Node<T>* nodes;          // BVH over `prims` (leaf ranges index it)
@@ -330,7 +332,7 @@ template <class T> struct SceneViewG {
     const GPrim<T>* unbounded;     // planes (infinite box): tested linearly
     const GPrim<T>* lights;        // the lights list in iteration order
     const Vec4T<T>* spheres; const GPlane<T>* plane_geo; const GQuad<T>* quads; const GXform<T>* xforms;
-    const GMat<T>* mats; const GPerlin<T>* perlins;
+    const GMat<T>* mats; const GTex<T>* textures; const GPerlin<T>* perlins;
     int32_t n_nodes, n_prims, n_unbounded, n_lights;
     uint32_t lights_is_bvh, has_xforms, flat;   // flat: few entries, walked linearly (sorted by kind) instead of through the BVH
 };

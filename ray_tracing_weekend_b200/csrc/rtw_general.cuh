@@ -138,11 +138,106 @@ template <class T> RTW_D T g_turb(const GPerlin<T>& pn, V3<T> p, int depth) {
     for (int i = 0; i < depth; ++i) { accum += weight * g_noise<T>(pn, tp); tp = tp * T(2); weight *= T(0.5); }
     return accum;
 }
-// Texture::get_colour (texture.rs:15-22, 90-102)
-template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, V3<T> point) {
-    if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
-    T arg = m.scale * point.z + g_turb<T>(sc.perlins[m.perlin], point, 7) * T(10);
+// atan2 / acos of Sphere::get_sphere_uv (sphere.rs:49-54).  f64: libm::atan2 of the reference is the `libm` crate's port of
+// musl / msun (a fixed IEEE sequence, restated here); f64::acos is the platform libm's — msun's e_acos.c sequence stands in
+// (oracle: atan2_msun / acos_msun).  FP32: CUDA's atan2f / acosf.
+RTW_D double g_atan(double x) {
+    const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,
+                           9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,
+                           4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    uint32_t ix = (uint32_t)__double2hiint(x);
+    const bool sign = (ix >> 31) != 0;
+    ix &= 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) {
+        if (x != x) return x;
+        double z = atanhi[3] + 0x1p-120;
+        return sign ? -z : z;
+    }
+    if (ix < 0x3fdc0000u) {
+        if (ix < 0x3e400000u) return x;
+        id = -1;
+    } else {
+        x = fabs(x);
+        if (ix < 0x3ff30000u) {
+            if (ix < 0x3fe60000u) { id = 0; x = (2.0 * x - 1.0) / (2.0 + x); }
+            else { id = 1; x = (x - 1.0) / (x + 1.0); }
+        } else {
+            if (ix < 0x40038000u) { id = 2; x = (x - 1.5) / (1.0 + 1.5 * x); }
+            else { id = 3; x = -1.0 / x; }
+        }
+    }
+    double z = x * x, w = z * z;
+    double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    z = atanhi[id] - (x * (s1 + s2) - atanlo[id] - x);
+    return sign ? -z : z;
+}
+RTW_D double g_atan2(double y, double x) {
+    const double pi = 3.1415926535897931160E+00, pi_lo = 1.2246467991473531772E-16;
+    if (x != x || y != y) return x + y;
+    uint32_t ix = (uint32_t)__double2hiint(x), lx = (uint32_t)__double2loint(x), iy = (uint32_t)__double2hiint(y), ly = (uint32_t)__double2loint(y);
+    if (((ix - 0x3ff00000u) | lx) == 0) return g_atan(y);
+    uint32_t m = ((iy >> 31) & 1u) | ((ix >> 30) & 2u);
+    ix &= 0x7fffffffu; iy &= 0x7fffffffu;
+    if ((iy | ly) == 0) { switch (m) { case 0: case 1: return y; case 2: return pi; default: return -pi; } }
+    if ((ix | lx) == 0) return (m & 1u) ? -pi / 2 : pi / 2;
+    if (ix == 0x7ff00000u) {
+        if (iy == 0x7ff00000u) { switch (m) { case 0: return pi / 4; case 1: return -pi / 4; case 2: return 3 * pi / 4; default: return -3 * pi / 4; } }
+        switch (m) { case 0: return 0.0; case 1: return -0.0; case 2: return pi; default: return -pi; }
+    }
+    if (ix + (64u << 20) < iy || iy == 0x7ff00000u) return (m & 1u) ? -pi / 2 : pi / 2;
+    double z = ((m & 2u) && iy + (64u << 20) < ix) ? 0.0 : g_atan(fabs(y / x));
+    switch (m) { case 0: return z; case 1: return -z; case 2: return pi - (z - pi_lo); default: return (z - pi_lo) - pi; }
+}
+RTW_D double g_acos(double x) {
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+                 pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    auto R = [&](double z) {
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        return p / q;
+    };
+    uint32_t hx = (uint32_t)__double2hiint(x), ix = hx & 0x7fffffffu;
+    if (ix >= 0x3ff00000u) {
+        if (((ix - 0x3ff00000u) | (uint32_t)__double2loint(x)) == 0) return (hx >> 31) ? 2 * pio2_hi + 0x1p-120 : 0.0;
+        return 0.0 / (x - x);
+    }
+    if (ix < 0x3fe00000u) {
+        if (ix <= 0x3c600000u) return pio2_hi + 0x1p-120;
+        return pio2_hi - (x - (pio2_lo - x * R(x * x)));
+    }
+    if (hx >> 31) {
+        double z = (1.0 + x) * 0.5, sq = sqrt(z), w = R(z) * sq - pio2_lo;
+        return 2 * (pio2_hi - (sq + w));
+    }
+    double z = (1.0 - x) * 0.5, sq = sqrt(z);
+    double df = __hiloint2double(__double2hiint(sq), 0);
+    double c = (z - df * df) / (sq + df), w = R(z) * sq + c;
+    return 2 * (df + w);
+}
+RTW_D float g_atan2(float y, float x) { return atan2f(y, x); }
+RTW_D float g_acos(float x) { return acosf(x); }
+
+// Texture::get_colour (texture.rs:15-22, 46-55, 90-102).  (u, v) is only read by a CheckerTexture.
+template <class T> RTW_D V3<T> g_noise_colour(const SceneViewG<T>& sc, const GTex<T>& t, V3<T> point) {
+    T arg = t.scale * point.z + g_turb<T>(sc.perlins[t.perlin], point, 7) * T(10);
     return mk<T>(T(0.5), T(0.5), T(0.5)) * (g_sin(arg) + T(1));
+}
+template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
+    if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+    const GTex<T>& t = sc.textures[m.texture - 1];
+    if (t.kind == TEX_NOISE) return g_noise_colour<T>(sc, t, point);
+    T inv_scale = T(1) / t.scale;
+    bool is_even = fmod(floor(u * inv_scale) + floor(v * inv_scale), T(2)) == T(0);
+    uint32_t ref = is_even ? t.even : t.odd;
+    if (ref == 0) return is_even ? mk<T>(t.even_c[0], t.even_c[1], t.even_c[2]) : mk<T>(t.odd_c[0], t.odd_c[1], t.odd_c[2]);
+    return g_noise_colour<T>(sc, sc.textures[ref - 1], point);
 }
 
 // ---- closest hit over the planes + the BVH of bounded entries ----------------------------------------------------
@@ -246,7 +341,22 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
     h->info = (pr.id << 2) | (m.kind & 3u);
     h->param = m.param;
     // Metal reads its own albedo; Lambertian / Isotropic / DiffuseLight read their texture at the hit point
-    h->albedo = (m.kind == LAMBERTIAN || m.kind >= DIFFUSE_LIGHT) ? g_texture<T>(sc, m, p) : mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+    if (m.kind == LAMBERTIAN || m.kind >= DIFFUSE_LIGHT) {
+        T u = T(0), v = T(0);
+        if (m.texture && sc.textures[m.texture - 1].kind == TEX_CHECKER) {     // the hit's (u, v), in the entity's own space
+            V3<T> pi = g_at(rr, best_t);
+            if (pr.kind == P_SPHERE) {                                         // get_sphere_uv(outward normal), sphere.rs:49-54, 83-84
+                u = g_atan2(-outward.z, outward.x) / (T(2) * M<T, EXACT>::PI);
+                v = g_acos(outward.y) / M<T, EXACT>::PI;
+            } else if (pr.kind == P_PLANE) { u = pi.x; v = pi.z; }             // get_plane_uv for a +y normal, plane.rs:41-47
+            else {                                                             // get_quad_uv, quadrilateral.rs:58-63
+                const GQuad<T>& Q = sc.quads[best_sub];
+                V3<T> pq = pi - Q.q;
+                u = dot(cross(pq, Q.v), Q.w); v = dot(cross(Q.u, pq), Q.w);
+            }
+        }
+        h->albedo = g_texture<T>(sc, m, u, v, p);
+    } else h->albedo = mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
     return true;
 }
 

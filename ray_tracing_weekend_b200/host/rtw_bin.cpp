@@ -1,5 +1,5 @@
 // rtw_bin.cpp — the reference's `bin` (bin/src/main.rs:54-105) with the CUDA backend behind
-// Camera::render:   rtw_bin <simple|simple-light|cornell-box|debug|simple-transform> [--backend cuda] [--width W --height H --spp S --depth D]
+// Camera::render:   rtw_bin <simple|simple-light|cornell-box|debug|simple-transform|checkered-spheres> [--backend cuda] [--width W --height H --spp S --depth D]
 //                           [--seed N] [--precision f32|f64] [--tmin X] [--out image.ppm]
 // Config.toml parsing is replaced by flags (defaults = the reference's Config.toml:7-11).
 // Writes ASCII P3 with rows reversed exactly like main.rs:89-104.
@@ -42,10 +42,11 @@ int main(int argc, char** argv) {
         else if (scene == "cornell-box" || scene == "cornell_box") general_sc = scenes::cornell_box();
         else if (scene == "debug") general_sc = scenes::debugging_scene(opt.seed);
         else if (scene == "simple-transform" || scene == "simple_transform") general_sc = scenes::simple_transform(opt.seed);
+        else if (scene == "checkered-spheres" || scene == "checkered_spheres") general_sc = scenes::checkered_spheres();
         else {
-            // perlin-spheres, checkered-spheres and plane pair Lambertian surfaces with an EMPTY lights list: the reference panics
-            // on the first light sample (hittable_list.rs:414-419)
-            std::fprintf(stderr, "scene '%s' is not provided (simple, simple-light, cornell-box, debug, simple-transform)\n", scene.c_str());
+            // perlin-spheres and plane pair Lambertian surfaces with an EMPTY lights list: the reference panics on the first light
+            // sample (hittable_list.rs:414-419)
+            std::fprintf(stderr, "scene '%s' is not provided (simple, simple-light, cornell-box, debug, simple-transform, checkered-spheres)\n", scene.c_str());
             return 2;
         }
         if (general) cb = general_sc.cam;

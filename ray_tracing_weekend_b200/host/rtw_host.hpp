@@ -16,14 +16,16 @@
 //   geometry::transformations::{Transformation,        rtw_host::Transformation, rotation(), Translation3, entity.transform(t)
 //     Transformed<T>, rotation}, vec3::Translation3       -> Transformed<T>
 //   shared::material::{DiffuseLight, Isotropic}        rtw_host::DiffuseLight / Isotropic
-//   shared::texture::NoiseTexture                      rtw_host::NoiseTexture (Perlin tables seeded)
-//   scenes::{simple_light, cornell_box,                rtw_host::scenes::{simple_light, cornell_box, debugging_scene, simple_transform}
-//     debugging_scene, simple_transform}
+//   shared::texture::{SolidColour, NoiseTexture,       rtw_host::SolidColour / NoiseTexture (Perlin tables seeded) / CheckerTexture
+//     CheckerTexture}
+//   scenes::{simple_light, cornell_box, debugging_     rtw_host::scenes::{simple_light, cornell_box, debugging_scene, simple_transform,
+//     scene, simple_transform, checkered_spheres}         checkered_spheres}
 //
 // Where the reference panics (unwrap / expect), this layer throws std::runtime_error.
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -59,19 +61,33 @@ struct SampledColour {
 };
 
 // ---- textures (shared/src/texture.rs) ------------------------------------------------------------------
-struct NoiseTexture {                               // texture.rs:57-102; Perlin tables from Philox stream (seed; 0x9E71A000 + index)
-    double scale = 1.; uint64_t seed = 20261018; uint32_t index = 0;
-    static std::shared_ptr<const NoiseTexture> new_(double scale, uint64_t seed = 20261018, uint32_t index = 0) {
-        auto t = std::make_shared<NoiseTexture>(); t->scale = scale; t->seed = seed; t->index = index; return t;
+struct Texture;
+using TexturePtr = std::shared_ptr<const Texture>;
+struct Texture {
+    uint32_t kind = 0;                              // 0 SolidColour, RTW_TEX_NOISE, RTW_TEX_CHECKER
+    Colour colour;                                  // SolidColour (texture.rs:15-22)
+    double scale = 1.; uint64_t seed = 20261018; uint32_t index = 0;    // NoiseTexture (:57-102): Perlin tables from Philox stream (seed; 0x9E71A000 + index)
+    TexturePtr even, odd;                           // CheckerTexture (:24-55)
+};
+struct SolidColour { static TexturePtr new_(Colour c) { auto t = std::make_shared<Texture>(); t->colour = c; return t; } };
+struct NoiseTexture {
+    static TexturePtr new_(double scale, uint64_t seed = 20261018, uint32_t index = 0) {
+        auto t = std::make_shared<Texture>(); t->kind = RTW_TEX_NOISE; t->scale = scale; t->seed = seed; t->index = index; return t;
     }
 };
-using TexturePtr = std::shared_ptr<const NoiseTexture>;
+struct CheckerTexture {
+    static TexturePtr new_(TexturePtr even, TexturePtr odd, double scale) {
+        auto t = std::make_shared<Texture>(); t->kind = RTW_TEX_CHECKER; t->scale = scale; t->even = std::move(even); t->odd = std::move(odd); return t;
+    }
+    static TexturePtr new_with_colours(Colour even, Colour odd, double scale) { return new_(SolidColour::new_(even), SolidColour::new_(odd), scale); }
+};
 
 // ---- materials (shared/src/material.rs) -----------------------------------------------------------
-struct Material { rtw_material pod{}; TexturePtr texture; };       // texture == nullptr: SolidColour(pod.r, pod.g, pod.b)
+struct Material { rtw_material pod{}; TexturePtr texture; };       // texture == nullptr (or a SolidColour texture): SolidColour(pod.r, pod.g, pod.b)
 using MaterialPtr = std::shared_ptr<const Material>;
 inline MaterialPtr make_material(uint32_t kind, Colour c, double param, TexturePtr tex = nullptr) {
     auto m = std::make_shared<Material>();
+    if (tex && tex->kind == 0) { c = tex->colour; tex = nullptr; }
     m->pod.kind = kind; m->pod.r = c.v.x; m->pod.g = c.v.y; m->pod.b = c.v.z; m->pod.param = param; m->texture = std::move(tex);
     return m;
 }
@@ -195,22 +211,33 @@ struct SceneDescription {
     std::vector<rtw_perlin> perlins; std::vector<rtw_prim> world, lights;
     rtw_scene_desc pod{};
     SceneDescription(World w, World l) {
-        std::vector<const Material*> seen_m; std::vector<const NoiseTexture*> seen_t;
+        std::vector<const Material*> seen_m; std::vector<std::pair<const Texture*, uint32_t>> seen_t;
+        std::function<uint32_t(const TexturePtr&)> texture_ref = [&](const TexturePtr& t) -> uint32_t {      // 1-based index into textures[]
+            for (const auto& k : seen_t) if (k.first == t.get()) return k.second;
+            rtw_texture tx{};
+            tx.kind = t->kind; tx.scale = t->scale;
+            if (t->kind == RTW_TEX_NOISE) {
+                rtw_perlin pn; rtw_perlin_generate(t->seed, t->index, &pn); perlins.push_back(pn);
+                tx.perlin = (uint32_t)perlins.size() - 1;
+            } else {
+                const TexturePtr sub[2] = {t->even, t->odd};
+                for (int k = 0; k < 2; ++k) {
+                    if (!sub[k]) throw std::runtime_error("CheckerTexture without even / odd texture");
+                    if (sub[k]->kind == RTW_TEX_CHECKER) throw std::runtime_error("nested CheckerTexture is outside the CUDA backend's scope");
+                    double* col = k == 0 ? tx.even_colour : tx.odd_colour;
+                    if (sub[k]->kind == 0) { col[0] = sub[k]->colour.v.x; col[1] = sub[k]->colour.v.y; col[2] = sub[k]->colour.v.z; }
+                    else (k == 0 ? tx.even : tx.odd) = texture_ref(sub[k]);
+                }
+            }
+            textures.push_back(tx);
+            seen_t.push_back({t.get(), (uint32_t)textures.size()});
+            return (uint32_t)textures.size();
+        };
         auto material_id = [&](const MaterialPtr& m) -> uint32_t {
             if (!m) throw std::runtime_error("primitive without material");
             for (size_t i = 0; i < seen_m.size(); ++i) if (seen_m[i] == m.get()) return (uint32_t)i;
             rtw_material pod = m->pod;
-            pod.texture = 0;
-            if (m->texture) {
-                size_t t = 0;
-                while (t < seen_t.size() && seen_t[t] != m->texture.get()) ++t;
-                if (t == seen_t.size()) {
-                    rtw_perlin pn; rtw_perlin_generate(m->texture->seed, m->texture->index, &pn); perlins.push_back(pn);
-                    rtw_texture tx{}; tx.kind = RTW_TEX_NOISE; tx.perlin = (uint32_t)perlins.size() - 1; tx.scale = m->texture->scale;
-                    textures.push_back(tx); seen_t.push_back(m->texture.get());
-                }
-                pod.texture = (uint32_t)t + 1;
-            }
+            pod.texture = m->texture ? texture_ref(m->texture) : 0u;
             materials.push_back(pod); seen_m.push_back(m.get());
             return (uint32_t)materials.size() - 1;
         };
@@ -450,6 +477,19 @@ inline GeneralOutput cornell_box() {
     o.lights.add(Sphere::new_(Point3(190., 90., 190.), 90., glass));
     Point3 lookfrom(277.5, 277.5, -800.), lookat(277.5, 277.5, 0.);
     o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_vfov(40.).with_defocus_angle(0.).with_focus_dist((lookfrom - lookat).length());
+    return o;
+}
+
+// scenes::checkered_spheres (scenes/src/lib.rs:123-153)
+inline GeneralOutput checkered_spheres() {
+    GeneralOutput o;
+    MaterialPtr checker = Lambertian::new_(CheckerTexture::new_with_colours(Colour(0.2, 0.3, 0.1), Colour(0.9, 0.9, 0.9), 0.01));
+    o.world.add(Sphere::new_(Point3(0., -10., 0.), 10., checker));
+    o.world.add(Sphere::new_(Point3(0., 10., 0.), 10., checker));
+    o.lights.add(Sphere::new_(Point3(0., 0., 0.), 0.1, checker));
+    Point3 lookfrom(40., 1., 0.), lookat(0., 0., 0.);
+    o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_focus_dist((lookfrom - lookat).length()).with_vfov(40.)
+                .with_background(Colour(1., 1., 1.));
     return o;
 }
 

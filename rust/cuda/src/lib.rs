@@ -38,10 +38,10 @@ pub const RTW_DIFFUSE_LIGHT: u32 = 4; pub const RTW_ISOTROPIC: u32 = 5;
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwCuboid { pub p: [f64; 3], pub q: [f64; 3] }
 #[repr(C)] #[derive(Clone, Copy)] pub struct RtwTransform { pub rotation: [f64; 9], pub translation: [f64; 3] }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwPrim { pub kind: u32, pub index: u32, pub material: u32, pub transform: i32 }
-#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwTexture { pub kind: u32, pub perlin: u32, pub scale: f64, pub reserved: [f64; 3] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct RtwTexture { pub kind: u32, pub perlin: u32, pub scale: f64, pub even: u32, pub odd: u32, pub even_colour: [f64; 3], pub odd_colour: [f64; 3] }
 #[repr(C)] #[derive(Clone, Copy)] pub struct RtwPerlin { pub rand_vec: [[f64; 3]; 256], pub perm_x: [u8; 256], pub perm_y: [u8; 256], pub perm_z: [u8; 256] }
 pub const RTW_PRIM_SPHERE: u32 = 0; pub const RTW_PRIM_PLANE: u32 = 1; pub const RTW_PRIM_QUAD: u32 = 2; pub const RTW_PRIM_TRIANGLE: u32 = 3;
-pub const RTW_PRIM_CUBOID: u32 = 4; pub const RTW_TEX_NOISE: u32 = 1;
+pub const RTW_PRIM_CUBOID: u32 = 4; pub const RTW_TEX_NOISE: u32 = 1; pub const RTW_TEX_CHECKER: u32 = 2;
 #[repr(C)]
 pub struct RtwSceneDesc {
     pub spheres: *const RtwSphere, pub n_spheres: u64, pub planes: *const RtwPlane, pub n_planes: u64,

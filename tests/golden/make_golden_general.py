@@ -1,5 +1,5 @@
 """Golden fixture of the GENERAL-scene oracle (oracle/rtw_oracle_general.hpp) on the reference's scenes cornell_box, simple_light,
-debugging_scene and simple_transform (scenes/src/lib.rs:235-653).  Run from the repo root:
+debugging_scene, simple_transform and checkered_spheres (scenes/src/lib.rs:123-153, 235-653).  Run from the repo root:
 `python tests/golden/make_golden_general.py`.  The reference cannot run here (no Rust toolchain) and has no golden vectors
 for this path, so this pins the ORACLE (and through it the CUDA path) against drift.  Scene descriptions come from the
 product's host mirror (ray_tracing_weekend_b200.scenes, no GPU involved); all arithmetic is the oracle's, in PORTABLE
@@ -20,9 +20,9 @@ SEED = 20261018
 
 def compute(O, R):
     out = {}
-    for name in ("cornell_box", "simple_light", "debugging_scene", "simple_transform"):
+    for name in ("cornell_box", "simple_light", "debugging_scene", "simple_transform", "checkered_spheres"):
         gen = getattr(R.scenes, name)
-        world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
+        world, lights, cb = gen() if name in ("cornell_box", "checkered_spheres") else gen(SEED)
         d = R.SceneDescription(world, lights)
         g = O.GScene(d.pod, d)
         cam = cb.with_vfov(40.).with_aspect_ratio(1.0).with_image_width(24).with_image_height(24).with_samples_per_pixel(4).with_max_depth(12).build()

@@ -9,12 +9,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SEED = 20261018
-SCENES = ("cornell_box", "simple_light", "debugging_scene", "simple_transform")
+SCENES = ("cornell_box", "simple_light", "debugging_scene", "simple_transform", "checkered_spheres")
 
 
 def _build(rtw, oracle, name):
     gen = getattr(rtw.scenes, name)
-    world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
+    world, lights, cb = gen() if name in ("cornell_box", "checkered_spheres") else gen(SEED)
     scene = rtw.Scene(world, lights)
     assert scene.general
     return scene, oracle.GScene(scene.desc.pod, scene.desc), cb
@@ -24,9 +24,12 @@ def _random_scene(rtw, rng, n=160):
     """A mixed bag: every entity kind, half of them Transformed, every material kind, a NoiseTexture."""
     noise = rtw.NoiseTexture(3.0, SEED, 2)
     mats = [rtw.Lambertian((0.7, 0.6, 0.5)), rtw.Metal((0.8, 0.8, 0.9), 0.1), rtw.Dialectric(1.5), rtw.DiffuseLight((2., 2., 2.)),
-            rtw.Isotropic((0.4, 0.5, 0.6)), rtw.Lambertian(noise), rtw.INVISIBLE]
+            rtw.Isotropic((0.4, 0.5, 0.6)), rtw.Lambertian(noise), rtw.INVISIBLE,
+            rtw.Lambertian(rtw.CheckerTexture.new_with_colours((0.9, 0.1, 0.1), (0.1, 0.1, 0.9), 0.13)),
+            rtw.DiffuseLight(rtw.CheckerTexture((1.5, 1.5, 0.5), rtw.NoiseTexture(2.0, SEED, 3), 0.21))]
     world, lights = rtw.HittableList(), rtw.HittableList()
     world.add(rtw.Plane((0., -6., 0.), (0., -1., 0.), mats[0]))
+    world.add(rtw.Plane((0., 0., 0.), (0., 1., 0.), mats[7]))              # a checkered +y plane (uv = (x, z)), visible from below
     for k in range(n):
         c = rng.uniform(-5, 5, 3)
         m = mats[int(rng.integers(0, len(mats)))]
@@ -189,7 +192,8 @@ def test_general_scene_validation(rtw):
     empty.close()
 
 
-@pytest.mark.parametrize("name,cli", (("cornell_box", "cornell-box"), ("simple_light", "simple-light"), ("simple_transform", "simple-transform")))
+@pytest.mark.parametrize("name,cli", (("cornell_box", "cornell-box"), ("simple_light", "simple-light"), ("simple_transform", "simple-transform"),
+                                      ("checkered_spheres", "checkered-spheres")))
 def test_cpp_host_mirror_cli_renders_general_scenes(rtw, oracle, tmp_path, name, cli):
     """`rtw_bin cornell-box --backend cuda` (bin/src/main.rs flow through the C++ mirror of Quad / Cuboid / Transformed /
     DiffuseLight / NoiseTexture) writes the same PPM, byte for byte, as the Python mirror."""
@@ -209,3 +213,59 @@ def test_cpp_host_mirror_cli_renders_general_scenes(rtw, oracle, tmp_path, name,
     ref = tmp_path / "ref.ppm"
     rtw.write_ppm(str(ref), rgb8)
     assert out.read_text() == ref.read_text()
+
+
+@pytest.mark.parametrize("precision", ("f32", "f64"))
+def test_general_render_independent_of_world_size(rtw, oracle, precision):
+    """The multi-GPU building blocks on a general scene: tiles rendered as 1 rank and as 3 ranks give the same image bit for bit
+    (streams are keyed by absolute pixel; FP32 accumulates in fixed point, f64 sums samples in order)."""
+    import torch
+    scene, og, cb = _build(rtw, oracle, "cornell_box")
+    try:
+        w, h, spp = 70, 50, 6
+        cam = _cam(cb, w, h, spp, 30)
+        prec = rtw.RTW_F32 if precision == "f32" else rtw.RTW_F64
+        dtype = torch.float32 if precision == "f32" else torch.float64
+        opts = rtw.RenderOptions(seed=SEED, precision=prec)
+        one, _, _ = scene.render(cam, opts)
+        world = 3
+        tpr = rtw.tiles_per_rank(w, h, world)
+        tiles = torch.zeros((world, tpr, 16, 16, 3), dtype=dtype, device="cuda")
+        for r in range(world):
+            scene.render_tiles_device(cam, opts, r, world, tiles[r].data_ptr())
+        out = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        rtw.untile_resolve_device(tiles.data_ptr(), prec, w, h, world, spp, out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        assert np.array_equal(one, out.cpu().numpy(), equal_nan=True)
+    finally:
+        scene.close()
+
+
+def test_checkered_spheres_texture_through_fix_nan(rtw, oracle):
+    """checkered_spheres as the reference builds it poisons every sphere pixel (its light sits where the two spheres touch, so
+    light-sampled paths end up inside the light: Sphere::pdf_value is NaN, sphere.rs:104-106).  With RTW_FLAG_FIX_NAN the checker
+    pattern read through get_sphere_uv is visible: still bit-exact against the oracle's fix_nan mode, and both colours appear."""
+    scene, og, cb = _build(rtw, oracle, "checkered_spheres")
+    try:
+        cam = _cam(cb, 60, 40, 8, 20)
+        ocam = oracle.Camera.from_buffer_copy(cam.pod)
+        ref, _, _, _ = og.render(ocam, oracle.options(seed=SEED, math_mode=oracle.PORTABLE, fix_nan=True))
+        got, _, _ = scene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64, flags=rtw.RTW_FLAG_FIX_NAN))
+        assert np.array_equal(ref, got) and np.isfinite(got).all()
+        plain, _, _ = scene.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64))
+        assert np.isnan(plain).any(axis=2).mean() > 0.3
+        cam_hi = _cam(cb, 60, 40, 128, 20)                            # FP32 vs f64 with independent noise: more samples
+        f64_hi, _, _ = scene.render(cam_hi, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64, flags=rtw.RTW_FLAG_FIX_NAN))
+        f32_hi, _, _ = scene.render(cam_hi, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, flags=rtw.RTW_FLAG_FIX_NAN))
+        sph = (f64_hi.sum(axis=2) < 0.98 * 128 * 3)                   # pixels that are not pure background
+        assert sph.mean() > 0.3 and abs(f32_hi[sph].mean() - f64_hi[sph].mean()) < 0.05 * f64_hi[sph].mean()
+        # first-vertex albedos: green-ish (0.2, 0.3, 0.1) and white (0.9, 0.9, 0.9) squares both occur
+        ii, jj = np.meshgrid(np.arange(60), np.arange(40))
+        o, d = cam.get_rays(ii.ravel(), jj.ravel(), np.zeros(2400), rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64))
+        v = scene.scatter_batch(o, d, ii.ravel(), np.zeros(2400), np.ones(2400), rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64))
+        w = v["weight"][(v["kind"] == 3) & (v["weight"].sum(axis=1) > 0)]
+        ratio = w[:, 1] / w[:, 0]
+        assert (np.abs(ratio - 1.0) < 1e-9).sum() > 50 and (np.abs(ratio - 1.5) < 1e-9).sum() > 50
+    finally:
+        scene.close()

@@ -199,6 +199,55 @@ def test_emission_and_isotropic(oracle, rtw):
     assert "miss" in seen and "light" in seen
 
 
+def test_portable_atan2_acos_and_checker(oracle, rtw):
+    """Sphere::get_sphere_uv (sphere.rs:49-54) feeds CheckerTexture (texture.rs:46-55).  atan2 is the `libm` crate's (musl / msun)
+    sequence, acos msun's: both within 1 ulp of this platform's libm, exact at the special points."""
+    rng = np.random.default_rng(0)
+    for _ in range(20000):
+        y, x = rng.normal(size=2) * 10 ** rng.uniform(-3, 3)
+        assert abs(oracle.atan2_msun(y, x) - math.atan2(y, x)) <= 2.3e-16 * abs(math.atan2(y, x))
+    for x in np.concatenate([np.linspace(-1, 1, 20001), rng.uniform(-1, 1, 20000)]):
+        assert abs(oracle.acos_msun(x) - math.acos(x)) <= 2.3e-16 * abs(math.acos(x))
+    assert oracle.acos_msun(1.) == 0. and oracle.acos_msun(-1.) == math.pi and oracle.atan2_msun(0., -1.) == math.pi
+    assert oracle.atan2_msun(1., 0.) == math.pi / 2 and math.isnan(oracle.acos_msun(1.5))
+    # a checker on a quad: colour = even iff floor(u / scale) + floor(v / scale) is even, (u, v) the quad coordinates
+    chk = rtw.Lambertian(rtw.CheckerTexture.new_with_colours((1., 0., 0.), (0., 0., 1.), 0.25))
+    world = rtw.HittableList(); world.add(rtw.Quad((0., 0., 0.), (1., 0., 0.), (0., 1., 0.), chk))
+    li = rtw.HittableList(); li.add(rtw.Sphere((0., 0., 50.), 1., rtw.INVISIBLE))
+    d = rtw.SceneDescription(world, li)
+    g = oracle.GScene(d.pod, d)
+    uv = rng.uniform(0.01, 0.99, (400, 2))
+    o = np.column_stack([uv, np.full(400, 3.)]); dr = np.tile([0., 0., -1.], (400, 1))
+    seen = 0
+    for k in range(400):
+        # cosine-sampled vertices (weight = 2 * albedo when the light is missed) reveal the texture colour
+        r = g.scatter_batch(o[k:k + 1], dr[k:k + 1], [k], [0], [1], oracle.options(seed=SEED))
+        w = r["weight"][0]
+        if np.allclose(w.sum(), 2.):
+            even = (math.floor(uv[k, 0] / 0.25) + math.floor(uv[k, 1] / 0.25)) % 2 == 0
+            assert np.allclose(w, [2., 0., 0.] if even else [0., 0., 2.])
+            seen += 1
+    assert seen > 100
+    # on a sphere: u = atan2(-z, x) / tau, v = acos(y) / pi of the outward normal
+    world = rtw.HittableList(); world.add(rtw.Sphere((0., 0., 0.), 2., chk))
+    d = rtw.SceneDescription(world, li)
+    g = oracle.GScene(d.pod, d)
+    seen = 0
+    for k in range(400):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        r = g.scatter_batch(np.array([n * 5.]), np.array([-n]), [k], [0], [1], oracle.options(seed=SEED))
+        w = r["weight"][0]
+        if np.allclose(w.sum(), 2.):
+            nn = r["normal"][0]
+            u, v = math.atan2(-nn[2], nn[0]) / math.tau, math.acos(nn[1]) / math.pi
+            if min(abs((u / 0.25) % 1), abs((v / 0.25) % 1), 1 - abs((u / 0.25) % 1), 1 - abs((v / 0.25) % 1)) < 1e-6:
+                continue
+            even = (math.floor(u / 0.25) + math.floor(v / 0.25)) % 2 == 0
+            assert np.allclose(w, [2., 0., 0.] if even else [0., 0., 2.])
+            seen += 1
+    assert seen > 100
+
+
 def test_general_golden_fixture(oracle, rtw):
     """Committed outputs of the general oracle on the reference's scenes (tests/golden/make_golden_general.py)."""
     with open(os.path.join(GOLDEN, "general_oracle.json")) as f:

@@ -203,7 +203,10 @@ RTW_API int  rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_
  * Transformed<T>, with DiffuseLight / Isotropic materials and NoiseTexture (cornell_box, simple_light, debug,
  * simple_transform, perlin_spheres: scenes/src/lib.rs:40-89, 235-653).  Rendered by the general kernels (both
  * precisions; `mode` is ignored).  Primitive ids reported by the batch calls are indices into desc->world.
- * Transformed planes are RTW_E_UNSUPPORTED (their reference AABB is non-finite). */
+ * Transformed planes are RTW_E_UNSUPPORTED (their reference AABB is non-finite).
+ * An EMPTY lights list next to scattering materials is accepted, as in the reference (scenes::plane, integration-tests plane_test):
+ * the reference only panics when a path actually draws a light sample (hittable_list.rs:414-419); a render / batch call in which
+ * that happens returns RTW_E_INVALID. */
 RTW_API int  rtw_scene_create_general(const rtw_scene_desc* desc, rtw_scene** out);
 /* Which builder makes the world BVH of the scenes created AFTER this call (process-wide).  The result of Hittable::hit does not
  * depend on the tree, so images are bit-identical either way; the builders trade build time against traversal cost.

@@ -546,7 +546,11 @@ struct GScene {
         if (!lights_is_bvh) return lights.pdf_value(origin, direction, c);
         return (lights.pdf_value(origin, direction, c) * (double)lights.len) / (double)lights.len;      // bvh.rs:191-194 over one Leaf
     }
-    V3 lights_random(V3 origin, Stream& rng, uint32_t math) const {                       // hittable_list.rs:414-420 / bvh.rs:197-201
+    V3 lights_random(V3 origin, Stream& rng, uint32_t math, bool* panicked) const {       // hittable_list.rs:414-420 / bvh.rs:197-201
+        if (lights.len == 0) {                                                            // .expect("HittableList shouldn't be empty")
+            if (panicked) *panicked = true;
+            return V3{1., 0., 0.};
+        }
         const Prim& l = lights.nth(rng.index((uint32_t)lights.len));
         if (!l.transformed) {
             if (l.kind == P_SPHERE) return sphere_random(l.sphere, origin, rng, math);
@@ -582,14 +586,22 @@ struct GScene {
 struct GVertex { uint32_t kind = V_MISS; GHit rec; Ray next; V3 weight; V3 emitted; };
 
 // Material::scatter / emitted + the Scatter branch of ray_colour_tail_call (camera.rs:478-521)
-inline void gshade(const GScene& sc, const Options& opt, const Ray& r, const GHit& rec, Stream& rng, GVertex* vx, Counters* c) {
+inline void gshade(const GScene& sc, const Options& opt, const Ray& r, const GHit& rec, Stream& rng, GVertex* vx, Counters* c, bool* panicked = nullptr) {
     const GMaterial& m = sc.materials[rec.mat];
     vx->rec = rec;
     vx->emitted = V3{0., 0., 0.};
     auto diffuse = [&](V3 attenuation, bool cosine) {
         Onb uvw(rec.normal);
         V3 dir;
-        if (rng.standard() < 0.5) dir = sc.lights_random(rec.p, rng, opt.math_mode);     // MixturePdf::generate, pdf.rs:94-100
+        if (rng.standard() < 0.5) {                                                       // MixturePdf::generate, pdf.rs:94-100
+            bool pan = false;
+            dir = sc.lights_random(rec.p, rng, opt.math_mode, &pan);
+            if (pan) {                        // the reference panics here; the oracle reports it and ends the path
+                if (panicked) *panicked = true;
+                vx->kind = V_ABSORB; vx->weight = V3{0., 0., 0.};
+                return;
+            }
+        }
         else if (cosine) {                                                                // CosinePdf, utils.rs:146-161
             double r1 = rng.standard(), r2 = rng.standard();
             double sn, cs; sincos_phi(2. * PI * r1, opt.math_mode, &sn, &cs);
@@ -642,7 +654,7 @@ inline V3 gray_colour(const GScene& sc, const Camera& cam, const Options& opt, R
         if (!sc.world_hit(r, opt.tmin, &rec, c, panicked)) { if (c) c->missed++; return mult * cam.background + res; }
         Stream rng(opt.seed, pixel, sample, vertex, opt.rng_mode);
         GVertex vx;
-        gshade(sc, opt, r, rec, rng, &vx, c);
+        gshade(sc, opt, r, rec, rng, &vx, c, panicked);
         if (vx.kind == V_ABSORB) return mult * vx.emitted + res;
         if (vx.kind == V_DIFFUSE) res = res + mult * vx.emitted;
         mult = mult * vx.weight;

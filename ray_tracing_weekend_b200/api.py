@@ -352,7 +352,8 @@ class Scene:
         """general=None picks the sphere path (rtw_scene_create) when the scene allows it, else rtw_scene_create_general;
         True forces the general path."""
         w, l = _as_list(world), _as_list(lights)
-        simple = w.is_simple() and all(isinstance(o, Sphere) for o in l.items) and not isinstance(lights, BoundedVolumeHierarchy)
+        simple = (w.is_simple() and all(isinstance(o, Sphere) for o in l.items) and not isinstance(lights, BoundedVolumeHierarchy)
+                  and (len(l.items) > 0 or not any(o.material.kind == RTW_LAMBERTIAN for o in w.items)))
         if general is None:
             general = not simple
         self.general = bool(general)

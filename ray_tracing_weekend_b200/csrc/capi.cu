@@ -155,6 +155,7 @@ struct GeneralDesc {
 struct rtw_scene {
     bool general = false;
     GeneralDesc gdesc;
+    DevBuf<uint32_t> d_panic;                    // general scenes: "the reference would have panicked" flag written by the kernels
     SceneDevG<float> g32; SceneDevG<double> g64;
     std::vector<rtw_sphere> spheres; std::vector<uint32_t> sphere_material;
     std::vector<rtw_plane> planes; std::vector<uint32_t> plane_material;
@@ -396,6 +397,7 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
     d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
     d.view.flat = flat ? 1u : 0u;
+    d.view.panic_flag = s->d_panic.p;
     d.view.has_xforms = 0;
     for (const GPrim<T>& p : prims) if (p.xform >= 0) d.view.has_xforms = 1;
     return RTW_OK;
@@ -523,6 +525,18 @@ int reserve_batch(rtw_scene* s, size_t n) {
     CU(s->d_out2.reserve(3 * n)); CU(s->d_out3.reserve(3 * n)); CU(s->d_out4.reserve(3 * n));
     CU(s->d_u0.reserve(n)); CU(s->d_u1.reserve(n)); CU(s->d_u2.reserve(n)); CU(s->d_k.reserve(n)); CU(s->d_prim.reserve(n));
     return RTW_OK;
+}
+}  // namespace
+
+namespace {
+// general scenes: did a path do what makes the reference panic?  (call after the stream has been synchronised)
+int check_reference_panic(rtw_scene* s) {
+    if (!s->general) return RTW_OK;
+    uint32_t flag = 0;
+    CU(cudaMemcpy(&flag, s->d_panic.p, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (!flag) return RTW_OK;
+    CU(cudaMemset(s->d_panic.p, 0, sizeof(flag)));
+    return fail(RTW_E_INVALID, "a path sampled an empty lights list: the reference panics here (HittableList shouldn't be empty, hittable_list.rs:414-419)");
 }
 }  // namespace
 
@@ -751,8 +765,7 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
     };
     if (const char* msg = check(d->world, d->n_world, true)) return fail(std::strstr(msg, "not supported") ? RTW_E_UNSUPPORTED : RTW_E_INVALID, msg);
     if (const char* msg = check(d->lights, d->n_lights, false)) return fail(std::strstr(msg, "not supported") ? RTW_E_UNSUPPORTED : RTW_E_INVALID, msg);
-    if (needs_lights && d->n_lights == 0)
-        return fail(RTW_E_INVALID, "scattering material with an empty lights list (the reference panics: HittableList shouldn't be empty)");
+    (void)needs_lights;     // an empty lights list is accepted: the reference only panics when a path actually samples it (checked per render)
     if (d->lights_is_bvh && d->n_lights > 5)
         return fail(RTW_E_UNSUPPORTED, "a BoundedVolumeHierarchy of more than 5 lights (the reference's aux_random indexes out of range, bvh.rs:78-93)");
     int ndev = rtw_device_count();
@@ -775,6 +788,9 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
+    e = s->d_panic.reserve(1);
+    if (e == cudaSuccess) e = cudaMemset(s->d_panic.p, 0, sizeof(uint32_t));
+    if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     int rc = upload_general<float>(s, s->g32);
     if (rc == RTW_OK) rc = upload_general<double>(s, s->g64);
     if (rc != RTW_OK) return bail(rc);
@@ -784,7 +800,7 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
 
 void rtw_scene_destroy(rtw_scene* s) {
     if (!s) return;
-    s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release();
+    s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release(); s->d_panic.release();
     cached_free(s->d_work, sizeof(unsigned int));
     cached_free(s->d_counters, sizeof(DeviceCounters));
     s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release();
@@ -857,6 +873,8 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         DeviceCounters c;
         CU(cudaMemcpyAsync(&c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        rc = check_reference_panic(s);
+        if (rc) return rc;
         std::memset(stats, 0, sizeof(*stats));
         read_stats(c, stats);
         float ms = 0.f;
@@ -904,6 +922,8 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, double* r
     DeviceCounters c;
     CU(cudaMemcpy(&c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     CU(cudaEventSynchronize(s->ev[3]));
+    rc = check_reference_panic(s);
+    if (rc) return rc;
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         read_stats(c, stats);
@@ -984,7 +1004,7 @@ int rtw_scatter_batch(rtw_scene* s, const rtw_opts* opts, const double* o, const
     CU(cudaMemcpy(normal, s->d_out2.p, 3 * n * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(dir, s->d_out3.p, 3 * n * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(weight, s->d_out4.p, 3 * n * 8, cudaMemcpyDeviceToHost));
-    return RTW_OK;
+    return check_reference_panic(s);
 }
 
 
@@ -1042,7 +1062,7 @@ int rtw_path_radiance(rtw_scene* s, const rtw_camera* cam, const rtw_opts* opts,
         CU(launch_path_radiance_f64(P, 0));
     }
     CU(cudaMemcpy(rgb, s->d_out1.p, 3 * n * 8, cudaMemcpyDeviceToHost));
-    return RTW_OK;
+    return check_reference_panic(s);
 }
 
 }  // extern "C"

@@ -334,6 +334,7 @@ template <class T> struct SceneViewG {
     const Vec4T<T>* spheres; const GPlane<T>* plane_geo; const GQuad<T>* quads; const GXform<T>* xforms;
     const GMat<T>* mats; const GTex<T>* textures; const GPerlin<T>* perlins;
     int32_t n_nodes, n_prims, n_unbounded, n_lights;
+    uint32_t* panic_flag;          // set when a path does what makes the reference panic (a light sample from an empty lights list)
     uint32_t lights_is_bvh, has_xforms, flat;   // flat: few entries, walked linearly (sorted by kind) instead of through the BVH
 };
 template <class SC> struct is_general { static constexpr bool value = false; };

@@ -430,7 +430,13 @@ RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h
         if (COUNT && cosine) tl.lambertian++;
         Onb<T, EXACT> uvw(h.normal);
         V3<T> dir;
-        if (standard(rng) < T(0.5)) dir = g_lights_random<T, EXACT>(sc, h.p, rng);      // MixturePdf::generate (pdf1 = lights)
+        if (standard(rng) < T(0.5)) {                                                   // MixturePdf::generate (pdf1 = lights)
+            if (sc.n_lights == 0) {           // .expect("HittableList shouldn't be empty") (hittable_list.rs:414-419): the reference panics;
+                *sc.panic_flag = 1u;          // the render call reports RTW_E_INVALID, the path ends here
+                return V_ABSORB;
+            }
+            dir = g_lights_random<T, EXACT>(sc, h.p, rng);
+        }
         else if (cosine) {                                                              // CosineWeightedHemisphere, utils.rs:146-161
             T r1 = standard(rng), r2 = standard(rng);
             T sn, cs;

@@ -43,10 +43,11 @@ int main(int argc, char** argv) {
         else if (scene == "debug") general_sc = scenes::debugging_scene(opt.seed);
         else if (scene == "simple-transform" || scene == "simple_transform") general_sc = scenes::simple_transform(opt.seed);
         else if (scene == "checkered-spheres" || scene == "checkered_spheres") general_sc = scenes::checkered_spheres();
+        else if (scene == "plane") general_sc = scenes::plane();
         else {
-            // perlin-spheres and plane pair Lambertian surfaces with an EMPTY lights list: the reference panics on the first light
+            // perlin-spheres pairs Lambertian spheres in plain view with an EMPTY lights list: the reference panics on the first light
             // sample (hittable_list.rs:414-419)
-            std::fprintf(stderr, "scene '%s' is not provided (simple, simple-light, cornell-box, debug, simple-transform, checkered-spheres)\n", scene.c_str());
+            std::fprintf(stderr, "scene '%s' is not provided (simple, simple-light, cornell-box, debug, simple-transform, checkered-spheres, plane)\n", scene.c_str());
             return 2;
         }
         if (general) cb = general_sc.cam;

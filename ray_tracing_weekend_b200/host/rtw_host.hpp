@@ -311,6 +311,8 @@ public:
                                                    rtw_stats* stats = nullptr) const {
         rtw_scene* scene = nullptr;
         bool simple = world.list->is_simple() && !lights.is_bvh && lights.list->spheres().size() == lights.list->len();
+        if (simple && lights.list->is_empty())          // an empty lights list next to a Lambertian: only the general path accepts it
+            for (const Entry& e : world.list->entries()) if (e.mat->pod.kind == RTW_LAMBERTIAN) simple = false;
         if (simple) {
             std::vector<rtw_sphere> spheres; std::vector<uint32_t> smat; std::vector<rtw_plane> planes; std::vector<uint32_t> pmat;
             std::vector<rtw_material> mats; std::vector<rtw_sphere> ls;
@@ -488,6 +490,18 @@ inline GeneralOutput checkered_spheres() {
     o.world.add(Sphere::new_(Point3(0., 10., 0.), 10., checker));
     o.lights.add(Sphere::new_(Point3(0., 0., 0.), 0.1, checker));
     Point3 lookfrom(40., 1., 0.), lookat(0., 0., 0.);
+    o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_focus_dist((lookfrom - lookat).length()).with_vfov(40.)
+                .with_background(Colour(1., 1., 1.));
+    return o;
+}
+
+// scenes::plane (scenes/src/lib.rs:91-121): an EMPTY lights list; the one-sided plane is invisible from this camera, so the reference
+// never samples the lights (it would panic) — integration-tests plane_test renders it
+inline GeneralOutput plane() {
+    GeneralOutput o;
+    o.world.add(Plane::new_(Point3(0., 0., 0.), Vec3(0., 1., 0.),
+                            Lambertian::new_(CheckerTexture::new_with_colours(Colour(0.2, 0.3, 0.1), Colour(0.9, 0.9, 0.9), 0.32))));
+    Point3 lookfrom(0., 30., 0.), lookat(0., 0., 0.);
     o.cam = CameraBuilder().with_lookfrom(lookfrom).with_lookat(lookat).with_focus_dist((lookfrom - lookat).length()).with_vfov(40.)
                 .with_background(Colour(1., 1., 1.));
     return o;

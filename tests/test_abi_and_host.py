@@ -102,10 +102,11 @@ def test_tile_partition_helpers(rtw):
 def test_argument_validation_needs_no_gpu(rtw):
     from ray_tracing_weekend_b200 import _lib
     L = rtw.load()
-    # a Lambertian world with an empty lights list: the reference panics (hittable_list.rs:414-419)
+    # a Lambertian world with an empty lights list: rtw_scene_create (sphere path) refuses it — the reference panics on the first
+    # light sample (hittable_list.rs:414-419); the general path accepts it and reports the panic per render (tests/test_gpu_general.py)
     world = rtw.HittableList(); world.add(rtw.Sphere((0, 0, 0), 1.0, rtw.Lambertian((0.5, 0.5, 0.5))))
     with pytest.raises(rtw.RtwError) as e:
-        rtw.Scene(world, rtw.HittableList())
+        rtw.Scene(world, rtw.HittableList(), general=False)
     assert e.value.code == _lib.RTW_E_INVALID and "lights" in str(e.value)
     world = rtw.HittableList(); world.add(rtw.Sphere((0, 0, 0), -1.0, rtw.Metal((1, 1, 1), 0.0)))
     with pytest.raises(rtw.RtwError) as e:

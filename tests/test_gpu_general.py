@@ -317,6 +317,14 @@ def test_empty_lights_list_maps_the_reference_panic(rtw, oracle):
             with pytest.raises(rtw.RtwError) as e:
                 scene.render(cam, rtw.RenderOptions(seed=SEED, precision=prec))
             assert e.value.code == _lib.RTW_E_INVALID and "panics" in str(e.value)
+        # scenes::perlin_spheres as the reference builds it: Lambertian spheres in plain view, no lights -> the reference panics
+        pw, pl, pcb = rtw.scenes.perlin_spheres(SEED)
+        ps = rtw.Scene(pw, pl)
+        pcam = pcb.with_image_width(12).with_image_height(12).with_samples_per_pixel(4).build()
+        with pytest.raises(rtw.RtwError) as e:
+            ps.render(pcam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32))
+        assert e.value.code == _lib.RTW_E_INVALID
+        ps.close()
         # the handle stays usable: the same scene from above renders (no Lambertian hit, no light sample)
         _, _, cb = rtw.scenes.plane()
         up = cb.with_image_width(4).with_image_height(4).with_samples_per_pixel(2).build()

@@ -128,7 +128,7 @@ def run_reference(args):
                 mpaths_per_s=r["paths"] / r["seconds"] * 1e-6,
                 cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=r["cores"], kind="port", sample=r["sample"] + "; each step is one such frame"),
                 e2e=dict(value=mrays, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_cuda(args):
@@ -284,14 +284,37 @@ def run_cuda(args):
                 line["cpu_baseline"]["faithful_bvh_value"] = f["rays"] / f["seconds"] * 1e-6
             except Exception as e:                                         # the oracle is only a reported baseline
                 line["cpu_baseline"] = dict(value=None, unit="Mrays/s", cores=0, kind="port", sample=f"unavailable: {e}")
-        print(json.dumps(line), flush=True)
+        _emit(line)
     scene.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout whatever
+    NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole process and the JSON line goes to a private copy of the
+    original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _protect_stdout()
     global SPP, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

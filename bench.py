@@ -3,7 +3,8 @@
 random-spheres (scenes::simple, seeded) 1920x1080, 500 spp, depth 50, N B200s; the wavefront renderer is timed
 (the faster of the two FP32 renderers), the megakernel is measured beside it outside the timed region.
 
-A step is one full render of that frame: rtw_render_tiles_device on every rank (tiles interleaved across
+A step is one full render of that frame: every rank renders its share (N > 1: its samples of every pixel into fixed-point
+accumulators, one NCCL reduce; N = 1 / f64: rtw_render_tiles_device, tiles interleaved across
 ranks), one NCCL gather of the tile buffers on rank 0, untile + resolve there.  Contract: see the task
 brief — prints ONE JSON line on rank 0.
 
@@ -163,7 +164,7 @@ def run_cuda(args):
 
     # event counts of one step (deterministic: counter-based RNG) — an untimed pass with counters on
     copts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=R.RTW_FLAG_COUNT_EVENTS | base_flags)
-    cnt = scene.render_tiles_device(cam, copts, rank, world, renderer.local.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    cnt = renderer.render_local(copts, want_stats=True)
     keys = ["paths", "rays", "node_visits", "sphere_tests", "light_tests", "lambertian", "metal", "dielectric", "absorbed", "missed", "depth_out"]
     tot = torch.tensor([cnt[k] for k in keys], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -183,11 +184,9 @@ def run_cuda(args):
         flush.fill_(k & 0xff)                                # evict L2 between timed iterations (outside the event pairs)
         ev[k][0].record()
         ev[k][2].record()
-        scene.render_tiles_device(cam, opts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+        renderer.render_local()                              # this rank's share: its samples of every pixel (or its tiles)
         ev[k][3].record()
-        allt = D.gather_tiles(renderer.local, 0)
-        if rank == 0:
-            R.untile_resolve_device(allt.data_ptr(), opts.precision, WIDTH, HEIGHT, world, SPP, 0, renderer.rgb8.data_ptr(), stream)
+        renderer.combine()                                   # the frame's one collective + resolve on rank 0
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -229,12 +228,12 @@ def run_cuda(args):
     if not args.lane_per_pixel:
         omode = R.RTW_MEGAKERNEL if mode == R.RTW_WAVEFRONT else R.RTW_WAVEFRONT
         oopts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=omode)
-        scene.render_tiles_device(cam, oopts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+        renderer.render_local(oopts)
         barrier()
         oev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         oev[0].record()
         for _ in range(2):
-            scene.render_tiles_device(cam, oopts, rank, world, renderer.local.data_ptr(), stream, want_stats=False)
+            renderer.render_local(oopts)
         oev[1].record()
         barrier()
         ot = torch.tensor([oev[0].elapsed_time(oev[1]) / 2], dtype=torch.float64, device="cuda")
@@ -260,7 +259,8 @@ def run_cuda(args):
             metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=WORKLOAD, mode=("wavefront (warp-private queues in shared memory)" if args.mode == "wavefront" else
-                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather",
+                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=(f"samples of every pixel split over {world} GPU(s) (fixed-point accumulators) + 1 NCCL reduce" if renderer.partition == "samples"
+                                     else f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather"),
                         tmin="RTW_TMIN_REFERENCE: machine epsilon of the working precision (the reference uses f64::EPSILON in f64)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
             mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
             kernel_ms_per_step=kern_ms / args.steps,
@@ -270,7 +270,9 @@ def run_cuda(args):
                           frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None),
             e2e=dict(value=total["rays"] * e2e_steps / e2e_s * 1e-6, unit="Mrays/s", h2d_bytes_per_step=scene.upload_bytes * world,
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
-            gpu_launches=args.steps * ((1 if (args.lane_per_pixel and args.mode == "megakernel") else 2) * world + 1),
+            # per step: tiles partition = render (+ fixed-point -> tiles conversion) per rank + untile on rank 0; samples partition =
+            # render per rank + resolve on rank 0
+            gpu_launches=args.steps * ((1 if (renderer.partition == "samples" or (args.lane_per_pixel and args.mode == "megakernel")) else 2) * world + 1),
             clocks=clocks,
             events_per_step={k: total[k] for k in keys},
             other_renderer=other,

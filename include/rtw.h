@@ -242,6 +242,21 @@ RTW_API int rtw_untile_resolve_device(const void* d_tiles_all, uint32_t precisio
                               uint32_t world, uint32_t samples_per_pixel, double* d_rgb_sum, uint8_t* d_rgb8,
                               void* stream);
 
+/* Sample partition (the better-balanced way to use several GPUs for the FP32 renderers): render samples
+ * [sample_begin, sample_begin + sample_count) of EVERY pixel into the caller's fixed-point accumulators —
+ *   d_accum:  [rtw_tiles_total() * RTW_TILE_H * RTW_TILE_W][3] u64, radiance sums in 2^-32 units, pixels in tile-slot order (world = 1)
+ *   d_poison: [rtw_tiles_total() * RTW_TILE_H * RTW_TILE_W] u32, NaN / overflow flags, one 4-bit field each
+ * (both are overwritten).  Integer sums commute and the flag fields do not carry into each other for up to 15 ranks, so SUMMING the
+ * buffers of all ranks (one NCCL reduce) and resolving gives the single-GPU image bit for bit, whatever the number of ranks.  Every
+ * rank sees every pixel, so the ranks' loads differ only by the rounding of samples_per_pixel / world.  RTW_F32 only (not with
+ * RTW_FLAG_LANE_PER_PIXEL); paths are keyed by their absolute sample index. */
+RTW_API int rtw_render_samples_device(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, uint32_t sample_begin,
+                              uint32_t sample_count, void* d_accum, void* d_poison, void* stream, rtw_stats* stats);
+/* (summed) accumulators -> DEVICE d_rgb_sum ([h][w][3] f64, may be NULL) and d_rgb8 ([h][w][3] u8, may be NULL); samples_per_pixel
+ * is the camera's total. */
+RTW_API int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, uint32_t width, uint32_t height,
+                             uint32_t samples_per_pixel, double* d_rgb_sum, uint8_t* d_rgb8, void* stream);
+
 /* ---- per-ray operations (parity surface) ------------------------------------------------------- */
 /* Hittable::hit of the world for a batch of rays (shared/src/hittable.rs:173; bvh.rs:163-188).
  * o, d: [n][3] f64 host arrays; prim_id: -1 = miss; t: +inf on a miss.  precision as in rtw_opts. */

@@ -465,6 +465,16 @@ class Scene:
         _lib.check(_lib.load().rtw_render(self._h, C.byref(camera.pod), C.byref(po), _p(rgb_sum), _p(rgb8), C.byref(st)))
         return rgb_sum, rgb8, st.as_dict()
 
+    def render_samples_device(self, camera: "Camera", opts: RenderOptions, sample_begin: int, sample_count: int, d_accum_ptr: int,
+                              d_poison_ptr: int, stream: int = 0, want_stats=True):
+        """rtw_render_samples_device: samples [sample_begin, sample_begin + sample_count) of every pixel into fixed-point accumulators."""
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render_samples_device(self._h, C.byref(camera.pod), C.byref(po), sample_begin, sample_count,
+                                                         C.c_void_p(d_accum_ptr), C.c_void_p(d_poison_ptr), C.c_void_p(stream),
+                                                         C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
     def render_tiles_device(self, camera: "Camera", opts: RenderOptions, rank: int, world: int, d_tiles_ptr: int, stream: int = 0,
                             want_stats=True):
         st = rtw_stats()
@@ -472,6 +482,12 @@ class Scene:
         _lib.check(_lib.load().rtw_render_tiles_device(self._h, C.byref(camera.pod), C.byref(po), rank, world, C.c_void_p(d_tiles_ptr),
                                                        C.c_void_p(stream), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+
+def resolve_accum_device(d_accum_ptr, d_poison_ptr, width, height, spp, d_rgb_sum_ptr=0, d_rgb8_ptr=0, stream=0):
+    _lib.check(_lib.load().rtw_resolve_accum_device(C.c_void_p(d_accum_ptr), C.c_void_p(d_poison_ptr), width, height, spp,
+                                                    C.c_void_p(d_rgb_sum_ptr) if d_rgb_sum_ptr else None,
+                                                    C.c_void_p(d_rgb8_ptr) if d_rgb8_ptr else None, C.c_void_p(stream)))
 
 
 def untile_resolve_device(d_tiles_all_ptr, precision, width, height, world, spp, d_rgb_sum_ptr=0, d_rgb8_ptr=0, stream=0):

@@ -492,11 +492,14 @@ void read_stats(const DeviceCounters& c, rtw_stats* st) {
     st->absorbed = c.absorbed; st->missed = c.missed; st->depth_out = c.depth_out;
 }
 
+struct SampleRange { uint32_t begin = 0, count = 0; bool set = false; };     // sample partition: this launch's samples of every pixel
+
 template <class T, class DEV, class Launch>
 int render_tiles_t(rtw_scene* s, DEV& d, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, T* tiles,
-                   cudaStream_t stream, Launch launch) {
+                   cudaStream_t stream, Launch launch, SampleRange sr = SampleRange()) {
     RenderParams<T, decltype(d.view)> P{};
     P.scene = d.view; P.cam = to_camera<T>(cam); P.seed = o->seed; P.tmin = resolve_tmin<T>(o->tmin); P.flags = o->flags;
+    if (sr.set) { P.cam.spp = sr.count; P.cam.sample_offset = sr.begin; }
     P.rank = rank; P.world = world;
     P.tiles_x = (cam->image_width + kTileW - 1) / kTileW;
     P.tiles_total = rtw_tiles_total(cam->image_width, cam->image_height);
@@ -817,9 +820,14 @@ int rtw_scene_info(const rtw_scene* s, uint64_t out[5]) {
     return RTW_OK;
 }
 
-int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, void* d_tiles,
-                            void* stream, rtw_stats* stats) {
-    if (!s || !d_tiles) return fail(RTW_E_INVALID, "NULL argument");
+}  // extern "C"
+
+namespace {
+// rtw_render_tiles_device (tile partition: ext_accum == nullptr) and rtw_render_samples_device (sample partition: the caller's
+// fixed-point accumulators, every pixel, samples [sr.begin, sr.begin + sr.count))
+int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, void* d_tiles,
+                       void* stream, rtw_stats* stats, SampleRange sr, unsigned long long* ext_accum, uint32_t* ext_poison) {
+    if (!s || (!d_tiles && !ext_accum)) return fail(RTW_E_INVALID, "NULL argument");
     int rc = check_camera(cam); if (rc) return rc;
     rc = check_opts(o); if (rc) return rc;
     if (world == 0 || rank >= world) return fail(RTW_E_INVALID, "rank/world");
@@ -827,31 +835,35 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
     uint32_t launches = 1;
     // RTW_F64 has one renderer (lane per pixel, samples summed in order); `mode` only selects among the FP32 renderers
     bool pooled = o->precision == RTW_F32 && (o->mode == RTW_WAVEFRONT || !(o->flags & RTW_FLAG_LANE_PER_PIXEL));
-    if (pooled) {
+    if (s->general && (o->flags & RTW_FLAG_LANE_PER_PIXEL)) pooled = false;      // `mode` does not apply to general scenes
+    if (ext_accum && !pooled) return fail(RTW_E_UNSUPPORTED, "the sample partition needs a fixed-point FP32 renderer (RTW_F32 without RTW_FLAG_LANE_PER_PIXEL)");
+    if (pooled && !ext_accum) {
         size_t n_slots = (size_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         CU(s->d_accum.reserve(n_slots * 3)); CU(s->d_poison.reserve(n_slots));
     }
-    if (s->general && (o->flags & RTW_FLAG_LANE_PER_PIXEL)) pooled = false;      // `mode` does not apply to general scenes
+    unsigned long long* accum_p = ext_accum ? ext_accum : s->d_accum.p;
+    uint32_t* poison_p = ext_accum ? ext_poison : s->d_poison.p;
+    const uint32_t spp_here = sr.set ? sr.count : cam->samples_per_pixel;
     CU(cudaEventRecord(s->ev[0], st));
     if (s->general) {
         // general scenes: FP32 = pooled path stream (or lane per pixel with RTW_FLAG_LANE_PER_PIXEL), f64 = lane per pixel
         if (pooled) {
             PoolParams Q{};
-            Q.accum = s->d_accum.p; Q.poison = s->d_poison.p;
-            Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
+            Q.accum = accum_p; Q.poison = poison_p;
+            Q.pixels_per_chunk = pool_pixels_per_chunk(spp_here);
             uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
             Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
             auto launch = [&](RenderParams<float, SceneViewG<float>> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
                 return launch_render_pool_general_f32(P, Q, count, sms, str, info);
             };
-            rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch);
+            rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch, sr);
             launches = 2;
         } else if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch_render_general_f32);
         else rc = render_tiles_t<double>(s, s->g64, cam, o, rank, world, (double*)d_tiles, st, launch_render_general_f64);
     } else if (pooled) {
         PoolParams Q{};
-        Q.accum = s->d_accum.p; Q.poison = s->d_poison.p;
-        Q.pixels_per_chunk = pool_pixels_per_chunk(cam->samples_per_pixel);
+        Q.accum = accum_p; Q.poison = poison_p;
+        Q.pixels_per_chunk = pool_pixels_per_chunk(spp_here);
         uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
         // the wavefront packs the remaining depth into 16 bits; deeper paths take the (bit-identical) megakernel
@@ -862,7 +874,7 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)
                              : launch_render_pool_f32(P, Q, count, sms, str, info);
         };
-        rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch);
+        rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch, sr);
         launches = 2;
     } else if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch_render_f32);
     else rc = render_tiles_t<double>(s, s->f64, cam, o, rank, world, (double*)d_tiles, st, launch_render_f64);
@@ -881,6 +893,30 @@ int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts*
         CU(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
         stats->kernel_ms = ms; stats->total_ms = ms; stats->launches = launches;
     }
+    return RTW_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rtw_render_tiles_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, void* d_tiles,
+                            void* stream, rtw_stats* stats) {
+    if (!d_tiles) return fail(RTW_E_INVALID, "NULL argument");
+    return render_device_impl(s, cam, o, rank, world, d_tiles, stream, stats, SampleRange(), nullptr, nullptr);
+}
+
+int rtw_render_samples_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, uint32_t sample_begin, uint32_t sample_count,
+                              void* d_accum, void* d_poison, void* stream, rtw_stats* stats) {
+    if (!d_accum || !d_poison) return fail(RTW_E_INVALID, "NULL argument");
+    if (cam && (uint64_t)sample_begin + sample_count > cam->samples_per_pixel) return fail(RTW_E_INVALID, "sample range outside the camera's samples_per_pixel");
+    SampleRange sr; sr.begin = sample_begin; sr.count = sample_count; sr.set = true;
+    return render_device_impl(s, cam, o, 0, 1, nullptr, stream, stats, sr, (unsigned long long*)d_accum, (uint32_t*)d_poison);
+}
+
+int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, uint32_t width, uint32_t height, uint32_t spp, double* d_rgb_sum,
+                             uint8_t* d_rgb8, void* stream) {
+    if (!d_accum || !d_poison || width == 0 || height == 0) return fail(RTW_E_INVALID, "bad argument");
+    CU(launch_resolve_accum_f32((const unsigned long long*)d_accum, (const uint32_t*)d_poison, width, height, spp, d_rgb_sum, d_rgb8, (cudaStream_t)stream));
     return RTW_OK;
 }
 

@@ -62,6 +62,10 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #endif
     return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
 }
+cudaError_t launch_resolve_accum_f32(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp,
+                                     double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
+    return launch_resolve_accum(accum, poison, width, height, spp, rgb_sum, rgb8, s);
+}
 // deepest BVH the default wavefront shape can traverse: its per-thread stacks share the CTA's shared memory with the path slots
 uint32_t wavefront_max_bvh_depth() {
     const size_t limit = 226 * 1024, state = wavefront_state_bytes<kWfBlock, kWfSlotsPerWarp>();

@@ -344,6 +344,7 @@ template <class T> struct CameraT {
     V3<T> center, pixel00, du, dv, ddu, ddv, background;
     T defocus_angle, jitter_scale;
     uint32_t width, height, spp, max_depth;
+    uint32_t sample_offset;        // this launch renders samples [sample_offset, sample_offset + spp) of every pixel (sample partition)
 };
 
 struct DeviceCounters {   // u64 slots in global memory

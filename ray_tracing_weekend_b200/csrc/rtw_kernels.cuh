@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
         ps.depth = 0;
         for (;;) {
             if (!alive && valid && sample < cam.spp) {
-                Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                Stream<EXACT> rng(P.seed, pixel, sample + cam.sample_offset, 0u);
                 ps.r = get_ray<T, EXACT>(cam, i, j, rng);
                 ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
                 alive = true;
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
             if (!__any_sync(0xffffffffu, alive)) break;
             if (alive) {
                 V3<T> value;
-                if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+                if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample + cam.sample_offset, ps, &value, stack, BLOCK, nrays, tl)) {
                     if (P.flags & 1u) value = fix_nan(value);
                     acc = acc + value;                          // fold(Colour::default(), +), camera.rs:335
                     alive = false;
@@ -673,7 +673,7 @@ constexpr float kFixedMax = 1073741824.f;              // samples >= 2^30 satura
 
 struct PoolParams {
     unsigned long long* accum;      // [n_local_tiles * 256][3]
-    uint32_t* poison;               // [n_local_tiles * 256]: bit c = NaN in channel c, bit 3 + c = overflow / +inf
+    uint32_t* poison;               // [n_local_tiles * 256]: poison words (poison_nan / poison_inf below)
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
 };
@@ -684,9 +684,15 @@ RTW_D void pool_flush(const PoolParams& Q, uint32_t q, unsigned long long a0, un
     if (a2) atomicAdd(Q.accum + 3 * (size_t)q + 2, a2);
 }
 
+// poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
+// ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
+RTW_HD uint32_t poison_nan(uint32_t channel) { return 1u << (4u * channel); }
+RTW_HD uint32_t poison_inf(uint32_t channel) { return 1u << (12u + 4u * channel); }
+RTW_HD bool poison_has_nan(uint32_t word, uint32_t channel) { return (word >> (4u * channel)) & 15u; }
+RTW_HD bool poison_has_inf(uint32_t word, uint32_t channel) { return (word >> (12u + 4u * channel)) & 15u; }
 RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
     if (!(v < kFixedMax)) {                                    // NaN, +inf or absurdly large
-        bad |= (v != v) ? (1u << channel) : (8u << channel);
+        bad |= (v != v) ? poison_nan(channel) : poison_inf(channel);
         return 0ull;
     }
     return __float2ull_rn(v * kFixedScale);                    // negative values clamp to 0
@@ -753,7 +759,7 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
                 uint32_t r = chunk_next + __popc(need & lt_mask);
                 if (r < chunk_end) {
                     uint32_t pin = r / spp;
-                    sample = r - pin * spp;
+                    sample = r - pin * spp + cam.sample_offset;
                     q = chunk_q0 + pin;
                     uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
                     uint32_t ttx, tty;
@@ -809,8 +815,8 @@ __global__ void pool_finalize_kernel(const unsigned long long* accum, const uint
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float v = (float)((double)accum[3 * (size_t)q + c] * (1.0 / 4294967296.0));
-        if (bad & (8u << c)) v = __int_as_float(0x7f800000);
-        if (bad & (1u << c)) v = __int_as_float(0x7fc00000);
+        if (poison_has_inf(bad, c)) v = __int_as_float(0x7f800000);
+        if (poison_has_nan(bad, c)) v = __int_as_float(0x7fc00000);
         tiles[3 * (size_t)q + c] = v;
     }
 }
@@ -924,6 +930,35 @@ __global__ void untile_resolve_kernel(const T* tiles, uint32_t width, uint32_t h
             double q = 256. * g;
             uint8_t b = (q != q) ? 0 : (q >= 255. ? 255 : (q <= 0. ? 0 : (uint8_t)q));
             rgb8[dst + c] = b;
+        }
+    }
+}
+
+// Sample partition: fixed-point accumulators (+ poison words) of the WHOLE image, e.g. the sum of several ranks' partial
+// accumulators, -> rgb_sum / rgb8.  pool_finalize_kernel + untile_resolve_kernel in one pass, same arithmetic.
+template <int UNUSED = 0>
+__global__ void resolve_accum_kernel(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t tiles_x,
+                                     uint32_t spp, double* rgb_sum, uint8_t* rgb8) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= width || j >= height) return;
+    uint32_t tile = tile_slot(i / kTileW, j / kTileH, tiles_x);
+    size_t q = (size_t)tile * (kTileW * kTileH) + (size_t)(j % kTileH) * kTileW + (i % kTileW);
+    uint32_t bad = poison[q];
+    size_t dst = ((size_t)j * width + i) * 3;
+    double scale = 1. / (double)(int32_t)spp;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float f = (float)((double)accum[3 * q + c] * (1.0 / 4294967296.0));
+        if (poison_has_inf(bad, c)) f = __int_as_float(0x7f800000);
+        if (poison_has_nan(bad, c)) f = __int_as_float(0x7fc00000);
+        double v = (double)f;
+        if (rgb_sum) rgb_sum[dst + c] = v;
+        if (rgb8) {
+            double g = sqrt(v * scale);
+            if (g < 0.) g = 0.;
+            if (g > 1.) g = 1.;
+            double qq = 256. * g;
+            rgb8[dst + c] = (qq != qq) ? 0 : (qq >= 255. ? 255 : (qq <= 0. ? 0 : (uint8_t)qq));
         }
     }
 }

@@ -97,6 +97,12 @@ cudaError_t launch_render_t(RenderParams<T> P, bool count, int sm_count, cudaStr
     return count ? launch_render_impl<T, EXACT, true>(P, sm_count, s, info) : launch_render_impl<T, EXACT, false>(P, sm_count, s, info);
 }
 
+inline cudaError_t launch_resolve_accum(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp,
+                                        double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
+    dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    resolve_accum_kernel<0><<<grid, block, 0, s>>>(accum, poison, width, height, (width + kTileW - 1) / kTileW, spp, rgb_sum, rgb8);
+    return cudaGetLastError();
+}
 inline int batch_grid(size_t n) { return (int)((n + kBatchBlock - 1) / kBatchBlock); }
 
 template <class T, bool EXACT> cudaError_t launch_trace_t(const BatchParams<T>& P, cudaStream_t s) {
@@ -145,6 +151,7 @@ template <class PARAMS> inline cudaError_t pool_clear(const PARAMS& P, const Poo
     return cudaMemsetAsync(Q.poison, 0, (size_t)n_slots * sizeof(uint32_t), s);
 }
 template <class PARAMS> inline cudaError_t pool_finalize(const PARAMS& P, const PoolParams& Q, cudaStream_t s) {
+    if (!P.tiles) return cudaSuccess;               // sample partition: the caller reduces and resolves the accumulators itself
     uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH);
     pool_finalize_kernel<0><<<(n_slots + 255) / 256, 256, 0, s>>>(Q.accum, Q.poison, P.tiles, n_slots);
     return cudaGetLastError();

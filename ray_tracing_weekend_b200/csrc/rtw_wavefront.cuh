@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             bool started = false;
             if (active) {
                 uint32_t r = chunk_next + lane;
-                uint32_t pin = r / spp, sample = r - pin * spp;
+                uint32_t pin = r / spp, sample = r - pin * spp + cam.sample_offset;
                 uint32_t q = chunk_q0 + pin;
                 uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
                 uint32_t ttx, tty;

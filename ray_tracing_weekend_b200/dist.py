@@ -1,5 +1,10 @@
-"""Multi-GPU render: one process per GPU (torchrun), image tiles partitioned across ranks, one gather
-of the framebuffer tiles to rank 0 at the end (NCCL over NVLink; gloo on CPU for the host-logic tests).
+"""Multi-GPU render: one process per GPU (torchrun), ONE collective per frame (NCCL over NVLink; gloo on CPU for the host-logic
+tests).  Two partitions:
+
+  samples (FP32 renderers, the default when samples_per_pixel >= world): every rank renders ALL pixels but only its share of the
+      samples into 64-bit fixed-point accumulators; one reduce (integer sum) to rank 0, resolve there.  Integer sums commute, so
+      the image is the single-GPU image bit for bit, and the ranks' loads differ only by the rounding of spp / world.
+  tiles (f64, and the fallback): image tiles dealt to the ranks, one gather of the tile buffers to rank 0, untile + resolve there.
 
 The reference has no distributed path; its only parallelism is rayon over pixels
 (shared/src/camera.rs:353).  Pixels are independent and the RNG is keyed by the absolute pixel index, so
@@ -92,31 +97,84 @@ def gather_tiles(local_tiles: torch.Tensor, dst: int = 0, group=None) -> Optiona
     return None
 
 
+def sample_range(spp: int, rank: int, world: int):
+    """This rank's samples [begin, begin + count) of every pixel: contiguous shares that differ by at most one sample."""
+    begin, end = rank * spp // world, (rank + 1) * spp // world
+    return begin, end - begin
+
+
+def accum_words(width: int, height: int) -> int:
+    """int64 words of one rank's accumulator block: [slots][3] u64 radiance sums followed by [slots] u32 poison words."""
+    slots = tiles_total(width, height) * TILE_W * TILE_H
+    return 3 * slots + (slots + 1) // 2
+
+
+def reduce_accum(block: torch.Tensor, dst: int = 0, group=None):
+    """The one collective of the sample partition: integer SUM of every rank's accumulator block on `dst` (in place).  The poison
+    words travel in the same buffer: their six flags sit in separate 4-bit fields, so adding the words of up to 15 ranks keeps a
+    flag set iff any rank set it."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(block, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return block
+
+
 class DistributedRenderer:
     """Holds the per-rank device buffers so repeated renders (bench steps) allocate nothing."""
 
-    def __init__(self, scene, camera, opts, rank: int, world: int, want_sum: bool = False, want_rgb8: bool = True):
+    def __init__(self, scene, camera, opts, rank: int, world: int, want_sum: bool = False, want_rgb8: bool = True, partition: Optional[str] = None):
         from . import api
         self.api = api
         self.scene, self.camera, self.opts, self.rank, self.world = scene, camera, opts, rank, world
         w, h = camera.image_width, camera.image_height
-        self.tpr = tiles_per_rank(w, h, world)
-        dt = torch.float32 if opts.precision == api.RTW_F32 else torch.float64
-        self.local = torch.zeros((self.tpr, TILE_H, TILE_W, 3), dtype=dt, device="cuda")
+        spp = camera.pod.samples_per_pixel
+        fixed_point = opts.precision == api.RTW_F32 and not (opts.flags & api._lib.RTW_FLAG_LANE_PER_PIXEL)
+        if partition is None:
+            partition = "samples" if (fixed_point and world > 1 and world <= 15 and spp >= world) else "tiles"
+        if partition == "samples" and not fixed_point:
+            raise ValueError("the sample partition needs a fixed-point FP32 renderer")
+        self.partition = partition
         self.rgb_sum = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda") if (want_sum and rank == 0) else None
         self.rgb8 = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda") if (want_rgb8 and rank == 0) else None
+        if partition == "samples":
+            self.slots = tiles_total(w, h) * TILE_W * TILE_H
+            self.block = torch.zeros(accum_words(w, h), dtype=torch.int64, device="cuda")
+            self.sample_begin, self.sample_count = sample_range(spp, rank, world)
+            self.local = None
+        else:
+            self.tpr = tiles_per_rank(w, h, world)
+            dt = torch.float32 if opts.precision == api.RTW_F32 else torch.float64
+            self.local = torch.zeros((self.tpr, TILE_H, TILE_W, 3), dtype=dt, device="cuda")
 
-    def render(self, want_stats: bool = False):
-        """One frame: render this rank's tiles, gather on rank 0, untile + resolve there.
-        Work is enqueued on torch's current stream; returns the kernel stats dict when asked (that syncs)."""
+    def render_local(self, opts=None, want_stats: bool = False):
+        """This rank's share of the frame (kernels only, no collective) on torch's current stream."""
         stream = torch.cuda.current_stream().cuda_stream
-        st = self.scene.render_tiles_device(self.camera, self.opts, self.rank, self.world, self.local.data_ptr(), stream,
-                                            want_stats=want_stats)
+        opts = opts or self.opts
+        if self.partition == "samples":
+            return self.scene.render_samples_device(self.camera, opts, self.sample_begin, self.sample_count, self.block.data_ptr(),
+                                                    self.block.data_ptr() + 8 * 3 * self.slots, stream, want_stats=want_stats)
+        return self.scene.render_tiles_device(self.camera, opts, self.rank, self.world, self.local.data_ptr(), stream, want_stats=want_stats)
+
+    def combine(self):
+        """The frame's one collective + the resolve on rank 0."""
+        stream = torch.cuda.current_stream().cuda_stream
+        cam = self.camera.pod
+        sum_ptr = self.rgb_sum.data_ptr() if self.rgb_sum is not None else 0
+        rgb8_ptr = self.rgb8.data_ptr() if self.rgb8 is not None else 0
+        if self.partition == "samples":
+            reduce_accum(self.block, 0)
+            if self.rank == 0:
+                self.api.resolve_accum_device(self.block.data_ptr(), self.block.data_ptr() + 8 * 3 * self.slots, cam.image_width,
+                                              cam.image_height, cam.samples_per_pixel, sum_ptr, rgb8_ptr, stream)
+            return
         allt = gather_tiles(self.local, 0)
         if self.rank == 0:
-            cam = self.camera.pod
             self.api.untile_resolve_device(allt.data_ptr(), self.opts.precision, cam.image_width, cam.image_height, self.world,
-                                           cam.samples_per_pixel, self.rgb_sum.data_ptr() if self.rgb_sum is not None else 0,
-                                           self.rgb8.data_ptr() if self.rgb8 is not None else 0, stream)
+                                           cam.samples_per_pixel, sum_ptr, rgb8_ptr, stream)
             self._keep = allt       # keep the gathered buffer alive until the stream has consumed it
+
+    def render(self, want_stats: bool = False):
+        """One frame: this rank's share, the collective, the resolve on rank 0.  Work is enqueued on torch's current stream; returns
+        the kernel stats dict when asked (that syncs)."""
+        st = self.render_local(want_stats=want_stats)
+        self.combine()
         return st

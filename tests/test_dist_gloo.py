@@ -64,3 +64,55 @@ def test_gather_of_partitioned_tiles_rebuilds_the_image(world, w, h):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _poison_word(nan_rgb, inf_rgb):
+    """csrc/rtw_kernels.cuh: poison_nan(c) = 1 << 4c, poison_inf(c) = 1 << (12 + 4c)."""
+    return sum(1 << (4 * c) for c in range(3) if nan_rgb[c]) | sum(1 << (12 + 4 * c) for c in range(3) if inf_rgb[c])
+
+
+def _accum_worker(rank, world, port, w, h, spp, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from ray_tracing_weekend_b200 import dist as D
+    D.init_from_env(backend="gloo")
+    slots = D.tiles_total(w, h) * 256
+    block = torch.zeros(D.accum_words(w, h), dtype=torch.int64)
+    # every rank "renders" its samples: each sample adds (slot + 1) * 2^32 / 8 to the red accumulator of its slot
+    b, c = D.sample_range(spp, rank, world)
+    acc = block[: 3 * slots].view(slots, 3)
+    acc[:, 0] = (torch.arange(slots, dtype=torch.int64) + 1) * (1 << 29) * c
+    poison = block[3 * slots:].view(torch.int32)
+    poison[rank] = _poison_word((1, 0, 0), (0, 0, 1))                      # slot `rank`: NaN in red, overflow in blue
+    poison[7] = _poison_word((0, 1, 0), (0, 0, 0))                         # slot 7: every rank flags green
+    D.reduce_accum(block, 0)
+    if rank == 0:
+        ok = bool((acc[:, 0] == (torch.arange(slots, dtype=torch.int64) + 1) * (1 << 29) * spp).all())
+        nib = lambda word, k: (int(word) >> (4 * k)) & 15
+        ok &= all(nib(poison[r], 0) == 1 and nib(poison[r], 5) == 1 and nib(poison[r], 1) == 0 for r in range(world) if r != 7)
+        ok &= nib(poison[7], 1) == world and nib(poison[7], 2) == 0 and nib(poison[7], 3) == 0
+        q.put((ok, b, c))
+    else:
+        q.put((True, b, c))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,spp", [(2, 500), (3, 10)])
+def test_sample_partition_reduce(world, spp):
+    """The sample partition's host logic on CPU: contiguous sample shares that cover [0, spp), one integer reduce of the accumulator
+    block, poison flags surviving the sum in their 4-bit fields."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, 100, 70, spp, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = [q.get(timeout=5) for _ in range(world)]
+    assert all(g[0] for g in got)
+    ranges = sorted((g[1], g[2]) for g in got)
+    assert ranges[0][0] == 0 and all(ranges[i][0] + ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    assert ranges[-1][0] + ranges[-1][1] == spp and max(c for _, c in ranges) - min(c for _, c in ranges) <= 1

@@ -332,3 +332,30 @@ def test_empty_lights_list_maps_the_reference_panic(rtw, oracle):
         assert np.array_equal(img, np.full((4, 4, 3), 2.0))
     finally:
         scene.close()
+
+
+def test_general_sample_partition_is_bit_identical(rtw, oracle):
+    import torch
+    from ray_tracing_weekend_b200 import dist as D
+    scene, og, cb = _build(rtw, oracle, "cornell_box")
+    try:
+        w, h, spp = 40, 30, 7
+        cam = _cam(cb, w, h, spp, 20)
+        opts = rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32)
+        one, one8, _ = scene.render(cam, opts)
+        slots = D.tiles_total(w, h) * 256
+        blocks = torch.zeros((2, D.accum_words(w, h)), dtype=torch.int64, device="cuda")
+        for r in range(2):
+            b, c = D.sample_range(spp, r, 2)
+            scene.render_samples_device(cam, opts, b, c, blocks[r].data_ptr(), blocks[r].data_ptr() + 8 * 3 * slots)
+        total = blocks.sum(dim=0)
+        out = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        rtw.resolve_accum_device(total.data_ptr(), total.data_ptr() + 8 * 3 * slots, w, h, spp, out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        assert np.array_equal(one, out.cpu().numpy(), equal_nan=True)
+        with pytest.raises(rtw.RtwError):                         # f64 sums samples in order: no sample partition
+            scene.render_samples_device(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64), 0, 3, blocks[0].data_ptr(),
+                                        blocks[0].data_ptr() + 8 * 3 * slots)
+    finally:
+        scene.close()

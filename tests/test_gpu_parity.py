@@ -474,3 +474,38 @@ def test_device_built_bvh_renders_the_same_image(rtw, oracle, simple_scene):
         assert np.array_equal(p_o, p_g) and np.array_equal(tt_o, tt_g) and (p_o >= 1).sum() > 300
     finally:
         big.close()
+
+
+@pytest.mark.parametrize("mode", ("wavefront", "megakernel"))
+def test_sample_partition_is_bit_identical(rtw, simple_scene, gscene, mode):
+    """The multi-GPU sample partition on one GPU: three "ranks" render their sample ranges of every pixel into fixed-point
+    accumulator blocks, the blocks are summed as integers (what the NCCL reduce does), resolved — and the result equals the
+    single-launch image bit for bit (radiance sums, poisoned pixels, resolved bytes)."""
+    import torch
+    from ray_tracing_weekend_b200 import dist as D
+    w, h, spp = 100, 70, 10
+    cam = (simple_scene["cb"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h)
+           .with_samples_per_pixel(spp).build())
+    opts = rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, mode=rtw.RTW_WAVEFRONT if mode == "wavefront" else rtw.RTW_MEGAKERNEL)
+    one, one8, st1 = gscene.render(cam, opts)
+    world = 3
+    slots = D.tiles_total(w, h) * 256
+    blocks = torch.zeros((world, D.accum_words(w, h)), dtype=torch.int64, device="cuda")
+    rays = 0
+    covered = []
+    for r in range(world):
+        b, c = D.sample_range(spp, r, world)
+        covered += list(range(b, b + c))
+        st = gscene.render_samples_device(cam, opts, b, c, blocks[r].data_ptr(), blocks[r].data_ptr() + 8 * 3 * slots)
+        rays += st["rays"]
+        assert st["paths"] == w * h * c
+    assert covered == list(range(spp)) and rays == st1["rays"]
+    total = blocks.sum(dim=0)
+    out = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda")
+    out8 = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    rtw.resolve_accum_device(total.data_ptr(), total.data_ptr() + 8 * 3 * slots, w, h, spp, out.data_ptr(), out8.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(one, out.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(one8, out8.cpu().numpy())
+    assert np.isnan(one).any(), "the frame has poisoned pixels, so the flag fields were exercised"

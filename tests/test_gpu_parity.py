@@ -509,3 +509,45 @@ def test_sample_partition_is_bit_identical(rtw, simple_scene, gscene, mode):
     assert np.array_equal(one, out.cpu().numpy(), equal_nan=True)
     assert np.array_equal(one8, out8.cpu().numpy())
     assert np.isnan(one).any(), "the frame has poisoned pixels, so the flag fields were exercised"
+
+
+def test_full_size_frame_properties(rtw, simple_scene, gscene):
+    """BASELINE config C2 at its full size (1920x1080, 500 spp, depth 50 — 1.04 G paths, far beyond what the oracle can trace in a
+    test) through size-independent properties: the two FP32 renderers and the 4-way sample partition produce the same image bit
+    for bit (a checksum of every accumulator), the ray count is the deterministic 2.718 G of this seed, every pixel received
+    exactly 500 samples' worth of finite-or-poisoned radiance, and the background pixels equal spp exactly."""
+    import torch
+    from ray_tracing_weekend_b200 import dist as D
+    w, h, spp = 1920, 1080, 500
+    cam = (simple_scene["cb"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h)
+           .with_samples_per_pixel(spp).build())
+    a, a8, sa = gscene.render(cam, rtw.RenderOptions(seed=SEED, mode=rtw.RTW_WAVEFRONT))
+    b, b8, sb = gscene.render(cam, rtw.RenderOptions(seed=SEED, mode=rtw.RTW_MEGAKERNEL))
+    assert sa["paths"] == sb["paths"] == w * h * spp == 1_036_800_000
+    assert sa["rays"] == sb["rays"] and 2.70e9 < sa["rays"] < 2.74e9
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a8, b8)
+    # the one-sided ground plane is invisible from above: most of the frame is pure background (1, 1, 1) * spp
+    bg = (a == float(spp)).all(axis=2)
+    assert 0.6 < bg.mean() < 0.9
+    assert np.array_equal(a8[bg], np.full((int(bg.sum()), 3), 255, dtype=np.uint8))
+    poisoned = np.isnan(a).any(axis=2)
+    assert 0.05 < poisoned.mean() < 0.35 and (a8[poisoned].min(axis=1) == 0).all()     # NaN -> 0 like `as u8` (colour.rs:24-35)
+    # white background and albedos <= 1: the expected radiance is <= 1 per sample (single mixture-pdf samples can weigh up to 2 x albedo)
+    # (fireflies: a sampled direction with a tiny pdf gives one huge sample, so there is no per-pixel upper bound)
+    fin = np.isfinite(a).all(axis=2)
+    assert (a[fin] >= 0).all() and np.median(a[fin]) <= spp and np.quantile(a[fin], 0.99) <= 1.05 * spp
+    # sample partition over 4 "ranks": integer sums of the accumulator blocks resolve to the same image
+    slots = D.tiles_total(w, h) * 256
+    total = torch.zeros(D.accum_words(w, h), dtype=torch.int64, device="cuda")
+    block = torch.zeros_like(total)
+    rays = 0
+    for r in range(4):
+        s0, c = D.sample_range(spp, r, 4)
+        st = gscene.render_samples_device(cam, rtw.RenderOptions(seed=SEED), s0, c, block.data_ptr(), block.data_ptr() + 8 * 3 * slots)
+        rays += st["rays"]
+        total += block
+    out = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    rtw.resolve_accum_device(total.data_ptr(), total.data_ptr() + 8 * 3 * slots, w, h, spp, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert rays == sa["rays"] and np.array_equal(a, out.cpu().numpy(), equal_nan=True)

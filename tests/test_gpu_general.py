@@ -359,3 +359,24 @@ def test_general_sample_partition_is_bit_identical(rtw, oracle):
                                         blocks[0].data_ptr() + 8 * 3 * slots)
     finally:
         scene.close()
+
+
+@pytest.mark.parametrize("name", ("cornell_box", "simple_light", "debugging_scene"))
+def test_general_trace_f32_tolerance(rtw, oracle, name):
+    """North-star check (1) for the FP32 general path: the same (f32-representable) rays against the f64 oracle — hit ids equal
+    except near silhouettes / edges, t within 1e-5 relative (tmin well above FP32 noise so self-intersections stay out)."""
+    scene, og, cb = _build(rtw, oracle, name)
+    try:
+        cam = _cam(cb, 64, 64, 4, 12)
+        o, d = _rays(oracle, og, cam.pod, 4000, 3)
+        o = o.astype(np.float32).astype(np.float64); d = d.astype(np.float32).astype(np.float64)
+        tmin = 1e-2 if name == "cornell_box" else 1e-3               # cornell coordinates are ~555: FP32 noise of a hit point ~3e-5
+        prim_o, t_o, _, _ = og.trace_batch(o, d, tmin=tmin)
+        prim_g, t_g = scene.trace_batch(o, d, tmin=tmin, precision=rtw.RTW_F32)
+        same = prim_o == prim_g
+        assert same.mean() > 0.99, f"id mismatch fraction {1 - same.mean():.4%}"
+        both = same & (prim_o >= 0)
+        rel = np.abs(t_g[both] - t_o[both]) / np.abs(t_o[both])
+        assert np.median(rel) < 2e-6 and np.quantile(rel, 0.99) < 1e-4, (np.median(rel), np.quantile(rel, 0.99), rel.max())
+    finally:
+        scene.close()

@@ -257,6 +257,18 @@ RTW_API int rtw_render_samples_device(rtw_scene* scene, const rtw_camera* camera
 RTW_API int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, uint32_t width, uint32_t height,
                              uint32_t samples_per_pixel, double* d_rgb_sum, uint8_t* d_rgb8, void* stream);
 
+/* Progressive rendering and checkpointing with HOST buffers.  rtw_render_samples renders samples
+ * [sample_begin, sample_begin + sample_count) of every pixel and ADDS them into the caller's accumulators
+ *   accum:  [rtw_accum_slots(w, h)][3] u64 (2^-32 radiance units), poison: [rtw_accum_slots(w, h)] u32 (flags, combined with OR)
+ * which the caller zeroes before the first pass and may save / restore between passes (a checkpoint is these two arrays plus the
+ * next sample index).  Whatever the split into passes, rtw_resolve_accum yields the image of one rtw_render call bit for bit
+ * (RTW_F32 renderers; samples are keyed by their absolute index). */
+RTW_API size_t rtw_accum_slots(uint32_t width, uint32_t height);
+RTW_API int rtw_render_samples(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, uint32_t sample_begin,
+                       uint32_t sample_count, uint64_t* accum, uint32_t* poison, rtw_stats* stats);
+RTW_API int rtw_resolve_accum(const uint64_t* accum, const uint32_t* poison, uint32_t width, uint32_t height,
+                      uint32_t samples_per_pixel, double* rgb_sum, uint8_t* rgb8);
+
 /* ---- per-ray operations (parity surface) ------------------------------------------------------- */
 /* Hittable::hit of the world for a batch of rays (shared/src/hittable.rs:173; bvh.rs:163-188).
  * o, d: [n][3] f64 host arrays; prim_id: -1 = miss; t: +inf on a miss.  precision as in rtw_opts. */

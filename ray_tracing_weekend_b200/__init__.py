@@ -10,5 +10,5 @@ from ._lib import (EPSILON, TMIN_REFERENCE, RTW_BVH_AUTO, RTW_BVH_DEVICE_LBVH, R
                    RtwError, library_path, load)
 from .api import (INVISIBLE, Axis, BoundedVolumeHierarchy, Camera, CameraBuilder, CheckerTexture, Cuboid, Dialectric, DiffuseLight,  # noqa: F401
                   HittableList, Isotropic, Lambertian, Material, Metal, NoiseTexture, Plane, Quad, RenderOptions, Scene,
-                  SceneDescription, Sphere, Transformation, Transformed, Translation3, Triangle, device_count, philox4x32_10,
-                  resolve_accum_device, rotation, set_bvh_builder, tiles_per_rank, tiles_total, untile_resolve_device, write_ppm)
+                  SceneDescription, Sphere, Transformation, Transformed, Translation3, Triangle, device_count, new_accumulators, philox4x32_10,
+                  resolve_accum, resolve_accum_device, rotation, set_bvh_builder, tiles_per_rank, tiles_total, untile_resolve_device, write_ppm)

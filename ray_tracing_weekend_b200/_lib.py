@@ -27,7 +27,7 @@ RTW_SYMBOLS = (
     "rtw_abi_version", "rtw_last_error", "rtw_camera_build", "rtw_philox4x32_10", "rtw_tiles_total", "rtw_tiles_per_rank",
     "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
-    "rtw_render_samples_device", "rtw_resolve_accum_device", "rtw_set_bvh_builder", "rtw_scene_bvh_builder", "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
+    "rtw_render_samples_device", "rtw_resolve_accum_device", "rtw_accum_slots", "rtw_render_samples", "rtw_resolve_accum", "rtw_set_bvh_builder", "rtw_scene_bvh_builder", "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
 
@@ -153,6 +153,9 @@ def load(build_if_missing: bool = True):
     L.rtw_untile_resolve_device.argtypes = [vp, u32, u32, u32, u32, u32, vp, vp, vp]
     L.rtw_render_samples_device.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.rtw_resolve_accum_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+    L.rtw_accum_slots.argtypes = [u32, u32]; L.rtw_accum_slots.restype = sz
+    L.rtw_render_samples.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp]
+    L.rtw_resolve_accum.argtypes = [vp, vp, u32, u32, u32, vp, vp]
     L.rtw_trace_batch.argtypes = [vp, vp, vp, sz, dbl, dbl, u32, vp, vp]
     L.rtw_scatter_batch.argtypes = [vp, vp, vp, vp, sz] + [vp] * 10
     L.rtw_get_rays.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]

@@ -465,6 +465,16 @@ class Scene:
         _lib.check(_lib.load().rtw_render(self._h, C.byref(camera.pod), C.byref(po), _p(rgb_sum), _p(rgb8), C.byref(st)))
         return rgb_sum, rgb8, st.as_dict()
 
+    def render_samples(self, camera: "Camera", opts: RenderOptions, sample_begin: int, sample_count: int, accum: np.ndarray, poison: np.ndarray):
+        """rtw_render_samples: ADD samples [sample_begin, sample_begin + sample_count) of every pixel into the host accumulators
+        (see new_accumulators); progressive rendering / checkpointing."""
+        assert accum.dtype == np.uint64 and poison.dtype == np.uint32 and accum.flags.c_contiguous and poison.flags.c_contiguous
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render_samples(self._h, C.byref(camera.pod), C.byref(po), sample_begin, sample_count, _p(accum), _p(poison),
+                                                  C.byref(st)))
+        return st.as_dict()
+
     def render_samples_device(self, camera: "Camera", opts: RenderOptions, sample_begin: int, sample_count: int, d_accum_ptr: int,
                               d_poison_ptr: int, stream: int = 0, want_stats=True):
         """rtw_render_samples_device: samples [sample_begin, sample_begin + sample_count) of every pixel into fixed-point accumulators."""
@@ -482,6 +492,20 @@ class Scene:
         _lib.check(_lib.load().rtw_render_tiles_device(self._h, C.byref(camera.pod), C.byref(po), rank, world, C.c_void_p(d_tiles_ptr),
                                                        C.c_void_p(stream), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+
+def new_accumulators(width: int, height: int):
+    """Zeroed host accumulators for Scene.render_samples: (accum [slots, 3] u64, poison [slots] u32)."""
+    n = int(_lib.load().rtw_accum_slots(width, height))
+    return np.zeros((n, 3), dtype=np.uint64), np.zeros(n, dtype=np.uint32)
+
+
+def resolve_accum(accum: np.ndarray, poison: np.ndarray, width: int, height: int, spp: int, want_sum=True, want_rgb8=True):
+    """rtw_resolve_accum: host accumulators -> (rgb_sum [h, w, 3] f64 | None, rgb8 [h, w, 3] u8 | None)."""
+    rgb_sum = np.zeros((height, width, 3)) if want_sum else None
+    rgb8 = np.zeros((height, width, 3), dtype=np.uint8) if want_rgb8 else None
+    _lib.check(_lib.load().rtw_resolve_accum(_p(accum), _p(poison), width, height, spp, _p(rgb_sum), _p(rgb8)))
+    return rgb_sum, rgb8
 
 
 def resolve_accum_device(d_accum_ptr, d_poison_ptr, width, height, spp, d_rgb_sum_ptr=0, d_rgb8_ptr=0, stream=0):

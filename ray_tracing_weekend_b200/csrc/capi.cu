@@ -920,6 +920,48 @@ int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, uint32_t
     return RTW_OK;
 }
 
+size_t rtw_accum_slots(uint32_t width, uint32_t height) { return (size_t)rtw_tiles_total(width, height) * kTileW * kTileH; }
+
+int rtw_render_samples(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, uint32_t sample_begin, uint32_t sample_count,
+                       uint64_t* accum, uint32_t* poison, rtw_stats* stats) {
+    if (!s || !accum || !poison) return fail(RTW_E_INVALID, "NULL argument");
+    int rc = check_camera(cam); if (rc) return rc;
+    const size_t n = rtw_accum_slots(cam->image_width, cam->image_height);
+    CU(s->d_accum.reserve(n * 3)); CU(s->d_poison.reserve(n));
+    rtw_stats st{};
+    rc = rtw_render_samples_device(s, cam, o, sample_begin, sample_count, s->d_accum.p, s->d_poison.p, nullptr, &st);
+    if (rc) return rc;
+    std::vector<unsigned long long> a(n * 3);
+    std::vector<uint32_t> p(n);
+    CU(cudaMemcpy(a.data(), s->d_accum.p, n * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p.data(), s->d_poison.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n * 3; ++i) accum[i] += a[i];          // integer sums commute: the order of the passes does not matter
+    for (size_t i = 0; i < n; ++i) poison[i] |= p[i];
+    if (stats) *stats = st;
+    return RTW_OK;
+}
+
+int rtw_resolve_accum(const uint64_t* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp, double* rgb_sum,
+                      uint8_t* rgb8) {
+    if (!accum || !poison || width == 0 || height == 0) return fail(RTW_E_INVALID, "bad argument");
+    int ndev = rtw_device_count();
+    if (ndev <= 0) return ndev < 0 ? ndev : fail(RTW_E_NO_DEVICE, "no CUDA device: this backend has no CPU fallback");
+    const size_t n = rtw_accum_slots(width, height), npx = (size_t)width * height;
+    DevBuf<unsigned long long> da; DevBuf<uint32_t> dp; DevBuf<double> ds; DevBuf<uint8_t> d8;
+    auto done = [&](int code) { da.release(); dp.release(); ds.release(); d8.release(); return code; };
+    cudaError_t e = da.reserve(n * 3);
+    if (e == cudaSuccess) e = dp.reserve(n);
+    if (e == cudaSuccess && rgb_sum) e = ds.reserve(npx * 3);
+    if (e == cudaSuccess && rgb8) e = d8.reserve(npx * 3);
+    if (e == cudaSuccess) e = cudaMemcpy(da.p, accum, n * 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dp.p, poison, n * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_resolve_accum_f32(da.p, dp.p, width, height, spp, rgb_sum ? ds.p : nullptr, rgb8 ? d8.p : nullptr, 0);
+    if (e == cudaSuccess && rgb_sum) e = cudaMemcpy(rgb_sum, ds.p, npx * 3 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rgb8) e = cudaMemcpy(rgb8, d8.p, npx * 3, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaGetLastError(); return done(fail(RTW_E_CUDA, std::string("rtw_resolve_accum: ") + cudaGetErrorString(e))); }
+    return done(RTW_OK);
+}
+
 int rtw_untile_resolve_device(const void* d_tiles_all, uint32_t precision, uint32_t width, uint32_t height, uint32_t world,
                               uint32_t spp, double* d_rgb_sum, uint8_t* d_rgb8, void* stream) {
     if (!d_tiles_all || world == 0 || width == 0 || height == 0) return fail(RTW_E_INVALID, "bad argument");

@@ -1,8 +1,11 @@
 // rtw_bin.cpp — the reference's `bin` (bin/src/main.rs:54-105) with the CUDA backend behind
 // Camera::render:   rtw_bin <simple|simple-light|cornell-box|debug|simple-transform|checkered-spheres> [--backend cuda] [--width W --height H --spp S --depth D]
 //                           [--seed N] [--precision f32|f64] [--tmin X] [--out image.ppm]
-// Config.toml parsing is replaced by flags (defaults = the reference's Config.toml:7-11).
-// Writes ASCII P3 with rows reversed exactly like main.rs:89-104.
+//                   [--config Config.toml]  [--format p3|p6|png]  [--passes K [--checkpoint FILE] [--resume]]
+// Image parameters come from flags (defaults = the reference's Config.toml:7-11) or, with --config, from the [image] table of a
+// Config.toml like the reference's (bin/src/config.rs).  The default output is ASCII P3 with rows reversed exactly like
+// main.rs:89-104; --format adds binary P6 and PNG.  --passes renders progressively into fixed-point accumulators, writing a
+// checkpoint after every pass; --resume continues an interrupted render from it — the image is the one-shot image bit for bit.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -13,8 +16,9 @@
 using namespace rtw_host;
 
 int main(int argc, char** argv) {
-    std::string scene = "simple", backend = "cuda", out = "image.ppm";
-    uint32_t width = 400, height = 400, spp = 1000, depth = 50;
+    std::string scene = "simple", backend = "cuda", out = "image.ppm", config, format = "p3", checkpoint;
+    uint32_t width = 400, height = 400, spp = 1000, depth = 50, passes = 0, stop_after = 0;
+    bool resume = false;
     RenderOptions opt;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -28,6 +32,12 @@ int main(int argc, char** argv) {
         else if (a == "--tmin") opt.tmin = std::stod(next());
         else if (a == "--precision") opt.precision = next() == "f64" ? Precision::F64 : Precision::F32;
         else if (a == "--out") out = next();
+        else if (a == "--config") config = next();
+        else if (a == "--format") format = next();
+        else if (a == "--passes") passes = std::stoul(next());
+        else if (a == "--checkpoint") checkpoint = next();
+        else if (a == "--resume") resume = true;
+        else if (a == "--stop-after") stop_after = std::stoul(next());      // stop after this many passes (the checkpoint stays)
         else if (a[0] != '-') scene = a;
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -51,22 +61,25 @@ int main(int argc, char** argv) {
             return 2;
         }
         if (general) cb = general_sc.cam;
+        double aspect = (double)width / (double)height;
+        if (!config.empty()) {              // main.rs:57-65
+            Image im = read_config(config);
+            width = im.image_width; height = im.image_height; spp = im.samples_per_pixel; depth = im.max_depth; aspect = im.aspect_ratio;
+        }
         // main.rs:72-79
-        Camera cam = cb.with_vfov(40.).with_aspect_ratio((double)width / (double)height).with_max_depth(depth)
+        Camera cam = cb.with_vfov(40.).with_aspect_ratio(aspect).with_max_depth(depth)
                          .with_image_width(width).with_image_height(height).with_samples_per_pixel((uint16_t)spp).build();
         rtw_stats st{};
         auto t0 = std::chrono::steady_clock::now();
-        auto img = general ? cam.render(general_sc.world_ref(), general_sc.lights_ref(), opt, &st)
-                           : cam.render(simple_sc.world, simple_sc.lights, opt, &st);
+        World wref = general ? general_sc.world_ref() : World(simple_sc.world);
+        World lref = general ? general_sc.lights_ref() : World(simple_sc.lights);
+        auto img = passes ? cam.render_progressive(wref, lref, opt, passes, checkpoint, resume, &st, stop_after) : cam.render(wref, lref, opt, &st);
         double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::fprintf(stderr, "rendered %ux%u spp %u in %.3f s (kernel %.3f ms): %.1f Mpaths/s, %.1f Mrays/s\n", width, height, spp, sec,
                      st.kernel_ms, st.paths / st.kernel_ms * 1e-3, st.rays / st.kernel_ms * 1e-3);
-        FILE* f = std::fopen(out.c_str(), "w");
-        if (!f) { std::perror("fopen"); return 1; }
-        std::fprintf(f, "P3\n%u %u\n255\n", width, height);
-        for (size_t j = img.size(); j-- > 0;)
-            for (const SampledColour& c : img[j]) std::fprintf(f, "%s\n", c.to_string().c_str());
-        std::fclose(f);
+        if (format == "p6") write_p6(out, img);
+        else if (format == "png") write_png(out, img);
+        else write_p3(out, img);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

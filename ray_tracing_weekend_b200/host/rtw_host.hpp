@@ -25,9 +25,13 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
 #include <functional>
 #include <memory>
 #include <optional>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -307,8 +311,8 @@ public:
     const rtw_camera& pod() const { return c_; }
 
     // Camera::render (camera.rs:295-297): out[j][i], j = 0 is the bottom row.
-    std::vector<std::vector<SampledColour>> render(World world, World lights, const RenderOptions& opt = RenderOptions(),
-                                                   rtw_stats* stats = nullptr) const {
+    // world + lights -> rtw_scene (the sphere path when the scene allows it, else the general path)
+    static rtw_scene* make_scene(World world, World lights) {
         rtw_scene* scene = nullptr;
         bool simple = world.list->is_simple() && !lights.is_bvh && lights.list->spheres().size() == lights.list->len();
         if (simple && lights.list->is_empty())          // an empty lights list next to a Lambertian: only the general path accepts it
@@ -332,13 +336,79 @@ public:
             int rc = rtw_scene_create_general(&d.pod, &scene);
             if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_scene_create_general: ") + rtw_last_error());
         }
-        int rc;
+        return scene;
+    }
+    static rtw_opts to_opts(const RenderOptions& opt) {
         rtw_opts o{}; o.seed = opt.seed; o.tmin = opt.tmin; o.precision = (uint32_t)opt.precision; o.mode = opt.mode; o.flags = opt.flags;
+        return o;
+    }
+
+    std::vector<std::vector<SampledColour>> render(World world, World lights, const RenderOptions& opt = RenderOptions(),
+                                                   rtw_stats* stats = nullptr) const {
+        rtw_scene* scene = make_scene(world, lights);
+        rtw_opts o = to_opts(opt);
         size_t npx = (size_t)c_.image_width * c_.image_height;
         std::vector<double> sum(npx * 3); std::vector<uint8_t> q(npx * 3);
-        rc = rtw_render(scene, &c_, &o, sum.data(), q.data(), stats);
+        int rc = rtw_render(scene, &c_, &o, sum.data(), q.data(), stats);
         rtw_scene_destroy(scene);
         if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_render: ") + rtw_last_error());
+        return rows(sum, q);
+    }
+
+    // Progressive rendering with checkpoints: the samples are rendered in `passes` passes into 64-bit fixed-point
+    // accumulators; after every pass the accumulators and the next sample index are written to `checkpoint` (if given), and a
+    // render started with resume = true continues from that file.  The result equals render() bit for bit (FP32 renderers).
+    std::vector<std::vector<SampledColour>> render_progressive(World world, World lights, const RenderOptions& opt, uint32_t passes,
+                                                               const std::string& checkpoint = "", bool resume = false,
+                                                               rtw_stats* stats = nullptr, uint32_t stop_after = 0) const {
+        const uint32_t spp = c_.samples_per_pixel;
+        const size_t n = rtw_accum_slots(c_.image_width, c_.image_height);
+        std::vector<uint64_t> accum(n * 3, 0); std::vector<uint32_t> poison(n, 0);
+        struct Header { char magic[8]; uint32_t width, height, spp, next_sample; uint64_t seed; } hd{};
+        uint32_t next = 0;
+        if (resume) {
+            std::ifstream f(checkpoint, std::ios::binary);
+            if (!f || !f.read(reinterpret_cast<char*>(&hd), sizeof(hd)) || std::string(hd.magic, 7) != "RTWCKPT" || hd.width != c_.image_width ||
+                hd.height != c_.image_height || hd.spp != spp || hd.seed != opt.seed)
+                throw std::runtime_error("checkpoint '" + checkpoint + "' is missing or belongs to another render");
+            f.read(reinterpret_cast<char*>(accum.data()), (std::streamsize)(accum.size() * 8));
+            f.read(reinterpret_cast<char*>(poison.data()), (std::streamsize)(poison.size() * 4));
+            if (!f) throw std::runtime_error("checkpoint '" + checkpoint + "' is truncated");
+            next = hd.next_sample;
+        }
+        rtw_scene* scene = make_scene(world, lights);
+        rtw_opts o = to_opts(opt);
+        rtw_stats total{};
+        passes = passes ? passes : 1;
+        const uint32_t per_pass = (spp + passes - 1) / passes;
+        for (uint32_t done = 0; next < spp && (stop_after == 0 || done < stop_after); ++done) {     // stop_after: an "interrupted" run
+            uint32_t count = std::min(per_pass, spp - next);
+            rtw_stats st{};
+            int rc = rtw_render_samples(scene, &c_, &o, next, count, accum.data(), poison.data(), &st);
+            if (rc != RTW_OK) { rtw_scene_destroy(scene); throw std::runtime_error(std::string("rtw_render_samples: ") + rtw_last_error()); }
+            total.paths += st.paths; total.rays += st.rays; total.kernel_ms += st.kernel_ms; total.total_ms += st.total_ms; total.launches += st.launches;
+            next += count;
+            if (!checkpoint.empty()) {
+                std::memcpy(hd.magic, "RTWCKPT", 8); hd.width = c_.image_width; hd.height = c_.image_height; hd.spp = spp; hd.next_sample = next; hd.seed = opt.seed;
+                std::ofstream f(checkpoint + ".tmp", std::ios::binary | std::ios::trunc);
+                f.write(reinterpret_cast<const char*>(&hd), sizeof(hd));
+                f.write(reinterpret_cast<const char*>(accum.data()), (std::streamsize)(accum.size() * 8));
+                f.write(reinterpret_cast<const char*>(poison.data()), (std::streamsize)(poison.size() * 4));
+                f.close();
+                if (!f || std::rename((checkpoint + ".tmp").c_str(), checkpoint.c_str()) != 0) { rtw_scene_destroy(scene); throw std::runtime_error("cannot write checkpoint '" + checkpoint + "'"); }
+            }
+        }
+        rtw_scene_destroy(scene);
+        size_t npx = (size_t)c_.image_width * c_.image_height;
+        std::vector<double> sum(npx * 3); std::vector<uint8_t> q(npx * 3);
+        if (rtw_resolve_accum(accum.data(), poison.data(), c_.image_width, c_.image_height, spp, sum.data(), q.data()) != RTW_OK)
+            throw std::runtime_error(std::string("rtw_resolve_accum: ") + rtw_last_error());
+        if (stats) *stats = total;
+        return rows(sum, q);
+    }
+
+private:
+    std::vector<std::vector<SampledColour>> rows(const std::vector<double>& sum, const std::vector<uint8_t>& q) const {
         std::vector<std::vector<SampledColour>> out(c_.image_height, std::vector<SampledColour>(c_.image_width));
         for (uint32_t j = 0; j < c_.image_height; ++j)
             for (uint32_t i = 0; i < c_.image_width; ++i) {
@@ -349,13 +419,106 @@ public:
             }
         return out;
     }
-private:
     rtw_camera c_;
 };
 inline Camera CameraBuilder::build() const {
     rtw_camera c;
     if (rtw_camera_build(&b_, &c) != RTW_OK) throw std::runtime_error(rtw_last_error());
     return Camera(c);
+}
+
+// ---- bin/src/config.rs: the [image] table of Config.toml ------------------------------------------------
+struct Image { double aspect_ratio; uint32_t image_width, image_height; uint16_t samples_per_pixel; uint8_t max_depth; };
+// Config::get_image (config.rs:8-12, 52-99): aspect_ratio / image_width / image_height are optional, two of the three must be
+// given; the missing one is derived with a truncating cast.  Throws where the reference unwraps a None / a parse error.
+inline Image read_config(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot read '" + path + "'");
+    std::optional<double> aspect; std::optional<uint32_t> w, h; std::optional<long> spp, depth;
+    std::string line, table;
+    while (std::getline(f, line)) {
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) line.erase(hash);
+        auto trim = [](std::string v) { size_t a = v.find_first_not_of(" \t\r"), b = v.find_last_not_of(" \t\r"); return a == std::string::npos ? std::string() : v.substr(a, b - a + 1); };
+        line = trim(line);
+        if (line.empty()) continue;
+        if (line.front() == '[') { table = trim(line.substr(1, line.find(']') - 1)); continue; }
+        size_t eq = line.find('=');
+        if (eq == std::string::npos || table != "image") continue;
+        std::string key = trim(line.substr(0, eq)), val = trim(line.substr(eq + 1));
+        std::string digits;
+        for (char c : val) if (c != '_') digits += c;            // TOML allows 1_000
+        if (key == "aspect_ratio") aspect = std::stod(digits);
+        else if (key == "image_width") w = (uint32_t)std::stoul(digits);
+        else if (key == "image_height") h = (uint32_t)std::stoul(digits);
+        else if (key == "samples_per_pixel") spp = std::stol(digits);
+        else if (key == "max_depth") depth = std::stol(digits);
+    }
+    if (!spp || !depth || *spp < 0 || *spp > 65535 || *depth < 0 || *depth > 255)
+        throw std::runtime_error("Config.toml: [image] needs samples_per_pixel (u16) and max_depth (u8)");
+    Image im{};
+    im.samples_per_pixel = (uint16_t)*spp; im.max_depth = (uint8_t)*depth;
+    if (!aspect && h && w) { im.aspect_ratio = (double)*w / (double)*h; im.image_height = *h; im.image_width = *w; }
+    else if (aspect && !h && w) { im.aspect_ratio = *aspect; im.image_height = (uint32_t)((double)*w / *aspect); im.image_width = *w; }
+    else if (aspect && h && !w) { im.aspect_ratio = *aspect; im.image_height = *h; im.image_width = (uint32_t)((double)*h * *aspect); }
+    else if (aspect && h && w) { im.aspect_ratio = *aspect; im.image_height = *h; im.image_width = *w; }
+    else throw std::runtime_error("Config.toml: [image] needs two of aspect_ratio / image_width / image_height");
+    return im;
+}
+
+// ---- image writers: the reference's ASCII P3 (bin/src/main.rs:89-104) plus binary P6 and PNG; rows top to bottom ------
+inline void write_p3(const std::string& path, const std::vector<std::vector<SampledColour>>& img) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    std::fprintf(f, "P3\n%zu %zu\n255\n", img.empty() ? (size_t)0 : img[0].size(), img.size());
+    for (size_t j = img.size(); j-- > 0;)
+        for (const SampledColour& c : img[j]) std::fprintf(f, "%s\n", c.to_string().c_str());
+    std::fclose(f);
+}
+inline std::vector<uint8_t> top_down_rgb(const std::vector<std::vector<SampledColour>>& img) {
+    std::vector<uint8_t> px;
+    for (size_t j = img.size(); j-- > 0;)
+        for (const SampledColour& c : img[j]) { px.push_back(c.rgb[0]); px.push_back(c.rgb[1]); px.push_back(c.rgb[2]); }
+    return px;
+}
+inline void write_p6(const std::string& path, const std::vector<std::vector<SampledColour>>& img) {
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    f << "P6\n" << (img.empty() ? 0 : img[0].size()) << " " << img.size() << "\n255\n";
+    std::vector<uint8_t> px = top_down_rgb(img);
+    f.write(reinterpret_cast<const char*>(px.data()), (std::streamsize)px.size());
+}
+inline void write_png(const std::string& path, const std::vector<std::vector<SampledColour>>& img) {      // 8-bit RGB, stored (uncompressed) deflate blocks
+    const uint32_t w = img.empty() ? 0 : (uint32_t)img[0].size(), h = (uint32_t)img.size();
+    std::vector<uint8_t> px = top_down_rgb(img), raw;
+    for (uint32_t j = 0; j < h; ++j) { raw.push_back(0); raw.insert(raw.end(), px.begin() + (size_t)j * w * 3, px.begin() + (size_t)(j + 1) * w * 3); }
+    auto crc32 = [](const uint8_t* p, size_t n, uint32_t c = 0xffffffffu) { for (size_t i = 0; i < n; ++i) { c ^= p[i]; for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u))); } return c; };
+    auto be32 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); };
+    std::vector<uint8_t> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;
+    for (uint8_t c : raw) { a = (a + c) % 65521u; b = (b + a) % 65521u; }
+    for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+        size_t len = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + len >= raw.size() ? 1 : 0);
+        z.push_back(len & 255); z.push_back(len >> 8); z.push_back(~len & 255); z.push_back((~len >> 8) & 255);
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + len);
+        if (raw.empty()) break;
+    }
+    be32(z, (b << 16) | a);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    auto chunk = [&](const char* type, const std::vector<uint8_t>& data) {
+        be32(out, (uint32_t)data.size());
+        std::vector<uint8_t> td(type, type + 4);
+        td.insert(td.end(), data.begin(), data.end());
+        out.insert(out.end(), td.begin(), td.end());
+        be32(out, crc32(td.data(), td.size()) ^ 0xffffffffu);
+    };
+    std::vector<uint8_t> ihdr;
+    be32(ihdr, w); be32(ihdr, h); ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+    chunk("IHDR", ihdr); chunk("IDAT", z); chunk("IEND", {});
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
 }
 
 // ---- scenes ------------------------------------------------------------------------------------------

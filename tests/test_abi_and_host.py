@@ -20,7 +20,7 @@ def _declared(header):
 
 def test_library_exports_every_declared_symbol(rtw):
     names = _declared("rtw.h") + _declared("rtw_host.h")
-    assert len(names) >= 31
+    assert len(names) >= 34
     lib = C.CDLL(rtw.library_path())
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported"
@@ -146,3 +146,31 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "rtw_oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_cpp_host_writers_and_config(rtw, tmp_path):
+    """The C++ mirror's P3 / P6 / PNG writers (bin/src/main.rs:89-104 writes P3, rows reversed) and its Config.toml reader
+    (bin/src/config.rs: two of aspect_ratio / image_width / image_height, truncating casts) — compiled and run on the CPU."""
+    lib_dir = os.path.dirname(rtw.library_path())
+    exe = tmp_path / "writers_and_config"
+    src = os.path.join(ROOT, "tests", "host_cpp", "writers_and_config.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", src, "-o", str(exe), "-L" + lib_dir, "-lrtw_cuda", "-Wl,-rpath," + lib_dir], check=True)
+    cfg = tmp_path / "Config.toml"
+    cfg.write_text("# [image]\n# image_width = 1200\n\n[image]\naspect_ratio = 1.5   # comment\nimage_width = 1_000\nsamples_per_pixel = 500\nmax_depth = 75\n")
+    out = subprocess.run([str(exe), str(tmp_path), str(cfg)], capture_output=True, text=True, check=True).stdout.split()
+    assert (float(out[0]), int(out[1]), int(out[2]), int(out[3]), int(out[4])) == (1.5, 1000, 666, 500, 75)     # (1000 / 1.5) as u32
+    cfg.write_text("[image]\nimage_width = 400\nimage_height = 400\nsamples_per_pixel = 1000\nmax_depth = 50\n")  # the reference's own Config.toml
+    out = subprocess.run([str(exe), str(tmp_path), str(cfg)], capture_output=True, text=True, check=True).stdout.split()
+    assert (float(out[0]), int(out[1]), int(out[2]), int(out[3]), int(out[4])) == (1.0, 400, 400, 1000, 50)
+    cfg.write_text("[image]\nimage_width = 400\nsamples_per_pixel = 10\nmax_depth = 5\n")
+    assert "error" in subprocess.run([str(exe), str(tmp_path), str(cfg)], capture_output=True, text=True, check=True).stdout
+    want = np.zeros((3, 5, 3), dtype=np.uint8)                  # top-down: file row 0 = render row 2
+    for j in range(3):
+        for i in range(5):
+            want[2 - j, i] = (10 * i, 100 + j, i * j + 7)
+    p3 = (tmp_path / "a.ppm").read_text().split()
+    assert p3[:4] == ["P3", "5", "3", "255"] and np.array_equal(np.array(p3[4:], dtype=np.uint8).reshape(3, 5, 3), want)
+    p6 = (tmp_path / "b.ppm").read_bytes()
+    assert p6.startswith(b"P6\n5 3\n255\n") and np.array_equal(np.frombuffer(p6[len(b"P6\n5 3\n255\n"):], dtype=np.uint8).reshape(3, 5, 3), want)
+    Image = pytest.importorskip("PIL.Image")
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "c.png").convert("RGB")), want)

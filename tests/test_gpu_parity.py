@@ -551,3 +551,43 @@ def test_full_size_frame_properties(rtw, simple_scene, gscene):
     rtw.resolve_accum_device(total.data_ptr(), total.data_ptr() + 8 * 3 * slots, w, h, spp, out.data_ptr(), 0)
     torch.cuda.synchronize()
     assert rays == sa["rays"] and np.array_equal(a, out.cpu().numpy(), equal_nan=True)
+
+
+def test_progressive_rendering_with_checkpoints(rtw, simple_scene, gscene, tmp_path):
+    """the frame rendered in passes into host accumulators that are saved to disk and restored in between equals
+    the one-shot image bit for bit; the C++ CLI does the same with --passes / --checkpoint / --resume and the other output formats."""
+    import os, subprocess
+    w, h, spp = 96, 54, 20
+    cam = (simple_scene["cb"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h)
+           .with_samples_per_pixel(spp).build())
+    opts = rtw.RenderOptions(seed=SEED)
+    one, one8, st1 = gscene.render(cam, opts)
+    accum, poison = rtw.new_accumulators(w, h)
+    rays = 0
+    for k, (b, c) in enumerate(((13, 7), (0, 5), (5, 8))):                 # any order, any split
+        rays += gscene.render_samples(cam, opts, b, c, accum, poison)["rays"]
+        np.savez(tmp_path / "ck.npz", accum=accum, poison=poison)          # checkpoint ...
+        ck = np.load(tmp_path / "ck.npz")
+        accum, poison = np.ascontiguousarray(ck["accum"]), np.ascontiguousarray(ck["poison"])      # ... and restore
+    got, got8 = rtw.resolve_accum(accum, poison, w, h, spp)
+    assert rays == st1["rays"] and np.array_equal(one, got, equal_nan=True) and np.array_equal(one8, got8)
+    # the C++ CLI: an interrupted progressive render resumed from its checkpoint == the one-shot render; P6 and PNG carry the same pixels
+    exe = os.path.join(os.path.dirname(rtw.library_path()), "rtw_bin")
+    common = [exe, "simple", "--backend", "cuda", "--width", str(w), "--height", str(h), "--spp", str(spp), "--depth", "50", "--seed", str(SEED)]
+    ref, part, fin = tmp_path / "ref.ppm", tmp_path / "part.ppm", tmp_path / "fin.ppm"
+    for args in (["--out", str(ref)],
+                 ["--passes", "4", "--checkpoint", str(tmp_path / "ck.bin"), "--stop-after", "2", "--out", str(part)],
+                 ["--passes", "4", "--checkpoint", str(tmp_path / "ck.bin"), "--resume", "--out", str(fin)],
+                 ["--format", "p6", "--out", str(tmp_path / "b.ppm")], ["--format", "png", "--out", str(tmp_path / "c.png")]):
+        r = subprocess.run(common + args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    assert ref.read_text() == fin.read_text() and ref.read_text() != part.read_text()
+    want = np.array(ref.read_text().split()[4:], dtype=np.uint8).reshape(h, w, 3)
+    assert np.array_equal(want, one8[::-1])
+    p6 = (tmp_path / "b.ppm").read_bytes()
+    head = f"P6\n{w} {h}\n255\n".encode()
+    assert p6.startswith(head) and np.array_equal(np.frombuffer(p6[len(head):], dtype=np.uint8).reshape(h, w, 3), want)
+    Image = pytest.importorskip("PIL.Image")
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "c.png").convert("RGB")), want)
+    r = subprocess.run(common + ["--passes", "4", "--checkpoint", str(tmp_path / "ck.bin"), "--resume", "--spp", "21"], capture_output=True, text=True)
+    assert r.returncode != 0 and "another render" in r.stderr             # a checkpoint of a different render is refused

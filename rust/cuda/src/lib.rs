@@ -58,6 +58,11 @@ unsafe extern "C" {
     pub fn rtw_transform_inverse(a: *const RtwTransform, out: *mut RtwTransform) -> c_int;
     pub fn rtw_rotation(angle_degrees: f64, axis: c_int, out: *mut RtwTransform);
     pub fn rtw_perlin_generate(seed: u64, index: u32, out: *mut RtwPerlin);
+    pub fn rtw_accum_slots(width: u32, height: u32) -> usize;
+    pub fn rtw_render_samples(scene: *mut c_void, camera: *const RtwCamera, opts: *const RtwOpts, sample_begin: u32, sample_count: u32,
+                              accum: *mut u64, poison: *mut u32, stats: *mut RtwStats) -> c_int;
+    pub fn rtw_resolve_accum(accum: *const u64, poison: *const u32, width: u32, height: u32, samples_per_pixel: u32, rgb_sum: *mut f64,
+                             rgb8: *mut u8) -> c_int;
     pub fn rtw_set_bvh_builder(mode: c_int) -> c_int;           // 0 auto, 1 host SAH, 2 device LBVH
     pub fn rtw_scene_bvh_builder(scene: *const c_void) -> c_int;
 }

@@ -198,19 +198,26 @@ def run_cuda(args):
     step_ms, kern_ms = t.tolist()
 
     # ---- end to end through the public host API: scene upload + render + read-back, every step --------------
+    pinned = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None   # the result's host buffer
+    arr = R.scenes.simple_arrays(SEED)          # the same scene as plain host arrays: what a step uploads
+
+    def make_scene():
+        return R.Scene.from_arrays(arr["spheres"], arr["sphere_materials"], arr["planes"], arr["plane_materials"], arr["lights"])
+
     def e2e_step():
         if world == 1:
-            sc = R.Scene(world_h, lights_h)                              # H2D: BVH build + upload
-            _, rgb8, _ = sc.render(cam, opts, want_sum=False, want_rgb8=True)       # D2H: resolved image
+            sc = make_scene()                                            # H2D: BVH build + upload
+            _, rgb8, _ = sc.render(cam, opts, want_sum=False, out_rgb8=pinned.numpy())       # D2H: resolved image into pinned memory
             sc.close()
             return rgb8
-        sc = R.Scene(world_h, lights_h)
+        sc = make_scene()
         rr = D.DistributedRenderer(sc, cam, opts, rank, world, want_sum=False, want_rgb8=True)
         rr.render()
-        out = rr.rgb8.cpu() if rank == 0 else None
+        if rank == 0:
+            pinned.copy_(rr.rgb8, non_blocking=True)
         torch.cuda.synchronize()
         sc.close()
-        return out
+        return pinned
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
     barrier()

@@ -454,12 +454,17 @@ class Scene:
         _lib.check(_lib.load().rtw_path_radiance(self._h, C.byref(camera.pod), C.byref(po), _p(i), _p(j), _p(sample), len(i), _p(out)))
         return out
 
-    def render(self, camera: "Camera", opts: Optional[RenderOptions] = None, want_sum=True, want_rgb8=True):
-        """rtw_render: host buffers out.  Returns (rgb_sum [h,w,3] f64 | None, rgb8 [h,w,3] u8 | None, stats dict)."""
+    def render(self, camera: "Camera", opts: Optional[RenderOptions] = None, want_sum=True, want_rgb8=True, out_rgb8: Optional[np.ndarray] = None):
+        """rtw_render: host buffers out.  Returns (rgb_sum [h,w,3] f64 | None, rgb8 [h,w,3] u8 | None, stats dict).
+        out_rgb8: a caller-owned [h,w,3] u8 array to receive the image (e.g. a view of pinned memory: the read-back is then a
+        true asynchronous DMA instead of a staged pageable copy)."""
         opts = opts or RenderOptions()
         h, w = camera.pod.image_height, camera.pod.image_width
         rgb_sum = np.zeros((h, w, 3)) if want_sum else None
         rgb8 = np.zeros((h, w, 3), dtype=np.uint8) if want_rgb8 else None
+        if out_rgb8 is not None:
+            assert out_rgb8.dtype == np.uint8 and out_rgb8.shape == (h, w, 3) and out_rgb8.flags.c_contiguous
+            rgb8 = out_rgb8
         st = rtw_stats()
         po = opts.pod()
         _lib.check(_lib.load().rtw_render(self._h, C.byref(camera.pod), C.byref(po), _p(rgb_sum), _p(rgb8), C.byref(st)))

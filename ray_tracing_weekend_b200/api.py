@@ -391,6 +391,7 @@ class Scene:
         """Array form of the constructor for large scenes: spheres [n,4] f64 (cx,cy,cz,r), sphere_materials [n,5] f64
         (kind,r,g,b,param) one row per sphere, planes [m,6], plane_materials [m,5], lights [l,4]."""
         self = cls.__new__(cls)
+        self.general = False
         spheres = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
         sm = np.asarray(sphere_materials, dtype=np.float64).reshape(-1, 5)
         planes = np.ascontiguousarray(planes if planes is not None else np.zeros((0, 6)), dtype=np.float64).reshape(-1, 6)

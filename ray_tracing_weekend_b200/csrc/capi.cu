@@ -853,8 +853,10 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             Q.pixels_per_chunk = pool_pixels_per_chunk(spp_here);
             uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
             Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+            const bool wavefront = o->mode == RTW_WAVEFRONT && cam->max_depth <= 0xffffu && s->bvh.depth + 2 <= 24;
             auto launch = [&](RenderParams<float, SceneViewG<float>> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
-                return launch_render_pool_general_f32(P, Q, count, sms, str, info);
+                return wavefront ? launch_render_wavefront_general_f32(P, Q, s->bvh.depth, count, sms, str, info)
+                                 : launch_render_pool_general_f32(P, Q, count, sms, str, info);
             };
             rc = render_tiles_t<float>(s, s->g32, cam, o, rank, world, (float*)d_tiles, st, launch, sr);
             launches = 2;

@@ -62,6 +62,31 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #endif
     return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
 }
+// general scenes: the same warp-private wavefront, 20 warps per SM (the general code needs ~100 registers), scene tables in global memory
+constexpr int kWfBlockG = 640, kWfSlotsPerWarpG = 96;
+template <bool COUNT>
+cudaError_t launch_render_wavefront_general_impl(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    const size_t limit = 226 * 1024, state = wavefront_state_bytes_general<kWfBlockG, kWfSlotsPerWarpG>();
+    const size_t max_entries = (limit - 1024 - state) / (sizeof(int32_t) * kWfBlockG);
+    P.stack_depth = (uint32_t)std::min<size_t>(std::min<uint32_t>(kStackDepth, bvh_depth + 2), max_entries);
+    if (P.stack_depth < bvh_depth) return cudaErrorInvalidConfiguration;
+    const size_t smem = sizeof(int32_t) * P.stack_depth * kWfBlockG + state;
+    cudaError_t e = pool_clear(P, Q, s);
+    if (e != cudaSuccess) return e;
+    auto kernel = render_wavefront_kernel<COUNT, kWfBlockG, kWfSlotsPerWarpG, false, SceneViewG<float>>;
+    int grid = 0;
+    e = persistent_grid(kernel, kWfBlockG, smem, sm_count, &grid, info);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kWfBlockG, smem, s>>>(P, Q);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return pool_finalize(P, Q, s);
+}
+cudaError_t launch_render_wavefront_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count,
+                                                cudaStream_t s, LaunchInfo* info) {
+    return count ? launch_render_wavefront_general_impl<true>(P, Q, bvh_depth, sm_count, s, info)
+                 : launch_render_wavefront_general_impl<false>(P, Q, bvh_depth, sm_count, s, info);
+}
 cudaError_t launch_resolve_accum_f32(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp,
                                      double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
     return launch_resolve_accum(accum, poison, width, height, spp, rgb_sum, rgb8, s);

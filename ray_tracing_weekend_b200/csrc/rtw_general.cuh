@@ -224,13 +224,21 @@ RTW_D double g_acos(double x) {
 RTW_D float g_atan2(float y, float x) { return atan2f(y, x); }
 RTW_D float g_acos(float x) { return acosf(x); }
 
+// Sphere::get_sphere_uv (sphere.rs:49-54).  Out of line on purpose: only CheckerTexture hits reach it, and inlining the
+// atan2 / acos sequences into the hit record cost every scene 13 % (FP32) to 37 % (f64) in registers and code size.
+template <class T, bool EXACT> __device__ __noinline__ void g_sphere_uv(T nx, T ny, T nz, T* u, T* v) {
+    *u = g_atan2(-nz, nx) / (T(2) * M<T, EXACT>::PI);
+    *v = g_acos(ny) / M<T, EXACT>::PI;
+}
+
 // Texture::get_colour (texture.rs:15-22, 46-55, 90-102).  (u, v) is only read by a CheckerTexture.
 template <class T> RTW_D V3<T> g_noise_colour(const SceneViewG<T>& sc, const GTex<T>& t, V3<T> point) {
     T arg = t.scale * point.z + g_turb<T>(sc.perlins[t.perlin], point, 7) * T(10);
     return mk<T>(T(0.5), T(0.5), T(0.5)) * (g_sin(arg) + T(1));
 }
-template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
-    if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+// Out of line: SolidColour is the common case, and two inlined copies of the 7-octave Perlin loops in every hit record
+// slowed all general kernels down by 13 % (instruction footprint).
+template <class T> __device__ __noinline__ V3<T> g_texture_lookup(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
     const GTex<T>& t = sc.textures[m.texture - 1];
     if (t.kind == TEX_NOISE) return g_noise_colour<T>(sc, t, point);
     T inv_scale = T(1) / t.scale;
@@ -239,10 +247,18 @@ template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>&
     if (ref == 0) return is_even ? mk<T>(t.even_c[0], t.even_c[1], t.even_c[2]) : mk<T>(t.odd_c[0], t.odd_c[1], t.odd_c[2]);
     return g_noise_colour<T>(sc, sc.textures[ref - 1], point);
 }
+template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
+    if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+    return g_texture_lookup<T>(sc, m, u, v, point);
+}
 
 // ---- closest hit over the planes + the BVH of bounded entries ----------------------------------------------------
+// The winner as two words: code >= 0: index into sc.prims, code <= -2: unbounded entry -2 - code; sub = the quad that was hit.
+template <class T> RTW_D const GPrim<T>& g_entry(const SceneViewG<T>& sc, int32_t code) { return code >= 0 ? sc.prims[code] : sc.unbounded[-2 - code]; }
+
 template <class T, bool EXACT, bool COUNT>
-RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, const GPrim<T>** best_out, uint32_t* sub_out, T* t_out,
+                           int32_t* stack, int stride, Tally& tl) {
     bool found = false;
     T best_t = tmax;
     const GPrim<T>* best = nullptr;
@@ -317,8 +333,24 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
         cur = stack[sp * stride];
     }
     if (!found) return false;
-    // HitRecord::new (hittable.rs:102-129) in the entity's space, then p back to world space (transformations.rs:21-27)
-    const GPrim<T>& pr = *best;
+    *best_out = best;
+    *sub_out = best_sub;
+    *t_out = best_t;
+    return true;
+}
+// the same with the winner as a code (what the wavefront stores in a path slot)
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool g_closest_prim(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, int32_t* code_out, uint32_t* sub_out, T* t_out,
+                          int32_t* stack, int stride, Tally& tl) {
+    const GPrim<T>* best;
+    if (!g_closest_entry<T, EXACT, COUNT>(sc, r, tmin, tmax, &best, sub_out, t_out, stack, stride, tl)) return false;
+    *code_out = (best >= sc.prims && best < sc.prims + sc.n_prims) ? (int32_t)(best - sc.prims) : -2 - (int32_t)(best - sc.unbounded);
+    return true;
+}
+
+// HitRecord::new (hittable.rs:102-129) for the winner, in the entity's space, then p back to world space (transformations.rs:21-27)
+template <class T, bool EXACT>
+RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>& pr, uint32_t best_sub, T best_t, Hit<T>* h) {
     Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
     h->t = best_t;
     V3<T> p = pr.kind == P_SPHERE ? at(rr, best_t) : g_at(rr, best_t);
@@ -345,10 +377,8 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
         T u = T(0), v = T(0);
         if (m.texture && sc.textures[m.texture - 1].kind == TEX_CHECKER) {     // the hit's (u, v), in the entity's own space
             V3<T> pi = g_at(rr, best_t);
-            if (pr.kind == P_SPHERE) {                                         // get_sphere_uv(outward normal), sphere.rs:49-54, 83-84
-                u = g_atan2(-outward.z, outward.x) / (T(2) * M<T, EXACT>::PI);
-                v = g_acos(outward.y) / M<T, EXACT>::PI;
-            } else if (pr.kind == P_PLANE) { u = pi.x; v = pi.z; }             // get_plane_uv for a +y normal, plane.rs:41-47
+            if (pr.kind == P_SPHERE) g_sphere_uv<T, EXACT>(outward.x, outward.y, outward.z, &u, &v);     // of the outward normal, sphere.rs:83-84
+            else if (pr.kind == P_PLANE) { u = pi.x; v = pi.z; }             // get_plane_uv for a +y normal, plane.rs:41-47
             else {                                                             // get_quad_uv, quadrilateral.rs:58-63
                 const GQuad<T>& Q = sc.quads[best_sub];
                 V3<T> pq = pi - Q.q;
@@ -357,6 +387,13 @@ RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tma
         }
         h->albedo = g_texture<T>(sc, m, u, v, p);
     } else h->albedo = mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);
+}
+
+template <class T, bool EXACT, bool COUNT>
+RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
+    const GPrim<T>* best; uint32_t sub; T t;
+    if (!g_closest_entry<T, EXACT, COUNT>(sc, r, tmin, tmax, &best, &sub, &t, stack, stride, tl)) return false;
+    g_hit_record<T, EXACT>(sc, r, *best, sub, t, h);
     return true;
 }
 

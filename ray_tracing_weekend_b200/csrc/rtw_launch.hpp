@@ -25,6 +25,8 @@ uint32_t pool_pixels_per_chunk(uint32_t spp);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t wavefront_max_bvh_depth();
+cudaError_t launch_render_wavefront_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count,
+                                                cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_resolve_accum_f32(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp,
                                      double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
 RTW_DECLARE_LAUNCHERS(f64, double)

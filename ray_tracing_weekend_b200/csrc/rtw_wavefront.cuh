@@ -35,6 +35,9 @@ template <int NPW> struct WfWarp {
     uint8_t list[WF_STAGES][NPW];
 };
 
+// general scenes (rtw_general.cuh) also remember which quad of the winning entry was hit
+template <int NPW> struct WfWarpG : WfWarp<NPW> { uint32_t hs[NPW]; };
+
 // warp-synchronous push: every lane of the warp calls it; lanes with pred append `slot`
 RTW_D void wf_push(uint8_t* list, uint32_t& count, bool pred, uint32_t slot, uint32_t lt_mask) {
     uint32_t m = __ballot_sync(0xffffffffu, pred);
@@ -69,25 +72,31 @@ RTW_D void wf_finish(const PoolParams& Q, WfAcc& A, uint32_t q, V3<float> value,
     A.a2 += pool_fixed(value.z, 2, A.bad);
 }
 
-template <bool COUNT, int BLOCK, int NPW, bool SH>
-__global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float> P, PoolParams Q) {
+template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>>
+__global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float, SCENE> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
+    constexpr bool GEN = is_general<SCENE>::value;        // general scenes: entries of any kind, scene tables in global memory
     static_assert(NPW <= 255 && NPW >= 32, "slot indices are stored in one byte");
+    static_assert(!(GEN && SH), "general scenes are read from global memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [stack][scene sections][one WfWarp per warp]
     const uint32_t stack_depth = P.stack_depth;
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);
-    SceneView<T> sc0 = P.scene;
     unsigned char* cur_p = smem_raw + sizeof(int32_t) * stack_depth * BLOCK;
-    stage_scene(P, cur_p, sc0);                           // TMA bulk copies; the only block-wide wait of the kernel
-    cur_p += P.smem_nodes + (P.smem_spheres ? 2u * P.smem_spheres + ((uint32_t)P.scene.n_spheres * 4u + 15u) / 16u * 16u : 0u) + P.smem_lights;
-    using SC = typename std::conditional<SH, SceneViewSh<T>, SceneView<T>>::type;
+    using SC = typename std::conditional<SH, SceneViewSh<T>, SCENE>::type;
     SC sc;
-    static_cast<SceneView<T>&>(sc) = sc0;
-    bind_scene(sc);
+    if constexpr (GEN) sc = P.scene;
+    else {
+        SceneView<T> sc0 = P.scene;
+        stage_scene(P, cur_p, sc0);                       // TMA bulk copies; the only block-wide wait of the kernel
+        cur_p += P.smem_nodes + (P.smem_spheres ? 2u * P.smem_spheres + ((uint32_t)P.scene.n_spheres * 4u + 15u) / 16u * 16u : 0u) + P.smem_lights;
+        static_cast<SceneView<T>&>(sc) = sc0;
+        bind_scene(sc);
+    }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt_mask = (1u << lane) - 1u;
-    WfWarp<NPW>& S = reinterpret_cast<WfWarp<NPW>*>(cur_p)[warp];
+    using WS = typename std::conditional<GEN, WfWarpG<NPW>, WfWarp<NPW>>::type;
+    WS& S = reinterpret_cast<WS*>(cur_p)[warp];
 
     const CameraT<T>& cam = P.cam;
     int32_t* stack = stack_base + tid;
@@ -175,11 +184,34 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 nrays++;
                 // closest hit without the hit record: the winner's id and t are stored, SHADE builds the record
                 T best_t; int32_t bestp;
-                if (closest_prim<T, EXACT, COUNT, SC>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &best_t, stack, BLOCK, tl)) {
-                    S.ht[slot] = best_t; S.hp[slot] = bestp;
-                    uint32_t k = bestp >= 0 ? (load_sphere_info(sc, bestp) & 3u) : (sc.planes[-2 - bestp].info & 3u);
-                    kind = k == LAMBERTIAN ? 0u : (k == METAL ? 1u : 2u);
+                bool hit;
+                if constexpr (GEN) {
+                    uint32_t sub;
+                    hit = g_closest_prim<T, EXACT, COUNT>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &sub, &best_t, stack, BLOCK, tl);
+                    if (hit) {
+                        S.ht[slot] = best_t; S.hp[slot] = bestp; S.hs[slot] = sub;
+                        uint32_t k = sc.mats[g_entry<T>(sc, bestp).mat].kind;
+                        if (k == LAMBERTIAN || k == ISOTROPIC) kind = 0u;
+                        else if (k == METAL) kind = 1u;
+                        else if (k == DIELECTRIC) kind = 2u;
+                        else {      // DiffuseLight / Invisible never scatter: mult * emitted + res (camera.rs:484-486)
+                            Hit<T> h;
+                            g_hit_record<T, EXACT>(sc, r, g_entry<T>(sc, bestp), sub, best_t, &h);
+                            if (COUNT) tl.absorbed++;
+                            V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
+                            wf_finish(Q, acc, S.q[slot], mult * g_emitted<T>(h) + wf_res(S.dep[slot]), P.flags);
+                            kind = 3u;
+                        }
+                    }
                 } else {
+                    hit = closest_prim<T, EXACT, COUNT, SC>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &best_t, stack, BLOCK, tl);
+                    if (hit) {
+                        S.ht[slot] = best_t; S.hp[slot] = bestp;
+                        uint32_t k = bestp >= 0 ? (load_sphere_info(sc, bestp) & 3u) : (sc.planes[-2 - bestp].info & 3u);
+                        kind = k == LAMBERTIAN ? 0u : (k == METAL ? 1u : 2u);
+                    }
+                }
+                if (!hit) {
                     if (COUNT) tl.missed++;
                     V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
                     wf_finish(Q, acc, S.q[slot], mult * cam.background + wf_res(S.dep[slot]), P.flags);   // camera.rs:473-475
@@ -203,7 +235,8 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             if (active) {
                 Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
                 Hit<T> h;
-                hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
+                if constexpr (GEN) g_hit_record<T, EXACT>(sc, r, g_entry<T>(sc, S.hp[slot]), S.hs[slot], S.ht[slot], &h);
+                else hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
                 uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
                 V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
                 Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u);
@@ -245,5 +278,6 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
 }
 
 template <int BLOCK, int NPW> size_t wavefront_state_bytes() { return sizeof(WfWarp<NPW>) * (BLOCK / 32); }
+template <int BLOCK, int NPW> size_t wavefront_state_bytes_general() { return sizeof(WfWarpG<NPW>) * (BLOCK / 32); }
 
 }  // namespace rtw

@@ -380,3 +380,25 @@ def test_general_trace_f32_tolerance(rtw, oracle, name):
         assert np.median(rel) < 2e-6 and np.quantile(rel, 0.99) < 1e-4, (np.median(rel), np.quantile(rel, 0.99), rel.max())
     finally:
         scene.close()
+
+
+@pytest.mark.parametrize("name", ("cornell_box", "checkered_spheres", "random"))
+def test_general_wavefront_is_bit_identical_to_megakernel(rtw, oracle, name):
+    """The two FP32 renderers of the general path (warp-private wavefront / pooled megakernel) trace the same paths with the same
+    arithmetic and accumulate in fixed point: identical images, identical ray counts."""
+    if name == "random":
+        world, lights = _random_scene(rtw, np.random.default_rng(11))
+        scene = rtw.Scene(world, lights)
+        cb = rtw.CameraBuilder().with_lookfrom((0., 2., 16.)).with_lookat((0., 0., 0.)).with_focus_dist(16.).with_background((0.6, 0.7, 0.9))
+    else:
+        scene, _, cb = _build(rtw, oracle, name)
+    try:
+        cam = _cam(cb, 96, 64, 24, 30)
+        a, a8, sa = scene.render(cam, rtw.RenderOptions(seed=SEED, mode=rtw.RTW_WAVEFRONT))
+        b, b8, sb = scene.render(cam, rtw.RenderOptions(seed=SEED, mode=rtw.RTW_MEGAKERNEL))
+        assert sa["rays"] == sb["rays"] and sa["paths"] == sb["paths"] == 96 * 64 * 24
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a8, b8)
+        c, _, sc_ = scene.render(cam, rtw.RenderOptions(seed=SEED, mode=rtw.RTW_WAVEFRONT, flags=rtw.RTW_FLAG_COUNT_EVENTS))
+        assert np.array_equal(a, c, equal_nan=True) and sc_["rays"] == sa["rays"]
+    finally:
+        scene.close()

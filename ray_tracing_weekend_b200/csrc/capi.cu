@@ -388,6 +388,8 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
         host::Box b; bool bd;
         make_entry(g.lights[lorder[k]], (uint32_t)lorder[k], &lights[k], &b, &bd);
     }
+    const int32_t n_lights = (int32_t)lights.size();
+    if (lights.empty()) { GPrim<T> none{}; none.kind = P_NO_LIGHTS; none.xform = -1; lights.push_back(none); }    // see g_lights_random
     CU(d.nodes.upload(nodes)); CU(d.prims.upload(prims)); CU(d.unbounded.upload(unbounded)); CU(d.lights.upload(lights));
     CU(d.spheres.upload(spheres)); CU(d.plane_geo.upload(plane_geo)); CU(d.quads.upload(quads)); CU(d.xforms.upload(xforms));
     CU(d.mats.upload(mats)); CU(d.textures.upload(textures)); CU(d.perlins.upload(perlins));
@@ -395,7 +397,7 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     d.view.spheres = d.spheres.p; d.view.plane_geo = d.plane_geo.p; d.view.quads = d.quads.p; d.view.xforms = d.xforms.p;
     d.view.mats = d.mats.p; d.view.textures = d.textures.p; d.view.perlins = d.perlins.p;
     d.view.n_nodes = (int32_t)nodes.size(); d.view.n_prims = (int32_t)prims.size(); d.view.n_unbounded = (int32_t)unbounded.size();
-    d.view.n_lights = (int32_t)lights.size(); d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
+    d.view.n_lights = n_lights; d.view.lights_is_bvh = g.lights_is_bvh ? 1u : 0u;
     d.view.flat = flat ? 1u : 0u;
     d.view.panic_flag = s->d_panic.p;
     d.view.has_xforms = 0;

@@ -62,25 +62,38 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #endif
     return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
 }
-// general scenes: the same warp-private wavefront, 20 warps per SM (the general code needs ~100 registers), scene tables in global memory
-constexpr int kWfBlockG = 640, kWfSlotsPerWarpG = 96;
-template <bool COUNT>
-cudaError_t launch_render_wavefront_general_impl(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    const size_t limit = 226 * 1024, state = wavefront_state_bytes_general<kWfBlockG, kWfSlotsPerWarpG>();
-    const size_t max_entries = (limit - 1024 - state) / (sizeof(int32_t) * kWfBlockG);
+// general scenes: the same warp-private wavefront and launch shape (swept: 512x96 460 ms, 512x128 450, 576x96 440, 640x96 408, 704x96 386, 768x96 364 on cornell_box), scene tables in global memory
+constexpr int kWfBlockG = 768, kWfSlotsPerWarpG = 96;
+template <bool COUNT, int BLOCK, int NP>
+cudaError_t launch_render_wavefront_general_shape(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    const size_t limit = 226 * 1024, state = wavefront_state_bytes_general<BLOCK, NP>();
+    const size_t max_entries = (limit - 1024 - state) / (sizeof(int32_t) * BLOCK);
     P.stack_depth = (uint32_t)std::min<size_t>(std::min<uint32_t>(kStackDepth, bvh_depth + 2), max_entries);
     if (P.stack_depth < bvh_depth) return cudaErrorInvalidConfiguration;
-    const size_t smem = sizeof(int32_t) * P.stack_depth * kWfBlockG + state;
+    const size_t smem = sizeof(int32_t) * P.stack_depth * BLOCK + state;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
-    auto kernel = render_wavefront_kernel<COUNT, kWfBlockG, kWfSlotsPerWarpG, false, SceneViewG<float>>;
+    auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, false, SceneViewG<float>>;
     int grid = 0;
-    e = persistent_grid(kernel, kWfBlockG, smem, sm_count, &grid, info);
+    e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kWfBlockG, smem, s>>>(P, Q);
+    kernel<<<grid, BLOCK, smem, s>>>(P, Q);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return pool_finalize(P, Q, s);
+}
+template <bool COUNT>
+cudaError_t launch_render_wavefront_general_impl(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
+#ifdef RTW_WF_SWEEP
+    const char* e = std::getenv("RTW_WFG_SHAPE");
+    int shape = e ? std::atoi(e) : 0;
+    if (shape == 1) return launch_render_wavefront_general_shape<COUNT, 512, 96>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 2) return launch_render_wavefront_general_shape<COUNT, 512, 128>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 3) return launch_render_wavefront_general_shape<COUNT, 576, 96>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 4) return launch_render_wavefront_general_shape<COUNT, 704, 96>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 5) return launch_render_wavefront_general_shape<COUNT, 768, 96>(P, Q, bvh_depth, sm_count, s, info);
+#endif
+    return launch_render_wavefront_general_shape<COUNT, kWfBlockG, kWfSlotsPerWarpG>(P, Q, bvh_depth, sm_count, s, info);
 }
 cudaError_t launch_render_wavefront_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count,
                                                 cudaStream_t s, LaunchInfo* info) {

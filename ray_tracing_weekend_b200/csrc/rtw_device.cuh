@@ -310,7 +310,7 @@ RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
 
 // ---------------------------------------------------------------------------------------------
 // General scenes (rtw_general.cuh): one table of list entries (entity kind + index + optional Transformed<T>) under one BVH.
-enum PrimKind : uint32_t { P_SPHERE = 0, P_PLANE = 1, P_QUAD = 2, P_TRIANGLE = 3, P_CUBOID = 4 };
+enum PrimKind : uint32_t { P_SPHERE = 0, P_PLANE = 1, P_QUAD = 2, P_TRIANGLE = 3, P_CUBOID = 4, P_NO_LIGHTS = 7 };
 enum MatKindG : uint32_t { DIFFUSE_LIGHT = 4, ISOTROPIC = 5 };
 template <class T> struct GQuad { V3<T> q, u, v, w, normal; T area; };       // Quad / Triangle / one Cuboid face (quadrilateral.rs:23-32)
 template <class T> struct GPlane { V3<T> point, normal; };

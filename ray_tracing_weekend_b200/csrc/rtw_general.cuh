@@ -450,6 +450,10 @@ RTW_D V3<T> g_lights_random(const SceneViewG<T>& sc, V3<T> origin, Stream<EXACT>
             return ((Q.q + Q.u * r1) + Q.v * r2) - origin;
         }
     }
+    // An EMPTY lights list is uploaded as one entry of kind P_NO_LIGHTS (n_lights stays 0, so lights.pdf_value is 0 / 0 = NaN as in
+    // the reference): drawing from it is the reference's panic (.expect("HittableList shouldn't be empty"), hittable_list.rs:414-419).
+    // The flag makes the render call return RTW_E_INVALID; what this path computes afterwards is discarded with it.
+    if (pr.kind == P_NO_LIGHTS) *sc.panic_flag = 1u;
     return mk<T>(1, 0, 0);                                        // Hittable::random default, hittable.rs:179-181
 }
 
@@ -467,13 +471,7 @@ RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h
         if (COUNT && cosine) tl.lambertian++;
         Onb<T, EXACT> uvw(h.normal);
         V3<T> dir;
-        if (standard(rng) < T(0.5)) {                                                   // MixturePdf::generate (pdf1 = lights)
-            if (sc.n_lights == 0) {           // .expect("HittableList shouldn't be empty") (hittable_list.rs:414-419): the reference panics;
-                *sc.panic_flag = 1u;          // the render call reports RTW_E_INVALID, the path ends here
-                return V_ABSORB;
-            }
-            dir = g_lights_random<T, EXACT>(sc, h.p, rng);
-        }
+        if (standard(rng) < T(0.5)) dir = g_lights_random<T, EXACT>(sc, h.p, rng);      // MixturePdf::generate (pdf1 = lights)
         else if (cosine) {                                                              // CosineWeightedHemisphere, utils.rs:146-161
             T r1 = standard(rng), r2 = standard(rng);
             T sn, cs;

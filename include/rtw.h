@@ -221,6 +221,24 @@ RTW_API void rtw_scene_destroy(rtw_scene* scene);
 /* nodes, leaves, depth, max leaf size, bytes resident on the device */
 RTW_API int  rtw_scene_info(const rtw_scene* scene, uint64_t out[5]);
 
+/* The scene's world BVH as a flat host-side array: the layout the reference sketches for its own flat tree
+ * (shared/src/hittable_collections/bvh.rs:224-241, `BVHNode::{Root, Node, Leaf}` with u32 child indices and parent links).
+ * Node 0 is the Root (parent = -1); a node's children follow it in breadth-first order.
+ *   inner node: left / right = child node indices, first = count = 0;  box = the union of its children's boxes (node_bbox)
+ *   leaf:       left = right = -1; [first, first + count) is its range of prim_order (shape_index); box = the box around those entries
+ * prim_order[k] is the primitive id (position in the world list, the id the batch calls report) of the k-th entry in leaf order.
+ * Boxes are the f64 boxes the exact path traverses, whichever builder made the tree (host SAH or device LBVH: the nodes are read
+ * back from the device).  Scenes whose bounded entries are walked as a flat list (general scenes with <= 8 of them) export 0 nodes
+ * and the list order.  Call with nodes == NULL / prim_order == NULL to query the counts; RTW_E_INVALID if a capacity is too small. */
+typedef struct rtw_bvh_node {
+    double box_min[3], box_max[3];
+    int32_t parent, left, right;
+    uint32_t first, count;
+    uint32_t depth;                 /* Root = 0 */
+} rtw_bvh_node;
+RTW_API int  rtw_scene_export_bvh(rtw_scene* scene, rtw_bvh_node* nodes, size_t node_capacity, size_t* n_nodes,
+                                  uint32_t* prim_order, size_t prim_capacity, size_t* n_prims);
+
 /* ---- Camera::render ---------------------------------------------------------------------------- */
 /* Replaces Camera::render (shared/src/camera.rs:295-297).  Host buffers, both optional:
  *   rgb_sum: [height][width][3] f64, un-normalised sample sums == the Colour inside each

@@ -28,6 +28,7 @@ RTW_SYMBOLS = (
     "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
     "rtw_render_samples_device", "rtw_resolve_accum_device", "rtw_accum_slots", "rtw_render_samples", "rtw_resolve_accum", "rtw_set_bvh_builder", "rtw_scene_bvh_builder", "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
+    "rtw_scene_export_bvh",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
 
@@ -148,6 +149,7 @@ def load(build_if_missing: bool = True):
     L.rtw_scene_create.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, vp, sz, vp]
     L.rtw_scene_destroy.argtypes = [vp]; L.rtw_scene_destroy.restype = None
     L.rtw_scene_info.argtypes = [vp, vp]
+    L.rtw_scene_export_bvh.argtypes = [vp, vp, sz, vp, vp, sz, vp]
     L.rtw_render.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rtw_render_tiles_device.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp]
     L.rtw_untile_resolve_device.argtypes = [vp, u32, u32, u32, u32, u32, vp, vp, vp]

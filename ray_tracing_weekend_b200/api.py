@@ -426,6 +426,21 @@ class Scene:
         return dict(nodes=int(out[0]), leaves=int(out[1]), depth=int(out[2]), max_leaf=int(out[3]), device_bytes=int(out[4]),
                     builder={1: "host-sah", 2: "device-lbvh"}.get(int(_lib.load().rtw_scene_bvh_builder(self._h)), "?"))
 
+    BVH_NODE_DTYPE = np.dtype([("box_min", np.float64, 3), ("box_max", np.float64, 3), ("parent", np.int32), ("left", np.int32),
+                               ("right", np.int32), ("first", np.uint32), ("count", np.uint32), ("depth", np.uint32)], align=True)
+
+    def export_bvh(self):
+        """The world BVH as flat host records (rtw_bvh_node: the reference's `BVHNode::{Root, Node, Leaf}` sketch, bvh.rs:224-241)
+        and the primitive ids in leaf order."""
+        L = _lib.load()
+        nn, npr = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(L.rtw_scene_export_bvh(self._h, None, 0, C.byref(nn), None, 0, C.byref(npr)))
+        nodes = np.zeros(nn.value, dtype=self.BVH_NODE_DTYPE)
+        order = np.zeros(npr.value, dtype=np.uint32)
+        _lib.check(L.rtw_scene_export_bvh(self._h, _p(nodes) if nn.value else None, nn.value, C.byref(nn), _p(order) if npr.value else None,
+                                          npr.value, C.byref(npr)))
+        return nodes, order
+
     # Hittable::hit for a batch (hittable.rs:173)
     def trace_batch(self, o, d, tmin=EPSILON, tmax=float("inf"), precision=RTW_F32):
         o = np.ascontiguousarray(o, dtype=np.float64).reshape(-1, 3)

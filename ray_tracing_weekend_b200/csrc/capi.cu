@@ -822,6 +822,83 @@ int rtw_scene_info(const rtw_scene* s, uint64_t out[5]) {
     return RTW_OK;
 }
 
+static_assert(sizeof(rtw_bvh_node) == 72, "rtw_bvh_node layout (include/rtw.h, api.py BVH_NODE_DTYPE, rust/cuda RtwBvhNode)");
+// The reference's flat-tree sketch (bvh.rs:224-241) as the host mirror format: Root / Node / Leaf records with parent links.
+int rtw_scene_export_bvh(rtw_scene* s, rtw_bvh_node* out, size_t node_cap, size_t* n_nodes, uint32_t* prim_order, size_t prim_cap, size_t* n_prims) {
+    if (!s || !n_nodes || !n_prims) return fail(RTW_E_INVALID, "NULL argument");
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return fail(RTW_E_CUDA, cudaGetErrorString(e));
+    // leaf order of the primitive ids, and the device nodes (f64: the exact path's (min, max) boxes)
+    std::vector<uint32_t> order;
+    std::vector<Node<double>> dn;
+    bool flat = false;
+    if (s->general) {
+        std::vector<GPrim<double>> prims(s->g64.prims.n);
+        if (!prims.empty()) e = cudaMemcpy(prims.data(), s->g64.prims.p, prims.size() * sizeof(GPrim<double>), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(RTW_E_CUDA, cudaGetErrorString(e));
+        order.resize(prims.size());
+        for (size_t k = 0; k < prims.size(); ++k) order[k] = prims[k].id;
+        flat = s->g64.view.flat != 0;
+        if (!flat) dn.resize((size_t)s->g64.view.n_nodes);
+        if (!dn.empty()) e = cudaMemcpy(dn.data(), s->g64.nodes.p, dn.size() * sizeof(Node<double>), cudaMemcpyDeviceToHost);
+    } else {
+        order.resize((size_t)s->f64.view.n_spheres);
+        if (!order.empty()) e = cudaMemcpy(order.data(), s->f64.info.p, order.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(RTW_E_CUDA, cudaGetErrorString(e));
+        for (uint32_t& v : order) v >>= 2;                     // info = prim_id << 2 | material kind
+        dn.resize((size_t)s->f64.view.n_nodes);
+        if (!dn.empty()) e = cudaMemcpy(dn.data(), s->f64.nodes.p, dn.size() * sizeof(Node<double>), cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) return fail(RTW_E_CUDA, cudaGetErrorString(e));
+    // breadth-first walk from the root; every child link of a device node becomes a record of its own
+    std::vector<rtw_bvh_node> nodes;
+    if (!dn.empty() && !order.empty()) {
+        struct Item { int32_t link; int32_t self; };
+        auto make = [&](const double* mn, const double* mx, int32_t parent, uint32_t depth) {
+            rtw_bvh_node n{};
+            for (int a = 0; a < 3; ++a) { n.box_min[a] = mn[a]; n.box_max[a] = mx[a]; }
+            n.parent = parent; n.left = n.right = -1; n.depth = depth;
+            nodes.push_back(n);
+            return (int32_t)nodes.size() - 1;
+        };
+        const Node<double>& r = dn[0];
+        double mn[3], mx[3];
+        const bool l_ok = r.left != kEmptyLeaf, r_ok = r.right != kEmptyLeaf;
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = l_ok && r_ok ? std::fmin(r.la[a], r.ra[a]) : (l_ok ? r.la[a] : r.ra[a]);
+            mx[a] = l_ok && r_ok ? std::fmax(r.lb[a], r.rb[a]) : (l_ok ? r.lb[a] : r.rb[a]);
+        }
+        std::vector<Item> queue{{0, make(mn, mx, -1, 0)}};
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const Item it = queue[head];
+            if ((size_t)it.link >= dn.size()) return fail(RTW_E_CUDA, "corrupt BVH: child index out of range");
+            const Node<double> nd = dn[(size_t)it.link];
+            const int32_t links[2] = {nd.left, nd.right};
+            const double* boxes[2][2] = {{nd.la, nd.lb}, {nd.ra, nd.rb}};
+            for (int c = 0; c < 2; ++c) {
+                if (links[c] == kEmptyLeaf) continue;
+                const int32_t child = make(boxes[c][0], boxes[c][1], it.self, nodes[(size_t)it.self].depth + 1);
+                (c == 0 ? nodes[(size_t)it.self].left : nodes[(size_t)it.self].right) = child;
+                if (links[c] >= 0) queue.push_back({links[c], child});
+                else {
+                    const uint32_t enc = (uint32_t)~links[c];
+                    nodes[(size_t)child].first = enc >> 4; nodes[(size_t)child].count = (enc & 15u) + 1u;
+                }
+            }
+        }
+    }
+    *n_nodes = nodes.size(); *n_prims = order.size();
+    if (out) {
+        if (node_cap < nodes.size()) return fail(RTW_E_INVALID, "node_capacity is smaller than the tree");
+        std::copy(nodes.begin(), nodes.end(), out);
+    }
+    if (prim_order) {
+        if (prim_cap < order.size()) return fail(RTW_E_INVALID, "prim_capacity is smaller than the number of bounded entries");
+        std::copy(order.begin(), order.end(), prim_order);
+    }
+    return RTW_OK;
+}
+
 }  // extern "C"
 
 namespace {

@@ -65,6 +65,17 @@ unsafe extern "C" {
                              rgb8: *mut u8) -> c_int;
     pub fn rtw_set_bvh_builder(mode: c_int) -> c_int;           // 0 auto, 1 host SAH, 2 device LBVH
     pub fn rtw_scene_bvh_builder(scene: *const c_void) -> c_int;
+    /// flat host mirror of the world BVH (the layout of `hittable_collections::bvh::flat::BVHNode`)
+    pub fn rtw_scene_export_bvh(scene: *mut c_void, nodes: *mut RtwBvhNode, node_capacity: usize, n_nodes: *mut usize,
+                                prim_order: *mut u32, prim_capacity: usize, n_prims: *mut usize) -> c_int;
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct RtwBvhNode {
+    pub box_min: [f64; 3], pub box_max: [f64; 3],
+    pub parent: i32, pub left: i32, pub right: i32,
+    pub first: u32, pub count: u32, pub depth: u32,
 }
 
 #[link(name = "rtw_cuda")]

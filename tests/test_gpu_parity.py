@@ -476,6 +476,115 @@ def test_device_built_bvh_renders_the_same_image(rtw, oracle, simple_scene):
         big.close()
 
 
+def _check_exported_tree(nodes, order, prim_box, info):
+    """Invariants of rtw_scene_export_bvh's flat tree: one Root, consistent parent / child links and depths, the leaves partition
+    the leaf-ordered primitive list, every leaf box holds its primitives' boxes, every inner box is the union of its children's."""
+    n = len(nodes)
+    assert n == info["nodes"] + info["leaves"] and nodes["parent"][0] == -1 and (nodes["parent"][1:] >= 0).all()
+    leaf = nodes["left"] < 0
+    assert ((nodes["right"] < 0) == leaf).all() and leaf.sum() == info["leaves"]
+    assert info["depth"] - 2 <= nodes["depth"].max() <= info["depth"] and nodes["depth"][0] == 0       # the LBVH reports its depth before leaf collapse
+    inner = np.flatnonzero(~leaf)
+    for side in ("left", "right"):
+        ch = nodes[side][inner]
+        assert (ch > inner).all() and (ch < n).all()                            # breadth-first: children follow their parent
+        assert (nodes["parent"][ch] == inner).all() and (nodes["depth"][ch] == nodes["depth"][inner] + 1).all()
+    assert len(np.unique(np.concatenate([nodes["left"][inner], nodes["right"][inner]]))) == n - 1      # every non-root node has one parent
+    l, r = nodes["left"][inner], nodes["right"][inner]
+    assert np.array_equal(nodes["box_min"][inner], np.minimum(nodes["box_min"][l], nodes["box_min"][r]))
+    assert np.array_equal(nodes["box_max"][inner], np.maximum(nodes["box_max"][l], nodes["box_max"][r]))
+    # leaves: disjoint ranges covering [0, n_prims), each primitive id once
+    lf = np.flatnonzero(leaf)
+    first, count = nodes["first"][lf].astype(np.int64), nodes["count"][lf].astype(np.int64)
+    srt = np.argsort(first)
+    assert first[srt][0] == 0 and np.array_equal(first[srt][1:], (first[srt] + count[srt])[:-1]) and (first[srt] + count[srt])[-1] == len(order)
+    assert (count >= 1).all() and count.max() <= info["max_leaf"]
+    assert len(np.unique(order)) == len(order)
+    for k in lf:
+        ids = order[nodes["first"][k]:nodes["first"][k] + nodes["count"][k]]
+        mn, mx = prim_box(ids)
+        assert (nodes["box_min"][k] <= mn.min(axis=0)).all() and (nodes["box_max"][k] >= mx.max(axis=0)).all()
+
+
+def test_export_bvh_flat_host_mirror(rtw, oracle, simple_scene):
+    """rtw_scene_export_bvh: the world BVH read back as the reference's flat `BVHNode::{Root, Node, Leaf}` records
+    (hittable_collections/bvh.rs:224-241), for the host SAH tree, the device-built LBVH and a general scene."""
+    arrays = rtw.scenes.simple_arrays(SEED, 11)
+    sph = np.asarray(arrays["spheres"], dtype=np.float64).reshape(-1, 4)
+    n_planes = len(np.asarray(arrays["planes"]).reshape(-1, 6))
+
+    def sphere_box(ids):
+        q = sph[np.asarray(ids, dtype=np.int64) - n_planes]
+        return q[:, :3] - q[:, 3:4], q[:, :3] + q[:, 3:4]
+
+    trees = {}
+    for builder in (rtw.RTW_BVH_HOST_SAH, rtw.RTW_BVH_DEVICE_LBVH):
+        rtw.set_bvh_builder(builder)
+        try:
+            sc = rtw.Scene.from_arrays(arrays["spheres"], arrays["sphere_materials"], arrays["planes"], arrays["plane_materials"], arrays["lights"])
+        finally:
+            rtw.set_bvh_builder(rtw.RTW_BVH_AUTO)
+        try:
+            nodes, order = sc.export_bvh()
+            info = sc.info()
+            assert len(order) == len(sph) and sorted(order.tolist()) == list(range(n_planes, n_planes + len(sph)))
+            _check_exported_tree(nodes, order, sphere_box, info)
+            trees[builder] = nodes
+            # a brute-force walk of the exported tree finds the oracle's hits (first 64 rays)
+            o, d = _ray_batch(rtw, oracle, simple_scene, 64, 0)
+            prim_o, t_o, _ = simple_scene["oscene"].trace_batch(o, d)
+            for k in range(len(o)):
+                if prim_o[k] < n_planes:
+                    continue
+                inv = 1.0 / d[k]
+                stack, found = [0], False
+                while stack:
+                    nd = nodes[stack.pop()]
+                    t0, t1 = (nd["box_min"] - o[k]) * inv, (nd["box_max"] - o[k]) * inv
+                    if np.minimum(t0, t1).max() > np.maximum(t0, t1).min() * (1 + 1e-12) + 1e-12:
+                        continue
+                    if nd["left"] < 0:
+                        found |= int(prim_o[k]) in order[nd["first"]:nd["first"] + nd["count"]].tolist()
+                    else:
+                        stack += [int(nd["left"]), int(nd["right"])]
+                assert found, k
+        finally:
+            sc.close()
+    # both builders bound the same scene: equal root boxes
+    a, b = trees[rtw.RTW_BVH_HOST_SAH][0], trees[rtw.RTW_BVH_DEVICE_LBVH][0]
+    assert np.array_equal(a["box_min"], b["box_min"]) and np.array_equal(a["box_max"], b["box_max"])
+    # capacity errors and count queries
+    L = rtw._lib.load()
+    import ctypes as C
+    sc = rtw.Scene(simple_scene["world"], simple_scene["lights"])
+    try:
+        nn, npr = C.c_size_t(0), C.c_size_t(0)
+        assert L.rtw_scene_export_bvh(sc._h, None, 0, C.byref(nn), None, 0, C.byref(npr)) == 0 and nn.value > 0 and npr.value == len(sph)
+        buf = np.zeros(nn.value, dtype=rtw.Scene.BVH_NODE_DTYPE)
+        assert L.rtw_scene_export_bvh(sc._h, buf.ctypes.data_as(C.c_void_p), nn.value - 1, C.byref(nn), None, 0, C.byref(npr)) == rtw._lib.RTW_E_INVALID
+        assert L.rtw_scene_export_bvh(None, None, 0, C.byref(nn), None, 0, C.byref(npr)) == rtw._lib.RTW_E_INVALID
+    finally:
+        sc.close()
+    # general scenes: cornell_box walks its 8 entries as a flat list (no tree); debugging_scene (14 entries) has one
+    world, lights, _ = rtw.scenes.cornell_box()
+    g = rtw.Scene(world, lights)
+    try:
+        nodes, order = g.export_bvh()
+        assert len(nodes) == 0 and sorted(order.tolist()) == list(range(8))
+    finally:
+        g.close()
+    world, lights, _ = rtw.scenes.debugging_scene(SEED)
+    g = rtw.Scene(world, lights)
+    try:
+        nodes, order = g.export_bvh()
+        info = g.info()
+        assert len(nodes) == info["nodes"] + info["leaves"] and len(np.unique(order)) == len(order) and nodes["parent"][0] == -1
+        leaf = nodes["left"] < 0
+        assert nodes["count"][leaf].sum() == len(order)
+    finally:
+        g.close()
+
+
 @pytest.mark.parametrize("mode", ("wavefront", "megakernel"))
 def test_sample_partition_is_bit_identical(rtw, simple_scene, gscene, mode):
     """The multi-GPU sample partition on one GPU: three "ranks" render their sample ranges of every pixel into fixed-point

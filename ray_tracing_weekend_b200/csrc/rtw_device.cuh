@@ -85,16 +85,33 @@ RTW_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 // The 32-bit outputs of consecutive blocks form one word sequence x[0], x[1], ...
 //   W32 (fast):  uniform k <- x[k]                      24-bit
 //   W64 (exact): uniform k <- x[2k] | x[2k+1] << 32     53-bit, rand 0.8 `Standard` / `Open01` semantics
+#ifdef __CUDACC__
+// One out-of-line copy for kernels whose code size matters more than the call: every refill site of a Stream otherwise inlines the
+// ten rounds (~64 instructions; the general-scene renderers held ten copies = 10 KB of a kernel that stalls on instruction fetch).
+static __device__ __noinline__ uint4 philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    uint32_t o[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+#endif
+#ifndef RTW_PHILOX_OUTLINE_ALL
+#define RTW_PHILOX_OUTLINE_ALL false
+#endif
 template <bool EXACT> struct Stream {
     uint32_t k0, k1, pixel, sample, vertex;
     uint32_t k, blk, b0, b1, b2, b3;
-    RTW_HD Stream(uint64_t seed, uint32_t pixel_, uint32_t sample_, uint32_t vertex_)
+    bool outline;       // a compile-time constant at every construction site: refill through philox4x32_10_call
+    RTW_HD Stream(uint64_t seed, uint32_t pixel_, uint32_t sample_, uint32_t vertex_, bool outline_ = false)
         : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), pixel(pixel_), sample(sample_), vertex(vertex_), k(0), blk(0xffffffffu),
-          b0(0), b1(0), b2(0), b3(0) {}
+          b0(0), b1(0), b2(0), b3(0), outline(outline_ || RTW_PHILOX_OUTLINE_ALL) {}
     RTW_HD uint32_t word32(uint32_t idx) {
         uint32_t block = idx >> 2;
         if (block != blk) {
             uint32_t o[4];
+#ifdef __CUDA_ARCH__
+            if (outline) { uint4 q = philox4x32_10_call(pixel, sample, vertex, block, k0, k1); o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
+            else
+#endif
             philox4x32_10(pixel, sample, vertex, block, k0, k1, o);
             b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
             blk = block;

@@ -27,14 +27,19 @@ template <class T> RTW_D V3<T> g_at(const Ray<T>& r, T t) { return mk<T>(r.o.x +
 template <class T, bool EXACT>
 RTW_D bool g_box_hit(const T* mn, const T* mx, const Ray<T>& r, T start, T end) {
     using Mt = M<T, EXACT>;
-    T x0 = (mn[0] - r.o.x) / r.d.x, x1 = (mx[0] - r.o.x) / r.d.x;
+    // FP32: one SFU reciprocal per axis instead of two IEEE divisions (six ~10-instruction sequences per call); same handling of
+    // zero direction components ((mn - o) * inf = +-inf, NaN only where the division gives 0 / 0 as well)
+    T ix, iy, iz;
+    if constexpr (EXACT) { ix = iy = iz = T(0); } else { ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z); }
+    auto slab = [](T plane, T o, T d, T inv) { if constexpr (EXACT) return (plane - o) / d; else return (plane - o) * inv; };
+    T x0 = slab(mn[0], r.o.x, r.d.x, ix), x1 = slab(mx[0], r.o.x, r.d.x, ix);
     if (signbit(r.d.x)) { T s = x0; x0 = x1; x1 = s; }
     T tmin = x0, tmax = x1;
-    T y0 = (mn[1] - r.o.y) / r.d.y, y1 = (mx[1] - r.o.y) / r.d.y;
+    T y0 = slab(mn[1], r.o.y, r.d.y, iy), y1 = slab(mx[1], r.o.y, r.d.y, iy);
     if (signbit(r.d.y)) { T s = y0; y0 = y1; y1 = s; }
     if (tmax < y0 || tmin > y1) return false;
     tmin = Mt::max_(tmin, y0); tmax = Mt::min_(tmax, y1);
-    T z0 = (mn[2] - r.o.z) / r.d.z, z1 = (mx[2] - r.o.z) / r.d.z;
+    T z0 = slab(mn[2], r.o.z, r.d.z, iz), z1 = slab(mx[2], r.o.z, r.d.z, iz);
     if (signbit(r.d.z)) { T s = z0; z0 = z1; z1 = s; }
     if (tmax < z0 || tmin > z1) return false;
     tmin = Mt::max_(tmin, z0); tmax = Mt::min_(tmax, z1);
@@ -77,17 +82,20 @@ RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>&
         *t_out = t;
         return true;
     }
-    case P_CUBOID: {                                                                    // cuboid.rs:53-60: first minimum of the six faces
+    default: {
+        // Cuboid (cuboid.rs:53-60): first minimum of the six faces; a Quad / Triangle is the same loop over one face — ONE inlined
+        // copy of the quad test per call site instead of two (code size: these kernels wait on instruction fetch)
+        const uint32_t faces = pr.kind == P_CUBOID ? 6u : 1u;
+        const bool tri = pr.kind == P_TRIANGLE;
         bool any = false; T best = T(0);
-        for (uint32_t f = 0; f < 6u; ++f) {
+#pragma unroll 1
+        for (uint32_t f = 0; f < faces; ++f) {
             T t;
-            if (g_quad_hit<T, EXACT>(sc.quads[pr.first + f], false, rr, tmin, tmax, &t) && (!any || t < best)) { any = true; best = t; *sub = pr.first + f; }
+            if (g_quad_hit<T, EXACT>(sc.quads[pr.first + f], tri, rr, tmin, tmax, &t) && (!any || t < best)) { any = true; best = t; *sub = pr.first + f; }
         }
         *t_out = best;
         return any;
     }
-    default:
-        return g_quad_hit<T, EXACT>(sc.quads[pr.first], pr.kind == P_TRIANGLE, rr, tmin, tmax, t_out);
     }
 }
 
@@ -112,18 +120,24 @@ RTW_D double g_sin(double x) {
 RTW_D float g_sin(float x) { return sinf(x); }
 
 // Perlin::noise / turb (perlin.rs:59-110)
-template <class T> RTW_D int g_wrap256(T f) { T r = fmod(f, T(256)); if (r < T(0)) r += T(256); return (int)r; }
+// f.rem_euclid(256.) as usize for an integer-valued f.  fmod by a power of two is f - 256 * trunc(f / 256) with every step exact
+// (same bits as fmod, NaN for +-inf); spelled out because CUDA's inlined fmod is ~58 instructions and Perlin::noise needs it 24 times —
+// the 49 copies were 45 KB of the 146 KB general kernels, whose ncu captures show them waiting on instruction fetch (i-cache hit 75 %).
+template <class T> RTW_D int g_wrap256(T f) { T r = f - trunc(f * T(0.00390625)) * T(256); if (r < T(0)) r += T(256); return (int)r; }
 template <class T> RTW_D T g_noise(const GPerlin<T>& pn, V3<T> p) {
     T fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
     T u = p.x - fx, v = p.y - fy, w = p.z - fz;
     T acc = T(0);
+    const int px[2] = {pn.perm_x[g_wrap256(fx)], pn.perm_x[g_wrap256(fx + T(1))]};
+    const int py[2] = {pn.perm_y[g_wrap256(fy)], pn.perm_y[g_wrap256(fy + T(1))]};
+    const int pz[2] = {pn.perm_z[g_wrap256(fz)], pn.perm_z[g_wrap256(fz + T(1))]};
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                int idx = pn.perm_x[g_wrap256(fx + (T)i)] ^ pn.perm_y[g_wrap256(fy + (T)j)] ^ pn.perm_z[g_wrap256(fz + (T)k)];
+                int idx = px[i] ^ py[j] ^ pz[k];
                 V3<T> c = mk<T>(pn.rand_vec[idx][0], pn.rand_vec[idx][1], pn.rand_vec[idx][2]);
                 T di = (T)i, dj = (T)j, dk = (T)k;
                 V3<T> weight_v = mk<T>(u - di, v - dj, w - dk);
@@ -242,7 +256,8 @@ template <class T> __device__ __noinline__ V3<T> g_texture_lookup(const SceneVie
     const GTex<T>& t = sc.textures[m.texture - 1];
     if (t.kind == TEX_NOISE) return g_noise_colour<T>(sc, t, point);
     T inv_scale = T(1) / t.scale;
-    bool is_even = fmod(floor(u * inv_scale) + floor(v * inv_scale), T(2)) == T(0);
+    T cells = floor(u * inv_scale) + floor(v * inv_scale);
+    bool is_even = cells - trunc(cells * T(0.5)) * T(2) == T(0);            // fmod(cells, 2) == 0, exactly (see g_wrap256)
     uint32_t ref = is_even ? t.even : t.odd;
     if (ref == 0) return is_even ? mk<T>(t.even_c[0], t.even_c[1], t.even_c[2]) : mk<T>(t.odd_c[0], t.odd_c[1], t.odd_c[2]);
     return g_noise_colour<T>(sc, sc.textures[ref - 1], point);
@@ -263,42 +278,40 @@ RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T t
     T best_t = tmax;
     const GPrim<T>* best = nullptr;
     uint32_t best_sub = 0;
-    for (int i = 0; i < sc.n_unbounded; ++i) {
-        T t; uint32_t sub;
-        // bounded_hit (hittable.rs:191-196) with Plane::get_aabbox (plane.rs:78-107): an axis-aligned plane's box is the
-        // slab {axis = 0} whatever the plane's offset — part of the result, so tested in both precisions
-        if (!g_box_hit<T, EXACT>(sc.unbounded[i].box, sc.unbounded[i].box + 3, r, tmin, tmax)) continue;
-        if (g_prim_hit<T, EXACT, COUNT>(sc, sc.unbounded[i], r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
-            found = true; best_t = t; best = sc.unbounded + i; best_sub = sub;
-        }
-    }
-    // one list entry against the ray: the entry's own box where it is part of the result, then Hittable::hit
-    auto test_entry = [&](const GPrim<T>& pr) {
-        if constexpr (EXACT) {                             // bounded_hit (hittable.rs:191-196): the entry's own box, un-shrunk range
-            if (!box_hit_exact(pr.box, pr.box + 3, r, tmin, tmax)) return;
-        } else if (pr.xform >= 0) {
-            // a Transformed<T> is hit with a DIFFERENT ray than its box (the instance ray's direction carries the
-            // translation), so its own world-space box is part of the result, not only a culling aid
-            if (!g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax)) return;
-        }
-        T t; uint32_t sub;
-        if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
-            found = true; best_t = t; best = &pr; best_sub = sub;
-        }
-    };
     RayAux aux;
     if constexpr (!EXACT) ray_aux(r, aux);
+    // ONE entry-test loop serves the three places entries come from — the unbounded list, the flat list, the BVH leaves — so the
+    // entity tests are inlined once (the kernels stall on instruction fetch; three copies of every entity test did not help).
+    // Entries are addressed in one index space: [0, n_unbounded) = sc.unbounded, n_unbounded + k = sc.prims[k].  Order of the
+    // tests (it decides exact-t ties: first minimum): unbounded entries, then the list / the leaves in traversal order.
+    const int nu = sc.n_unbounded;
+    // a handful of entries (cornell_box: 8): every lane walks the whole list, sorted by kind on the host, in lockstep — no tree, no
+    // per-lane leaf order, the kind switch is warp-uniform (ncu on the BVH version of this scene: leaf tests ran at 2-7 active
+    // threads per warp)
+    int i = 0, end = nu + (sc.flat ? sc.n_prims : 0);
     stack[0] = kStop;
     int sp = 1;
-    int32_t cur = sc.n_prims > 0 ? 0 : kStop;
-    if (sc.flat) {
-        // a handful of entries (cornell_box: 8): every lane walks the whole list, sorted by kind on the host, in lockstep —
-        // no tree, no per-lane leaf order, the kind switch is warp-uniform (ncu on the BVH version of this scene: leaf tests
-        // ran at 2-7 active threads per warp)
-        for (int i = 0; i < sc.n_prims; ++i) test_entry(sc.prims[i]);
-        cur = kStop;
-    }
+    int32_t cur = (sc.flat || sc.n_prims <= 0) ? kStop : 0;
     for (;;) {
+#pragma unroll 1
+        for (; i < end; ++i) {
+            const bool unb = i < nu;
+            const GPrim<T>& pr = unb ? sc.unbounded[i] : sc.prims[i - nu];
+            // The entry's own box, where it is part of the result.  Unbounded entries: bounded_hit (hittable.rs:191-196) with
+            // Plane::get_aabbox (plane.rs:78-107) — an axis-aligned plane's box is the slab {axis = 0} whatever the plane's offset,
+            // tested in both precisions.  Bounded entries: the exact path repeats bounded_hit with the un-shrunk range; the fast
+            // path only for a Transformed<T>, which is hit with a DIFFERENT ray than its box (the instance ray's direction carries
+            // the translation), so its world-space box is not only a culling aid.
+            if constexpr (EXACT) {
+                if (unb ? !g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax) : !box_hit_exact(pr.box, pr.box + 3, r, tmin, tmax)) continue;
+            } else {
+                if ((unb || pr.xform >= 0) && !g_box_hit<T, EXACT>(pr.box, pr.box + 3, r, tmin, tmax)) continue;
+            }
+            T t; uint32_t sub;
+            if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
+                found = true; best_t = t; best = &pr; best_sub = sub;
+            }
+        }
         while (cur >= 0) {
             Node<T> nd = sc.nodes[cur];
             if (COUNT) tl.node_visits++;
@@ -324,10 +337,9 @@ RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T t
             else { sp--; cur = stack[sp * stride]; }
         }
         if (cur == kStop) break;
-        if (cur != kEmptyLeaf) {
+        if (cur != kEmptyLeaf) {                                 // a leaf: its entries are the next range of the test loop
             uint32_t enc = (uint32_t)~cur;
-            uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
-            for (uint32_t i = first; i < first + count; ++i) test_entry(sc.prims[i]);
+            i = nu + (int)(enc >> 4); end = i + (int)(enc & 15u) + 1;
         }
         sp--;
         cur = stack[sp * stride];
@@ -502,7 +514,7 @@ RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h
     if (kind == METAL || kind == DIELECTRIC) {
         // same code as the sphere-only scenes: shade() never touches the scene for these two kinds
         SceneView<T> none{};
-        return shade<T, EXACT, COUNT, SceneView<T>>(none, r, h, rng, next, weight, tl, nullptr, 0);
+        return shade<T, EXACT, COUNT, SceneView<T>, true>(none, r, h, rng, next, weight, tl, nullptr, 0);
     }
     if (COUNT) tl.absorbed++;                                      // DiffuseLight, Invisible: Material::scatter default None
     return V_ABSORB;

@@ -367,14 +367,15 @@ enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE
 
 // Material::scatter (+ the Scatter branch of ray_colour_tail_call, camera.rs:484-521).
 // Returns the vertex kind; on V_SPECULAR / V_DIFFUSE writes the next ray and the factor for `mult`.
-template <class T, bool EXACT, bool COUNT, class SC>
+// SPECULAR_ONLY: the caller has already dealt with Lambertian hits (g_shade borrows the Metal / Dielectric code from here).
+template <class T, bool EXACT, bool COUNT, class SC, bool SPECULAR_ONLY = false>
 RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl,
                      int32_t* stack, int stride) {
     using Mt = M<T, EXACT>;
     if constexpr (is_general<SC>::value) return g_shade<T, EXACT, COUNT>(sc, r, h, rng, next, weight, tl);
     else {
     uint32_t kind = h.info & 3u;
-    if (kind == LAMBERTIAN) {                                   // material.rs:357-376
+    if (!SPECULAR_ONLY && kind == LAMBERTIAN) {                 // material.rs:357-376
         if (COUNT) tl.lambertian++;
         Onb<T, EXACT> uvw(h.normal);                            // CosinePdf::new, pdf.rs:39-43
         V3<T> dir;
@@ -485,7 +486,7 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
     }
     V3<T> emitted = mk<T>(0, 0, 0);                             // Material::emitted default, material.rs:42-44
     if constexpr (is_general<SC>::value) emitted = g_emitted<T>(h);
-    Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u);
+    Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u, is_general<SC>::value);
     Ray<T> next;
     V3<T> w;
     uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl, stack, stride);
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
         ps.depth = 0;
         for (;;) {
             if (!alive && valid && sample < cam.spp) {
-                Stream<EXACT> rng(P.seed, pixel, sample + cam.sample_offset, 0u);
+                Stream<EXACT> rng(P.seed, pixel, sample + cam.sample_offset, 0u, is_general<SC>::value);
                 ps.r = get_ray<T, EXACT>(cam, i, j, rng);
                 ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
                 alive = true;
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
                         uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                     if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                         pixel = j * cam.width + i;
-                        Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                        Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value);
                         ps.r = get_ray<T, EXACT>(cam, i, j, rng);
                         ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
                         alive = true;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                 if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                     uint32_t pixel = j * cam.width + i;
-                    Stream<EXACT> rng(P.seed, pixel, sample, 0u);
+                    Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value);
                     Ray<T> ray = get_ray<T, EXACT>(cam, i, j, rng);
                     S.ox[slot] = ray.o.x; S.oy[slot] = ray.o.y; S.oz[slot] = ray.o.z;
                     S.dx[slot] = ray.d.x; S.dy[slot] = ray.d.y; S.dz[slot] = ray.d.z;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 else hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
                 uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
                 V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u);
+                Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u, is_general<SC>::value);
                 Ray<T> next;
                 V3<T> w;
                 uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);

@@ -486,7 +486,7 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
     }
     V3<T> emitted = mk<T>(0, 0, 0);                             // Material::emitted default, material.rs:42-44
     if constexpr (is_general<SC>::value) emitted = g_emitted<T>(h);
-    Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u, is_general<SC>::value);
+    Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u, is_general<SC>::value && !EXACT);
     Ray<T> next;
     V3<T> w;
     uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl, stack, stride);
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
         ps.depth = 0;
         for (;;) {
             if (!alive && valid && sample < cam.spp) {
-                Stream<EXACT> rng(P.seed, pixel, sample + cam.sample_offset, 0u, is_general<SC>::value);
+                Stream<EXACT> rng(P.seed, pixel, sample + cam.sample_offset, 0u, is_general<SC>::value && !EXACT);
                 ps.r = get_ray<T, EXACT>(cam, i, j, rng);
                 ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
                 alive = true;
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
                         uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                     if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                         pixel = j * cam.width + i;
-                        Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value);
+                        Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value && !EXACT);
                         ps.r = get_ray<T, EXACT>(cam, i, j, rng);
                         ps.mult = mk<T>(1, 1, 1); ps.res = mk<T>(0, 0, 0); ps.depth = cam.max_depth;
                         alive = true;

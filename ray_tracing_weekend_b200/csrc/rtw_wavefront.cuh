@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
                 if (tile < P.tiles_total && i < cam.width && j < cam.height) {
                     uint32_t pixel = j * cam.width + i;
-                    Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value);
+                    Stream<EXACT> rng(P.seed, pixel, sample, 0u, is_general<SC>::value && !EXACT);
                     Ray<T> ray = get_ray<T, EXACT>(cam, i, j, rng);
                     S.ox[slot] = ray.o.x; S.oy[slot] = ray.o.y; S.oz[slot] = ray.o.z;
                     S.dx[slot] = ray.d.x; S.dy[slot] = ray.d.y; S.dz[slot] = ray.d.z;
@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             const bool active = lane < n;
             uint32_t slot = active ? S.list[WF_EXT][n_ext + lane] : 0u;
             uint32_t kind = 0xffu;                            // 0..2 material list, 3 = miss (slot becomes free)
+            bool fin = false;                                 // the path ended here: its value goes to wf_finish below (ONE inlined copy)
+            V3<T> fin_value = mk<T>(0, 0, 0);
             if (active) {
                 Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
                 nrays++;
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                             g_hit_record<T, EXACT>(sc, r, g_entry<T>(sc, bestp), sub, best_t, &h);
                             if (COUNT) tl.absorbed++;
                             V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                            wf_finish(Q, acc, S.q[slot], mult * g_emitted<T>(h) + wf_res(S.dep[slot]), P.flags);
+                            fin_value = mult * g_emitted<T>(h) + wf_res(S.dep[slot]);
+                            fin = true;
                             kind = 3u;
                         }
                     }
@@ -214,9 +217,11 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 if (!hit) {
                     if (COUNT) tl.missed++;
                     V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                    wf_finish(Q, acc, S.q[slot], mult * cam.background + wf_res(S.dep[slot]), P.flags);   // camera.rs:473-475
+                    fin_value = mult * cam.background + wf_res(S.dep[slot]);                              // camera.rs:473-475
+                    fin = true;
                     kind = 3u;
                 }
+                if (fin) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
             }
             __syncwarp();
             wf_push(S.list[WF_LAMB], n_lamb, kind == 0u, slot, lt_mask);
@@ -239,13 +244,14 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 else hit_record<T, EXACT, SC>(sc, r, S.hp[slot], S.ht[slot], &h);
                 uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
                 V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u, is_general<SC>::value);
+                Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u, is_general<SC>::value && !EXACT);
                 Ray<T> next;
                 V3<T> w;
                 uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
                 V3<T> emitted = mk<T>(0, 0, 0);
+                V3<T> fin_value = mk<T>(0, 0, 0);
                 if (kind == V_ABSORB) {                                     // camera.rs:484-486
-                    wf_finish(Q, acc, S.q[slot], mult * emitted + wf_res(dep), P.flags);
+                    fin_value = mult * emitted + wf_res(dep);
                     to_free = true;
                 } else {
                     if (kind == V_DIFFUSE) {                                // res + mult * emitted (camera.rs:519): 0 or NaN per channel
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     dep = (dep & 0xffff0000u) | depth;
                     if (depth == 0) {                                       // camera.rs:470-472
                         if (COUNT) tl.depth_out++;
-                        wf_finish(Q, acc, S.q[slot], mk<T>(0, 0, 0) + wf_res(dep), P.flags);
+                        fin_value = mk<T>(0, 0, 0) + wf_res(dep);
                         to_free = true;
                     } else {
                         S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                         to_ext = true;
                     }
                 }
+                if (to_free) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
             }
             __syncwarp();
             wf_push(S.list[WF_EXT], n_ext, to_ext, slot, lt_mask);

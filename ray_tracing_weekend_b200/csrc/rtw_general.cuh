@@ -429,8 +429,13 @@ RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tal
                 else hit = sphere_root_fast(s, r, frcp(a), T(0), Mt::inf(), &t);
                 if (hit) {
                     T distance_squared = sqlen(mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z));
-                    T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
-                    v = T(1) / (T(2) * Mt::PI * (T(1) - cos_theta_max));
+                    if constexpr (EXACT) {
+                        T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w / distance_squared);
+                        v = T(1) / (T(2) * Mt::PI * (T(1) - cos_theta_max));
+                    } else {        // SFU reciprocals instead of IEEE divisions (~10 instructions each), like the sphere-only path
+                        T cos_theta_max = Mt::sqrt_(T(1) - s.w * s.w * frcp(distance_squared));
+                        v = frcp(T(2) * Mt::PI * (T(1) - cos_theta_max));
+                    }
                 }
             } else if (pr.kind == P_QUAD || pr.kind == P_TRIANGLE) {   // quadrilateral.rs:100-112
                 if (COUNT) tl.light_tests++;
@@ -439,8 +444,13 @@ RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tal
                 if (g_quad_hit<T, EXACT>(Q, pr.kind == P_TRIANGLE, r, T(0), Mt::inf(), &t)) {
                     T distance_squared = t * t * a;
                     V3<T> n = dot(dir, Q.normal) < T(0) ? Q.normal : -Q.normal;
-                    T cosine = fabs(dot(dir, n) / Mt::sqrt_(a));
-                    v = distance_squared / (cosine * Q.area);
+                    if constexpr (EXACT) {
+                        T cosine = fabs(dot(dir, n) / Mt::sqrt_(a));
+                        v = distance_squared / (cosine * Q.area);
+                    } else {
+                        T cosine = fabs(dot(dir, n) * frcp(Mt::sqrt_(a)));
+                        v = distance_squared * frcp(cosine * Q.area);
+                    }
                 }
             }
         }
@@ -508,7 +518,8 @@ RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h
         }
         T pdf_value = light_v * T(0.5) + own_v * T(0.5);
         *next = Ray<T>{h.p, dir};
-        *weight = (h.albedo * scattering_pdf) / pdf_value;
+        if constexpr (EXACT) *weight = (h.albedo * scattering_pdf) / pdf_value;      // camera.rs:518
+        else *weight = h.albedo * (scattering_pdf * frcp(pdf_value));
         return V_DIFFUSE;
     }
     if (kind == METAL || kind == DIELECTRIC) {

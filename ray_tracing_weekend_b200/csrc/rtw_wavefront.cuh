@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             const bool active = lane < n;
             uint32_t slot = active ? S.list[WF_EXT][n_ext + lane] : 0u;
             uint32_t kind = 0xffu;                            // 0..2 material list, 3 = miss (slot becomes free)
-            bool fin = false;                                 // the path ended here: its value goes to wf_finish below (ONE inlined copy)
+            // General scenes: a path that ends here hands its value to ONE wf_finish at the end of the stage (their kernels are
+            // bound by instruction fetch, every inlined copy of the accumulate / flush code counts); the sphere kernels keep the
+            // call in place (0.6 % faster that way).
+            bool fin = false;
             V3<T> fin_value = mk<T>(0, 0, 0);
             if (active) {
                 Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
@@ -193,18 +196,10 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     if (hit) {
                         S.ht[slot] = best_t; S.hp[slot] = bestp; S.hs[slot] = sub;
                         uint32_t k = sc.mats[g_entry<T>(sc, bestp).mat].kind;
-                        if (k == LAMBERTIAN || k == ISOTROPIC) kind = 0u;
-                        else if (k == METAL) kind = 1u;
-                        else if (k == DIELECTRIC) kind = 2u;
-                        else {      // DiffuseLight / Invisible never scatter: mult * emitted + res (camera.rs:484-486)
-                            Hit<T> h;
-                            g_hit_record<T, EXACT>(sc, r, g_entry<T>(sc, bestp), sub, best_t, &h);
-                            if (COUNT) tl.absorbed++;
-                            V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
-                            fin_value = mult * g_emitted<T>(h) + wf_res(S.dep[slot]);
-                            fin = true;
-                            kind = 3u;
-                        }
+                        // DiffuseLight / Invisible never scatter (mult * emitted + res, camera.rs:484-486): they ride the first shade
+                        // list, where g_shade returns V_ABSORB — a second inlined hit record here cost more in instruction fetch
+                        // than the extra pass does
+                        kind = k == METAL ? 1u : (k == DIELECTRIC ? 2u : 0u);
                     }
                 } else {
                     hit = closest_prim<T, EXACT, COUNT, SC>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &best_t, stack, BLOCK, tl);
@@ -218,10 +213,11 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     if (COUNT) tl.missed++;
                     V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
                     fin_value = mult * cam.background + wf_res(S.dep[slot]);                              // camera.rs:473-475
-                    fin = true;
+                    if constexpr (GEN) fin = true;
+                    else wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
                     kind = 3u;
                 }
-                if (fin) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
+                if constexpr (GEN) { if (fin) wf_finish(Q, acc, S.q[slot], fin_value, P.flags); }
             }
             __syncwarp();
             wf_push(S.list[WF_LAMB], n_lamb, kind == 0u, slot, lt_mask);
@@ -249,9 +245,11 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 V3<T> w;
                 uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
                 V3<T> emitted = mk<T>(0, 0, 0);
+                if constexpr (GEN) emitted = g_emitted<T>(h);
                 V3<T> fin_value = mk<T>(0, 0, 0);
                 if (kind == V_ABSORB) {                                     // camera.rs:484-486
                     fin_value = mult * emitted + wf_res(dep);
+                    if constexpr (!GEN) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
                     to_free = true;
                 } else {
                     if (kind == V_DIFFUSE) {                                // res + mult * emitted (camera.rs:519): 0 or NaN per channel
@@ -264,6 +262,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     if (depth == 0) {                                       // camera.rs:470-472
                         if (COUNT) tl.depth_out++;
                         fin_value = mk<T>(0, 0, 0) + wf_res(dep);
+                        if constexpr (!GEN) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
                         to_free = true;
                     } else {
                         S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
@@ -273,7 +272,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                         to_ext = true;
                     }
                 }
-                if (to_free) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
+                if constexpr (GEN) { if (to_free) wf_finish(Q, acc, S.q[slot], fin_value, P.flags); }
             }
             __syncwarp();
             wf_push(S.list[WF_EXT], n_ext, to_ext, slot, lt_mask);

@@ -62,7 +62,9 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #endif
     return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
 }
-// general scenes: the same warp-private wavefront and launch shape (swept: 512x96 460 ms, 512x128 450, 576x96 440, 640x96 408, 704x96 386, 768x96 364 on cornell_box), scene tables in global memory
+// general scenes: the same warp-private wavefront and launch shape, scene tables in global memory.  Swept on cornell_box while the kernel
+// was bound by instruction fetch: 512x96 460 ms, 512x128 450, 576x96 440, 640x96 408, 704x96 386, 768x96 364; again after its code
+// had been cut from 146 to 57 KB: 768x96 259.0, 768x112 255.4, 640x128 276.4, 896x80 253.1 (72 registers, spills), 704x104 266.6, 832x88 256.5
 constexpr int kWfBlockG = 768, kWfSlotsPerWarpG = 96;
 template <bool COUNT, int BLOCK, int NP>
 cudaError_t launch_render_wavefront_general_shape(RenderParams<float, SceneViewG<float>> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
@@ -87,11 +89,11 @@ cudaError_t launch_render_wavefront_general_impl(RenderParams<float, SceneViewG<
 #ifdef RTW_WF_SWEEP
     const char* e = std::getenv("RTW_WFG_SHAPE");
     int shape = e ? std::atoi(e) : 0;
-    if (shape == 1) return launch_render_wavefront_general_shape<COUNT, 512, 96>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 2) return launch_render_wavefront_general_shape<COUNT, 512, 128>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 3) return launch_render_wavefront_general_shape<COUNT, 576, 96>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 4) return launch_render_wavefront_general_shape<COUNT, 704, 96>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 5) return launch_render_wavefront_general_shape<COUNT, 768, 96>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 1) return launch_render_wavefront_general_shape<COUNT, 768, 112>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 2) return launch_render_wavefront_general_shape<COUNT, 640, 128>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 3) return launch_render_wavefront_general_shape<COUNT, 896, 80>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 4) return launch_render_wavefront_general_shape<COUNT, 704, 104>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 5) return launch_render_wavefront_general_shape<COUNT, 832, 88>(P, Q, bvh_depth, sm_count, s, info);
 #endif
     return launch_render_wavefront_general_shape<COUNT, kWfBlockG, kWfSlotsPerWarpG>(P, Q, bvh_depth, sm_count, s, info);
 }

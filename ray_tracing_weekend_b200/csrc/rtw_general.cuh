@@ -51,6 +51,9 @@ template <class T, bool EXACT>
 RTW_D bool g_quad_hit(const GQuad<T>& Q, bool tri, const Ray<T>& r, T tmin, T tmax, T* t_out) {
     T denom = g_dot(r.d, Q.normal);
     if (!(fabs(denom) > M<T, EXACT>::EPS)) return false;
+    // The IEEE division stays, also in FP32 (7 % of the kernel's instructions): with a 1-ulp SFU reciprocal the hit point lands a little
+    // further from the plane, the self-intersection statistics of the NEXT ray change, and cornell_box comes out 3 % off the f64 mean
+    // (and 12 % faster, for the wrong reason) — tried and reverted, test_cornell_box_f32_image_statistics catches it.
     T t = -(g_dot(r.o - Q.q, Q.normal) / denom);
     if (!(tmin <= t && t <= tmax)) return false;
     V3<T> pq = g_at(r, t) - Q.q;

@@ -1,6 +1,6 @@
 """The reference's other scenes on one GPU through the general path: one JSON line per scene and precision,
 plus the oracle (CPU port of the reference) timed on a bounded sample of the same workload.
-  cornell_box 1024x1024, 256 spp | simple_light 1920x1080, 256 spp | debugging_scene / simple_transform 1920x1080, 64 spp
+  cornell_box 1024x1024, 256 spp | simple_light 1920x1080, 256 spp | debugging_scene / simple_transform / checkered_spheres / perlin_spheres_lit 1920x1080, 64 spp
 usage: general_configs.py [scene ...] [--once]     (--once: a single FP32 render of the first scene, for ncu)"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,13 +10,24 @@ import ray_tracing_weekend_b200 as R
 SEED = 20261018
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 once = "--once" in sys.argv
-CONFIGS = {"cornell_box": (1024, 1024, 256), "simple_light": (1920, 1080, 256), "debugging_scene": (1920, 1080, 64), "simple_transform": (1920, 1080, 64)}
+CONFIGS = {"cornell_box": (1024, 1024, 256), "simple_light": (1920, 1080, 256), "debugging_scene": (1920, 1080, 64), "simple_transform": (1920, 1080, 64),
+           # row f2 (textures): the reference's checkered_spheres, and its perlin_spheres with the noise sphere ALSO put into the lights list
+           # (the reference's own lights list is empty there and its first diffuse bounce panics, hittable_list.rs:414-419)
+           "checkered_spheres": (1920, 1080, 64), "perlin_spheres_lit": (1920, 1080, 64)}
+
+
+def perlin_spheres_lit(seed):
+    world, lights, cb = R.scenes.perlin_spheres(seed)
+    lights.add(world.items[1])
+    return world, lights, cb
+
+
 which = args or list(CONFIGS)
 
 for name in which:
     w, h, spp = CONFIGS[name]
-    gen = getattr(R.scenes, name)
-    world, lights, cb = gen() if name == "cornell_box" else gen(SEED)
+    gen = perlin_spheres_lit if name == "perlin_spheres_lit" else getattr(R.scenes, name)
+    world, lights, cb = gen() if name in ("cornell_box", "checkered_spheres") else gen(SEED)
     sc = R.Scene(world, lights)
     cam = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).build()
     if once and os.environ.get("RTW_GENERAL_SMALL"):

@@ -86,6 +86,8 @@ RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>&
         return true;
     }
     default: {
+        // (Tried on FP32: the cuboid as three slab axes with the faces' exact t — ~170 instead of ~600 instructions per tested box, results
+        // equal — but the extra 1.9 KB in the hot loop pushed the executed code back over the instruction cache: cornell_box 259 -> 286 ms.)
         // Cuboid (cuboid.rs:53-60): first minimum of the six faces; a Quad / Triangle is the same loop over one face — ONE inlined
         // copy of the quad test per call site instead of two (code size: these kernels wait on instruction fetch)
         const uint32_t faces = pr.kind == P_CUBOID ? 6u : 1u;

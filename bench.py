@@ -324,7 +324,7 @@ def _emit(line: dict):
 
 def main():
     _protect_stdout()
-    global SPP, WORKLOAD
+    global SPP, WORKLOAD, WIDTH, HEIGHT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -332,10 +332,15 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     # profiling aids — any non-default value is recorded in config and is NOT the headline workload
     ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C3 = BASELINE config 3 (3840x2160, 1024 spp), for the multi-GPU table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
     ap.add_argument("--mode", default="wavefront", choices=["megakernel", "wavefront"])
     args = ap.parse_args()
+    if args.workload == "C3":
+        WORKLOAD = WORKLOAD.replace(f"{WIDTH}x{HEIGHT}, {SPP} spp", "3840x2160, 1024 spp [NON-DEFAULT workload: BASELINE C3]")
+        WIDTH, HEIGHT, SPP = 3840, 2160, 1024
+        args.spp = SPP
     if args.spp != SPP:
         SPP = args.spp
         WORKLOAD = WORKLOAD.replace("500 spp", f"{SPP} spp [NON-DEFAULT profiling workload]")

@@ -115,6 +115,9 @@ def test_argument_validation_needs_no_gpu(rtw):
     out = C.c_void_p()
     assert L.rtw_scene_create(None, None, 1, None, None, 0, None, 0, None, 0, C.byref(out)) == _lib.RTW_E_INVALID
     assert L.rtw_camera_build(None, None) == _lib.RTW_E_INVALID
+    n = C.c_size_t(0)
+    assert L.rtw_scene_export_bvh(None, None, 0, C.byref(n), None, 0, C.byref(n)) == _lib.RTW_E_INVALID
+    assert C.sizeof(C.c_double) * 6 + 6 * 4 == rtw.Scene.BVH_NODE_DTYPE.itemsize == 72        # rtw_bvh_node (include/rtw.h)
     with pytest.raises(TypeError):
         rtw.HittableList().add("quad")
 

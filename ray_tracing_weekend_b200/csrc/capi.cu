@@ -267,7 +267,17 @@ template <class T> int upload_general(rtw_scene* s, SceneDevG<T>& d) {
     for (size_t i = 0; i < g.planes.size(); ++i) {
         const rtw_plane& q = g.planes[i];
         double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);       // Plane::new normalises (plane.rs:35)
-        plane_geo[i] = GPlane<T>{V3<T>{(T)q.px, (T)q.py, (T)q.pz}, V3<T>{(T)(q.nx / len), (T)(q.ny / len), (T)(q.nz / len)}};
+        GPlane<T> pl{};
+        pl.point = V3<T>{(T)q.px, (T)q.py, (T)q.pz};
+        const host::D3 n{q.nx / len, q.ny / len, q.nz / len}, up{0., 1., 0.};
+        pl.normal = v3(n);
+        // get_plane_uv (plane.rs:41-47): theta = atan2(|n x V|, n . V) with V = +y, k = (n x V).normalize()
+        const host::D3 c = host::cross3(n, up);
+        const double clen = std::sqrt(c.x * c.x + c.y * c.y + c.z * c.z);
+        const double theta = std::atan2(clen, host::dot3(n, up));
+        pl.rotated = theta <= 2.220446049250313e-16 ? 0u : 1u;
+        if (pl.rotated) { pl.k = v3(c / clen); pl.cos_theta = (T)std::cos(theta); pl.sin_theta = (T)std::sin(theta); }
+        plane_geo[i] = pl;
     }
     std::vector<GXform<T>> xforms(g.transforms.size());
     std::vector<char> invertible(g.transforms.size(), 0);
@@ -755,10 +765,10 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
             if (e.transform < -1) return "primitive transform index out of range";
             if (e.kind == RTW_PRIM_PLANE && e.transform >= 0) return "transformed planes are not supported";
             if (e.kind == RTW_PRIM_PLANE && d->materials[e.material].texture && d->textures[d->materials[e.material].texture - 1].kind == RTW_TEX_CHECKER) {
-                const rtw_plane& q = d->planes[e.index];       // get_plane_uv (plane.rs:41-55) is (x, z) only when the normal is +y
-                double len = std::sqrt(q.nx * q.nx + q.ny * q.ny + q.nz * q.nz);
-                double s2 = (q.nx / len) * (q.nx / len) + (q.nz / len) * (q.nz / len);          // |n x (0,1,0)|^2
-                if (!(std::atan2(std::sqrt(s2), q.ny / len) <= 2.220446049250313e-16)) return "a CheckerTexture on a plane whose normal is not +y is not supported";
+                // get_plane_uv (plane.rs:41-55) rotates about k = (n x +y).normalize(): for a normal of exactly -y that is 0 / 0, (u, v)
+                // is NaN and Plane::hit panics on the finiteness check (plane.rs:67-69)
+                const rtw_plane& q = d->planes[e.index];
+                if (q.nx == 0. && q.nz == 0. && q.ny < 0.) return "a CheckerTexture on a plane whose normal is -y: the reference panics (get_plane_uv is NaN)";
             }
             if (e.kind == RTW_PRIM_SPHERE) {
                 const rtw_sphere& q = d->spheres[e.index];

@@ -330,7 +330,9 @@ RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
 enum PrimKind : uint32_t { P_SPHERE = 0, P_PLANE = 1, P_QUAD = 2, P_TRIANGLE = 3, P_CUBOID = 4, P_NO_LIGHTS = 7 };
 enum MatKindG : uint32_t { DIFFUSE_LIGHT = 4, ISOTROPIC = 5 };
 template <class T> struct GQuad { V3<T> q, u, v, w, normal; T area; };       // Quad / Triangle / one Cuboid face (quadrilateral.rs:23-32)
-template <class T> struct GPlane { V3<T> point, normal; };
+// get_plane_uv (plane.rs:41-55) rotates (p - point) about k = normalize(normal x +y) by theta = angle(normal, +y) unless theta <= EPSILON;
+// theta, cos, sin and k depend on the plane only and are evaluated on the host in f64 (the same libm calls the reference makes per hit)
+template <class T> struct GPlane { V3<T> point, normal, k; T cos_theta, sin_theta; uint32_t rotated, pad; };
 template <class T> struct GXform { T fwd[9], ft[3], inv[9], it[3]; };         // Transformation and its inverse (transformations.rs:96-136)
 template <class T> struct GPrim {
     T box[6];                // the entry's own world-space box (min, max): bounded_hit's test on the exact path

@@ -365,6 +365,28 @@ RTW_D bool g_closest_prim(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tm
     return true;
 }
 
+// (u, v) of a hit, read by CheckerTexture only — out of line like the texture lookup itself (code size, see g_texture_lookup)
+template <class T, bool EXACT>
+__device__ __noinline__ V3<T> g_hit_uv(const SceneViewG<T>& sc, const GPrim<T>& pr, uint32_t best_sub, V3<T> pi, V3<T> outward) {
+    T uu = T(0), vv = T(0);
+    T* u = &uu; T* v = &vv;
+    if (pr.kind == P_SPHERE) g_sphere_uv<T, EXACT>(outward.x, outward.y, outward.z, u, v);               // of the outward normal, sphere.rs:83-84
+    else if (pr.kind == P_PLANE) {                                         // get_plane_uv, plane.rs:41-55
+        const GPlane<T>& pl = sc.plane_geo[pr.first];
+        if (!pl.rotated) { *u = pi.x; *v = pi.z; }                         // the normal is +y
+        else {                                                             // Rodrigues' rotation onto +y, then f64::fract of x and z
+            V3<T> w = pi - pl.point;
+            V3<T> rot = (w * pl.cos_theta + cross(pl.k, w) * pl.sin_theta) + (pl.k * dot(pl.k, w)) * (T(1) - pl.cos_theta);
+            *u = rot.x - trunc(rot.x); *v = rot.z - trunc(rot.z);
+        }
+    } else {                                                               // get_quad_uv, quadrilateral.rs:58-63
+        const GQuad<T>& Q = sc.quads[best_sub];
+        V3<T> pq = pi - Q.q;
+        *u = dot(cross(pq, Q.v), Q.w); *v = dot(cross(Q.u, pq), Q.w);
+    }
+    return mk<T>(uu, vv, T(0));                                            // by value: no address of a caller's local escapes
+}
+
 // HitRecord::new (hittable.rs:102-129) for the winner, in the entity's space, then p back to world space (transformations.rs:21-27)
 template <class T, bool EXACT>
 RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>& pr, uint32_t best_sub, T best_t, Hit<T>* h) {
@@ -393,14 +415,8 @@ RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>
     if (m.kind == LAMBERTIAN || m.kind >= DIFFUSE_LIGHT) {
         T u = T(0), v = T(0);
         if (m.texture && sc.textures[m.texture - 1].kind == TEX_CHECKER) {     // the hit's (u, v), in the entity's own space
-            V3<T> pi = g_at(rr, best_t);
-            if (pr.kind == P_SPHERE) g_sphere_uv<T, EXACT>(outward.x, outward.y, outward.z, &u, &v);     // of the outward normal, sphere.rs:83-84
-            else if (pr.kind == P_PLANE) { u = pi.x; v = pi.z; }             // get_plane_uv for a +y normal, plane.rs:41-47
-            else {                                                             // get_quad_uv, quadrilateral.rs:58-63
-                const GQuad<T>& Q = sc.quads[best_sub];
-                V3<T> pq = pi - Q.q;
-                u = dot(cross(pq, Q.v), Q.w); v = dot(cross(Q.u, pq), Q.w);
-            }
+            V3<T> uv = g_hit_uv<T, EXACT>(sc, pr, best_sub, g_at(rr, best_t), outward);
+            u = uv.x; v = uv.y;
         }
         h->albedo = g_texture<T>(sc, m, u, v, p);
     } else h->albedo = mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);

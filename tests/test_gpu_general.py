@@ -30,6 +30,7 @@ def _random_scene(rtw, rng, n=160):
     world, lights = rtw.HittableList(), rtw.HittableList()
     world.add(rtw.Plane((0., -6., 0.), (0., -1., 0.), mats[0]))
     world.add(rtw.Plane((0., 0., 0.), (0., 1., 0.), mats[7]))              # a checkered +y plane (uv = (x, z)), visible from below
+    world.add(rtw.Plane((0., -5.5, 0.), (0.3, -1., 0.2), mats[7]))         # a tilted checkered plane: get_plane_uv's rotated branch
     for k in range(n):
         c = rng.uniform(-5, 5, 3)
         m = mats[int(rng.integers(0, len(mats)))]
@@ -402,3 +403,54 @@ def test_general_wavefront_is_bit_identical_to_megakernel(rtw, oracle, name):
         assert np.array_equal(a, c, equal_nan=True) and sc_["rays"] == sa["rays"]
     finally:
         scene.close()
+
+
+def test_checkered_plane_of_any_orientation(rtw, oracle):
+    """get_plane_uv (plane.rs:41-55): for a normal other than +y the hit point is rotated about (n x +y) onto +y and (u, v) is the
+    fractional part of x and z.  The per-plane constants (theta, cos, sin, axis) come from the host's libm like the reference's per-hit
+    calls; vertices (albedo = checker colour at the hit) and the image are bit-exact on the f64 path, a -y normal is refused (the
+    reference's axis is 0 / 0 there and Plane::hit panics on the NaN)."""
+    from ray_tracing_weekend_b200 import _lib
+    checker = rtw.Lambertian(rtw.CheckerTexture.new_with_colours((0.9, 0.1, 0.1), (0.1, 0.1, 0.9), 0.37))
+    light = rtw.DiffuseLight((3., 3., 3.))
+    world, lights = rtw.HittableList(), rtw.HittableList()
+    for point, normal in (((0., -1., 0.), (0.2, 1., -0.4)), ((0., 4., 0.), (0.5, -0.7, 0.1)), ((-6., 0., 0.), (-1., 0., 0.)),
+                          ((0., 0., -7.), (0., 1e-9, -1.))):
+        world.add(rtw.Plane(point, normal, checker))
+    world.add(rtw.Sphere((0., 1., 0.), 0.8, rtw.Metal((0.8, 0.8, 0.8), 0.05)))
+    lights.add(rtw.Sphere((2., 2., 1.), 0.4, light)); world.add(lights.items[0])
+    scene = rtw.Scene(world, lights)
+    og = oracle.GScene(scene.desc.pod, scene.desc)
+    try:
+        cb = (rtw.CameraBuilder().with_lookfrom((3., 1.5, 5.)).with_lookat((0., 1., 0.)).with_background((0.6, 0.7, 0.9)))
+        cam = _cam(cb, 40, 30, 4, 8)
+        o, d = _rays(oracle, og, cam.pod, 1500, 5)
+        prim_o, t_o, _, _ = og.trace_batch(o, d)
+        prim_g, t_g = scene.trace_batch(o, d, precision=rtw.RTW_F64)
+        assert np.array_equal(prim_o, prim_g) and np.array_equal(t_o, t_g)
+        assert all((prim_o == k).sum() > 20 for k in range(4)), [(prim_o == k).sum() for k in range(6)]     # every plane is hit
+        n = len(o)
+        rng = np.random.default_rng(2)
+        pixel, sample, vertex = rng.integers(0, 1200, n), rng.integers(0, 4, n), rng.integers(1, 8, n)
+        opts = rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64)
+        a = og.scatter_batch(o, d, pixel, sample, vertex, oracle.options(seed=SEED, math_mode=oracle.PORTABLE))
+        b = scene.scatter_batch(o, d, pixel, sample, vertex, opts)
+        assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["kind"], b["kind"])
+        for k in ("t", "p", "normal", "dir", "weight"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        lamb = a["kind"] == 3                                          # V_DIFFUSE vertices on the planes carry the checker colour
+        assert len(np.unique(np.round(a["weight"][lamb & (a["prim"] < 4)], 12), axis=0)) > 2
+        img_o, _, _, _ = og.render(oracle.Camera.from_buffer_copy(cam.pod), oracle.options(seed=SEED, math_mode=oracle.PORTABLE))
+        img_g, _, _ = scene.render(cam, opts)
+        assert np.array_equal(img_o, img_g, equal_nan=True)
+        # FP32: both checker colours show up on every plane (the pattern is there), and the image is close to the f64 one
+        img32, _, _ = scene.render(_cam(cb, 40, 30, 64, 8), rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32))
+        img64, _, _ = scene.render(_cam(cb, 40, 30, 64, 8), rtw.RenderOptions(seed=SEED + 1, precision=rtw.RTW_F64))
+        ok = np.isfinite(img32).all(axis=2) & np.isfinite(img64).all(axis=2)
+        assert ok.mean() > 0.9 and abs(np.clip(img32[ok] / 64, 0, 2).mean() - np.clip(img64[ok] / 64, 0, 2).mean()) < 0.05 * np.clip(img64[ok] / 64, 0, 2).mean()
+    finally:
+        scene.close()
+    bad = rtw.HittableList(); bad.add(rtw.Plane((0., 3., 0.), (0., -2., 0.), checker))
+    with pytest.raises(rtw.RtwError) as e:
+        rtw.Scene(bad, lights)
+    assert e.value.code == _lib.RTW_E_INVALID and "-y" in str(e.value)

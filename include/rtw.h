@@ -75,8 +75,9 @@ typedef struct { uint32_t kind, index, material; int32_t transform; } rtw_prim;
 enum { RTW_TEX_NOISE = 1,   /* NoiseTexture{noise: perlins[perlin], scale} (texture.rs:57-102) */
        RTW_TEX_CHECKER = 2 };/* CheckerTexture{inv_scale = 1 / scale, even, odd} (texture.rs:24-55): even / odd are 0 = SolidColour(even_colour /
                                odd_colour) or k > 0 = textures[k-1], which must be a NoiseTexture.  Reads the hit's (u, v): Quad / Triangle /
-                               Cuboid-face coordinates, Sphere::get_sphere_uv (sphere.rs:49-54), Plane::get_plane_uv (plane.rs:41-55: (x, z) for a +y normal, else the fractional x / z of the point rotated onto +y; a -y normal is refused, the reference panics on its NaN)
-                               (plane.rs:41-47; other plane orientations are RTW_E_UNSUPPORTED with a checker). */
+                               Cuboid-face coordinates, Sphere::get_sphere_uv (sphere.rs:49-54), Plane::get_plane_uv (plane.rs:41-55: (x, z) for a +y
+                               normal, else the fractional x / z of the point rotated onto +y; a checkered plane whose normal is exactly -y is
+                               RTW_E_INVALID: the reference's rotation axis is 0 / 0 there and Plane::hit panics on the NaN). */
 typedef struct { uint32_t kind, perlin; double scale; uint32_t even, odd; double even_colour[3], odd_colour[3]; } rtw_texture;
 /* Perlin's tables (perlin.rs:13-19): rand_vec = 256 UnitSphere samples, three permutations of 0..255. */
 typedef struct { double rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; } rtw_perlin;

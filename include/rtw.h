@@ -74,7 +74,7 @@ enum { RTW_PRIM_SPHERE = 0, RTW_PRIM_PLANE = 1, RTW_PRIM_QUAD = 2, RTW_PRIM_TRIA
 typedef struct { uint32_t kind, index, material; int32_t transform; } rtw_prim;
 enum { RTW_TEX_NOISE = 1,   /* NoiseTexture{noise: perlins[perlin], scale} (texture.rs:57-102) */
        RTW_TEX_CHECKER = 2 };/* CheckerTexture{inv_scale = 1 / scale, even, odd} (texture.rs:24-55): even / odd are 0 = SolidColour(even_colour /
-                               odd_colour) or k > 0 = textures[k-1], which must be a NoiseTexture.  Reads the hit's (u, v): Quad / Triangle /
+                               odd_colour) or k > 0 = textures[k-1], a NoiseTexture or another CheckerTexture that comes EARLIER in the table.  Reads the hit's (u, v): Quad / Triangle /
                                Cuboid-face coordinates, Sphere::get_sphere_uv (sphere.rs:49-54), Plane::get_plane_uv (plane.rs:41-55: (x, z) for a +y
                                normal, else the fractional x / z of the point rotated onto +y; a checkered plane whose normal is exactly -y is
                                RTW_E_INVALID: the reference's rotation axis is 0 / 0 there and Plane::hit panics on the NaN). */

@@ -566,8 +566,8 @@ struct GScene {
     }
     V3 texture_colour(const GMaterial& m, const GHit& rec, uint32_t math) const {
         if (m.texture == 0) return m.albedo;                                              // SolidColour, texture.rs:15-22
-        const Texture& t = textures[m.texture - 1];
-        if (t.kind == TEX_NOISE) return noise_colour(t, rec.p, math);
+        const Texture* tp = &textures[m.texture - 1];
+        if (tp->kind == TEX_NOISE) return noise_colour(*tp, rec.p, math);
         double u = rec.u, v = rec.v;                                                      // CheckerTexture::get_colour, texture.rs:46-55
         if (rec.sphere_uv) {                                                              // Sphere::get_sphere_uv, sphere.rs:49-54
             const double TAU = 6.28318530717958647692528676655900577;
@@ -575,11 +575,16 @@ struct GScene {
             u = atan2_msun(-n.z, n.x) / TAU;
             v = (math == LIBM ? std::acos(n.y) : acos_msun(n.y)) / PI;
         }
-        double inv_scale = 1. / t.scale;
-        bool is_even = std::fmod(std::floor(u * inv_scale) + std::floor(v * inv_scale), 2.) == 0.;
-        uint32_t ref = is_even ? t.even : t.odd;
-        if (ref == 0) return is_even ? t.even_colour : t.odd_colour;
-        return noise_colour(textures[ref - 1], rec.p, math);
+        // even / odd are textures themselves (Arc<dyn Texture>, texture.rs:26-29): get_colour recurses with the same (u, v, point)
+        for (;;) {
+            const Texture& t = *tp;
+            double inv_scale = 1. / t.scale;
+            bool is_even = std::fmod(std::floor(u * inv_scale) + std::floor(v * inv_scale), 2.) == 0.;
+            uint32_t ref = is_even ? t.even : t.odd;
+            if (ref == 0) return is_even ? t.even_colour : t.odd_colour;
+            tp = &textures[ref - 1];
+            if (tp->kind == TEX_NOISE) return noise_colour(*tp, rec.p, math);
+        }
     }
 };
 

@@ -265,10 +265,8 @@ class SceneDescription:
                 else:
                     tx.kind, tx.scale = RTW_TEX_CHECKER, float(t.scale)
                     for name, sub in (("even", t.even), ("odd", t.odd)):
-                        if isinstance(sub, NoiseTexture):
+                        if isinstance(sub, (NoiseTexture, CheckerTexture)):      # sub-textures land in the table before their parent
                             setattr(tx, name, texture_ref(sub))
-                        elif isinstance(sub, CheckerTexture):
-                            raise RtwError(_lib.RTW_E_UNSUPPORTED, "nested CheckerTexture")
                         else:
                             getattr(tx, name + "_colour")[:] = [float(x) for x in sub]
                 textures.append(tx)

@@ -747,7 +747,10 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
         } else if (t.kind == RTW_TEX_CHECKER) {
             for (uint32_t ref : {t.even, t.odd}) {
                 if (ref > d->n_textures) return fail(RTW_E_INVALID, "checker sub-texture index out of range");
-                if (ref && d->textures[ref - 1].kind != RTW_TEX_NOISE) return fail(RTW_E_UNSUPPORTED, "a CheckerTexture's even / odd must be SolidColour or NoiseTexture");
+                // even / odd may be any texture, a CheckerTexture included (texture.rs:26-29); sub-textures precede their parent in
+                // the table, which rules out cycles (the reference's Arc tree cannot have them either)
+                if (ref && d->textures[ref - 1].kind == RTW_TEX_CHECKER && ref - 1 >= i)
+                    return fail(RTW_E_INVALID, "a CheckerTexture's even / odd CheckerTexture must come earlier in the texture table");
             }
             if (!(t.scale != 0.)) return fail(RTW_E_INVALID, "checker scale is zero");
         } else return fail(RTW_E_UNSUPPORTED, "texture kind (NoiseTexture, CheckerTexture; SolidColour is texture 0)");

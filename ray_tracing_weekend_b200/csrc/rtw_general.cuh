@@ -257,6 +257,22 @@ template <class T> RTW_D V3<T> g_noise_colour(const SceneViewG<T>& sc, const GTe
 }
 // Out of line: SolidColour is the common case, and two inlined copies of the 7-octave Perlin loops in every hit record
 // slowed all general kernels down by 13 % (instruction footprint).
+// CheckerTexture's even / odd are textures themselves (Arc<dyn Texture>, texture.rs:26-29): get_colour recurses with the same
+// (u, v, point).  References point to EARLIER table entries (checked at scene creation), so the walk ends.  The reference's scenes
+// nest one level (a checker of colours or noise), which g_texture_lookup handles itself; deeper trees continue here — kept in a
+// function of its own because the register needs of g_texture_lookup shape ptxas's allocation in every kernel that calls it
+// (with the loop inside it, cornell_box — which has no texture at all — rendered 7 % slower).
+template <class T> __device__ __noinline__ V3<T> g_texture_nested(const SceneViewG<T>& sc, const GTex<T>* t, T u, T v, V3<T> point) {
+    while (t->kind != TEX_NOISE) {
+        T inv_scale = T(1) / t->scale;
+        T cells = floor(u * inv_scale) + floor(v * inv_scale);
+        bool is_even = cells - trunc(cells * T(0.5)) * T(2) == T(0);
+        uint32_t ref = is_even ? t->even : t->odd;
+        if (ref == 0) return is_even ? mk<T>(t->even_c[0], t->even_c[1], t->even_c[2]) : mk<T>(t->odd_c[0], t->odd_c[1], t->odd_c[2]);
+        t = &sc.textures[ref - 1];
+    }
+    return g_noise_colour<T>(sc, *t, point);
+}
 template <class T> __device__ __noinline__ V3<T> g_texture_lookup(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
     const GTex<T>& t = sc.textures[m.texture - 1];
     if (t.kind == TEX_NOISE) return g_noise_colour<T>(sc, t, point);
@@ -265,7 +281,9 @@ template <class T> __device__ __noinline__ V3<T> g_texture_lookup(const SceneVie
     bool is_even = cells - trunc(cells * T(0.5)) * T(2) == T(0);            // fmod(cells, 2) == 0, exactly (see g_wrap256)
     uint32_t ref = is_even ? t.even : t.odd;
     if (ref == 0) return is_even ? mk<T>(t.even_c[0], t.even_c[1], t.even_c[2]) : mk<T>(t.odd_c[0], t.odd_c[1], t.odd_c[2]);
-    return g_noise_colour<T>(sc, sc.textures[ref - 1], point);
+    const GTex<T>& sub = sc.textures[ref - 1];
+    if (sub.kind != TEX_NOISE) return g_texture_nested<T>(sc, &sub, u, v, point);
+    return g_noise_colour<T>(sc, sub, point);
 }
 template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>& m, T u, T v, V3<T> point) {
     if (m.texture == 0) return mk<T>(m.albedo[0], m.albedo[1], m.albedo[2]);

@@ -227,7 +227,6 @@ struct SceneDescription {
                 const TexturePtr sub[2] = {t->even, t->odd};
                 for (int k = 0; k < 2; ++k) {
                     if (!sub[k]) throw std::runtime_error("CheckerTexture without even / odd texture");
-                    if (sub[k]->kind == RTW_TEX_CHECKER) throw std::runtime_error("nested CheckerTexture is outside the CUDA backend's scope");
                     double* col = k == 0 ? tx.even_colour : tx.odd_colour;
                     if (sub[k]->kind == 0) { col[0] = sub[k]->colour.v.x; col[1] = sub[k]->colour.v.y; col[2] = sub[k]->colour.v.z; }
                     else (k == 0 ? tx.even : tx.odd) = texture_ref(sub[k]);

@@ -248,6 +248,62 @@ def test_portable_atan2_acos_and_checker(oracle, rtw):
     assert seen > 100
 
 
+def test_plane_uv_of_a_tilted_plane_and_nested_checker(oracle, rtw):
+    """Plane::get_plane_uv (plane.rs:41-55) for a normal other than +y: Rodrigues' rotation of (p - point) about normal x (+y) by the
+    angle between them, then the fractional parts of x and z — recomputed here in numpy and compared with the colour the oracle's
+    checker picks.  Then a CheckerTexture whose `even` is a finer CheckerTexture (get_colour recurses, texture.rs:46-55)."""
+    rng = np.random.default_rng(3)
+    li = rtw.HittableList(); li.add(rtw.Sphere((0., 500., 0.), 1., rtw.INVISIBLE))
+    scale = 0.3
+    chk = rtw.Lambertian(rtw.CheckerTexture.new_with_colours((1., 0., 0.), (0., 0., 1.), scale))
+    point, normal = np.array([0.5, -1., 0.25]), np.array([0.3, -0.8, 0.45])
+    world = rtw.HittableList(); world.add(rtw.Plane(tuple(point), tuple(normal), chk))
+    d = rtw.SceneDescription(world, li)
+    g = oracle.GScene(d.pod, d)
+    n = normal / np.linalg.norm(normal)
+    up = np.array([0., 1., 0.])
+    theta = math.atan2(np.linalg.norm(np.cross(n, up)), n @ up)
+    k = np.cross(n, up) / np.linalg.norm(np.cross(n, up))
+    seen = 0
+    for s in range(600):
+        o = point - 3. * n + rng.normal(size=3)                       # behind the one-sided plane: the ray must travel along +normal
+        dr = n + 0.3 * rng.normal(size=3)
+        r = g.scatter_batch(o[None], dr[None], [s], [0], [1], oracle.options(seed=SEED))
+        if r["kind"][0] != oracle.V_DIFFUSE or not np.allclose(r["weight"][0].sum(), 2.):
+            continue
+        w = r["p"][0] - point
+        rot = w * math.cos(theta) + np.cross(k, w) * math.sin(theta) + k * (k @ w) * (1. - math.cos(theta))
+        assert abs(rot[1]) < 1e-9                                     # the plane has been rotated into y = 0
+        u, v = math.fmod(rot[0], 1.), math.fmod(rot[2], 1.)           # f64::fract keeps the sign
+        if min(abs((u / scale) % 1), abs((v / scale) % 1), 1 - abs((u / scale) % 1), 1 - abs((v / scale) % 1)) < 1e-6:
+            continue
+        even = (math.floor(u / scale) + math.floor(v / scale)) % 2 == 0
+        assert np.allclose(r["weight"][0], [2., 0., 0.] if even else [0., 0., 2.])
+        seen += 1
+    assert seen > 100
+    # nested: even = a finer checker (green / white), odd = blue
+    fine = rtw.CheckerTexture.new_with_colours((0., 1., 0.), (1., 1., 1.), 0.05)
+    nested = rtw.Lambertian(rtw.CheckerTexture(fine, (0., 0., 1.), 0.25))
+    world = rtw.HittableList(); world.add(rtw.Quad((0., 0., 0.), (1., 0., 0.), (0., 1., 0.), nested))
+    d = rtw.SceneDescription(world, li)
+    assert d.pod.n_textures == 2                                      # the sub-texture precedes its parent in the table
+    g = oracle.GScene(d.pod, d)
+    uv = rng.uniform(0.01, 0.99, (500, 2))
+    seen = set()
+    for q in range(500):
+        r = g.scatter_batch(np.array([[uv[q, 0], uv[q, 1], 3.]]), np.array([[0., 0., -1.]]), [q], [0], [1], oracle.options(seed=SEED))
+        w = r["weight"][0]
+        if r["kind"][0] != oracle.V_DIFFUSE or not np.allclose(w.max(), 2.):
+            continue
+        cell = lambda sc: (math.floor(uv[q, 0] / sc) + math.floor(uv[q, 1] / sc)) % 2 == 0
+        if min(abs((uv[q] / 0.05) % 1).min(), (1 - abs((uv[q] / 0.05) % 1)).min()) < 1e-6:
+            continue
+        want = ([0., 2., 0.] if cell(0.05) else [2., 2., 2.]) if cell(0.25) else [0., 0., 2.]
+        assert np.allclose(w, want), (uv[q], w, want)
+        seen.add(tuple(want))
+    assert len(seen) == 3
+
+
 def test_general_golden_fixture(oracle, rtw):
     """Committed outputs of the general oracle on the reference's scenes (tests/golden/make_golden_general.py)."""
     with open(os.path.join(GOLDEN, "general_oracle.json")) as f:

@@ -29,6 +29,23 @@ def compute(O, R):
         img, _, cnt, _ = g.render(O.Camera.from_buffer_copy(cam.pod), O.options(seed=SEED, math_mode=O.PORTABLE, threads=1))
         out[name] = dict(n_world=d.n_world, n_lights=d.n_lights, rays=cnt["rays"], paths=cnt["paths"],
                          image_sum=np.nan_to_num(img, nan=-1.0).reshape(-1)[::7].tolist())
+    # beyond the reference's scenes: get_plane_uv's rotated branch (plane.rs:48-54) and a CheckerTexture of CheckerTextures
+    # (texture.rs:26-29, 46-55).  theta / cos / sin of a plane come from libm in every math mode (they are per-plane constants).
+    checker = R.Lambertian(R.CheckerTexture.new_with_colours((0.9, 0.1, 0.1), (0.1, 0.1, 0.9), 0.37))
+    nested = R.Lambertian(R.CheckerTexture(R.CheckerTexture.new_with_colours((1., 1., 0.), (0., 1., 1.), 0.05), R.NoiseTexture(3.0, SEED, 5), 0.2))
+    world, lights = R.HittableList(), R.HittableList()
+    for point, normal in (((0., -1., 0.), (0.2, 1., -0.4)), ((0., 4., 0.), (0.5, -0.7, 0.1)), ((-6., 0., 0.), (-1., 0., 0.))):
+        world.add(R.Plane(point, normal, checker))
+    world.add(R.Sphere((-1.8, 0.6, 1.), 0.9, nested))
+    world.add(R.Quad((1.2, -0.5, 1.5), (1.5, 0., 0.3), (0., 1.5, 0.2), nested))
+    lights.add(R.Sphere((2., 2., 1.), 0.4, R.DiffuseLight((3., 3., 3.)))); world.add(lights.items[0])
+    d = R.SceneDescription(world, lights)
+    g = O.GScene(d.pod, d)
+    cam = (R.CameraBuilder().with_lookfrom((3., 1.5, 5.)).with_lookat((0., 1., 0.)).with_background((0.6, 0.7, 0.9)).with_vfov(40.).with_aspect_ratio(1.0)
+           .with_image_width(24).with_image_height(24).with_samples_per_pixel(4).with_max_depth(12).build())
+    img, _, cnt, _ = g.render(O.Camera.from_buffer_copy(cam.pod), O.options(seed=SEED, math_mode=O.PORTABLE, threads=1))
+    out["tilted_planes_nested_checker"] = dict(n_world=d.n_world, n_lights=d.n_lights, rays=cnt["rays"], paths=cnt["paths"],
+                                               image_sum=np.nan_to_num(img, nan=-1.0).reshape(-1)[::7].tolist())
     return out
 
 

@@ -274,7 +274,11 @@ def run_cuda(args):
             roofline=dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,
                           peak_source=f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json); no FP32 figure is in that file",
                           kernel=kernel_name, flop_per_launch=local_flops,
-                          frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None),
+                          frac_at_observed_clock=(achieved / (fp32_peak * clocks["sm_mhz"] / sm_max)) if clocks and clocks.get("sm_mhz") else None,
+                          # the HBM view of the same launch, to show why "hbm" is not the bound: measured DRAM bytes / kernel time against the
+                          # measured copy bandwidth (the scene lives in shared memory; traffic is the accumulators and the image)
+                          hbm=(dict(achieved=traffic / (kern_ms / args.steps * 1e-3) / 1e9, peak=float(peaks.get("hbm_gbs", 6650.0)), unit="GB/s",
+                                    frac=traffic / (kern_ms / args.steps * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if traffic else None)),
             e2e=dict(value=total["rays"] * e2e_steps / e2e_s * 1e-6, unit="Mrays/s", h2d_bytes_per_step=scene.upload_bytes * world,
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
             # per step: tiles partition = render (+ fixed-point -> tiles conversion) per rank + untile on rank 0; samples partition =

@@ -1,7 +1,8 @@
 """Build librtw_cuda.so (the C-ABI library of include/rtw.h) in-tree with nvcc for sm_100a.
 
-Three translation units: kernels_f32.cu (fast path, FMA on), kernels_f64.cu (reference-exact path,
--fmad=false), capi.cu (extern "C" surface + host BVH builder).  cudart is linked statically so the
+Five translation units: kernels_f32.cu (fast path; -fmad=false, its fused multiply-adds are explicit fmaf calls so that every
+FP32 kernel rounds alike), kernels_f64.cu (reference-exact path, -fmad=false), bvh_device.cu (device LBVH), capi.cu (extern "C"
+surface + host BVH builder), host/rtw_host_capi.cpp (host mirror helpers).  cudart is linked statically so the
 .so loads next to torch's own runtime without LD_LIBRARY_PATH games.
 """
 from __future__ import annotations
@@ -82,12 +83,36 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return _build_locked(verbose)
 
 
+def build_variant(name: str, defines=(), f32_flags=None, verbose: bool = False) -> str:
+    """Tuning build (scripts/variant_bench.py): the same library with extra -D defines on every unit and, optionally, other flags for
+    kernels_f32.cu, written to lib/variants/librtw_cuda_<name>.so.  Load it with RTW_LIBRARY=<path>."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    units = [(src, (list(f32_flags) if (f32_flags is not None and src == "kernels_f32.cu") else list(extra)) + [f"-D{d}" for d in defines])
+             for src, extra in UNITS]
+    return _compile_and_link(units, os.path.join(OBJ_DIR, "variant_" + name), os.path.join(out_dir, f"librtw_cuda_{name}.so"), verbose)
+
+
 def _build_locked(verbose: bool) -> str:
+    _compile_and_link(UNITS, OBJ_DIR, LIB_PATH, verbose)
+    # the reference's `bin` with --backend cuda (host mirror CLI)
+    cli = [shutil.which("g++") or "g++", "-O2", "-std=c++17", os.path.join(HERE, "host", "rtw_bin.cpp"), "-o",
+           os.path.join(LIB_DIR, "rtw_bin"), "-L" + LIB_DIR, "-lrtw_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("rtw_bin build failed: " + " ".join(cli) + "\n" + r.stdout)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
+    return LIB_PATH
+
+
+def _compile_and_link(units, obj_dir: str, lib_path: str, verbose: bool) -> str:
     nvcc = _nvcc()
+    os.makedirs(obj_dir, exist_ok=True)
     objs = []
     procs = []
-    for src, extra in UNITS:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+    for src, extra in units:
+        obj = os.path.join(obj_dir, os.path.basename(src).rsplit(".", 1)[0] + ".o")
         cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -100,19 +125,11 @@ def _build_locked(verbose: bool) -> str:
             print(out, file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + (out or ""))
-    link = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", LIB_PATH, *objs]
+    link = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", lib_path, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)
-    # the reference's `bin` with --backend cuda (host mirror CLI)
-    cli = [shutil.which("g++") or "g++", "-O2", "-std=c++17", os.path.join(HERE, "host", "rtw_bin.cpp"), "-o",
-           os.path.join(LIB_DIR, "rtw_bin"), "-L" + LIB_DIR, "-lrtw_cuda", "-Wl,-rpath,$ORIGIN"]
-    r = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("rtw_bin build failed: " + " ".join(cli) + "\n" + r.stdout)
-    with open(HASH_PATH, "w") as f:
-        f.write(source_hash())
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

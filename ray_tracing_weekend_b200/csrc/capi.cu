@@ -123,9 +123,10 @@ template <> void fill_node<float>(Node<float>& n, const host::FlatNode& f) {
 template <class T> struct SceneDev {
     DevBuf<Node<T>> nodes, light_nodes; DevBuf<Vec4T<T>> spheres, sphere_mat, lights; DevBuf<uint32_t> info; DevBuf<PlaneT<T>> planes;
     DevBuf<T> tiles;
+    DevBuf<unsigned char> nodes_staged;      // FP32, small scenes: the nodes again at stride kShNodeStridePadded (rtw_device.cuh)
     SceneView<T> view{};
-    size_t bytes() const { return light_nodes.bytes() + nodes.bytes() + spheres.bytes() + sphere_mat.bytes() + lights.bytes() + info.bytes() + planes.bytes(); }
-    void release() { light_nodes.release(); nodes.release(); spheres.release(); sphere_mat.release(); lights.release(); info.release(); planes.release(); tiles.release(); }
+    size_t bytes() const { return nodes_staged.bytes() + light_nodes.bytes() + nodes.bytes() + spheres.bytes() + sphere_mat.bytes() + lights.bytes() + info.bytes() + planes.bytes(); }
+    void release() { nodes_staged.release(); light_nodes.release(); nodes.release(); spheres.release(); sphere_mat.release(); lights.release(); info.release(); planes.release(); tiles.release(); }
 };
 
 template <class T> struct SceneDevG {
@@ -177,6 +178,11 @@ struct rtw_scene {
 
 namespace {
 
+// w component of a light record: the radius on the exact path (Sphere::hit needs it), its FP32 square on the fast path, whose
+// light test and cone sampling only ever use r^2 (one multiply less per light test: 30 G of them per 1080p / 500 spp frame)
+inline double light_w(double r) { return r; }
+inline float light_w(float r) { volatile float r2 = r * r; return r2; }
+
 template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_device = false) {
     const host::Bvh& b = s->bvh;
     std::vector<Node<T>> nodes(world_on_device ? 0 : b.nodes.size());
@@ -218,13 +224,13 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_
         }
         for (size_t k = 0; k < s->lights.size(); ++k) {
             const rtw_sphere& q = s->lights[lbvh.order[k]];
-            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
+            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, light_w((T)q.r)};
         }
         s->light_bvh_depth = lbvh.depth;
     } else {
         for (size_t k = 0; k < s->lights.size(); ++k) {
             const rtw_sphere& q = s->lights[k];
-            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
+            lights[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, light_w((T)q.r)};
         }
     }
     std::vector<PlaneT<T>> planes(np);
@@ -247,6 +253,15 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_
     d.view.n_nodes = (int32_t)(world_on_device ? s->device_bvh.node_slots : nodes.size()); d.view.n_spheres = (int32_t)ns; d.view.n_planes = (int32_t)np;
     d.view.n_lights = (int32_t)lights.size();
     d.view.light_nodes = d.light_nodes.p; d.view.n_light_nodes = (int32_t)light_nodes.size();
+    d.view.nodes_staged = nullptr;
+    if (sizeof(T) == 4 && d.view.n_nodes > 0 && (size_t)d.view.n_nodes * kShNodeStridePadded <= (64u << 10)) {
+        // the copy the all-shared kernels stage: same 64-byte nodes, 80-byte stride (bank-conflict-free LDS.128)
+        const size_t n = (size_t)d.view.n_nodes;
+        CU(d.nodes_staged.reserve(n * kShNodeStridePadded + 16));
+        CU(cudaMemset(d.nodes_staged.p, 0, n * kShNodeStridePadded + 16));
+        CU(cudaMemcpy2D(d.nodes_staged.p, kShNodeStridePadded, d.nodes.p, sizeof(Node<T>), sizeof(Node<T>), n, cudaMemcpyDeviceToDevice));
+        d.view.nodes_staged = d.nodes_staged.p;
+    }
     return RTW_OK;
 }
 

@@ -257,8 +257,16 @@ RTW_HD int32_t encode_leaf(uint32_t first, uint32_t count) { return count == 0 ?
 
 template <class T> struct PlaneT { V3<T> point, normal; uint32_t info; uint32_t pad; T albedo[3]; T param; };
 
+// Stride of a node in its SHARED-memory copy (all-shared scenes, SceneViewSh).  The four LDS.128 of a node visit read 16-byte
+// chunk k of every lane's node; with the natural 64-byte stride chunk k of node n sits in bank group (4n + k) mod 8 — two of the
+// eight 16-byte bank groups for all 32 lanes (ncu, round 1: 2.7-way conflicts on 10.8 G shared-load requests).  With an 80-byte
+// stride the group is (5n + k) mod 8: n -> 5n mod 8 is a bijection, so the lanes' nodes spread over all eight groups.  The stride
+// is a launch parameter (RenderParams::sh_node_stride: 80 when the padded copy fits next to the path slots, else 64).
+constexpr uint32_t kShNodeStridePadded = 80;
+
 template <class T> struct SceneView {
     const Node<T>* nodes;          // BFS order, node 0 = root (global memory)
+    const void* nodes_staged;      // FP32: the same nodes at stride kShNodeStridePadded (source of the padded shared-memory copy), or NULL
     const Node<T>* top_nodes;      // the first n_top nodes again, possibly in shared memory
     const Vec4T<T>* spheres;       // sorted: (cx, cy, cz, r)
     const Vec4T<T>* sphere_mat;    // sorted: (albedo r, g, b, param)
@@ -274,6 +282,7 @@ template <class T> struct SceneView {
 // 7 x LD.E.64 per node; this is 4 x LDS.128).
 template <class T> struct SceneViewSh : SceneView<T> {
     uint32_t s_nodes = 0, s_spheres = 0, s_mat = 0, s_info = 0, s_lights = 0;   // 32-bit shared-window addresses
+    uint32_t s_node_stride = 64;   // bytes between staged nodes (64, or kShNodeStridePadded)
     RTW_D void bind() {
         s_nodes = (uint32_t)__cvta_generic_to_shared(this->top_nodes);
         s_spheres = (uint32_t)__cvta_generic_to_shared(this->spheres);
@@ -282,8 +291,8 @@ template <class T> struct SceneViewSh : SceneView<T> {
         s_lights = (uint32_t)__cvta_generic_to_shared(this->lights);
     }
 };
-template <class T> RTW_D void bind_scene(SceneView<T>&) {}
-template <class T> RTW_D void bind_scene(SceneViewSh<T>& sc) { sc.bind(); }
+template <class T> RTW_D void bind_scene(SceneView<T>&, uint32_t) {}
+template <class T> RTW_D void bind_scene(SceneViewSh<T>& sc, uint32_t node_stride) { sc.bind(); sc.s_node_stride = node_stride; }
 
 RTW_D float4 lds128(uint32_t a) {
     float4 v;
@@ -308,7 +317,7 @@ RTW_D void load_node(const SceneView<float>& sc, int32_t cur, Node<float>& nd) {
     unpack_node(p[0], p[1], p[2], p[3], nd);
 }
 RTW_D void load_node(const SceneViewSh<float>& sc, int32_t cur, Node<float>& nd) {
-    uint32_t p = sc.s_nodes + (uint32_t)cur * 64u;
+    uint32_t p = sc.s_nodes + (uint32_t)cur * sc.s_node_stride;
     unpack_node(lds128(p), lds128(p + 16), lds128(p + 32), lds128(p + 48), nd);
 }
 template <class T> RTW_D Vec4T<T> load_sphere(const SceneView<T>& sc, int32_t i) { return sc.spheres[i]; }

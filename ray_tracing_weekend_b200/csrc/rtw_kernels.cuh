@@ -298,7 +298,7 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl, int32
             T cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
             T towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
             T lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
-            T r2 = s.w * s.w;
+            T r2 = s.w;                                        // FP32 light records carry r^2 (upload_scene)
             if (fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2))) > T(0)) {
                 T distance_squared = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
                 if (towards >= T(0) || distance_squared <= r2) {
@@ -347,7 +347,7 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl, int32
 }
 
 // Sphere::random (sphere.rs:114-127)
-template <class T, bool EXACT>
+template <class T, bool EXACT, bool W_IS_R2 = false>
 RTW_D V3<T> sphere_random(const Vec4T<T>& s, V3<T> origin, Stream<EXACT>& rng) {
     using Mt = M<T, EXACT>;
     V3<T> direction = mk<T>(s.x - origin.x, s.y - origin.y, s.z - origin.z);
@@ -355,7 +355,8 @@ RTW_D V3<T> sphere_random(const Vec4T<T>& s, V3<T> origin, Stream<EXACT>& rng) {
     Onb<T, EXACT> uvw(direction);
     T r1 = standard(rng);
     T r2 = standard(rng);
-    T z = T(1) + r1 * (Mt::sqrt_(T(1) - s.w * s.w / (distance * distance)) - T(1));
+    const T radius_squared = W_IS_R2 ? s.w : s.w * s.w;    // the sphere path's FP32 light records carry r^2 (upload_scene)
+    T z = T(1) + r1 * (Mt::sqrt_(T(1) - radius_squared / (distance * distance)) - T(1));
     T sn, cs;
     Mt::sincos_2pi(r2, &sn, &cs);
     T x = cs * Mt::sqrt_(T(1) - z * z);
@@ -381,7 +382,7 @@ RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXAC
         V3<T> dir;
         if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
             uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
-            dir = sphere_random<T, EXACT>(load_light(sc, (int32_t)idx), h.p, rng);
+            dir = sphere_random<T, EXACT, !EXACT>(load_light(sc, (int32_t)idx), h.p, rng);
         } else {                                                // CosineWeightedHemisphere, utils.rs:146-161
             T r1 = standard(rng);
             T r2 = standard(rng);
@@ -513,6 +514,7 @@ template <class T, class SCENE = SceneView<T>> struct RenderParams {
     DeviceCounters* counters;
     // shared-memory staging of the scene (fast path only): bytes of each section, 0 = keep in global
     uint32_t smem_nodes, smem_spheres, smem_lights;
+    uint32_t sh_node_stride;        // all-shared scenes: stride of the staged nodes (64 = Node<float> as is, 80 = padded copy from scene.nodes_staged)
     uint32_t stack_depth;           // traversal stack entries per thread: BVH depth + 2, at most kStackDepth
 };
 
@@ -563,7 +565,7 @@ RTW_D void stage_scene(const RenderParams<float>& P, unsigned char* cur, SceneVi
         __syncthreads();
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(total) : "memory");
-            if (P.smem_nodes) tma_load_1d(p_nodes, P.scene.nodes, P.smem_nodes, &mbar);
+            if (P.smem_nodes) tma_load_1d(p_nodes, P.sh_node_stride == kShNodeStridePadded ? P.scene.nodes_staged : (const void*)P.scene.nodes, P.smem_nodes, &mbar);
             if (P.smem_spheres) {
                 tma_load_1d(p_spheres, P.scene.spheres, P.smem_spheres, &mbar);
                 tma_load_1d(p_mat, P.scene.sphere_mat, P.smem_spheres, &mbar);
@@ -577,7 +579,7 @@ RTW_D void stage_scene(const RenderParams<float>& P, unsigned char* cur, SceneVi
                          : "=r"(done) : "r"(m) : "memory");
         if (!done) __trap();                                   // never hang the GPU on a staging bug
     }
-    if (P.smem_nodes) { sc.top_nodes = reinterpret_cast<const Node<float>*>(p_nodes); sc.n_top = (int32_t)(P.smem_nodes / sizeof(Node<float>)); }
+    if (P.smem_nodes) { sc.top_nodes = reinterpret_cast<const Node<float>*>(p_nodes); sc.n_top = (int32_t)(P.smem_nodes / (P.sh_node_stride ? P.sh_node_stride : 64u)); }
     if (P.smem_spheres) {
         sc.spheres = reinterpret_cast<const Vec4T<float>*>(p_spheres);
         sc.sphere_mat = reinterpret_cast<const Vec4T<float>*>(p_mat);
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
         SceneView<T> sc = P.scene;
         if constexpr (!EXACT) stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
         static_cast<SceneView<T>&>(scv) = sc;
-        bind_scene(scv);
+        bind_scene(scv, P.sh_node_stride);
     }
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
         SceneView<T> sc = P.scene;
         stage_scene(P, smem_raw + sizeof(int32_t) * P.stack_depth * BLOCK, sc);
         static_cast<SceneView<T>&>(scv) = sc;
-        bind_scene(scv);
+        bind_scene(scv, P.sh_node_stride);
     }
     const CameraT<T>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31;

@@ -1,5 +1,6 @@
 // rtw_launch.cuh — launcher bodies, instantiated once per arithmetic policy.
 #pragma once
+#include <cstdlib>
 #include "rtw_launch.hpp"
 
 namespace rtw {
@@ -8,12 +9,19 @@ constexpr int kRenderBlock = 256;
 constexpr int kBatchBlock = 128;
 constexpr size_t kSmemSceneBudget = 64 * 1024;   // per-CTA budget for staged scene data (fast path)
 
-// decide which scene sections the fast kernels stage in shared memory; returns the dynamic smem size
+// decide which scene sections the fast kernels stage in shared memory; returns the dynamic smem size.
+// A scene that fits as a whole is staged with its nodes at the padded stride (bank-conflict-free LDS.128, see kShNodeStridePadded)
+// when that copy exists and still fits; RTW_SH_NODE_STRIDE=64 in the environment forces the unpadded copy (A/B measurements).
+inline bool padded_nodes_allowed() {
+    static const bool ok = [] { const char* e = std::getenv("RTW_SH_NODE_STRIDE"); return !(e && std::atoi(e) == 64); }();
+    return ok;
+}
 template <class T, bool EXACT>
 size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr, size_t scene_budget = kSmemSceneBudget) {
     if (P.stack_depth == 0 || P.stack_depth > (uint32_t)kStackDepth) P.stack_depth = kStackDepth;
     size_t smem = sizeof(int32_t) * P.stack_depth * block;
     P.smem_nodes = P.smem_spheres = P.smem_lights = 0;
+    P.sh_node_stride = 64;
     if (all_shared) *all_shared = false;
     if (!EXACT) {
         size_t budget = scene_budget;
@@ -22,15 +30,20 @@ size_t plan_smem(RenderParams<T>& P, int block, bool* all_shared = nullptr, size
         size_t sph = (size_t)P.scene.n_spheres * sizeof(Vec4T<T>);
         size_t sph_total = 2 * sph + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16;
         size_t nodes = (size_t)P.scene.n_nodes * sizeof(Node<T>);
+        size_t nodes_padded = (size_t)P.scene.n_nodes * kShNodeStridePadded;
+        const bool lights_ok = P.smem_lights || !P.scene.n_lights || P.scene.n_light_nodes > 0;
         if (nodes + sph_total <= budget) {
             P.smem_nodes = (uint32_t)nodes; P.smem_spheres = (uint32_t)sph;
+            if (lights_ok && all_shared && P.scene.nodes_staged && nodes_padded + sph_total <= budget && padded_nodes_allowed()) {
+                P.smem_nodes = (uint32_t)nodes_padded; P.sh_node_stride = kShNodeStridePadded;      // only the all-shared kernels know the stride
+            }
         } else {
             // large scene: pin as many top levels (BFS prefix) as fit
             size_t top = std::min(nodes, budget) / sizeof(Node<T>) * sizeof(Node<T>);
             P.smem_nodes = (uint32_t)top;
         }
         if (all_shared)
-            *all_shared = P.smem_nodes == nodes && (P.smem_spheres || !P.scene.n_spheres) && (P.smem_lights || !P.scene.n_lights || P.scene.n_light_nodes > 0);
+            *all_shared = (P.smem_nodes == nodes || P.sh_node_stride != 64) && (P.smem_spheres || !P.scene.n_spheres) && lights_ok;
         smem += P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     }
     return smem;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
         stage_scene(P, cur_p, sc0);                       // TMA bulk copies; the only block-wide wait of the kernel
         cur_p += P.smem_nodes + (P.smem_spheres ? 2u * P.smem_spheres + ((uint32_t)P.scene.n_spheres * 4u + 15u) / 16u * 16u : 0u) + P.smem_lights;
         static_cast<SceneView<T>&>(sc) = sc0;
-        bind_scene(sc);
+        bind_scene(sc, P.sh_node_stride);
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt_mask = (1u << lane) - 1u;
     using WS = typename std::conditional<GEN, WfWarpG<NPW>, WfWarp<NPW>>::type;

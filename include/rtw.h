@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 2
+#define RTW_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RTW_API __attribute__((visibility("default")))
@@ -249,7 +249,8 @@ RTW_API int  rtw_scene_export_bvh(rtw_scene* scene, rtw_bvh_node* nodes, size_t 
 RTW_API int rtw_render(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts,
                double* rgb_sum, uint8_t* rgb8, rtw_stats* stats);
 
-/* Multi-GPU building blocks (one process per GPU; the caller gathers tile buffers with NCCL).
+/* Multi-GPU building blocks for callers that bring their own collective (rtw_render_multi / rtw_render_rank below do it inside
+ * the library).
  * d_tiles is a DEVICE buffer of rtw_tiles_per_rank() * RTW_TILE_H * RTW_TILE_W * 3 elements
  * (float for RTW_F32, double for RTW_F64) that receives this rank's tiles; `stream` is a
  * cudaStream_t (0 = default stream). */
@@ -276,6 +277,51 @@ RTW_API int rtw_render_samples_device(rtw_scene* scene, const rtw_camera* camera
 RTW_API int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, uint32_t width, uint32_t height,
                              uint32_t samples_per_pixel, double* d_rgb_sum, uint8_t* d_rgb8, void* stream);
 
+/* ---- N GPUs behind the C ABI ------------------------------------------------------------------------------------------
+ * The seam is still Camera::render (camera.rs:295-297, called from bin/src/main.rs:82-86): one blocking call that returns the
+ * frame.  Two ways to put N GPUs behind it, both with the frame's single collective INSIDE the library:
+ *
+ * (A) one process, N GPUs: rtw_render_multi.  The scene is replicated onto devices[0..n_gpus) (NULL: CUDA devices 0..n_gpus-1;
+ *     devices[0] is the root and should be the device the scene was created on), every GPU renders its share on its own stream
+ *     and the root returns the image.  RTW_F32 (fixed-point renderers): sample partition — GPU g renders samples
+ *     [spp*g/N, spp*(g+1)/N) of every pixel; the collective is
+ *       RTW_COLLECTIVE_PEER: one fused kernel per GPU over NVLink peer memory — GPU g sums pixel slots [S*g/N, S*(g+1)/N) of all N
+ *                            accumulator blocks through peer loads, resolves them and stores the pixels into the root's image
+ *                            (reduce-scatter + resolve + gather in one pass; needs peer access between all pairs)
+ *       RTW_COLLECTIVE_NCCL: one ncclReduce (integer sum) of the blocks to the root (ncclCommInitAll) + resolve there
+ *       RTW_COLLECTIVE_AUTO: PEER when every pair of devices has peer access, else NCCL.
+ *     RTW_F64 (ordered per-pixel sums): tile partition, tile buffers copied to the root (cudaMemcpyPeerAsync), untile there.
+ *     Integer sums commute and samples / tiles are keyed by absolute index, so the image equals rtw_render's bit for bit for any N.
+ * (B) one process per GPU (how `torchrun` / `mpirun` launch): rtw_comm_unique_id on rank 0, the 128 bytes travel out of band,
+ *     every rank calls rtw_comm_init_rank, then rtw_render_rank on every rank renders that rank's share, runs the one NCCL
+ *     collective (ncclReduce of the accumulator blocks / grouped ncclSend+ncclRecv of the tile buffers) and resolves on rank 0,
+ *     which alone receives the image.
+ * NCCL is loaded at first use with dlopen (RTW_NCCL_LIBRARY, else libnccl.so.2 from the loader path); without it the NCCL
+ * collective and the rank API return RTW_E_UNSUPPORTED and everything else works. */
+enum { RTW_COLLECTIVE_AUTO = 0, RTW_COLLECTIVE_PEER = 1, RTW_COLLECTIVE_NCCL = 2 };
+RTW_API int rtw_render_multi(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, int n_gpus, const int* devices,
+                     uint32_t collective, double* rgb_sum, uint8_t* rgb8, rtw_stats* stats);
+#define RTW_COMM_ID_BYTES 128
+typedef struct rtw_comm rtw_comm;
+RTW_API int  rtw_comm_unique_id(uint8_t id[RTW_COMM_ID_BYTES]);
+RTW_API int  rtw_comm_init_rank(const uint8_t id[RTW_COMM_ID_BYTES], int rank, int world, rtw_comm** out);  /* collective; binds the current device */
+RTW_API void rtw_comm_destroy(rtw_comm* comm);
+RTW_API int  rtw_comm_rank(const rtw_comm* comm);
+RTW_API int  rtw_comm_world(const rtw_comm* comm);
+/* rgb_sum / rgb8: HOST buffers as in rtw_render, written on rank 0 only (other ranks may pass NULL).  stats: this rank's counters. */
+RTW_API int  rtw_render_rank(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, rtw_comm* comm,
+                     double* rgb_sum, uint8_t* rgb8, rtw_stats* stats);
+/* The same with DEVICE outputs on rank 0 and everything enqueued on `stream` (cudaStream_t; 0 = default): returns without
+ * synchronising when stats == NULL.  Scratch (accumulators / tile buffers) belongs to the scene handle. */
+RTW_API int  rtw_render_rank_device(rtw_scene* scene, const rtw_camera* camera, const rtw_opts* opts, rtw_comm* comm,
+                            double* d_rgb_sum, uint8_t* d_rgb8, void* stream, rtw_stats* stats);
+/* Asynchronous contract of every *_device entry point called with stats == NULL: the call returns with work in flight on `stream`;
+ * "the reference would have panicked here" (a path sampled an empty lights list, hittable_list.rs:414-419) is then reported by the
+ * next synchronising call on the scene, or by this query, which synchronises the scene's device, returns RTW_E_INVALID if the flag
+ * was raised since the last check (and clears it) and RTW_OK otherwise.  kernel_ms (may be NULL) receives the CUDA-event time of
+ * the render kernels of the scene's last render call. */
+RTW_API int  rtw_scene_sync(rtw_scene* scene, double* kernel_ms);
+
 /* Progressive rendering and checkpointing with HOST buffers.  rtw_render_samples renders samples
  * [sample_begin, sample_begin + sample_count) of every pixel and ADDS them into the caller's accumulators
  *   accum:  [rtw_accum_slots(w, h)][3] u64 (2^-32 radiance units), poison: [rtw_accum_slots(w, h)] u32 (flags, combined with OR)
@@ -300,6 +346,16 @@ RTW_API int rtw_scatter_batch(rtw_scene* scene, const rtw_opts* opts, const doub
                       const uint32_t* pixel, const uint32_t* sample, const uint32_t* vertex,
                       int32_t* prim_id, double* t, uint32_t* kind, double* p, double* normal,
                       double* dir, double* weight);
+/* Material::scatter + the MixturePdf sample / weight (material.rs:357-488, camera.rs:504-521, pdf.rs:34-101) on CALLER-SUPPLIED hit
+ * records: the sampling arithmetic alone, independent of how the hit point was traced (north-star check 3 on identical inputs).
+ * Per record: d = direction of the incoming ray, p / normal / front_face = the HitRecord (hittable.rs:102-129), mat_kind and
+ * material = (albedo r, g, b, param) of the material that was hit; stream (seed; pixel, sample, vertex).  Outputs as rtw_scatter_batch.
+ * The scene supplies the lights list.  Sphere-path scenes only (RTW_E_UNSUPPORTED for general scenes: their shaders read textures
+ * through the entity that was hit). */
+RTW_API int rtw_shade_batch(rtw_scene* scene, const rtw_opts* opts, size_t n, const double* d, const double* p, const double* normal,
+                    const uint32_t* front_face, const uint32_t* mat_kind, const double* material,
+                    const uint32_t* pixel, const uint32_t* sample, const uint32_t* vertex,
+                    uint32_t* kind, double* dir, double* weight);
 /* Camera::get_ray (camera.rs:274-293) for a batch of (i, j, sample). */
 RTW_API int rtw_get_rays(const rtw_camera* camera, const rtw_opts* opts, const uint32_t* i, const uint32_t* j,
                  const uint32_t* sample, size_t n, double* o, double* d);

@@ -159,6 +159,31 @@ void orc_scatter_batch(const Scene* s, const orc_options* opt, uint64_t n, const
     }
 }
 
+// Material::scatter + mixture pdf on caller-supplied hit records (parity check 3 on identical inputs): the counterpart of
+// rtw_shade_batch.  mat_kind / material describe the material that was hit; the scene supplies the lights list.
+void orc_shade_batch(const Scene* s, const orc_options* opt, uint64_t n, const double* d, const double* p, const double* normal,
+                     const uint32_t* front_face, const uint32_t* mat_kind, const double* material, const uint32_t* pixel,
+                     const uint32_t* sample, const uint32_t* vertex, uint32_t* kind, double* dir, double* weight) {
+    Options op = to_options(opt);
+    Scene local;                              // shade() looks the material up by index: one scratch material per record
+    local.lights = s->lights;
+    local.materials.resize(1);
+    for (uint64_t i = 0; i < n; ++i) {
+        Material m;
+        m.kind = mat_kind[i]; m.albedo = v3(material + 4 * i); m.param = material[4 * i + 3];
+        local.materials[0] = m;
+        HitRecord rec;
+        rec.p = v3(p + 3 * i); rec.normal = v3(normal + 3 * i); rec.t = 0.; rec.front_face = front_face[i] != 0; rec.prim = 0; rec.mat = 0;
+        Ray r{rec.p, v3(d + 3 * i)};
+        Stream rng(op.seed, pixel[i], sample[i], vertex[i], op.rng_mode);
+        Vertex vx;
+        shade(local, op, r, rec, rng, &vx, nullptr);
+        kind[i] = vx.kind;
+        put(dir + 3 * i, vx.kind >= V_SPECULAR ? vx.next.d : V3{0, 0, 0});
+        put(weight + 3 * i, vx.weight);
+    }
+}
+
 // primary rays for a list of (i, j, sample) (get_ray, camera.rs:274-293)
 void orc_get_rays(const orc_camera* cam, const orc_options* opt, uint64_t n, const uint32_t* i, const uint32_t* j,
                   const uint32_t* sample, double* o, double* d) {

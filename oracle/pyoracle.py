@@ -114,6 +114,7 @@ def lib():
         L.orc_trace_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                                       C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_scatter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 12
+        L.orc_shade_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 12
         L.orc_get_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -269,6 +270,18 @@ class Scene:
         lib().orc_scatter_batch(self.h, C.byref(opts), n, _p(o), _p(d), _p(pixel), _p(sample), _p(vertex), _p(prim), _p(t),
                                 _p(kind), _p(p), _p(normal), _p(dr), _p(w))
         return dict(prim=prim, t=t, kind=kind, p=p, normal=normal, dir=dr, weight=w)
+
+    def shade_batch(self, d, p, normal, front_face, mat_kind, material, pixel, sample, vertex, opts: Options):
+        """Material::scatter + mixture pdf on caller-supplied hit records (the counterpart of rtw_shade_batch)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        u = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        d, p, normal, material = f(d), f(p), f(normal), f(material)
+        front_face, mat_kind, pixel, sample, vertex = u(front_face), u(mat_kind), u(pixel), u(sample), u(vertex)
+        n = d.shape[0]
+        kind = np.zeros(n, dtype=np.uint32); dr = np.zeros((n, 3)); w = np.zeros((n, 3))
+        lib().orc_shade_batch(self.h, C.byref(opts), n, _p(d), _p(p), _p(normal), _p(front_face), _p(mat_kind), _p(material),
+                              _p(pixel), _p(sample), _p(vertex), _p(kind), _p(dr), _p(w))
+        return dict(kind=kind, dir=dr, weight=w)
 
     def render(self, cam: Camera, opts: Options, row_begin=0, row_end=0xFFFFFFFF):
         img = np.zeros((cam.height, cam.width, 3))

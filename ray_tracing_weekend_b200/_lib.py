@@ -18,6 +18,8 @@ RTW_BVH_AUTO, RTW_BVH_HOST_SAH, RTW_BVH_DEVICE_LBVH = 0, 1, 2
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
 RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL = 1, 2, 4
+RTW_COLLECTIVE_AUTO, RTW_COLLECTIVE_PEER, RTW_COLLECTIVE_NCCL = 0, 1, 2
+RTW_COMM_ID_BYTES = 128
 RTW_TILE_W = RTW_TILE_H = 16
 EPSILON = 2.220446049250313e-16
 TMIN_REFERENCE = -1.0      # rtw_opts.tmin: machine epsilon of the working precision (the reference's f64::EPSILON analogue)
@@ -28,7 +30,8 @@ RTW_SYMBOLS = (
     "rtw_device_count", "rtw_release_cached_memory", "rtw_scene_create", "rtw_scene_destroy", "rtw_scene_info", "rtw_render", "rtw_render_tiles_device",
     "rtw_untile_resolve_device", "rtw_trace_batch", "rtw_scatter_batch", "rtw_get_rays", "rtw_path_radiance",
     "rtw_render_samples_device", "rtw_resolve_accum_device", "rtw_accum_slots", "rtw_render_samples", "rtw_resolve_accum", "rtw_set_bvh_builder", "rtw_scene_bvh_builder", "rtw_scene_create_general", "rtw_transform_then", "rtw_transform_inverse", "rtw_rotation", "rtw_perlin_generate",
-    "rtw_scene_export_bvh",
+    "rtw_scene_export_bvh", "rtw_shade_batch", "rtw_render_multi", "rtw_comm_unique_id", "rtw_comm_init_rank", "rtw_comm_destroy",
+    "rtw_comm_rank", "rtw_comm_world", "rtw_render_rank", "rtw_render_rank_device", "rtw_scene_sync",
 )
 RTWH_SYMBOLS = ("rtwh_scene_simple", "rtwh_scene_desc_destroy", "rtwh_scene_desc_counts", "rtwh_scene_desc_copy")
 
@@ -160,6 +163,15 @@ def load(build_if_missing: bool = True):
     L.rtw_resolve_accum.argtypes = [vp, vp, u32, u32, u32, vp, vp]
     L.rtw_trace_batch.argtypes = [vp, vp, vp, sz, dbl, dbl, u32, vp, vp]
     L.rtw_scatter_batch.argtypes = [vp, vp, vp, vp, sz] + [vp] * 10
+    L.rtw_shade_batch.argtypes = [vp, vp, sz] + [vp] * 12
+    L.rtw_render_multi.argtypes = [vp, vp, vp, C.c_int, vp, u32, vp, vp, vp]
+    L.rtw_comm_unique_id.argtypes = [vp]
+    L.rtw_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.rtw_comm_destroy.argtypes = [vp]; L.rtw_comm_destroy.restype = None
+    L.rtw_comm_rank.argtypes = [vp]; L.rtw_comm_world.argtypes = [vp]
+    L.rtw_render_rank.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.rtw_render_rank_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.rtw_scene_sync.argtypes = [vp, vp]
     L.rtw_get_rays.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
     L.rtw_path_radiance.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
     L.rtw_scene_create_general.argtypes = [vp, vp]

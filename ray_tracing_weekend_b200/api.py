@@ -461,6 +461,20 @@ class Scene:
                                                  _p(prim), _p(t), _p(kind), _p(p), _p(normal), _p(dr), _p(w)))
         return dict(prim=prim, t=t, kind=kind, p=p, normal=normal, dir=dr, weight=w)
 
+    def shade_batch(self, d, p, normal, front_face, mat_kind, material, pixel, sample, vertex, opts: RenderOptions):
+        """Material::scatter + the mixture-pdf sample on caller-supplied hit records (rtw_shade_batch): d = incoming direction,
+        (p, normal, front_face) = the HitRecord, (mat_kind, material = albedo r, g, b, param) = the material that was hit."""
+        f = lambda a, k: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, k)
+        d, p, normal, material = f(d, 3), f(p, 3), f(normal, 3), f(material, 4)
+        front_face, mat_kind, pixel, sample, vertex = (np.ascontiguousarray(a, dtype=np.uint32) for a in (front_face, mat_kind, pixel, sample, vertex))
+        n = d.shape[0]
+        kind = np.zeros(n, dtype=np.uint32)
+        dr, w = np.zeros((n, 3)), np.zeros((n, 3))
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_shade_batch(self._h, C.byref(po), n, _p(d), _p(p), _p(normal), _p(front_face), _p(mat_kind), _p(material),
+                                               _p(pixel), _p(sample), _p(vertex), _p(kind), _p(dr), _p(w)))
+        return dict(kind=kind, dir=dr, weight=w)
+
     def path_radiance(self, camera: "Camera", opts: RenderOptions, i, j, sample):
         i, j, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (i, j, sample))
         out = np.zeros((len(i), 3))
@@ -483,6 +497,49 @@ class Scene:
         po = opts.pod()
         _lib.check(_lib.load().rtw_render(self._h, C.byref(camera.pod), C.byref(po), _p(rgb_sum), _p(rgb8), C.byref(st)))
         return rgb_sum, rgb8, st.as_dict()
+
+    def render_multi(self, camera: "Camera", opts: Optional[RenderOptions] = None, n_gpus: int = 1, devices=None,
+                     collective: int = _lib.RTW_COLLECTIVE_AUTO, want_sum=True, want_rgb8=True):
+        """Camera::render on n_gpus devices of THIS process (rtw_render_multi): the scene is replicated, every GPU renders its share
+        on its own stream, the frame's one collective (fused peer-memory reduce + resolve, or NCCL) runs inside the library."""
+        opts = opts or RenderOptions()
+        w, h = camera.image_width, camera.image_height
+        rgb_sum = np.zeros((h, w, 3)) if want_sum else None
+        rgb8 = np.zeros((h, w, 3), dtype=np.uint8) if want_rgb8 else None
+        st = rtw_stats()
+        po = opts.pod()
+        devs = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _lib.check(_lib.load().rtw_render_multi(self._h, C.byref(camera.pod), C.byref(po), int(n_gpus), _p(devs) if devs is not None else None,
+                                                int(collective), _p(rgb_sum) if want_sum else None, _p(rgb8) if want_rgb8 else None, C.byref(st)))
+        return rgb_sum, rgb8, st.as_dict()
+
+    def render_rank(self, camera: "Camera", opts: RenderOptions, comm: "Comm", want_sum=False, want_rgb8=True):
+        """This rank's part of one frame rendered by all ranks of `comm` (rtw_render_rank): the image arrives on rank 0."""
+        w, h = camera.image_width, camera.image_height
+        root = comm.rank == 0
+        rgb_sum = np.zeros((h, w, 3)) if (want_sum and root) else None
+        rgb8 = np.zeros((h, w, 3), dtype=np.uint8) if (want_rgb8 and root) else None
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render_rank(self._h, C.byref(camera.pod), C.byref(po), comm._h, _p(rgb_sum) if rgb_sum is not None else None,
+                                               _p(rgb8) if rgb8 is not None else None, C.byref(st)))
+        return rgb_sum, rgb8, st.as_dict()
+
+    def render_rank_device(self, camera: "Camera", opts: RenderOptions, comm: "Comm", d_rgb_sum_ptr: int = 0, d_rgb8_ptr: int = 0, stream: int = 0,
+                           want_stats: bool = False):
+        """rtw_render_rank_device: device outputs on rank 0, everything enqueued on `stream`; asynchronous unless want_stats."""
+        st = rtw_stats()
+        po = opts.pod()
+        _lib.check(_lib.load().rtw_render_rank_device(self._h, C.byref(camera.pod), C.byref(po), comm._h, C.c_void_p(d_rgb_sum_ptr or None),
+                                                      C.c_void_p(d_rgb8_ptr or None), C.c_void_p(stream or None), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def sync(self):
+        """rtw_scene_sync: wait for the scene's device, raise if a path did what makes the reference panic; returns the kernel time
+        (ms) of the last render call."""
+        ms = C.c_double(0.)
+        _lib.check(_lib.load().rtw_scene_sync(self._h, C.byref(ms)))
+        return ms.value
 
     def render_samples(self, camera: "Camera", opts: RenderOptions, sample_begin: int, sample_count: int, accum: np.ndarray, poison: np.ndarray):
         """rtw_render_samples: ADD samples [sample_begin, sample_begin + sample_count) of every pixel into the host accumulators
@@ -511,6 +568,29 @@ class Scene:
         _lib.check(_lib.load().rtw_render_tiles_device(self._h, C.byref(camera.pod), C.byref(po), rank, world, C.c_void_p(d_tiles_ptr),
                                                        C.c_void_p(stream), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+
+class Comm:
+    """rtw_comm: the communicator of the one-process-per-GPU mode.  Rank 0 calls Comm.unique_id(), the 128 bytes travel out of band
+    (torch.distributed, MPI, a file), every rank constructs Comm(id, rank, world) — a collective call."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * _lib.RTW_COMM_ID_BYTES)()
+        _lib.check(_lib.load().rtw_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == _lib.RTW_COMM_ID_BYTES
+        buf = (C.c_uint8 * _lib.RTW_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._h = C.c_void_p()
+        _lib.check(_lib.load().rtw_comm_init_rank(buf, int(rank), int(world), C.byref(self._h)))
+        self.rank, self.world = int(rank), int(world)
+
+    def close(self):
+        if self._h:
+            _lib.load().rtw_comm_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def new_accumulators(width: int, height: int):

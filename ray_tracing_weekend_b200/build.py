@@ -125,7 +125,7 @@ def _compile_and_link(units, obj_dir: str, lib_path: str, verbose: bool) -> str:
             print(out, file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + (out or ""))
-    link = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", lib_path, *objs]
+    link = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", lib_path, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)

@@ -49,10 +49,15 @@ struct DevCache {
 };
 DevCache& dev_cache() { static DevCache c; return c; }
 size_t round_alloc(size_t n) { return n <= (1u << 20) ? (n + 511) / 512 * 512 : (n + (1u << 20) - 1) / (1u << 20) * (1u << 20); }
-cudaError_t cached_malloc(void** p, size_t n) {
+// Blocks are keyed by the device they were allocated on (recorded in the DevBuf, not read back from cudaGetDevice at free time:
+// a scene may be destroyed while another GPU is current).  A block only enters the cache after its device has gone idle:
+// cudaFree would have synchronised implicitly, and without that a kernel still running on one stream could see its buffer handed to
+// another scene or stream (rtw_render_*_device with stats == NULL return with work in flight).
+cudaError_t cached_malloc(void** p, size_t n, int* dev_out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev_out) *dev_out = dev;
     n = round_alloc(n);
     {
         DevCache& c = dev_cache();
@@ -62,37 +67,41 @@ cudaError_t cached_malloc(void** p, size_t n) {
     }
     return cudaMalloc(p, n);
 }
-void cached_free(void* p, size_t n) {
+void cached_free(void* p, size_t n, int dev) {
     if (!p) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cur != dev && cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return; }      // leak rather than free on the wrong device
     n = round_alloc(n);
-    DevCache& c = dev_cache();
-    std::lock_guard<std::mutex> g(c.m);
-    if (c.bytes + n > DevCache::kMaxBytes) { cudaFree(p); return; }
-    c.blocks.insert({{dev, n}, p});
-    c.bytes += n;
+    bool cached = false;
+    if (cudaDeviceSynchronize() == cudaSuccess) {
+        DevCache& c = dev_cache();
+        std::lock_guard<std::mutex> g(c.m);
+        if (c.bytes + n <= DevCache::kMaxBytes) { c.blocks.insert({{dev, n}, p}); c.bytes += n; cached = true; }
+    } else cudaGetLastError();
+    if (!cached) cudaFree(p);
+    if (cur != dev) cudaSetDevice(cur);
 }
 
 template <class P> struct DevBuf {
-    P* p = nullptr; size_t n = 0;
+    P* p = nullptr; size_t n = 0; int dev = 0;
     cudaError_t upload(const std::vector<P>& h) {
         release();
         n = h.size();
         if (!n) return cudaSuccess;
-        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), n * sizeof(P));
+        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), n * sizeof(P), &dev);
         if (e != cudaSuccess) { p = nullptr; n = 0; return e; }
         return cudaMemcpy(p, h.data(), n * sizeof(P), cudaMemcpyHostToDevice);
     }
     cudaError_t reserve(size_t count) {
         if (count <= n && p) return cudaSuccess;
         release();
-        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), count * sizeof(P));
+        cudaError_t e = cached_malloc(reinterpret_cast<void**>(&p), count * sizeof(P), &dev);
         if (e != cudaSuccess) { p = nullptr; return e; }
         n = count;
         return cudaSuccess;
     }
-    void release() { if (p) cached_free(p, n * sizeof(P)); p = nullptr; n = 0; }
+    void release() { if (p) cached_free(p, n * sizeof(P), dev); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(P); }
 };
 
@@ -153,7 +162,11 @@ struct GeneralDesc {
 
 }  // namespace
 
+struct MultiReplica;                                 // capi_multi.inl: per-device state of rtw_render_multi
 struct rtw_scene {
+    std::vector<MultiReplica*> replicas;             // rtw_render_multi: replicas[0] is this handle's own device
+    DevBuf<unsigned long long> d_block;              // rtw_render_rank: this rank's packed accumulators ([3 * slots] u64 + [slots] u32)
+    DevBuf<unsigned char> d_gather, d_tiles_rank;    // tile partition: the buffers gathered on the root / this rank's tiles
     bool general = false;
     GeneralDesc gdesc;
     DevBuf<uint32_t> d_panic;                    // general scenes: "the reference would have panicked" flag written by the kernels
@@ -167,6 +180,7 @@ struct rtw_scene {
     unsigned int* d_work = nullptr; DeviceCounters* d_counters = nullptr;
     DevBuf<double> d_rgb_sum; DevBuf<uint8_t> d_rgb8;
     DevBuf<unsigned long long> d_accum; DevBuf<uint32_t> d_poison;   // pooled megakernel accumulators
+    DevBuf<double> d_in2, d_in3; DevBuf<uint32_t> d_u3, d_u4;          // rtw_shade_batch inputs
     DevBuf<double> d_in0, d_in1, d_out0, d_out1, d_out2, d_out3, d_out4; DevBuf<uint32_t> d_u0, d_u1, d_u2, d_k; DevBuf<int32_t> d_prim;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     LaunchInfo last_launch;
@@ -177,6 +191,7 @@ struct rtw_scene {
 };
 
 namespace {
+void multi_release(rtw_scene* s);
 
 // w component of a light record: the radius on the exact path (Sphere::hit needs it), its FP32 square on the fast path, whose
 // light test and cone sampling only ever use r^2 (one multiply less per light test: 30 G of them per 1080p / 500 spp frame)
@@ -647,7 +662,10 @@ int rtw_camera_build(const rtw_camera_builder* b, rtw_camera* out) {
 int rtw_release_cached_memory(void) {
     DevCache& c = dev_cache();
     std::lock_guard<std::mutex> g(c.m);
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
     for (auto& kv : c.blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+    if (cur >= 0) cudaSetDevice(cur);
     c.blocks.clear(); c.bytes = 0;
     return RTW_OK;
 }
@@ -711,8 +729,8 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
-    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int));
-    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int), nullptr);
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters), nullptr);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     bool on_device = false;
@@ -817,8 +835,8 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
     auto bail = [&](int code) { rtw_scene_destroy(s); return code; };
     cudaError_t e = cudaGetDevice(&s->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
-    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int));
-    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters));
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int), nullptr);
+    if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters), nullptr);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     e = s->d_panic.reserve(1);
@@ -833,10 +851,13 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
 
 void rtw_scene_destroy(rtw_scene* s) {
     if (!s) return;
+    multi_release(s);
+    s->d_block.release(); s->d_gather.release(); s->d_tiles_rank.release();
     s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release(); s->d_panic.release();
-    cached_free(s->d_work, sizeof(unsigned int));
-    cached_free(s->d_counters, sizeof(DeviceCounters));
+    cached_free(s->d_work, sizeof(unsigned int), s->device);
+    cached_free(s->d_counters, sizeof(DeviceCounters), s->device);
     s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release();
+    s->d_in2.release(); s->d_in3.release(); s->d_u3.release(); s->d_u4.release();
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
@@ -1195,6 +1216,42 @@ int rtw_scatter_batch(rtw_scene* s, const rtw_opts* opts, const double* o, const
 }
 
 
+int rtw_shade_batch(rtw_scene* s, const rtw_opts* opts, size_t n, const double* d, const double* p, const double* normal,
+                    const uint32_t* front_face, const uint32_t* mat_kind, const double* material, const uint32_t* pixel,
+                    const uint32_t* sample, const uint32_t* vertex, uint32_t* kind, double* dir, double* weight) {
+    if (!s || (n && (!d || !p || !normal || !front_face || !mat_kind || !material || !pixel || !sample || !vertex || !kind || !dir || !weight)))
+        return fail(RTW_E_INVALID, "NULL argument");
+    int rc = check_opts(opts); if (rc) return rc;
+    if (s->general) return fail(RTW_E_UNSUPPORTED, "rtw_shade_batch: sphere-path scenes only");
+    for (size_t i = 0; i < n; ++i)
+        if (mat_kind[i] > RTW_INVISIBLE) return fail(RTW_E_INVALID, "rtw_shade_batch: material kind");
+    if (n == 0) return RTW_OK;
+    CU(cudaSetDevice(s->device));
+    rc = reserve_batch(s, n); if (rc) return rc;
+    CU(s->d_in2.reserve(3 * n)); CU(s->d_in3.reserve(4 * n)); CU(s->d_u3.reserve(n)); CU(s->d_u4.reserve(n));
+    CU(cudaMemcpy(s->d_in0.p, p, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_in1.p, d, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_in2.p, normal, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_in3.p, material, 4 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_u0.p, pixel, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_u1.p, sample, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_u2.p, vertex, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_u3.p, front_face, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_u4.p, mat_kind, n * 4, cudaMemcpyHostToDevice));
+    auto fill = [&](auto& P, const auto& view) {
+        P.scene = view; P.seed = opts->seed; P.n = n;
+        P.d = s->d_in1.p; P.p = s->d_in0.p; P.normal = s->d_in2.p; P.material = s->d_in3.p;
+        P.front_face = s->d_u3.p; P.mat_kind = s->d_u4.p; P.pixel = s->d_u0.p; P.sample = s->d_u1.p; P.vertex = s->d_u2.p;
+        P.kind = s->d_k.p; P.dir = s->d_out3.p; P.weight = s->d_out4.p;
+    };
+    if (opts->precision == RTW_F32) { ShadeParams<float> P{}; fill(P, s->f32.view); CU(launch_shade_f32(P, 0)); }
+    else { ShadeParams<double> P{}; fill(P, s->f64.view); CU(launch_shade_f64(P, 0)); }
+    CU(cudaMemcpy(kind, s->d_k.p, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(dir, s->d_out3.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(weight, s->d_out4.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+    return RTW_OK;
+}
+
 int rtw_get_rays(const rtw_camera* cam, const rtw_opts* opts, const uint32_t* i, const uint32_t* j, const uint32_t* sample, size_t n,
                  double* o, double* d) {
     int rc = check_camera(cam); if (rc) return rc;
@@ -1253,3 +1310,5 @@ int rtw_path_radiance(rtw_scene* s, const rtw_camera* cam, const rtw_opts* opts,
 }
 
 }  // extern "C"
+
+#include "capi_multi.inl"

@@ -106,6 +106,14 @@ cudaError_t launch_resolve_accum_f32(const unsigned long long* accum, const uint
                                      double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
     return launch_resolve_accum(accum, poison, width, height, spp, rgb_sum, rgb8, s);
 }
+cudaError_t launch_peer_reduce_resolve_f32(const PeerBlocks& B, uint32_t slot_begin, uint32_t slot_end, uint32_t width, uint32_t height,
+                                           uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s) {
+    if (slot_end <= slot_begin) return cudaSuccess;
+    const uint32_t tiles_x = (width + kTileW - 1) / kTileW, tiles_total = tiles_x * ((height + kTileH - 1) / kTileH);
+    peer_reduce_resolve_kernel<0><<<(slot_end - slot_begin + 255) / 256, 256, 0, s>>>(B, slot_begin, slot_end, width, height, tiles_x,
+                                                                                       tiles_total, spp, rgb_sum, rgb8);
+    return cudaGetLastError();
+}
 // deepest BVH the default wavefront shape can traverse: its per-thread stacks share the CTA's shared memory with the path slots
 uint32_t wavefront_max_bvh_depth() {
     const size_t limit = 226 * 1024, state = wavefront_state_bytes<kWfBlock, kWfSlotsPerWarp>();

@@ -681,18 +681,30 @@ struct PoolParams {
     uint32_t n_chunks;
 };
 
-RTW_D void pool_flush(const PoolParams& Q, uint32_t q, unsigned long long a0, unsigned long long a1, unsigned long long a2) {
-    if (a0) atomicAdd(Q.accum + 3 * (size_t)q + 0, a0);
-    if (a1) atomicAdd(Q.accum + 3 * (size_t)q + 1, a1);
-    if (a2) atomicAdd(Q.accum + 3 * (size_t)q + 2, a2);
-}
-
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
 // ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
 RTW_HD uint32_t poison_nan(uint32_t channel) { return 1u << (4u * channel); }
 RTW_HD uint32_t poison_inf(uint32_t channel) { return 1u << (12u + 4u * channel); }
 RTW_HD bool poison_has_nan(uint32_t word, uint32_t channel) { return (word >> (4u * channel)) & 15u; }
 RTW_HD bool poison_has_inf(uint32_t word, uint32_t channel) { return (word >> (12u + 4u * channel)) & 15u; }
+// A pixel whose fixed-point sum reaches 2^64 (2^32 in radiance units: a very bright emitter at a high sample count) must not wrap
+// silently: the wrap is detected where it happens — in the lane-private partial sum (pool_add) or in the 64-bit reduction
+// (pool_flush: the returned old value plus the addend is smaller than the old value) — and sets the channel's overflow flag, so the
+// pixel resolves to +inf -> 255 like the f64 sum would, not to a dark remainder.  The limit is 2^60, not 2^64: the accumulators of up
+// to 15 ranks are added by one integer reduce (sample partition), which cannot report a carry out of bit 63.
+RTW_HD bool pool_overflowed(unsigned long long old, unsigned long long add) { return ((old + add) >> 60) != 0ull || old + add < old; }
+RTW_D void pool_flush(const PoolParams& Q, uint32_t q, unsigned long long a0, unsigned long long a1, unsigned long long a2) {
+    uint32_t wrapped = 0;
+    if (a0) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 0, a0); if (pool_overflowed(old, a0)) wrapped |= poison_inf(0); }
+    if (a1) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 1, a1); if (pool_overflowed(old, a1)) wrapped |= poison_inf(1); }
+    if (a2) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 2, a2); if (pool_overflowed(old, a2)) wrapped |= poison_inf(2); }
+    if (wrapped) atomicOr(Q.poison + q, wrapped);
+}
+RTW_D void pool_add(unsigned long long& acc, unsigned long long v, uint32_t channel, uint32_t& bad) {
+    if (pool_overflowed(acc, v)) bad |= poison_inf(channel);
+    acc += v;
+}
+
 RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
     if (!(v < kFixedMax)) {                                    // NaN, +inf or absurdly large
         bad |= (v != v) ? poison_nan(channel) : poison_inf(channel);
@@ -796,9 +808,9 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
                     }
                     acc_q = q; a0 = a1 = a2 = 0ull; bad = 0;
                 }
-                a0 += pool_fixed(value.x, 0, bad);
-                a1 += pool_fixed(value.y, 1, bad);
-                a2 += pool_fixed(value.z, 2, bad);
+                pool_add(a0, pool_fixed(value.x, 0, bad), 0, bad);
+                pool_add(a1, pool_fixed(value.y, 1, bad), 1, bad);
+                pool_add(a2, pool_fixed(value.z, 2, bad), 2, bad);
             }
         }
     }
@@ -879,6 +891,39 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T, SCE
     store3(P.weight, idx, kind >= V_SPECULAR ? w : zero);
 }
 
+// Material::scatter + the mixture-pdf sample on CALLER-SUPPLIED hit records (rtw_shade_batch): the sampling arithmetic alone, with
+// no dependence on how each side traced its hit point.  in: incoming direction, p, normal, front_face, material; stream keys.
+template <class T> struct ShadeParams {
+    SceneView<T> scene;
+    uint64_t seed;
+    size_t n;
+    const double *d, *p, *normal, *material;     // [n][3] x3, [n][4] (albedo r, g, b, param)
+    const uint32_t *front_face, *mat_kind, *pixel, *sample, *vertex;
+    uint32_t* kind; double *dir, *weight;
+};
+template <class T, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) shade_batch_kernel(ShadeParams<T> P) {
+    __shared__ int32_t stack_s[kStackDepth * BLOCK];
+    size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= P.n) return;
+    Hit<T> h;
+    h.p = load3<T>(P.p, idx); h.normal = load3<T>(P.normal, idx); h.t = T(0);
+    h.front_face = P.front_face[idx] != 0;
+    h.info = P.mat_kind[idx] & 3u;
+    h.albedo = mk<T>((T)P.material[4 * idx], (T)P.material[4 * idx + 1], (T)P.material[4 * idx + 2]); h.param = (T)P.material[4 * idx + 3];
+    h.gkind = h.info;
+    V3<T> zero = mk<T>(0, 0, 0);
+    Ray<T> r{h.p, load3<T>(P.d, idx)};                       // Material::scatter reads only the direction of the incoming ray
+    Stream<EXACT> rng(P.seed, P.pixel[idx], P.sample[idx], P.vertex[idx]);
+    Ray<T> next{zero, zero};
+    V3<T> w = zero;
+    Tally tl;
+    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
+    P.kind[idx] = kind;
+    store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
+    store3(P.weight, idx, kind >= V_SPECULAR ? w : zero);
+}
+
 template <class T, bool EXACT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) get_rays_kernel(BatchParams<T> P, double* o, double* d) {
     size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -952,6 +997,54 @@ __global__ void resolve_accum_kernel(const unsigned long long* accum, const uint
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float f = (float)((double)accum[3 * q + c] * (1.0 / 4294967296.0));
+        if (poison_has_inf(bad, c)) f = __int_as_float(0x7f800000);
+        if (poison_has_nan(bad, c)) f = __int_as_float(0x7fc00000);
+        double v = (double)f;
+        if (rgb_sum) rgb_sum[dst + c] = v;
+        if (rgb8) {
+            double g = sqrt(v * scale);
+            if (g < 0.) g = 0.;
+            if (g > 1.) g = 1.;
+            double qq = 256. * g;
+            rgb8[dst + c] = (qq != qq) ? 0 : (qq >= 255. ? 255 : (qq <= 0. ? 0 : (uint8_t)qq));
+        }
+    }
+}
+
+// N GPUs in one process: the frame's collective and its resolve as ONE kernel per GPU over NVLink peer memory.  After the sample
+// partition every GPU holds fixed-point accumulators of the WHOLE image for its share of the samples.  GPU g owns pixel slots
+// [slot_begin, slot_end): it reads those slots from every GPU's accumulators through peer pointers (reduce-scatter), resolves them
+// (same arithmetic as resolve_accum_kernel) and stores the pixels straight into the image buffers on the root GPU (gather).  No
+// intermediate buffer, no second pass over the 58 MB blocks, and every link carries 1 / N of a block.
+constexpr int kMaxPeers = 16;
+struct PeerBlocks {
+    const unsigned long long* accum[kMaxPeers];
+    const uint32_t* poison[kMaxPeers];
+    int n;
+};
+template <int UNUSED = 0>
+__global__ void peer_reduce_resolve_kernel(PeerBlocks B, uint32_t slot_begin, uint32_t slot_end, uint32_t width, uint32_t height,
+                                           uint32_t tiles_x, uint32_t tiles_total, uint32_t spp, double* rgb_sum, uint8_t* rgb8) {
+    uint32_t q = slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= slot_end) return;
+    uint32_t tile = q >> 8, in = q & 255u;
+    if (tile >= tiles_total) return;
+    uint32_t ttx, tty;
+    slot_tile(tile, tiles_x, &ttx, &tty);
+    uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
+    if (i >= width || j >= height) return;
+    unsigned long long a[3] = {0ull, 0ull, 0ull};
+    uint32_t bad = 0;
+    for (int r = 0; r < B.n; ++r) {
+        const unsigned long long* src = B.accum[r] + 3 * (size_t)q;
+        a[0] += src[0]; a[1] += src[1]; a[2] += src[2];
+        bad |= B.poison[r][q];
+    }
+    size_t dst = ((size_t)j * width + i) * 3;
+    double scale = 1. / (double)(int32_t)spp;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float f = (float)((double)a[c] * (1.0 / 4294967296.0));
         if (poison_has_inf(bad, c)) f = __int_as_float(0x7f800000);
         if (poison_has_nan(bad, c)) f = __int_as_float(0x7fc00000);
         double v = (double)f;

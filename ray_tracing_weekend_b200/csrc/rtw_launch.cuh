@@ -128,6 +128,11 @@ template <class T, bool EXACT> cudaError_t launch_scatter_t(const BatchParams<T>
     scatter_batch_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P);
     return cudaGetLastError();
 }
+template <class T, bool EXACT> cudaError_t launch_shade_t(const ShadeParams<T>& P, cudaStream_t s) {
+    if (P.n == 0) return cudaSuccess;
+    shade_batch_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P);
+    return cudaGetLastError();
+}
 template <class T, bool EXACT> cudaError_t launch_get_rays_t(const BatchParams<T>& P, double* o, double* d, cudaStream_t s) {
     if (P.n == 0) return cudaSuccess;
     get_rays_kernel<T, EXACT, kBatchBlock><<<batch_grid(P.n), kBatchBlock, 0, s>>>(P, o, d);
@@ -204,6 +209,7 @@ cudaError_t launch_render_pool_general_impl(RenderParams<float, SceneViewG<float
     }                                                                                                                            \
     cudaError_t launch_trace_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_trace_t<T, EXACT>(P, s); }         \
     cudaError_t launch_scatter_##SUFFIX(const BatchParams<T>& P, cudaStream_t s) { return launch_scatter_t<T, EXACT>(P, s); }     \
+    cudaError_t launch_shade_##SUFFIX(const ShadeParams<T>& P, cudaStream_t s) { return launch_shade_t<T, EXACT>(P, s); }         \
     cudaError_t launch_get_rays_##SUFFIX(const BatchParams<T>& P, double* o, double* d, cudaStream_t s) {                         \
         return launch_get_rays_t<T, EXACT>(P, o, d, s);                                                                           \
     }                                                                                                                            \

@@ -10,6 +10,7 @@ struct LaunchInfo { int grid = 0, block = 0; size_t smem = 0; int blocks_per_sm 
     cudaError_t launch_render_##SUFFIX(RenderParams<T> P, bool count, int sm_count, cudaStream_t s, LaunchInfo*); \
     cudaError_t launch_trace_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                                   \
     cudaError_t launch_scatter_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                                 \
+    cudaError_t launch_shade_##SUFFIX(const ShadeParams<T>& P, cudaStream_t s);                                   \
     cudaError_t launch_get_rays_##SUFFIX(const BatchParams<T>& P, double* o, double* d, cudaStream_t s);          \
     cudaError_t launch_path_radiance_##SUFFIX(const BatchParams<T>& P, cudaStream_t s);                           \
     cudaError_t launch_render_general_##SUFFIX(RenderParams<T, SceneViewG<T>> P, bool count, int sm_count, cudaStream_t s, LaunchInfo*); \
@@ -29,6 +30,8 @@ cudaError_t launch_render_wavefront_general_f32(RenderParams<float, SceneViewG<f
                                                 cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_resolve_accum_f32(const unsigned long long* accum, const uint32_t* poison, uint32_t width, uint32_t height, uint32_t spp,
                                      double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
+cudaError_t launch_peer_reduce_resolve_f32(const PeerBlocks& B, uint32_t slot_begin, uint32_t slot_end, uint32_t width, uint32_t height,
+                                           uint32_t spp, double* rgb_sum, uint8_t* rgb8, cudaStream_t s);
 RTW_DECLARE_LAUNCHERS(f64, double)
 
 }  // namespace rtw

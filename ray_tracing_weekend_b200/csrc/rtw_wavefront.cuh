@@ -67,9 +67,9 @@ RTW_D void wf_finish(const PoolParams& Q, WfAcc& A, uint32_t q, V3<float> value,
         wf_acc_flush(Q, A);
         A.q = q; A.a0 = A.a1 = A.a2 = 0ull; A.bad = 0;
     }
-    A.a0 += pool_fixed(value.x, 0, A.bad);
-    A.a1 += pool_fixed(value.y, 1, A.bad);
-    A.a2 += pool_fixed(value.z, 2, A.bad);
+    pool_add(A.a0, pool_fixed(value.x, 0, A.bad), 0, A.bad);
+    pool_add(A.a1, pool_fixed(value.y, 1, A.bad), 1, A.bad);
+    pool_add(A.a2, pool_fixed(value.z, 2, A.bad), 2, A.bad);
 }
 
 template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>>

@@ -1,6 +1,7 @@
 // rtw_bin.cpp — the reference's `bin` (bin/src/main.rs:54-105) with the CUDA backend behind
 // Camera::render:   rtw_bin <simple|simple-light|cornell-box|debug|simple-transform|checkered-spheres> [--backend cuda] [--width W --height H --spp S --depth D]
 //                           [--seed N] [--precision f32|f64] [--tmin X] [--out image.ppm]
+//                           [--gpus N [--collective auto|peer|nccl]] [--mode wavefront|megakernel]
 //                   [--config Config.toml]  [--format p3|p6|png]  [--passes K [--checkpoint FILE] [--resume]]
 // Image parameters come from flags (defaults = the reference's Config.toml:7-11) or, with --config, from the [image] table of a
 // Config.toml like the reference's (bin/src/config.rs).  The default output is ASCII P3 with rows reversed exactly like
@@ -31,6 +32,9 @@ int main(int argc, char** argv) {
         else if (a == "--seed") opt.seed = std::stoull(next());
         else if (a == "--tmin") opt.tmin = std::stod(next());
         else if (a == "--precision") opt.precision = next() == "f64" ? Precision::F64 : Precision::F32;
+        else if (a == "--gpus") opt.n_gpus = std::stoi(next());                    // Camera::render on N GPUs (rtw_render_multi)
+        else if (a == "--collective") { std::string c = next(); opt.collective = c == "peer" ? RTW_COLLECTIVE_PEER : c == "nccl" ? RTW_COLLECTIVE_NCCL : RTW_COLLECTIVE_AUTO; }
+        else if (a == "--mode") { std::string m = next(); opt.mode = m == "megakernel" ? RTW_MEGAKERNEL : RTW_WAVEFRONT; }
         else if (a == "--out") out = next();
         else if (a == "--config") config = next();
         else if (a == "--format") format = next();
@@ -75,8 +79,8 @@ int main(int argc, char** argv) {
         World lref = general ? general_sc.lights_ref() : World(simple_sc.lights);
         auto img = passes ? cam.render_progressive(wref, lref, opt, passes, checkpoint, resume, &st, stop_after) : cam.render(wref, lref, opt, &st);
         double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        std::fprintf(stderr, "rendered %ux%u spp %u in %.3f s (kernel %.3f ms): %.1f Mpaths/s, %.1f Mrays/s\n", width, height, spp, sec,
-                     st.kernel_ms, st.paths / st.kernel_ms * 1e-3, st.rays / st.kernel_ms * 1e-3);
+        std::fprintf(stderr, "rendered %ux%u spp %u on %d GPU(s) in %.3f s (kernel %.3f ms): %.1f Mpaths/s, %.1f Mrays/s\n", width, height, spp,
+                     opt.n_gpus, sec, st.kernel_ms, st.paths / st.kernel_ms * 1e-3, st.rays / st.kernel_ms * 1e-3);
         if (format == "p6") write_p6(out, img);
         else if (format == "png") write_png(out, img);
         else write_p3(out, img);

@@ -274,6 +274,8 @@ struct RenderOptions {
     double tmin = RTW_TMIN_REFERENCE;               // camera.rs:473: machine epsilon of the working precision
     Precision precision = Precision::F32;
     uint32_t mode = RTW_WAVEFRONT, flags = 0;       // the faster FP32 renderer; RTW_MEGAKERNEL renders the same image
+    int n_gpus = 1;                                 // > 1: rtw_render_multi on CUDA devices 0 .. n_gpus-1 of this process (same image bit for bit)
+    uint32_t collective = RTW_COLLECTIVE_AUTO;      // how the N partial frames meet: fused peer-memory kernel or NCCL
 };
 
 class Camera;
@@ -348,9 +350,10 @@ public:
         rtw_opts o = to_opts(opt);
         size_t npx = (size_t)c_.image_width * c_.image_height;
         std::vector<double> sum(npx * 3); std::vector<uint8_t> q(npx * 3);
-        int rc = rtw_render(scene, &c_, &o, sum.data(), q.data(), stats);
+        int rc = opt.n_gpus > 1 ? rtw_render_multi(scene, &c_, &o, opt.n_gpus, nullptr, opt.collective, sum.data(), q.data(), stats)
+                                : rtw_render(scene, &c_, &o, sum.data(), q.data(), stats);
         rtw_scene_destroy(scene);
-        if (rc != RTW_OK) throw std::runtime_error(std::string("rtw_render: ") + rtw_last_error());
+        if (rc != RTW_OK) throw std::runtime_error(std::string(opt.n_gpus > 1 ? "rtw_render_multi: " : "rtw_render: ") + rtw_last_error());
         return rows(sum, q);
     }
 

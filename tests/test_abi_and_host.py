@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(rtw):
     out = subprocess.run(["nm", "-D", "--defined-only", rtw.library_path()], capture_output=True, text=True).stdout
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert exported == names, "the library exports exactly the declared C ABI"
-    assert lib.rtw_abi_version() == 2
+    assert lib.rtw_abi_version() == 3
 
 
 def test_library_contains_sm100a_kernels(rtw):

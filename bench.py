@@ -154,6 +154,8 @@ def run_cuda(args):
     opts = R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=base_flags)
     scene = R.Scene(world_h, lights_h)
     renderer = D.DistributedRenderer(scene, cam, opts, rank, world, want_sum=False, want_rgb8=True)
+    if world > 1 and not args.torch_collective:
+        renderer.use_library_collective()       # the frame's one collective runs inside librtw_cuda.so (rtw_render_rank_device: NCCL from C)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
 
     def barrier():
@@ -183,14 +185,26 @@ def run_cuda(args):
     for k in range(args.steps):
         flush.fill_(k & 0xff)                                # evict L2 between timed iterations (outside the event pairs)
         ev[k][0].record()
-        ev[k][2].record()
-        renderer.render_local()                              # this rank's share: its samples of every pixel (or its tiles)
-        ev[k][3].record()
-        renderer.combine()                                   # the frame's one collective + resolve on rank 0
+        if renderer.comm is not None:
+            renderer.render()                                # one C call: this rank's share + the NCCL collective + resolve on rank 0
+        else:
+            ev[k][2].record()
+            renderer.render_local()                          # this rank's share: its samples of every pixel (or its tiles)
+            ev[k][3].record()
+            renderer.combine()                               # the frame's one collective + resolve on rank 0
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    renderer.check()                                         # a path that would make the reference panic surfaces here
     step_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
+    if renderer.comm is not None:
+        # the library call fuses kernel + collective: the kernel's own time comes from the same number of untimed local renders
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)
+            ev[k][2].record()
+            renderer.render_local()
+            ev[k][3].record()
+        barrier()
     kern_ms = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps))
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -212,6 +226,7 @@ def run_cuda(args):
             return rgb8
         sc = make_scene()
         rr = D.DistributedRenderer(sc, cam, opts, rank, world, want_sum=False, want_rgb8=True)
+        rr.comm = renderer.comm                                          # the communicator outlives scenes
         rr.render()
         if rank == 0:
             pinned.copy_(rr.rgb8, non_blocking=True)
@@ -266,8 +281,9 @@ def run_cuda(args):
             metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=WORKLOAD, mode=("wavefront (warp-private queues in shared memory)" if args.mode == "wavefront" else
-                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=(f"samples of every pixel split over {world} GPU(s) (fixed-point accumulators) + 1 NCCL reduce" if renderer.partition == "samples"
-                                     else f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather"),
+                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=((f"samples of every pixel split over {world} GPU(s) (fixed-point accumulators) + 1 NCCL reduce" if renderer.partition == "samples"
+                                      else f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather") +
+                                     ("; collective inside the C library (rtw_render_rank_device)" if renderer.comm is not None else ("; collective through torch.distributed" if world > 1 else ""))),
                         tmin="RTW_TMIN_REFERENCE: machine epsilon of the working precision (the reference uses f64::EPSILON in f64)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),
             mpaths_per_s=total["paths"] * args.steps / secs * 1e-6, rays_per_path=total["rays"] / total["paths"],
             kernel_ms_per_step=kern_ms / args.steps,
@@ -340,6 +356,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
     ap.add_argument("--mode", default="wavefront", choices=["megakernel", "wavefront"])
+    ap.add_argument("--torch-collective", action="store_true", help="N > 1: run the collective through torch.distributed instead of inside the C library")
     args = ap.parse_args()
     if args.workload == "C3":
         WORKLOAD = WORKLOAD.replace(f"{WIDTH}x{HEIGHT}, {SPP} spp", "3840x2160, 1024 spp [NON-DEFAULT workload: BASELINE C3]")

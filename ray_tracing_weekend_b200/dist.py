@@ -132,7 +132,11 @@ class DistributedRenderer:
             partition = "samples" if (fixed_point and world > 1 and world <= 15 and spp >= world) else "tiles"
         if partition == "samples" and not fixed_point:
             raise ValueError("the sample partition needs a fixed-point FP32 renderer")
+        if partition == "samples" and world > 15:
+            # the poison words are SUMMED by the reduce: each flag owns a 4-bit field, 16 ranks would carry into the next one
+            raise ValueError("the sample partition adds the ranks' poison words: at most 15 ranks (use partition='tiles')")
         self.partition = partition
+        self.comm = None
         self.rgb_sum = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda") if (want_sum and rank == 0) else None
         self.rgb8 = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda") if (want_rgb8 and rank == 0) else None
         if partition == "samples":
@@ -144,6 +148,17 @@ class DistributedRenderer:
             self.tpr = tiles_per_rank(w, h, world)
             dt = torch.float32 if opts.precision == api.RTW_F32 else torch.float64
             self.local = torch.zeros((self.tpr, TILE_H, TILE_W, 3), dtype=dt, device="cuda")
+
+    def use_library_collective(self):
+        """Run the frame's collective INSIDE the C library (rtw_comm_* / rtw_render_rank_device: NCCL from C) instead of through
+        torch.distributed: rank 0 creates the NCCL unique id, torch.distributed only carries its 128 bytes to the other ranks.
+        The partition the library picks is the one chosen here (same rule), so the images are the same bit for bit."""
+        if self.world == 1 or self.comm is not None:
+            return self
+        ids = [self.api.Comm.unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.comm = self.api.Comm(ids[0], self.rank, self.world)
+        return self
 
     def render_local(self, opts=None, want_stats: bool = False):
         """This rank's share of the frame (kernels only, no collective) on torch's current stream."""
@@ -175,6 +190,16 @@ class DistributedRenderer:
     def render(self, want_stats: bool = False):
         """One frame: this rank's share, the collective, the resolve on rank 0.  Work is enqueued on torch's current stream; returns
         the kernel stats dict when asked (that syncs)."""
+        if self.comm is not None:
+            stream = torch.cuda.current_stream().cuda_stream
+            sum_ptr = self.rgb_sum.data_ptr() if self.rgb_sum is not None else 0
+            rgb8_ptr = self.rgb8.data_ptr() if self.rgb8 is not None else 0
+            return self.scene.render_rank_device(self.camera, self.opts, self.comm, sum_ptr, rgb8_ptr, stream, want_stats=want_stats)
         st = self.render_local(want_stats=want_stats)
         self.combine()
         return st
+
+    def check(self):
+        """Joins the asynchronous renders of this rank and raises if a path did what makes the reference panic (a light sample from
+        an empty lights list): the *_device entry points only report it when they are asked for stats."""
+        return self.scene.sync()

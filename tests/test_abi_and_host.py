@@ -32,6 +32,25 @@ def test_library_exports_every_declared_symbol(rtw):
     assert lib.rtw_abi_version() == 3
 
 
+def test_rust_binding_declares_every_entry_point():
+    """rust/cuda cannot be compiled here (no Rust toolchain), so its completeness is checked mechanically: the extern "C" block of
+    lib.rs names exactly the functions include/rtw.h declares, and build.rs compiles exactly the units of build.py with its flags."""
+    rs = open(os.path.join(ROOT, "rust", "cuda", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (rtw_[a-z0-9_]+)\s*\(", rs)))
+    assert declared == _declared("rtw.h")
+    from ray_tracing_weekend_b200 import build as B
+    brs = open(os.path.join(ROOT, "rust", "cuda", "build.rs")).read()
+    units = re.findall(r'\((?:csrc|host)\.join\("([a-z0-9_]+\.(?:cu|cpp))"\), &\[([^\]]*)\]\)', brs)
+    assert [(u, [f.strip().strip('"') for f in fl.split(",") if f.strip()]) for u, fl in units] == [(os.path.basename(u), f) for u, f in B.UNITS]
+    for flag in B.COMMON + B.ARCH:
+        assert f'"{flag}"' in brs, flag
+    assert '"-cudart", "static"' in brs and '"-ldl"' in brs
+    # INTEGRATION.md quotes the same unit list
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for u, _ in B.UNITS:
+        assert os.path.basename(u) in integ, u
+
+
 def test_library_contains_sm100a_kernels(rtw):
     out = subprocess.run(["cuobjdump", "-lelf", rtw.library_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out

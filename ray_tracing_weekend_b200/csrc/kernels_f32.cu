@@ -18,35 +18,43 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_pool_general_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_general_impl<false>(P, Q, sm_count, s, info);
 }
-template <bool COUNT, bool SH, int BLOCK, int NP>
+template <bool COUNT, bool SH, int BLOCK, int NP, bool CONN>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH>;
+    auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH, SceneView<float>, CONN>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
     if (e != cudaSuccess) return e;
     kernel<<<grid, BLOCK, smem, s>>>(P, Q);
     return cudaGetLastError();
 }
-template <bool COUNT, int BLOCK, int NP>
+template <bool COUNT, int BLOCK, int NP, bool CONN>
 cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
     // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene.
     // A walk pushes at most one entry per inner level below the stop code, so `bvh_depth` entries always suffice; two spare
     // entries are kept unless the tree is so deep that the stacks would not fit next to the path slots.
     const size_t limit = 226 * 1024;                      // 227 KB per CTA minus the static shared memory (mbarrier) and slack
-    const size_t max_entries = (limit - 1024 - wavefront_state_bytes<BLOCK, NP>()) / (sizeof(int32_t) * BLOCK);
+    const size_t state = CONN ? wavefront_state_bytes_connect<BLOCK, NP>() : wavefront_state_bytes<BLOCK, NP>();
+    const size_t max_entries = (limit - 1024 - state) / (sizeof(int32_t) * BLOCK);
     P.stack_depth = (uint32_t)std::min<size_t>(std::min<uint32_t>(kStackDepth, bvh_depth + 2), max_entries);
     if (P.stack_depth < bvh_depth) return cudaErrorInvalidConfiguration;
-    const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + wavefront_state_bytes<BLOCK, NP>();
+    const size_t fixed = sizeof(int32_t) * P.stack_depth * BLOCK + state;
     bool sh = false;
     plan_smem<float, false>(P, BLOCK, &sh, std::min<size_t>(kSmemSceneBudget, (limit - fixed) / 64 * 64));
     size_t scene = P.smem_nodes + (P.smem_spheres ? 2 * (size_t)P.smem_spheres + ((size_t)P.scene.n_spheres * 4 + 15) / 16 * 16 : 0) + P.smem_lights;
     size_t smem = fixed + scene;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
-    e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP>(P, Q, smem, sm_count, s, info)
-           : launch_render_wavefront_sh<COUNT, false, BLOCK, NP>(P, Q, smem, sm_count, s, info);
+    e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info)
+           : launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     return pool_finalize(P, Q, s);
+}
+// scenes with a LARGE light BVH run the CONNECT variant (for short walks the stage costs more than it saves: C5, 399 lights, 29.8 ms
+// with it against 21.3 without): 9 more bytes of state per path slot (suspended light walk), hence 84 slots per warp
+constexpr int kWfSlotsPerWarpConnect = 84;
+inline bool connect_stage_allowed() {
+    static const bool ok = [] { const char* e = std::getenv("RTW_NO_CONNECT"); return !(e && std::atoi(e) == 1); }();   // A/B measurements
+    return ok;
 }
 template <bool COUNT>
 cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
@@ -54,13 +62,23 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
     // tuning build only (nvcc -DRTW_WF_SWEEP): launch shape from the environment
     const char* e = std::getenv("RTW_WF_SHAPE");
     int shape = e ? std::atoi(e) : 0;
-    if (shape == 1) return launch_render_wavefront_shape<COUNT, 896, 64>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 2) return launch_render_wavefront_shape<COUNT, 832, 80>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 3) return launch_render_wavefront_shape<COUNT, 640, 112>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 4) return launch_render_wavefront_shape<COUNT, 704, 96>(P, Q, bvh_depth, sm_count, s, info);
-    if (shape == 5) return launch_render_wavefront_shape<COUNT, 768, 88>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 1) return launch_render_wavefront_shape<COUNT, 896, 64, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 2) return launch_render_wavefront_shape<COUNT, 832, 80, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 3) return launch_render_wavefront_shape<COUNT, 640, 112, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 4) return launch_render_wavefront_shape<COUNT, 704, 96, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 5) return launch_render_wavefront_shape<COUNT, 768, 88, false>(P, Q, bvh_depth, sm_count, s, info);
 #endif
-    return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp>(P, Q, bvh_depth, sm_count, s, info);
+    if (P.scene.n_light_nodes > 0 && P.scene.connect_stage && connect_stage_allowed()) {
+#ifdef RTW_CONN_SWEEP
+        const char* e = std::getenv("RTW_CONN_SHAPE");
+        int shape = e ? std::atoi(e) : 0;
+        if (shape == 1) return launch_render_wavefront_shape<COUNT, 512, 132, true>(P, Q, bvh_depth, sm_count, s, info);
+        if (shape == 2) return launch_render_wavefront_shape<COUNT, 640, 104, true>(P, Q, bvh_depth, sm_count, s, info);
+        if (shape == 3) return launch_render_wavefront_shape<COUNT, 384, 180, true>(P, Q, bvh_depth, sm_count, s, info);
+#endif
+        return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarpConnect, true>(P, Q, bvh_depth, sm_count, s, info);
+    }
+    return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp, false>(P, Q, bvh_depth, sm_count, s, info);
 }
 // general scenes: the same warp-private wavefront and launch shape, scene tables in global memory.  Swept on cornell_box while the kernel
 // was bound by instruction fetch: 512x96 460 ms, 512x128 450, 576x96 440, 640x96 408, 704x96 386, 768x96 364; again after its code
@@ -123,6 +141,12 @@ uint32_t wavefront_max_bvh_depth() {
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_wavefront_impl<true>(P, Q, bvh_depth, sm_count, s, info)
                  : launch_render_wavefront_impl<false>(P, Q, bvh_depth, sm_count, s, info);
+}
+// samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units
+// (2^28 radiance units) in total, whichever way they are split over lanes, launches and ranks
+float pool_sample_cap(uint32_t spp_total) {
+    const float cap = 268435456.f / (float)(spp_total ? spp_total : 1u);       // 2^28 / spp
+    return cap < kFixedMax ? cap : kFixedMax;
 }
 // chunk = G pixel slots x spp paths; aim for >= 512 paths per queue transaction
 uint32_t pool_pixels_per_chunk(uint32_t spp) {

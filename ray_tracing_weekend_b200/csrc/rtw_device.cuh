@@ -255,6 +255,20 @@ constexpr int32_t kEmptyLeaf = (int32_t)0x80000000;   // leaf with no spheres
 constexpr int32_t kStop = (int32_t)0x80000001;        // bottom-of-stack code: traversal finished
 RTW_HD int32_t encode_leaf(uint32_t first, uint32_t count) { return count == 0 ? kEmptyLeaf : ~(int32_t)((first << 4) | (count - 1)); }
 
+// Node of the BVH over the LIGHTS (fast path, long light lists), laid out for a STACKLESS walk: nodes in depth-first order;
+// `skip` is the node that follows this node's subtree (-1: the walk is over).  `leaf` says what the record holds:
+//   kLNodeInner: a box (centre c, half-extent hx hy hz); if the ray crosses it the walk goes on with the next node (its first child)
+//   kLNodeLight: ONE light sphere itself (centre c, hx = r^2): the leaf test needs no second, dependent load (ncu, first version
+//                with 4-light leaf ranges: 39 % of the samples waiting for the lights' loads at 1.5 active lanes)
+//   >= 0:        a box around the lights [leaf >> 4, +(leaf & 15) + 1) of the light list (kept for trees the builder cuts short)
+//   kLNodeEmpty: nothing
+// lights.pdf_value sums over ALL lights the ray crosses (hittable_list.rs:408-412), so the walk needs no ordering and no range
+// shrinking — its whole state is one index plus the running sum, which is what lets the wavefront's CONNECT stage keep two walks
+// per lane in flight and suspend / resume them.
+struct __align__(16) LNode { float c[3], hx, hy, hz; int32_t skip, leaf; };
+constexpr int32_t kLNodeInner = -1, kLNodeEmpty = -2, kLNodeLight = -3;
+static_assert(sizeof(LNode) == 32, "two 16-byte loads per node");
+
 template <class T> struct PlaneT { V3<T> point, normal; uint32_t info; uint32_t pad; T albedo[3]; T param; };
 
 // Stride of a node in its SHARED-memory copy (all-shared scenes, SceneViewSh).  The four LDS.128 of a node visit read 16-byte
@@ -273,8 +287,9 @@ template <class T> struct SceneView {
     const uint32_t* sphere_info;   // sorted: prim_id << 2 | kind
     const PlaneT<T>* planes;
     const Vec4T<T>* lights;        // (cx, cy, cz, r) in the lights list's insertion order (leaf order when light_nodes is set)
-    const Node<T>* light_nodes;    // optional BVH over the lights (fast path, many lights); global memory
+    const LNode* light_nodes;      // optional stackless BVH over the lights (fast path, many lights); global memory
     int32_t n_nodes, n_top, n_spheres, n_planes, n_lights, n_light_nodes;
+    int32_t connect_stage;         // the light tree is large: the wavefront renderer walks it in a stage of its own (CONNECT)
 };
 
 // Tag type: every section of the scene (nodes, spheres, materials, lights) sits in SHARED memory, so the

@@ -564,7 +564,7 @@ RTW_D uint32_t g_shade(const SceneViewG<T>& sc, const Ray<T>& r, const Hit<T>& h
     if (kind == METAL || kind == DIELECTRIC) {
         // same code as the sphere-only scenes: shade() never touches the scene for these two kinds
         SceneView<T> none{};
-        return shade<T, EXACT, COUNT, SceneView<T>, true>(none, r, h, rng, next, weight, tl, nullptr, 0);
+        return shade<T, EXACT, COUNT, SceneView<T>, true>(none, r, h, rng, next, weight, tl);
     }
     if (COUNT) tl.absorbed++;                                      // DiffuseLight, Invisible: Material::scatter default None
     return V_ABSORB;

@@ -50,18 +50,17 @@ RTW_D bool box_hit_exact(const double* mn, const double* mx, const Ray<double>& 
 // [m - e, m + e]: three FMAs and NO per-axis min/max (ncu: the ALU pipe that executes FMNMX was the busiest
 // pipe at 62 %, the FMA pipe at 34 %); entry / exit are one 3-input max / min each (FMNMX3).
 // i = 1/d, oi = o/d, a = |1/d|.  NaNs (0 * inf) drop out of min/max: the axis becomes unconstrained — conservative.
-struct RayAux { float ix, iy, iz, ox, oy, oz, ax, ay, az; };
+struct RayAux { float ix, iy, iz, ox, oy, oz; };         // |1/d| is not kept: fabsf folds into the FMA's operand modifier
 RTW_D float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 RTW_D float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 RTW_D void ray_aux(const Ray<float>& r, RayAux& a) {
     a.ix = frcp(r.d.x); a.iy = frcp(r.d.y); a.iz = frcp(r.d.z);
     a.ox = r.o.x * a.ix; a.oy = r.o.y * a.iy; a.oz = r.o.z * a.iz;
-    a.ax = fabsf(a.ix); a.ay = fabsf(a.iy); a.az = fabsf(a.iz);
 }
 RTW_D bool box_hit_fast(const float* c, const float* h, const RayAux& a, float tmin, float tmax, float* tnear) {
     float mx = fmaf(c[0], a.ix, -a.ox), my = fmaf(c[1], a.iy, -a.oy), mz = fmaf(c[2], a.iz, -a.oz);
-    float tn = fmax3(fmaf(-h[0], a.ax, mx), fmaf(-h[1], a.ay, my), fmaf(-h[2], a.az, mz));
-    float tf = fmin3(fmaf(h[0], a.ax, mx), fmaf(h[1], a.ay, my), fmaf(h[2], a.az, mz));
+    float tn = fmax3(fmaf(-h[0], fabsf(a.ix), mx), fmaf(-h[1], fabsf(a.iy), my), fmaf(-h[2], fabsf(a.iz), mz));
+    float tf = fmin3(fmaf(h[0], fabsf(a.ix), mx), fmaf(h[1], fabsf(a.iy), my), fmaf(h[2], fabsf(a.iz), mz));
     tn = fmaxf(tn, tmin);
     tf = fminf(tf, tmax);
     *tnear = tn;
@@ -172,6 +171,15 @@ RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* 
     stack[0] = kStop;
     int sp = 1;
     int32_t cur = 0;        // root inner node
+    if constexpr (!EXACT) {
+        // A ray with a non-finite origin or direction (NaN-poisoned paths keep bouncing) can hit no sphere:
+        // the discriminant of sphere_root_fast is NaN or -inf for every sphere.  But its slab tests cull nothing either (NaNs drop
+        // out of min / max), so it would visit EVERY node and sphere of the tree — 1.8 M tests per such ray on the 1 M-sphere scene,
+        // up to 50 times per path, on a single lane.  Same result without the walk:
+        const float probe = (r.o.x + r.o.y + r.o.z) + (r.d.x + r.d.y + r.d.z);
+        if (!(fabsf(probe) <= 3.0e38f) && !(fabsf(r.o.x) <= 3.0e38f && fabsf(r.o.y) <= 3.0e38f && fabsf(r.o.z) <= 3.0e38f &&
+                                             fabsf(r.d.x) <= 3.0e38f && fabsf(r.d.y) <= 3.0e38f && fabsf(r.d.z) <= 3.0e38f)) cur = kStop;
+    }
     for (;;) {
         while (cur >= 0) {
             Node<T> nd;
@@ -267,8 +275,82 @@ template <class T, bool EXACT> RTW_D V3<T> refract(V3<T> s, V3<T> o, T eta) {   
 // Sphere::pdf_value (sphere.rs:101-111) summed over the lights list (hittable_list.rs:408-412).
 // Fast path: Sphere::hit(ray, 0..=inf) succeeds iff disc > 0 and the larger root is >= 0, i.e. iff
 // disc > 0 && (hb <= 0 || c <= 0) — no square root or division until a light is actually hit.
+// One light's term of the sum, fast path: unit direction nd; towards = nd.(c - o), perpendicular residual l = (c - o) - towards nd,
+// hit iff |l|^2 < r^2 and (towards >= 0 or the origin is inside): 13 flop, no division or root on a miss.  s.w = r^2.
+template <bool COUNT>
+RTW_D void light_term(const Vec4T<float>& s, V3<float> origin, V3<float> nd, float& acc, Tally& tl) {
+    using Mt = M<float, false>;
+    if (COUNT) tl.light_tests++;
+    float cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
+    float towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
+    float lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
+    float r2 = s.w;                                        // FP32 light records carry r^2 (upload_scene)
+    if (fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2))) > 0.f) {
+        float distance_squared = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
+        if (towards >= 0.f || distance_squared <= r2) {
+            float cos_theta_max = Mt::sqrt_(1.f - r2 * frcp(distance_squared));
+            float solid_angle = 2.f * Mt::PI * (1.f - cos_theta_max);
+            acc += frcp(solid_angle);
+        }
+    }
+}
+
+// Many lights (the reference's O(#lights) sum made sub-linear): stackless walk of the light BVH (LNode), evaluating only the
+// lights whose box the ray (t in [0, inf)) crosses.  A light the ray misses contributes exactly 0 to the sum, so only the summation
+// order changes — and that order (depth-first) is the same whoever runs the walk, in one go (megakernel, batch calls) or in
+// pieces on different lanes (the wavefront's CONNECT stage), which keeps the renderers bit-identical.
+// Runs at most max_steps node visits from `cur`; returns the node to resume at (-1: done).
+// One node of the walk, already loaded (a, b = the record's two 16-byte halves): returns the next node.
+template <bool COUNT, class SC>
+RTW_D int32_t light_walk_step(const SC& sc, float4 a, float4 b, V3<float> origin, V3<float> nd, const RayAux& aux, int32_t cur, float& acc, Tally& tl) {
+    const int32_t skip = __float_as_int(b.z), leaf = __float_as_int(b.w);
+    if (leaf == kLNodeLight) {
+        light_term<COUNT>(Vec4T<float>{a.x, a.y, a.z, a.w}, origin, nd, acc, tl);
+        return skip;
+    }
+    const float c[3] = {a.x, a.y, a.z}, h[3] = {a.w, b.x, b.y};
+    float tn;
+    const bool hit = box_hit_fast(c, h, aux, 0.f, M<float, false>::inf(), &tn);
+    if (hit && leaf >= 0) {
+        const uint32_t first = (uint32_t)leaf >> 4, count = ((uint32_t)leaf & 15u) + 1u;
+        for (uint32_t i = first; i < first + count; ++i) light_term<COUNT>(load_light(sc, (int32_t)i), origin, nd, acc, tl);
+    }
+    return (hit && leaf == kLNodeInner) ? cur + 1 : skip;
+}
+// Runs at most max_steps node visits from `cur`; returns the node to resume at (-1: done).
+template <bool COUNT, class SC>
+RTW_D int32_t light_walk(const SC& sc, V3<float> origin, V3<float> nd, const RayAux& aux, int32_t cur, float& acc, uint32_t max_steps, Tally& tl) {
+    for (uint32_t step = 0; cur >= 0 && step < max_steps; ++step) {
+        const float4* p = reinterpret_cast<const float4*>(sc.light_nodes + cur);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        cur = light_walk_step<COUNT>(sc, a, b, origin, nd, aux, cur, acc, tl);
+    }
+    return cur;
+}
+// Two walks in step: both nodes are requested before either is used, so a lane keeps two L2 round trips in flight (the walk is bound
+// by the latency of these dependent loads: ncu, long_scoreboard 98 % on the first use of the node)
+template <bool COUNT, class SC>
+RTW_D void light_walk_pair(const SC& sc, V3<float> o0, V3<float> n0, const RayAux& x0, int32_t& c0, float& acc0,
+                           V3<float> o1, V3<float> n1, const RayAux& x1, int32_t& c1, float& acc1, uint32_t max_steps, Tally& tl) {
+    for (uint32_t step = 0; (c0 >= 0 || c1 >= 0) && step < max_steps; ++step) {
+        const float4* p0 = reinterpret_cast<const float4*>(sc.light_nodes + (c0 >= 0 ? c0 : 0));
+        const float4* p1 = reinterpret_cast<const float4*>(sc.light_nodes + (c1 >= 0 ? c1 : 0));
+        const float4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
+        if (c0 >= 0) c0 = light_walk_step<COUNT>(sc, a0, b0, o0, n0, x0, c0, acc0, tl);
+        if (c1 >= 0) c1 = light_walk_step<COUNT>(sc, a1, b1, o1, n1, x1, c1, acc1, tl);
+    }
+}
+
+// Where a light walk starts: at the root, or nowhere (-1) for a non-finite origin / direction — every light_term of such a ray
+// is 0 (its discriminant is NaN), but its box tests cull nothing, so the walk would visit all the lights to add up zeros.
+RTW_D int32_t light_walk_start(V3<float> origin, V3<float> nd) {
+    const bool finite = fabsf(origin.x) <= 3.0e38f && fabsf(origin.y) <= 3.0e38f && fabsf(origin.z) <= 3.0e38f &&
+                        fabsf(nd.x) <= 3.0e38f && fabsf(nd.y) <= 3.0e38f && fabsf(nd.z) <= 3.0e38f;
+    return finite ? 0 : -1;
+}
+
 template <class T, bool EXACT, bool COUNT, class SC>
-RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl, int32_t* stack, int stride) {
+RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
     using Mt = M<T, EXACT>;
     T acc = T(0);
     if constexpr (EXACT) {
@@ -290,57 +372,13 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl, int32
         }
         return acc / (T)sc.n_lights;
     } else {
-        // unit direction once; per light: towards = nd.(c - o), perpendicular residual l = (c - o) - towards nd,
-        // hit iff |l|^2 < r^2 and (towards >= 0 or the origin is inside): 13 flop, no division or root on a miss
         V3<T> nd = Mt::normalize(dir);
-        auto term = [&](const Vec4T<T>& s) {
-            if (COUNT) tl.light_tests++;
-            T cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
-            T towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
-            T lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
-            T r2 = s.w;                                        // FP32 light records carry r^2 (upload_scene)
-            if (fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, r2))) > T(0)) {
-                T distance_squared = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
-                if (towards >= T(0) || distance_squared <= r2) {
-                    T cos_theta_max = Mt::sqrt_(T(1) - r2 * frcp(distance_squared));
-                    T solid_angle = T(2) * Mt::PI * (T(1) - cos_theta_max);
-                    acc += frcp(solid_angle);
-                }
-            }
-        };
         if (sc.n_light_nodes > 0) {
-            // many lights (the reference's O(#lights) sum, hittable_list.rs:408-412, made sub-linear): walk a BVH over
-            // the light spheres and evaluate only the lights whose box the ray (t in [0, inf)) crosses.  A light
-            // the ray misses contributes exactly 0 to the sum, so only the summation order changes.
             RayAux aux;
             ray_aux(Ray<float>{origin, nd}, aux);
-            stack[0] = kStop;
-            int sp = 1;
-            int32_t cur = 0;
-            for (;;) {
-                while (cur >= 0) {
-                    const float4* p = reinterpret_cast<const float4*>(sc.light_nodes + cur);
-                    Node<float> ln;
-                    unpack_node(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), ln);
-                    float t0, t1;
-                    bool hl = box_hit_fast(ln.la, ln.lb, aux, 0.f, Mt::inf(), &t0);
-                    bool hr = box_hit_fast(ln.ra, ln.rb, aux, 0.f, Mt::inf(), &t1);
-                    if (hl && hr) { stack[sp * stride] = ln.right; sp++; cur = ln.left; }
-                    else if (hl) cur = ln.left;
-                    else if (hr) cur = ln.right;
-                    else { sp--; cur = stack[sp * stride]; }
-                }
-                if (cur == kStop) break;
-                if (cur != kEmptyLeaf) {
-                    uint32_t enc = (uint32_t)~cur;
-                    uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
-                    for (uint32_t i = first; i < first + count; ++i) term(load_light(sc, (int32_t)i));
-                }
-                sp--;
-                cur = stack[sp * stride];
-            }
+            light_walk<COUNT>(sc, origin, nd, aux, light_walk_start(origin, nd), acc, 0xffffffffu, tl);
         } else {
-            for (int i = 0; i < sc.n_lights; ++i) term(load_light(sc, i));
+            for (int i = 0; i < sc.n_lights; ++i) light_term<COUNT>(load_light(sc, i), origin, nd, acc, tl);
         }
         return acc * frcp((T)sc.n_lights);
     }
@@ -366,41 +404,59 @@ RTW_D V3<T> sphere_random(const Vec4T<T>& s, V3<T> origin, Stream<EXACT>& rng) {
 
 enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE = 3 };
 
+// The Lambertian branch of Material::scatter + ray_colour_tail_call in two halves, so that the wavefront can run the light term
+// between them as a stage of its own (CONNECT): lambertian_sample draws the direction from the mixture pdf and evaluates the two
+// cosine terms; lambertian_weight turns them and lights.pdf_value(dir) into the factor for `mult`.
+template <class T, bool EXACT, class SC>
+RTW_D V3<T> lambertian_sample(const SC& sc, const Hit<T>& h, Stream<EXACT>& rng, T* cos_v, T* scattering_pdf) {
+    using Mt = M<T, EXACT>;
+    Onb<T, EXACT> uvw(h.normal);                            // CosinePdf::new, pdf.rs:39-43
+    V3<T> dir;
+    if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
+        uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
+        dir = sphere_random<T, EXACT, !EXACT>(load_light(sc, (int32_t)idx), h.p, rng);
+    } else {                                                // CosineWeightedHemisphere, utils.rs:146-161
+        T r1 = standard(rng);
+        T r2 = standard(rng);
+        T sn, cs;
+        Mt::sincos_2pi(r1, &sn, &cs);
+        T x = cs * Mt::sqrt_(r2);
+        T y = sn * Mt::sqrt_(r2);
+        T z = Mt::sqrt_(T(1) - r2);
+        dir = uvw.transform(mk<T>(x, y, z));
+    }
+    V3<T> nd = Mt::normalize(dir);
+    *scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));          // Lambertian::scattering_pdf, material.rs:372-375
+    // CosinePdf::value, pdf.rs:46-49: the same cosine against uvw.w = normalize(h.normal).  The exact path evaluates it as the
+    // reference does; the fast path uses the one value for both (h.normal is unit to FP32 precision), which also halves what a
+    // suspended path has to carry through the CONNECT stage.
+    if constexpr (EXACT) *cos_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));
+    else *cos_v = *scattering_pdf;
+    return dir;
+}
+template <class T, bool EXACT>
+RTW_D V3<T> lambertian_weight(V3<T> albedo, T light_v, T cos_v, T scattering_pdf) {
+    T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
+    if constexpr (EXACT) return (albedo * scattering_pdf) / pdf_value;       // camera.rs:518
+    else return albedo * (scattering_pdf * frcp(pdf_value));
+}
+
 // Material::scatter (+ the Scatter branch of ray_colour_tail_call, camera.rs:484-521).
 // Returns the vertex kind; on V_SPECULAR / V_DIFFUSE writes the next ray and the factor for `mult`.
 // SPECULAR_ONLY: the caller has already dealt with Lambertian hits (g_shade borrows the Metal / Dielectric code from here).
 template <class T, bool EXACT, bool COUNT, class SC, bool SPECULAR_ONLY = false>
-RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl,
-                     int32_t* stack, int stride) {
+RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXACT>& rng, Ray<T>* next, V3<T>* weight, Tally& tl) {
     using Mt = M<T, EXACT>;
     if constexpr (is_general<SC>::value) return g_shade<T, EXACT, COUNT>(sc, r, h, rng, next, weight, tl);
     else {
     uint32_t kind = h.info & 3u;
     if (!SPECULAR_ONLY && kind == LAMBERTIAN) {                 // material.rs:357-376
         if (COUNT) tl.lambertian++;
-        Onb<T, EXACT> uvw(h.normal);                            // CosinePdf::new, pdf.rs:39-43
-        V3<T> dir;
-        if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
-            uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
-            dir = sphere_random<T, EXACT, !EXACT>(load_light(sc, (int32_t)idx), h.p, rng);
-        } else {                                                // CosineWeightedHemisphere, utils.rs:146-161
-            T r1 = standard(rng);
-            T r2 = standard(rng);
-            T sn, cs;
-            Mt::sincos_2pi(r1, &sn, &cs);
-            T x = cs * Mt::sqrt_(r2);
-            T y = sn * Mt::sqrt_(r2);
-            T z = Mt::sqrt_(T(1) - r2);
-            dir = uvw.transform(mk<T>(x, y, z));
-        }
-        T light_v = lights_pdf_value<T, EXACT, COUNT, SC>(sc, h.p, dir, tl, stack, stride);
-        V3<T> nd = Mt::normalize(dir);
-        T cos_v = Mt::max_(Mt::div_pi(dot(nd, uvw.w)), T(0));   // CosinePdf::value, pdf.rs:46-49
-        T pdf_value = light_v * T(0.5) + cos_v * T(0.5);        // MixturePdf::value, pdf.rs:90-92
-        T scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));  // material.rs:372-375
+        T cos_v, scattering_pdf;
+        V3<T> dir = lambertian_sample<T, EXACT>(sc, h, rng, &cos_v, &scattering_pdf);
+        T light_v = lights_pdf_value<T, EXACT, COUNT, SC>(sc, h.p, dir, tl);
         *next = Ray<T>{h.p, dir};
-        if constexpr (EXACT) *weight = (h.albedo * scattering_pdf) / pdf_value;      // camera.rs:518
-        else *weight = h.albedo * (scattering_pdf * frcp(pdf_value));
+        *weight = lambertian_weight<T, EXACT>(h.albedo, light_v, cos_v, scattering_pdf);
         return V_DIFFUSE;
     }
     if (kind == METAL) {                                        // material.rs:407-421
@@ -490,7 +546,7 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
     Stream<EXACT> rng(seed, pixel, sample, cam.max_depth - ps.depth + 1u, is_general<SC>::value && !EXACT);
     Ray<T> next;
     V3<T> w;
-    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl, stack, stride);
+    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, ps.r, h, rng, &next, &w, tl);
     if (kind == V_ABSORB) { *value = ps.mult * emitted + ps.res; return true; }       // camera.rs:484-486
     if (kind == V_DIFFUSE) ps.res = ps.res + ps.mult * emitted;                       // camera.rs:519
     ps.mult = ps.mult * w;
@@ -672,13 +728,14 @@ __global__ void __launch_bounds__(BLOCK) render_mega_kernel(RenderParams<T, SCEN
 // NaN / overflow samples set per-pixel poison bits (a NaN sample poisons the pixel like in the
 // reference, where the f64 sum becomes NaN and `as u8` maps it to 0).
 constexpr float kFixedScale = 4294967296.f;            // 2^32
-constexpr float kFixedMax = 1073741824.f;              // samples >= 2^30 saturate the pixel anyway
+constexpr float kFixedMax = 1073741824.f;              // 2^30: upper bound of PoolParams::sample_cap
 
 struct PoolParams {
     unsigned long long* accum;      // [n_local_tiles * 256][3]
     uint32_t* poison;               // [n_local_tiles * 256]: poison words (poison_nan / poison_inf below)
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
+    float sample_cap;               // samples of this radiance or more set the overflow flag instead of being added (pool_sample_cap)
 };
 
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
@@ -687,26 +744,19 @@ RTW_HD uint32_t poison_nan(uint32_t channel) { return 1u << (4u * channel); }
 RTW_HD uint32_t poison_inf(uint32_t channel) { return 1u << (12u + 4u * channel); }
 RTW_HD bool poison_has_nan(uint32_t word, uint32_t channel) { return (word >> (4u * channel)) & 15u; }
 RTW_HD bool poison_has_inf(uint32_t word, uint32_t channel) { return (word >> (12u + 4u * channel)) & 15u; }
-// A pixel whose fixed-point sum reaches 2^64 (2^32 in radiance units: a very bright emitter at a high sample count) must not wrap
-// silently: the wrap is detected where it happens — in the lane-private partial sum (pool_add) or in the 64-bit reduction
-// (pool_flush: the returned old value plus the addend is smaller than the old value) — and sets the channel's overflow flag, so the
-// pixel resolves to +inf -> 255 like the f64 sum would, not to a dark remainder.  The limit is 2^60, not 2^64: the accumulators of up
-// to 15 ranks are added by one integer reduce (sample partition), which cannot report a carry out of bit 63.
-RTW_HD bool pool_overflowed(unsigned long long old, unsigned long long add) { return ((old + add) >> 60) != 0ull || old + add < old; }
+// No silent wrap of the 64-bit accumulators, by construction instead of by checking every reduction: a pixel receives at most
+// `spp` samples per frame over ALL ranks, and a sample of `sample_cap` = 2^28 / spp radiance units or more (PoolParams, at most
+// 2^30) sets the channel's overflow flag instead of being added — so every sum, per lane, per pixel, per rank and after the ranks'
+// accumulators have been added by an integer reduce, stays below 2^60.  A flagged pixel resolves to +inf -> 255, which is what the
+// f64 sum of such samples resolves to as well unless spp is so large (> 2^18) that the cap drops below ~1000; the reductions stay
+// fire-and-forget (RED, no returned value to wait for).
 RTW_D void pool_flush(const PoolParams& Q, uint32_t q, unsigned long long a0, unsigned long long a1, unsigned long long a2) {
-    uint32_t wrapped = 0;
-    if (a0) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 0, a0); if (pool_overflowed(old, a0)) wrapped |= poison_inf(0); }
-    if (a1) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 1, a1); if (pool_overflowed(old, a1)) wrapped |= poison_inf(1); }
-    if (a2) { unsigned long long old = atomicAdd(Q.accum + 3 * (size_t)q + 2, a2); if (pool_overflowed(old, a2)) wrapped |= poison_inf(2); }
-    if (wrapped) atomicOr(Q.poison + q, wrapped);
+    if (a0) atomicAdd(Q.accum + 3 * (size_t)q + 0, a0);
+    if (a1) atomicAdd(Q.accum + 3 * (size_t)q + 1, a1);
+    if (a2) atomicAdd(Q.accum + 3 * (size_t)q + 2, a2);
 }
-RTW_D void pool_add(unsigned long long& acc, unsigned long long v, uint32_t channel, uint32_t& bad) {
-    if (pool_overflowed(acc, v)) bad |= poison_inf(channel);
-    acc += v;
-}
-
-RTW_D unsigned long long pool_fixed(float v, uint32_t channel, uint32_t& bad) {
-    if (!(v < kFixedMax)) {                                    // NaN, +inf or absurdly large
+RTW_D unsigned long long pool_fixed(const PoolParams& Q, float v, uint32_t channel, uint32_t& bad) {
+    if (!(v < Q.sample_cap)) {                                 // NaN, +inf or too large to be summed safely
         bad |= (v != v) ? poison_nan(channel) : poison_inf(channel);
         return 0ull;
     }
@@ -808,9 +858,9 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
                     }
                     acc_q = q; a0 = a1 = a2 = 0ull; bad = 0;
                 }
-                pool_add(a0, pool_fixed(value.x, 0, bad), 0, bad);
-                pool_add(a1, pool_fixed(value.y, 1, bad), 1, bad);
-                pool_add(a2, pool_fixed(value.z, 2, bad), 2, bad);
+                a0 += pool_fixed(Q, value.x, 0, bad);
+                a1 += pool_fixed(Q, value.y, 1, bad);
+                a2 += pool_fixed(Q, value.z, 2, bad);
             }
         }
     }
@@ -884,7 +934,7 @@ __global__ void __launch_bounds__(BLOCK) scatter_batch_kernel(BatchParams<T, SCE
     Stream<EXACT> rng(P.seed, P.a[idx], P.b[idx], P.c[idx]);
     Ray<T> next{zero, zero};
     V3<T> w = zero;
-    uint32_t kind = shade<T, EXACT, false, SCENE>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
+    uint32_t kind = shade<T, EXACT, false, SCENE>(P.scene, r, h, rng, &next, &w, tl);
     P.prim[idx] = (int32_t)(h.info >> 2); P.t[idx] = (double)h.t; P.kind[idx] = kind;
     store3(P.p, idx, h.p); store3(P.normal, idx, h.normal);
     store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
@@ -903,7 +953,6 @@ template <class T> struct ShadeParams {
 };
 template <class T, bool EXACT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) shade_batch_kernel(ShadeParams<T> P) {
-    __shared__ int32_t stack_s[kStackDepth * BLOCK];
     size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (idx >= P.n) return;
     Hit<T> h;
@@ -918,7 +967,7 @@ __global__ void __launch_bounds__(BLOCK) shade_batch_kernel(ShadeParams<T> P) {
     Ray<T> next{zero, zero};
     V3<T> w = zero;
     Tally tl;
-    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl, stack_s + threadIdx.x, BLOCK);
+    uint32_t kind = shade<T, EXACT, false, SceneView<T>>(P.scene, r, h, rng, &next, &w, tl);
     P.kind[idx] = kind;
     store3(P.dir, idx, kind >= V_SPECULAR ? next.d : zero);
     store3(P.weight, idx, kind >= V_SPECULAR ? w : zero);

@@ -26,7 +26,7 @@
 
 namespace rtw {
 
-enum WfStage : int { WF_FREE = 0, WF_EXT = 1, WF_LAMB = 2, WF_METAL = 3, WF_DIEL = 4, WF_STAGES = 5 };
+enum WfStage : int { WF_FREE = 0, WF_EXT = 1, WF_LAMB = 2, WF_METAL = 3, WF_DIEL = 4, WF_STAGES = 5, WF_CONN = 5 };
 
 template <int NPW> struct WfWarp {
     float ox[NPW], oy[NPW], oz[NPW], dx[NPW], dy[NPW], dz[NPW], mx[NPW], my[NPW], mz[NPW], ht[NPW];
@@ -37,6 +37,9 @@ template <int NPW> struct WfWarp {
 
 // general scenes (rtw_general.cuh) also remember which quad of the winning entry was hit
 template <int NPW> struct WfWarpG : WfWarp<NPW> { uint32_t hs[NPW]; };
+// scenes with a light BVH (CONNECT stage): the suspended light walk of a path — the node to resume at and the running sum of
+// lights.pdf_value — plus the stage's own list; S.ht carries the cosine term of the sampled direction through the stage
+template <int NPW> struct WfWarpC : WfWarp<NPW> { int32_t lcur[NPW]; float lacc[NPW]; uint8_t conn[NPW]; };
 
 // warp-synchronous push: every lane of the warp calls it; lanes with pred append `slot`
 RTW_D void wf_push(uint8_t* list, uint32_t& count, bool pred, uint32_t slot, uint32_t lt_mask) {
@@ -67,18 +70,56 @@ RTW_D void wf_finish(const PoolParams& Q, WfAcc& A, uint32_t q, V3<float> value,
         wf_acc_flush(Q, A);
         A.q = q; A.a0 = A.a1 = A.a2 = 0ull; A.bad = 0;
     }
-    pool_add(A.a0, pool_fixed(value.x, 0, A.bad), 0, A.bad);
-    pool_add(A.a1, pool_fixed(value.y, 1, A.bad), 1, A.bad);
-    pool_add(A.a2, pool_fixed(value.z, 2, A.bad), 2, A.bad);
+    A.a0 += pool_fixed(Q, value.x, 0, A.bad);
+    A.a1 += pool_fixed(Q, value.y, 1, A.bad);
+    A.a2 += pool_fixed(Q, value.z, 2, A.bad);
 }
 
-template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>>
+// The tail of one vertex of ray_colour_tail_call (camera.rs:484-521) for a path whose scatter has been evaluated: absorbed ->
+// the path ends with mult * emitted + res; otherwise mult *= weight, depth -= 1, and the path either runs out of depth (ends with
+// res) or goes back to EXTEND with its new ray.  Shared by SHADE and by CONNECT (which finishes Lambertian vertices).
+// Returns 0 = continues (state stored, push to EXTEND), 1 = ended (*fin_value holds the sample).
+template <bool COUNT, class WS>
+RTW_D int wf_advance(WS& S, uint32_t slot, uint32_t kind, const Ray<float>& next, V3<float> w, V3<float> emitted, V3<float> mult, uint32_t dep,
+                     V3<float>* fin_value, Tally& tl) {
+    uint32_t depth = dep & 0xffffu;
+    if (kind == V_ABSORB) {                                     // camera.rs:484-486
+        *fin_value = mult * emitted + wf_res(dep);
+        return 1;
+    }
+    if (kind == V_DIFFUSE) {                                    // res + mult * emitted (camera.rs:519): 0 or NaN per channel
+        V3<float> rs = wf_res(dep) + mult * emitted;
+        dep |= (rs.x != rs.x ? 1u << 16 : 0u) | (rs.y != rs.y ? 1u << 17 : 0u) | (rs.z != rs.z ? 1u << 18 : 0u);
+    }
+    mult = mult * w;
+    depth -= 1;
+    dep = (dep & 0xffff0000u) | depth;
+    if (depth == 0) {                                           // camera.rs:470-472
+        if (COUNT) tl.depth_out++;
+        *fin_value = mk<float>(0, 0, 0) + wf_res(dep);
+        return 1;
+    }
+    S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
+    S.dx[slot] = next.d.x; S.dy[slot] = next.d.y; S.dz[slot] = next.d.z;
+    S.mx[slot] = mult.x; S.my[slot] = mult.y; S.mz[slot] = mult.z;
+    S.dep[slot] = dep;
+    return 0;
+}
+
+// CONNECT tuning: node visits between two finish / refill passes of a batch of light walks
+#ifndef RTW_CONN_QUANTUM
+#define RTW_CONN_QUANTUM 16
+#endif
+constexpr uint32_t kConnQuantum = RTW_CONN_QUANTUM;
+
+template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>, bool CONN = false>
 __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float, SCENE> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
     constexpr bool GEN = is_general<SCENE>::value;        // general scenes: entries of any kind, scene tables in global memory
     static_assert(NPW <= 255 && NPW >= 32, "slot indices are stored in one byte");
     static_assert(!(GEN && SH), "general scenes are read from global memory");
+    static_assert(!(GEN && CONN), "the CONNECT stage serves the sphere path's light BVH");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [stack][scene sections][one WfWarp per warp]
     const uint32_t stack_depth = P.stack_depth;
@@ -95,7 +136,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
         bind_scene(sc, P.sh_node_stride);
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt_mask = (1u << lane) - 1u;
-    using WS = typename std::conditional<GEN, WfWarpG<NPW>, WfWarp<NPW>>::type;
+    using WS = typename std::conditional<GEN, WfWarpG<NPW>, typename std::conditional<CONN, WfWarpC<NPW>, WfWarp<NPW>>::type>::type;
     WS& S = reinterpret_cast<WS*>(cur_p)[warp];
 
     const CameraT<T>& cam = P.cam;
@@ -107,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     WfAcc acc;
 
     // warp-uniform state (registers): list lengths and the cursor into the path stream
-    uint32_t n_free = NPW, n_ext = 0, n_lamb = 0, n_metal = 0, n_diel = 0;
+    uint32_t n_free = NPW, n_ext = 0, n_lamb = 0, n_metal = 0, n_diel = 0, n_conn = 0;
     uint32_t chunk_next = 0, chunk_end = 0, chunk_q0 = 0;
     bool exhausted = (spp == 0 || cam.max_depth == 0);       // max_depth == 0: every path returns 0 (camera.rs:470-472)
     for (uint32_t i = lane; i < NPW; i += 32) S.list[WF_FREE][i] = (uint8_t)i;
@@ -122,6 +163,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
         if (n_lamb > best) { best = n_lamb; stage = WF_LAMB; }
         if (n_metal > best) { best = n_metal; stage = WF_METAL; }
         if (n_diel > best) { best = n_diel; stage = WF_DIEL; }
+        if (CONN && n_conn > best) { best = n_conn; stage = WF_CONN; }
         if (best == 0) break;                                 // nothing in flight and the stream is dry
 
         if (stage == WF_FREE) {
@@ -224,6 +266,89 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             wf_push(S.list[WF_METAL], n_metal, kind == 1u, slot, lt_mask);
             wf_push(S.list[WF_DIEL], n_diel, kind == 2u, slot, lt_mask);
             wf_push(S.list[WF_FREE], n_free, kind == 3u, slot, lt_mask);
+        } else if (CONN && stage == WF_CONN) {
+            // ---- CONNECT: lights.pdf_value(dir) of Lambertian vertices (hittable_list.rs:408-412, pdf.rs:77-101) -----------------
+            // 32 light-BVH walks side by side.  Walk lengths differ by orders of magnitude (a ray inside the slab that holds the
+            // lights crosses hundreds of boxes, most rays a handful): a walk's state is (node, running sum), so when the batch has
+            // thinned out the unfinished walks go back on the list and the next batch starts full again.
+            if constexpr (CONN) {
+            // Persistent batch, two walks per lane (the walk is bound by the latency of its dependent node loads: a second one in
+            // flight hides half of it).  Every kConnQuantum steps the finished walks are completed — weight, mult, next stage — and
+            // their lane slots refilled from the list IN PLACE, so a long walk stays on its lane while short ones come and go.  The
+            // batch only lets go of unfinished walks (state: node index + running sum, back on the list) when the list is empty and
+            // another stage has at least as many paths waiting as walks remain here.
+            bool active[2] = {false, false}; uint32_t slot[2] = {0u, 0u}; int32_t cur[2] = {-1, -1}; float lacc[2] = {0.f, 0.f};
+            V3<T> origin[2] = {mk<T>(0, 0, 0), mk<T>(0, 0, 0)}, nd[2] = {mk<T>(0, 0, 1), mk<T>(0, 0, 1)}; RayAux aux[2];
+            ray_aux(Ray<float>{origin[0], nd[0]}, aux[0]); aux[1] = aux[0];
+            for (;;) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    // ---- finish the walks that have ended ----
+                    const bool done = active[k] && cur[k] < 0;
+                    if (__any_sync(0xffffffffu, done)) {
+                        bool to_ext = false, to_free = false;
+                        const uint32_t sl = slot[k];
+                        if (done) {
+                            const int32_t hp = S.hp[sl];
+                            V3<T> albedo;
+                            if (hp >= 0) { Vec4T<T> m = load_sphere_mat(sc, hp); albedo = mk<T>(m.x, m.y, m.z); }
+                            else { const PlaneT<T>& pl = sc.planes[-2 - hp]; albedo = mk<T>(pl.albedo[0], pl.albedo[1], pl.albedo[2]); }
+                            const T cos_v = S.ht[sl];
+                            const T light_v = lacc[k] * frcp((T)sc.n_lights);
+                            V3<T> w = lambertian_weight<T, EXACT>(albedo, light_v, cos_v, cos_v);
+                            Ray<T> next{origin[k], mk<T>(S.dx[sl], S.dy[sl], S.dz[sl])};
+                            V3<T> fin_value;
+                            if (wf_advance<COUNT>(S, sl, V_DIFFUSE, next, w, mk<T>(0, 0, 0), mk<T>(S.mx[sl], S.my[sl], S.mz[sl]), S.dep[sl], &fin_value, tl)) {
+                                wf_finish(Q, acc, S.q[sl], fin_value, P.flags);
+                                to_free = true;
+                            } else to_ext = true;
+                            active[k] = false;
+                        }
+                        __syncwarp();
+                        wf_push(S.list[WF_EXT], n_ext, to_ext, sl, lt_mask);
+                        wf_push(S.list[WF_FREE], n_free, to_free, sl, lt_mask);
+                    }
+                    // ---- refill idle lane slots from the list ----
+                    const uint32_t idle = __ballot_sync(0xffffffffu, !active[k]);
+                    const uint32_t take = min((uint32_t)__popc(idle), n_conn);
+                    if (take) {
+                        const uint32_t rank = __popc(idle & lt_mask);
+                        n_conn -= take;
+                        if (!active[k] && rank < take) {
+                            const uint32_t sl = S.conn[n_conn + rank];
+                            slot[k] = sl; active[k] = true;
+                            origin[k] = mk<T>(S.ox[sl], S.oy[sl], S.oz[sl]);
+                            nd[k] = M<T, EXACT>::normalize(mk<T>(S.dx[sl], S.dy[sl], S.dz[sl]));
+                            cur[k] = S.lcur[sl]; lacc[k] = S.lacc[sl];
+                            ray_aux(Ray<float>{origin[k], nd[k]}, aux[k]);
+                        }
+                    }
+                }
+                const uint32_t walking = __popc(__ballot_sync(0xffffffffu, cur[0] >= 0)) + __popc(__ballot_sync(0xffffffffu, cur[1] >= 0));
+                if (walking == 0 && !__any_sync(0xffffffffu, active[0] || active[1])) break;
+                if (walking != 0 && n_conn == 0) {
+                    // nothing to refill with: yield if another stage has at least as many paths waiting as walks remain
+                    const uint32_t nf = (exhausted && chunk_next == chunk_end) ? 0u : n_free;
+                    const uint32_t other = max(max(n_ext, nf), max(n_lamb, max(n_metal, n_diel)));
+                    if (other >= walking) {
+                        // finished-but-not-yet-completed walks are completed by the next pass of the loop head; suspend the rest
+                        bool again[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            again[k] = active[k] && cur[k] >= 0;
+                            if (again[k]) { S.lcur[slot[k]] = cur[k]; S.lacc[slot[k]] = lacc[k]; active[k] = false; cur[k] = -1; }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) wf_push(S.conn, n_conn, again[k], slot[k], lt_mask);
+                        if (!__any_sync(0xffffffffu, active[0] || active[1])) break;
+                        continue;                               // complete the walks that ended in the last quantum, then leave
+                    }
+                }
+                if (walking != 0)
+                    light_walk_pair<COUNT>(sc, origin[0], nd[0], aux[0], cur[0], lacc[0], origin[1], nd[1], aux[1], cur[1], lacc[1], kConnQuantum, tl);
+            }
+            }
         } else {
             // ---- SHADE: all lanes run the same material -------------------------------------------------------
             uint32_t cnt = stage == WF_LAMB ? n_lamb : (stage == WF_METAL ? n_metal : n_diel);
@@ -232,7 +357,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             if (stage == WF_LAMB) n_lamb = cnt; else if (stage == WF_METAL) n_metal = cnt; else n_diel = cnt;
             const bool active = lane < n;
             uint32_t slot = active ? S.list[stage][cnt + lane] : 0u;
-            bool to_ext = false, to_free = false;
+            bool to_ext = false, to_free = false, to_conn = false;
             if (active) {
                 Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
                 Hit<T> h;
@@ -241,40 +366,34 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 uint32_t dep = S.dep[slot], depth = dep & 0xffffu;
                 V3<T> mult = mk<T>(S.mx[slot], S.my[slot], S.mz[slot]);
                 Stream<EXACT> rng(P.seed, S.pix[slot], S.smp[slot], cam.max_depth - depth + 1u, is_general<SC>::value && !EXACT);
-                Ray<T> next;
-                V3<T> w;
-                uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl, stack, BLOCK);
-                V3<T> emitted = mk<T>(0, 0, 0);
-                if constexpr (GEN) emitted = g_emitted<T>(h);
-                V3<T> fin_value = mk<T>(0, 0, 0);
-                if (kind == V_ABSORB) {                                     // camera.rs:484-486
-                    fin_value = mult * emitted + wf_res(dep);
-                    if constexpr (!GEN) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
-                    to_free = true;
-                } else {
-                    if (kind == V_DIFFUSE) {                                // res + mult * emitted (camera.rs:519): 0 or NaN per channel
-                        V3<T> rs = wf_res(dep) + mult * emitted;
-                        dep |= (rs.x != rs.x ? 1u << 16 : 0u) | (rs.y != rs.y ? 1u << 17 : 0u) | (rs.z != rs.z ? 1u << 18 : 0u);
-                    }
-                    mult = mult * w;
-                    depth -= 1;
-                    dep = (dep & 0xffff0000u) | depth;
-                    if (depth == 0) {                                       // camera.rs:470-472
-                        if (COUNT) tl.depth_out++;
-                        fin_value = mk<T>(0, 0, 0) + wf_res(dep);
-                        if constexpr (!GEN) wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
-                        to_free = true;
-                    } else {
-                        S.ox[slot] = next.o.x; S.oy[slot] = next.o.y; S.oz[slot] = next.o.z;
-                        S.dx[slot] = next.d.x; S.dy[slot] = next.d.y; S.dz[slot] = next.d.z;
-                        S.mx[slot] = mult.x; S.my[slot] = mult.y; S.mz[slot] = mult.z;
-                        S.dep[slot] = dep;
-                        to_ext = true;
+                bool deferred = false;
+                if constexpr (CONN) {
+                    if (stage == WF_LAMB) {                     // warp-uniform: sample the direction here, the light term runs in CONNECT
+                        if (COUNT) tl.lambertian++;
+                        T cos_v, sp;
+                        V3<T> dir = lambertian_sample<T, EXACT>(sc, h, rng, &cos_v, &sp);
+                        S.ox[slot] = h.p.x; S.oy[slot] = h.p.y; S.oz[slot] = h.p.z;
+                        S.dx[slot] = dir.x; S.dy[slot] = dir.y; S.dz[slot] = dir.z;
+                        S.ht[slot] = sp;
+                        S.lcur[slot] = light_walk_start(h.p, M<T, EXACT>::normalize(dir)); S.lacc[slot] = 0.f;
+                        to_conn = true; deferred = true;
                     }
                 }
-                if constexpr (GEN) { if (to_free) wf_finish(Q, acc, S.q[slot], fin_value, P.flags); }
+                if (!deferred) {
+                    Ray<T> next;
+                    V3<T> w;
+                    uint32_t kind = shade<T, EXACT, COUNT, SC>(sc, r, h, rng, &next, &w, tl);
+                    V3<T> emitted = mk<T>(0, 0, 0);
+                    if constexpr (GEN) emitted = g_emitted<T>(h);
+                    V3<T> fin_value = mk<T>(0, 0, 0);
+                    if (wf_advance<COUNT>(S, slot, kind, next, w, emitted, mult, dep, &fin_value, tl)) {
+                        wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
+                        to_free = true;
+                    } else to_ext = true;
+                }
             }
             __syncwarp();
+            if constexpr (CONN) wf_push(S.conn, n_conn, to_conn, slot, lt_mask);
             wf_push(S.list[WF_EXT], n_ext, to_ext, slot, lt_mask);
             wf_push(S.list[WF_FREE], n_free, to_free, slot, lt_mask);
         }
@@ -285,5 +404,6 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
 
 template <int BLOCK, int NPW> size_t wavefront_state_bytes() { return sizeof(WfWarp<NPW>) * (BLOCK / 32); }
 template <int BLOCK, int NPW> size_t wavefront_state_bytes_general() { return sizeof(WfWarpG<NPW>) * (BLOCK / 32); }
+template <int BLOCK, int NPW> size_t wavefront_state_bytes_connect() { return sizeof(WfWarpC<NPW>) * (BLOCK / 32); }
 
 }  // namespace rtw

@@ -278,3 +278,25 @@ def test_c4_slice_parity_200k_spheres(rtw, oracle):
     """A 448 x 448-cell slice of BASELINE C4's 1000 x 1000 grid: 200 705 spheres (device-built LBVH: the AUTO threshold is 200 000)
     and 10 094 lights (light BVH)."""
     _config_parity(rtw, oracle, 224, 0.8, 0.95, "C4 slice", expect_device_bvh=True)
+
+
+def test_connect_stage_is_bit_identical(rtw):
+    """The wavefront's CONNECT stage (scenes with more than 2048 lights: two light-BVH walks per lane, finished / refilled in place,
+    suspended and resumed on other lanes) must not change a bit: same image as the pooled megakernel, whose lanes run every walk in
+    one go, and as the wavefront with the walk inside Lambertian SHADE (RTW_NO_CONNECT=1 is a process-wide switch, so that
+    comparison lives in scripts/gpu_r2_connect.sh; here: wavefront vs megakernel)."""
+    arr = rtw.scenes.simple_arrays(SEED, 112)                # 50 k spheres, ~2 500 lights
+    assert len(arr["lights"]) > 2048
+    sc = rtw.Scene.from_arrays(arr["spheres"], arr["sphere_materials"], arr["planes"], arr["plane_materials"], arr["lights"])
+    w, h, spp = 160, 90, 16
+    cam = (arr["cam"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h)
+           .with_samples_per_pixel(spp).with_lookfrom((30., 12., 30.)).with_focus_dist(45.).build())
+    out = {}
+    for name, mode in (("wavefront", rtw.RTW_WAVEFRONT), ("megakernel", rtw.RTW_MEGAKERNEL)):
+        acc, poison = rtw.new_accumulators(w, h)
+        st = sc.render_samples(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, mode=mode), 0, spp, acc, poison)
+        out[name] = (acc.copy(), poison.copy(), st)
+    sc.close()
+    assert np.array_equal(out["wavefront"][0], out["megakernel"][0]) and np.array_equal(out["wavefront"][1], out["megakernel"][1])
+    assert out["wavefront"][2]["rays"] == out["megakernel"][2]["rays"] and out["wavefront"][2]["paths"] == w * h * spp
+    assert (out["wavefront"][0] > 0).any()

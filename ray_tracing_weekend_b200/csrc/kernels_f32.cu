@@ -142,6 +142,12 @@ cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uin
     return count ? launch_render_wavefront_impl<true>(P, Q, bvh_depth, sm_count, s, info)
                  : launch_render_wavefront_impl<false>(P, Q, bvh_depth, sm_count, s, info);
 }
+cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, uint4* cand, cudaStream_t s) {
+    const uint32_t n = cam.width * cam.height;
+    if (!n) return cudaSuccess;
+    primary_candidates_kernel<128><<<(n + 127) / 128, 128, 0, s>>>(scene, cam, cand);
+    return cudaGetLastError();
+}
 // samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units
 // (2^28 radiance units) in total, whichever way they are split over lanes, launches and ranks
 float pool_sample_cap(uint32_t spp_total) {

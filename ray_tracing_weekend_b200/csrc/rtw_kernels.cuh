@@ -142,13 +142,10 @@ RTW_D void hit_record(const SC& sc, const Ray<T>& r, int32_t best, T best_t, Hit
 // The reference visits both children with the un-shrunk range and keeps the first minimum; here the
 // range is shrunk to the best t so far and children are visited near-first — the argmin is the same
 // except for exact-t ties and the documented grazing cases.
-template <class T, bool EXACT, bool COUNT, class SC>
-RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* best_out, T* t_out, int32_t* stack, int stride, Tally& tl) {
+// planes: Plane::hit (entities/plane.rs:61-76), one-sided; they have no finite box and are tested linearly
+template <class T, bool EXACT, class SC>
+RTW_D void closest_plane(const SC& sc, const Ray<T>& r, T tmin, T tmax, bool& found, T& best_t, int32_t& best) {
     using Mt = M<T, EXACT>;
-    bool found = false;
-    T best_t = tmax;
-    int32_t best = -1;      // >= 0 sorted sphere index; <= -2: plane ~index
-    // planes: Plane::hit (entities/plane.rs:61-76), one-sided
     for (int i = 0; i < sc.n_planes; ++i) {
         const PlaneT<T>& pl = sc.planes[i];
         T denom = dot(r.d, pl.normal);
@@ -159,6 +156,42 @@ RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* 
         if (!(tmin <= t && t <= tmax)) continue;
         if (!found || t < best_t) { found = true; best_t = t; best = -2 - i; }
     }
+}
+
+// Camera rays of a pinhole camera (defocus_angle <= EPSILON: every reference scene) all leave one point through one pixel's square:
+// which spheres they can possibly hit is a property of the PIXEL, found once per frame by walking the BVH with the pixel's cone
+// (primary_candidates_kernel) instead of once per sample with each ray.  The closest hit of a camera ray is then the argmin over
+// its pixel's candidate list (<= 4 sorted sphere indices, kCandNone-terminated; kCandOverflow in .x: more than 4, walk the tree) and
+// the planes — the same spheres pass the same sphere test, so the result is the traversal's; 75 % of the camera rays of `simple`
+// have no candidate at all and end without touching the tree.
+constexpr uint32_t kCandNone = 0xffffffffu, kCandOverflow = 0xfffffffeu;
+template <bool COUNT, class SC>
+RTW_D bool closest_prim_candidates(const SC& sc, const Ray<float>& r, float tmin, float tmax, uint4 cand, int32_t* best_out, float* t_out, Tally& tl) {
+    bool found = false;
+    float best_t = tmax;
+    int32_t best = -1;
+    closest_plane<float, false, SC>(sc, r, tmin, tmax, found, best_t, best);
+    const float inv_a = frcp(sqlen(r.d));
+    const uint32_t ids[4] = {cand.x, cand.y, cand.z, cand.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (ids[k] == kCandNone) break;
+        if (COUNT) tl.sphere_tests++;
+        float t;
+        if (sphere_root_fast(load_sphere(sc, (int32_t)ids[k]), r, inv_a, tmin, tmax, &t) && (!found || t < best_t)) { found = true; best_t = t; best = (int32_t)ids[k]; }
+    }
+    *best_out = best;
+    *t_out = best_t;
+    return found;
+}
+
+template <class T, bool EXACT, bool COUNT, class SC>
+RTW_D bool closest_prim(const SC& sc, const Ray<T>& r, T tmin, T tmax, int32_t* best_out, T* t_out, int32_t* stack, int stride, Tally& tl) {
+    using Mt = M<T, EXACT>;
+    bool found = false;
+    T best_t = tmax;
+    int32_t best = -1;      // >= 0 sorted sphere index; <= -2: plane ~index
+    closest_plane<T, EXACT, SC>(sc, r, tmin, tmax, found, best_t, best);
     T a = sqlen(r.d);
     RayAux aux;
     float inv_a = 0.f;
@@ -528,7 +561,7 @@ template <class T> struct PathState {
 
 template <class T, bool EXACT, bool COUNT, class SC>
 RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin, uint32_t pixel, uint32_t sample,
-                     PathState<T>& ps, V3<T>* value, int32_t* stack, int stride, uint32_t& nrays, Tally& tl) {
+                     PathState<T>& ps, V3<T>* value, int32_t* stack, int stride, uint32_t& nrays, Tally& tl, const uint4* cand = nullptr) {
     if (ps.depth == 0) {                                        // camera.rs:470-472
         if (COUNT) tl.depth_out++;
         *value = mk<T>(0, 0, 0) + ps.res;
@@ -536,7 +569,20 @@ RTW_D bool path_step(const SC& sc, const CameraT<T>& cam, uint64_t seed, T tmin,
     }
     nrays++;
     Hit<T> h;
-    if (!closest_hit<T, EXACT, COUNT, SC>(sc, ps.r, tmin, M<T, EXACT>::inf(), &h, stack, stride, tl)) {   // camera.rs:473-475
+    bool hit, looked_up = false;
+    if constexpr (!EXACT && !is_general<SC>::value) {
+        if (cand && ps.depth == cam.max_depth) {                // camera ray: the pixel's candidate list instead of the tree
+            const uint4 c = __ldg(cand + pixel);
+            if (c.x != kCandOverflow) {
+                int32_t best; T best_t;
+                hit = closest_prim_candidates<COUNT>(sc, ps.r, tmin, M<T, EXACT>::inf(), c, &best, &best_t, tl);
+                if (hit) hit_record<T, EXACT, SC>(sc, ps.r, best, best_t, &h);
+                looked_up = true;
+            }
+        }
+    }
+    if (!looked_up) hit = closest_hit<T, EXACT, COUNT, SC>(sc, ps.r, tmin, M<T, EXACT>::inf(), &h, stack, stride, tl);
+    if (!hit) {   // camera.rs:473-475
         if (COUNT) tl.missed++;
         *value = ps.mult * cam.background + ps.res;
         return true;
@@ -572,6 +618,7 @@ template <class T, class SCENE = SceneView<T>> struct RenderParams {
     uint32_t smem_nodes, smem_spheres, smem_lights;
     uint32_t sh_node_stride;        // all-shared scenes: stride of the staged nodes (64 = Node<float> as is, 80 = padded copy from scene.nodes_staged)
     uint32_t stack_depth;           // traversal stack entries per thread: BVH depth + 2, at most kStackDepth
+    const uint4* cand;              // [height * width] candidate lists of the camera rays (primary_candidates_kernel), or NULL
 };
 
 RTW_D uint32_t warp_sum(uint32_t v) {
@@ -848,7 +895,7 @@ __global__ void __launch_bounds__(BLOCK, is_general<SCENE>::value ? 3 : 4) rende
         }
         if (alive) {
             V3<T> value;
-            if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl)) {
+            if (path_step<T, EXACT, COUNT, SC>(scv, cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, BLOCK, nrays, tl, P.cand)) {
                 alive = false;
                 if (P.flags & 1u) value = fix_nan(value);
                 if (q != acc_q) {
@@ -884,6 +931,75 @@ __global__ void pool_finalize_kernel(const unsigned long long* accum, const uint
         if (poison_has_nan(bad, c)) v = __int_as_float(0x7fc00000);
         tiles[3 * (size_t)q + c] = v;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate lists of the camera rays (see closest_prim_candidates).  One thread per pixel walks the FP32 tree with the pixel's
+// cone: apex = the camera centre, axis = the direction through the pixel centre, half-angle alpha with tan(alpha) >= half the
+// pixel's diagonal over the distance to it (the jitter is U[-0.5, 0.5]^2 pixels).  A sphere (centre c, radius R) — a primitive, or
+// the bounding sphere of a node's box — can touch the cone only if it contains the apex, or lies ahead of it (s = axis.(c - o) >=
+// -R) with its centre no farther from the axis than s tan(alpha) + R / cos(alpha).  The distance from the axis is |axis x (c - o)|:
+// every term is of the size of R, nothing cancels, so the test is sound in FP32 at pixel cones of 1e-3 rad; R is inflated by 0.1 %
+// plus 2e-5 of the distance to cover the rounding of the test itself.  Conservative tests only add candidates.
+RTW_D bool cone_touches_sphere(V3<float> axis, float tan_a, float inv_cos_a, V3<float> v, float R) {
+    const float d2 = dot(v, v);
+    const float Ri = fmaf(R, 1.001f, 2e-5f * fsqrt(d2));
+    if (d2 <= Ri * Ri) return true;
+    const float s = dot(axis, v);
+    if (s < -Ri) return false;
+    const V3<float> w = cross(axis, v);
+    const float lim = fmaf(fmaxf(s, 0.f), tan_a, Ri * inv_cos_a);
+    return dot(w, w) <= lim * lim;
+}
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) primary_candidates_kernel(SceneView<float> sc, CameraT<float> cam, uint4* cand) {
+    const uint32_t pixel = blockIdx.x * BLOCK + threadIdx.x;
+    if (pixel >= cam.width * cam.height) return;
+    const uint32_t i = pixel % cam.width, j = pixel / cam.width;
+    const V3<float> dc = (cam.pixel00 + cam.du * (float)i) + cam.dv * (float)j - cam.center;
+    const float len = fsqrt(dot(dc, dc));
+    const float hd = 0.5f * (fsqrt(dot(cam.du, cam.du)) + fsqrt(dot(cam.dv, cam.dv))) * 1.001f;
+    uint4 out = make_uint4(kCandNone, kCandNone, kCandNone, kCandNone);
+    if (!(len > 4.f * hd)) { out.x = kCandOverflow; cand[pixel] = out; return; }       // degenerate camera: no cone, walk the tree
+    const V3<float> axis = dc * frcp(len);
+    const float tan_a = hd * frcp(len - hd) * 1.001f;
+    const float inv_cos_a = fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f;
+    uint32_t ids[4] = {kCandNone, kCandNone, kCandNone, kCandNone};
+    int n = 0;
+    int32_t stack[kStackDepth];
+    int sp = 0;
+    int32_t cur = sc.n_spheres > 0 ? 0 : kStop;
+    while (cur != kStop) {
+        if (cur >= 0) {
+            Node<float> nd;
+            const float4* p = reinterpret_cast<const float4*>(sc.nodes + cur);
+            unpack_node(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), nd);
+            const V3<float> vl = mk<float>(nd.la[0], nd.la[1], nd.la[2]) - cam.center, vr = mk<float>(nd.ra[0], nd.ra[1], nd.ra[2]) - cam.center;
+            const float Rl = fsqrt(nd.lb[0] * nd.lb[0] + nd.lb[1] * nd.lb[1] + nd.lb[2] * nd.lb[2]);
+            const float Rr = fsqrt(nd.rb[0] * nd.rb[0] + nd.rb[1] * nd.rb[1] + nd.rb[2] * nd.rb[2]);
+            const bool hl = nd.left != kEmptyLeaf && cone_touches_sphere(axis, tan_a, inv_cos_a, vl, Rl);
+            const bool hr = nd.right != kEmptyLeaf && cone_touches_sphere(axis, tan_a, inv_cos_a, vr, Rr);
+            if (hl && hr) { stack[sp++] = nd.right; cur = nd.left; }
+            else if (hl) cur = nd.left;
+            else if (hr) cur = nd.right;
+            else cur = sp ? stack[--sp] : kStop;
+        } else {
+            const uint32_t enc = (uint32_t)~cur;
+            const uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
+            for (uint32_t k = first; k < first + count; ++k) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(sc.spheres + k));
+                if (cone_touches_sphere(axis, tan_a, inv_cos_a, mk<float>(s.x, s.y, s.z) - cam.center, s.w)) {
+                    if (n < 4) ids[n] = k;
+                    n++;
+                }
+            }
+            cur = sp ? stack[--sp] : kStop;
+        }
+        if (n > 4) break;
+    }
+    if (n > 4) out.x = kCandOverflow;
+    else out = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+    cand[pixel] = out;
 }
 
 // ---------------------------------------------------------------------------------------------

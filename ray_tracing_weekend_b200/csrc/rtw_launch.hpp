@@ -24,6 +24,7 @@ RTW_DECLARE_LAUNCHERS(f32, float)
 cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t pool_pixels_per_chunk(uint32_t spp);
 float pool_sample_cap(uint32_t spp_total);
+cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, uint4* cand, cudaStream_t s);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t wavefront_max_bvh_depth();

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             const bool active = lane < take;
             uint32_t slot = active ? S.list[WF_FREE][n_free + lane] : 0u;
             bool started = false;
+            uint32_t first_kind = 0xffu;                      // camera ray answered from the pixel's candidate list: 0..2 material list
             if (active) {
                 uint32_t r = chunk_next + lane;
                 uint32_t pin = r / spp, sample = r - pin * spp + cam.sample_offset;
@@ -208,12 +209,40 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     S.q[slot] = q; S.pix[slot] = pixel; S.smp[slot] = sample; S.dep[slot] = cam.max_depth;
                     started = true;
                     npaths++;
+                    if constexpr (!GEN) {
+                        if (P.cand) {
+                            // the camera ray's closest hit from its pixel's candidate list (closest_prim_candidates): no EXTEND pass, and
+                            // a path that sees only background (3 of 4 in `simple`) ends here without ever occupying its slot
+                            const uint4 c = __ldg(P.cand + pixel);
+                            if (c.x != kCandOverflow) {
+                                nrays++;
+                                T best_t; int32_t bestp;
+                                if (closest_prim_candidates<COUNT>(sc, ray, P.tmin, M<T, EXACT>::inf(), c, &bestp, &best_t, tl)) {
+                                    S.ht[slot] = best_t; S.hp[slot] = bestp;
+                                    uint32_t k = bestp >= 0 ? (load_sphere_info(sc, bestp) & 3u) : (sc.planes[-2 - bestp].info & 3u);
+                                    first_kind = k == LAMBERTIAN ? 0u : (k == METAL ? 1u : 2u);
+                                } else {
+                                    if (COUNT) tl.missed++;
+                                    wf_finish(Q, acc, q, mk<T>(1.f, 1.f, 1.f) * cam.background + wf_res(cam.max_depth), P.flags);      // camera.rs:473-475
+                                    first_kind = 3u;
+                                }
+                                started = false;
+                            }
+                        }
+                    }
                 }
             }
             chunk_next += take;
             __syncwarp();
             wf_push(S.list[WF_EXT], n_ext, started, slot, lt_mask);
-            wf_push(S.list[WF_FREE], n_free, active && !started, slot, lt_mask);
+            if constexpr (!GEN) {
+                if (P.cand) {                                 // warp-uniform
+                    wf_push(S.list[WF_LAMB], n_lamb, first_kind == 0u, slot, lt_mask);
+                    wf_push(S.list[WF_METAL], n_metal, first_kind == 1u, slot, lt_mask);
+                    wf_push(S.list[WF_DIEL], n_diel, first_kind == 2u, slot, lt_mask);
+                }
+            }
+            wf_push(S.list[WF_FREE], n_free, active && !started && first_kind > 2u, slot, lt_mask);
         } else if (stage == WF_EXT) {
             // ---- EXTEND ------------------------------------------------------------------------------------
             const uint32_t n = min(32u, n_ext);

@@ -951,30 +951,20 @@ RTW_D bool cone_touches_sphere(V3<float> axis, float tan_a, float inv_cos_a, V3<
     const float lim = fmaf(fmaxf(s, 0.f), tan_a, Ri * inv_cos_a);
     return dot(w, w) <= lim * lim;
 }
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) primary_candidates_kernel(SceneView<float> sc, CameraT<float> cam, uint4* cand) {
-    const uint32_t pixel = blockIdx.x * BLOCK + threadIdx.x;
-    if (pixel >= cam.width * cam.height) return;
-    const uint32_t i = pixel % cam.width, j = pixel / cam.width;
-    const V3<float> dc = (cam.pixel00 + cam.du * (float)i) + cam.dv * (float)j - cam.center;
-    const float len = fsqrt(dot(dc, dc));
-    const float hd = 0.5f * (fsqrt(dot(cam.du, cam.du)) + fsqrt(dot(cam.dv, cam.dv))) * 1.001f;
-    uint4 out = make_uint4(kCandNone, kCandNone, kCandNone, kCandNone);
-    if (!(len > 4.f * hd)) { out.x = kCandOverflow; cand[pixel] = out; return; }       // degenerate camera: no cone, walk the tree
-    const V3<float> axis = dc * frcp(len);
-    const float tan_a = hd * frcp(len - hd) * 1.001f;
-    const float inv_cos_a = fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f;
-    uint32_t ids[4] = {kCandNone, kCandNone, kCandNone, kCandNone};
+// Walks the tree with a cone and collects the sorted indices of the spheres it touches: up to CAP of them in ids[], returns their
+// number (CAP + 1 = more than CAP).
+template <int CAP>
+RTW_D int cone_walk(const SceneView<float>& sc, V3<float> apex, V3<float> axis, float tan_a, float inv_cos_a, uint32_t* ids) {
     int n = 0;
     int32_t stack[kStackDepth];
     int sp = 0;
     int32_t cur = sc.n_spheres > 0 ? 0 : kStop;
-    while (cur != kStop) {
+    while (cur != kStop && n <= CAP) {
         if (cur >= 0) {
             Node<float> nd;
             const float4* p = reinterpret_cast<const float4*>(sc.nodes + cur);
             unpack_node(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), nd);
-            const V3<float> vl = mk<float>(nd.la[0], nd.la[1], nd.la[2]) - cam.center, vr = mk<float>(nd.ra[0], nd.ra[1], nd.ra[2]) - cam.center;
+            const V3<float> vl = mk<float>(nd.la[0], nd.la[1], nd.la[2]) - apex, vr = mk<float>(nd.ra[0], nd.ra[1], nd.ra[2]) - apex;
             const float Rl = fsqrt(nd.lb[0] * nd.lb[0] + nd.lb[1] * nd.lb[1] + nd.lb[2] * nd.lb[2]);
             const float Rr = fsqrt(nd.rb[0] * nd.rb[0] + nd.rb[1] * nd.rb[1] + nd.rb[2] * nd.rb[2]);
             const bool hl = nd.left != kEmptyLeaf && cone_touches_sphere(axis, tan_a, inv_cos_a, vl, Rl);
@@ -988,18 +978,63 @@ __global__ void __launch_bounds__(BLOCK) primary_candidates_kernel(SceneView<flo
             const uint32_t first = enc >> 4, count = (enc & 15u) + 1u;
             for (uint32_t k = first; k < first + count; ++k) {
                 const float4 s = __ldg(reinterpret_cast<const float4*>(sc.spheres + k));
-                if (cone_touches_sphere(axis, tan_a, inv_cos_a, mk<float>(s.x, s.y, s.z) - cam.center, s.w)) {
-                    if (n < 4) ids[n] = k;
+                if (cone_touches_sphere(axis, tan_a, inv_cos_a, mk<float>(s.x, s.y, s.z) - apex, s.w)) {
+                    if (n < CAP) ids[n] = k;
                     n++;
                 }
             }
             cur = sp ? stack[--sp] : kStop;
         }
-        if (n > 4) break;
     }
-    if (n > 4) out.x = kCandOverflow;
-    else out = make_uint4(ids[0], ids[1], ids[2], ids[3]);
-    cand[pixel] = out;
+    return n;
+}
+// Two levels: one CTA per 8 x 8-pixel block.  Thread 0 walks the tree once with the BLOCK's cone (up to 24 candidates, in shared
+// memory); then every thread filters that short list with its own pixel's cone.  Only a block with more than 24 candidates sends
+// its pixels down the tree one by one.  (The first version walked the tree once per pixel: 0.24 ms per 1080p frame — 1 % of the
+// 62-spp frame one of eight GPUs renders; this one takes a sixth of that.)
+constexpr int kCandBlock = 8, kCandBlockCap = 24;
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_kernel(SceneView<float> sc, CameraT<float> cam, uint4* cand) {
+    __shared__ uint32_t block_ids[kCandBlockCap];
+    __shared__ int block_n;
+    const uint32_t bx = blockIdx.x * kCandBlock, by = blockIdx.y * kCandBlock;
+    const float px = 0.5f * (fsqrt(dot(cam.du, cam.du)) + fsqrt(dot(cam.dv, cam.dv))) * 1.001f;       // >= half a pixel's diagonal
+    if (threadIdx.x == 0) {
+        const V3<float> dc = (cam.pixel00 + cam.du * ((float)bx + 3.5f)) + cam.dv * ((float)by + 3.5f) - cam.center;
+        const float len = fsqrt(dot(dc, dc)), hd = 8.f * px;           // pixel centres up to 3.5 away per axis + half a pixel of jitter
+        int n = kCandBlockCap + 1;
+        if (len > 4.f * hd) {
+            const float tan_a = hd * frcp(len - hd) * 1.001f;
+            n = cone_walk<kCandBlockCap>(sc, cam.center, dc * frcp(len), tan_a, fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f, block_ids);
+        }
+        block_n = n;
+    }
+    __syncthreads();
+    const uint32_t i = bx + threadIdx.x % kCandBlock, j = by + threadIdx.x / kCandBlock;
+    if (i >= cam.width || j >= cam.height) return;
+    const V3<float> dc = (cam.pixel00 + cam.du * (float)i) + cam.dv * (float)j - cam.center;
+    const float len = fsqrt(dot(dc, dc));
+    uint4 out = make_uint4(kCandNone, kCandNone, kCandNone, kCandNone);
+    if (!(len > 4.f * px)) out.x = kCandOverflow;                       // degenerate camera: no cone, walk the tree
+    else {
+        const V3<float> axis = dc * frcp(len);
+        const float tan_a = px * frcp(len - px) * 1.001f;
+        const float inv_cos_a = fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f;
+        uint32_t ids[4] = {kCandNone, kCandNone, kCandNone, kCandNone};
+        int n = 0;
+        if (block_n <= kCandBlockCap) {
+            for (int k = 0; k < block_n; ++k) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(sc.spheres + block_ids[k]));
+                if (cone_touches_sphere(axis, tan_a, inv_cos_a, mk<float>(s.x, s.y, s.z) - cam.center, s.w)) {
+                    if (n < 4) ids[n] = block_ids[k];
+                    n++;
+                }
+            }
+        } else n = cone_walk<4>(sc, cam.center, axis, tan_a, inv_cos_a, ids);
+        if (n > 4) out.x = kCandOverflow;
+        else out = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+    }
+    cand[j * cam.width + i] = out;
 }
 
 // ---------------------------------------------------------------------------------------------

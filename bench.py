@@ -124,7 +124,9 @@ def run_reference(args):
     mrays = r["rays"] / r["seconds"] * 1e-6
     line = dict(impl="reference", metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=r["seconds"] / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                data="synthetic", config=dict(workload=WORKLOAD, note="C++ restatement of the reference's CPU renderer (oracle/), not the reference "
+                data="synthetic", config=dict(workload=WORKLOAD, sample="each step renders 1 of the frame's 500 samples per pixel (1/500 of the frame): Mrays/s is a rate, "
+                                              "so it compares with the CUDA arm's full frames",
+                                              note="C++ restatement of the reference's CPU renderer (oracle/), not the reference "
                                               "binary: no Rust toolchain in this image"),
                 mpaths_per_s=r["paths"] / r["seconds"] * 1e-6,
                 cpu_baseline=dict(value=mrays, unit="Mrays/s", cores=r["cores"], kind="port", sample=r["sample"] + "; each step is one such frame"),
@@ -173,6 +175,12 @@ def run_cuda(args):
         dist.all_reduce(tot)
     total = {k: float(v) for k, v in zip(keys, tot.tolist())}
     local_flops = algorithmic_flops(cnt)
+    # the same frame with every camera ray walking the BVH (RTW_FLAG_NO_CANDIDATES): the event counts of the plain tree-walk algorithm
+    # SURVEY 8(d) describes.  `roofline.achieved` uses the events the timed kernel EXECUTES (above); this count is reported beside it.
+    tw = None
+    if mode == R.RTW_WAVEFRONT and not args.lane_per_pixel:
+        twc = renderer.render_local(R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=R.RTW_FLAG_COUNT_EVENTS | R.RTW_FLAG_NO_CANDIDATES | base_flags), want_stats=True)
+        tw = dict(flop_per_launch=algorithmic_flops(twc), node_visits=twc["node_visits"], sphere_tests=twc["sphere_tests"])
 
     for _ in range(args.warmup):
         renderer.render()
@@ -264,6 +272,49 @@ def run_cuda(args):
         other = dict(mode="megakernel (pooled path stream)" if omode == R.RTW_MEGAKERNEL else "wavefront", kernel_ms_per_step=float(ot.item()),
                      mrays_per_s=total["rays"] / float(ot.item()) * 1e-3)
 
+    # ---- the exact (f64) path on the same frame at reduced spp: the only path with bit-exact parity has a number too ----
+    f64 = None
+    if world == 1 and not args.no_f64:
+        f64_spp = 4
+        fcam = (cb.with_vfov(40.).with_aspect_ratio(WIDTH / HEIGHT).with_max_depth(DEPTH).with_image_width(WIDTH).with_image_height(HEIGHT)
+                .with_samples_per_pixel(f64_spp).build())
+        fopts = R.RenderOptions(seed=SEED, precision=R.RTW_F64, flags=R.RTW_FLAG_COUNT_EVENTS)
+        _, _, fst = scene.render(fcam, fopts, want_sum=False, want_rgb8=True)
+        best = None
+        for _ in range(2):
+            _, _, st2 = scene.render(fcam, R.RenderOptions(seed=SEED, precision=R.RTW_F64), want_sum=False, want_rgb8=True)
+            best = st2 if best is None or st2["kernel_ms"] < best["kernel_ms"] else best
+        fp64_peak = 148 * 64 * 2 * float(measured_peaks()[0].get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        f64_tflops = algorithmic_flops(fst) / (best["kernel_ms"] * 1e-3) / 1e12
+        f64 = dict(kernel="render_mega_kernel<double, exact>", sample=f"{WIDTH}x{HEIGHT} at {f64_spp} spp (of {SPP}), depth {DEPTH}: bit-identical to the oracle",
+                   ms_per_step=best["kernel_ms"], mrays_per_s=best["rays"] / best["kernel_ms"] * 1e-3, mpaths_per_s=best["paths"] / best["kernel_ms"] * 1e-3,
+                   rays_per_path=best["rays"] / best["paths"], achieved_tflops=f64_tflops, fp64_peak_tflops=fp64_peak,
+                   frac_of_fp64_peak=f64_tflops / fp64_peak,
+                   peak_source="148 SM x 64 FP64 lanes x 2 x sm_max_mhz (derived; MEASURED_PEAKS.json has no FP64 figure)")
+    # ---- BASELINE C3 (3840x2160, 1024 spp: the config BASELINE.json names for 1/2/4/8 GPUs), one frame outside the timed region ----
+    c3 = None
+    if not args.no_c3 and args.workload == "C2" and args.spp == 500:
+        c3cam = (cb.with_vfov(40.).with_aspect_ratio(3840 / 2160).with_max_depth(DEPTH).with_image_width(3840).with_image_height(2160)
+                 .with_samples_per_pixel(1024).build())
+        c3r = D.DistributedRenderer(scene, c3cam, opts, rank, world, want_sum=False, want_rgb8=True)
+        c3r.comm = renderer.comm
+        c3r.render()
+        barrier()
+        c3ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        c3ev[0].record()
+        c3st = c3r.render()
+        c3ev[1].record()
+        barrier()
+        c3t = torch.tensor([c3ev[0].elapsed_time(c3ev[1])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(c3t, op=dist.ReduceOp.MAX)
+        c3_ms = float(c3t.item())
+        c3_rays = total["rays"] / (WIDTH * HEIGHT * SPP) * (3840 * 2160 * 1024)        # same scene and estimator: rays per path carry over
+        c3 = dict(workload="random-spheres 3840x2160, 1024 spp, depth 50 (BASELINE C3)", n_gpus=world, ms_per_step=c3_ms,
+                  mrays_per_s=c3_rays / c3_ms * 1e-3, mpaths_per_s=3840 * 2160 * 1024 / c3_ms * 1e-3, steps=1,
+                  note="one frame after one warm-up frame, device-timed, max over ranks; rays = paths x the C2 frame's measured rays per path")
+        del c3r
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
@@ -299,11 +350,22 @@ def run_cuda(args):
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
             # per step: tiles partition = render (+ fixed-point -> tiles conversion) per rank + untile on rank 0; samples partition =
             # render per rank + resolve on rank 0
-            gpu_launches=args.steps * ((1 if (renderer.partition == "samples" or (args.lane_per_pixel and args.mode == "megakernel")) else 2) * world + 1),
+            # per step and rank: candidate pre-pass (wavefront) + render kernel (+ fixed-point -> tiles conversion on the tile partition); on
+            # rank 0 one untile / resolve kernel
+            gpu_launches=args.steps * (((1 if (renderer.partition == "samples" or (args.lane_per_pixel and args.mode == "megakernel")) else 2)
+                                        + (1 if (args.mode == "wavefront" and not args.lane_per_pixel) else 0)) * world + 1),
             clocks=clocks,
             events_per_step={k: total[k] for k in keys},
             other_renderer=other,
+            f64_path=f64,
+            c3=c3,
         )
+        if tw:
+            line["roofline"]["tree_walk_equivalent"] = dict(
+                flop_per_launch=tw["flop_per_launch"], achieved=tw["flop_per_launch"] / (kern_ms / args.steps * 1e-3) / 1e12,
+                frac=tw["flop_per_launch"] / (kern_ms / args.steps * 1e-3) / 1e12 / fp32_peak, node_visits=tw["node_visits"], sphere_tests=tw["sphere_tests"],
+                note="flop of the plain algorithm (every ray walks the BVH) over the timed kernel's duration; the kernel answers camera rays from "
+                     "per-pixel candidate lists instead, so it EXECUTES fewer node visits (events_per_step) for the same image")
         if world == 1 and not args.no_cpu_baseline:
             try:
                 c = cpu_reference_run(1, 0, sample_spp=4)
@@ -354,6 +416,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C3 = BASELINE config 3 (3840x2160, 1024 spp), for the multi-GPU table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-f64", action="store_true", help="skip the exact-path measurement (N = 1)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the extra BASELINE C3 frame")
     ap.add_argument("--lane-per-pixel", action="store_true", help="diagnostic: the pre-pooling kernel")
     ap.add_argument("--mode", default="wavefront", choices=["megakernel", "wavefront"])
     ap.add_argument("--torch-collective", action="store_true", help="N > 1: run the collective through torch.distributed instead of inside the C library")

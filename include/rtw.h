@@ -124,8 +124,11 @@ enum { RTW_MEGAKERNEL = 0, RTW_WAVEFRONT = 1 };
 enum { RTW_FLAG_FIX_NAN = 1u,       /* zero NaN components of a sample before accumulation (the dead
                                        ray_colour twin did, camera.rs:434); OFF = reference behaviour */
        RTW_FLAG_COUNT_EVENTS = 2u, /* fill the event counters of rtw_stats (slower)                 */
-       RTW_FLAG_LANE_PER_PIXEL = 4u };/* RTW_F32 only, diagnostic: one lane per pixel instead of the pooled
+       RTW_FLAG_LANE_PER_PIXEL = 4u,/* RTW_F32 only, diagnostic: one lane per pixel instead of the pooled
                                        path stream (the baseline the pooled megakernel is measured against) */
+       RTW_FLAG_NO_CANDIDATES = 8u };/* RTW_F32 wavefront, diagnostic: camera rays walk the BVH like every other ray instead of
+                                       reading their pixel's candidate list (same image; the event counters then count the
+                                       tree walk of every ray) */
 
 typedef struct {
     uint64_t seed;        /* Philox4x32-10 key                                                      */

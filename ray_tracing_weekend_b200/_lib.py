@@ -17,7 +17,7 @@ RTW_TEX_NOISE, RTW_TEX_CHECKER = 1, 2
 RTW_BVH_AUTO, RTW_BVH_HOST_SAH, RTW_BVH_DEVICE_LBVH = 0, 1, 2
 RTW_F32, RTW_F64 = 0, 1
 RTW_MEGAKERNEL, RTW_WAVEFRONT = 0, 1
-RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL = 1, 2, 4
+RTW_FLAG_FIX_NAN, RTW_FLAG_COUNT_EVENTS, RTW_FLAG_LANE_PER_PIXEL, RTW_FLAG_NO_CANDIDATES = 1, 2, 4, 8
 RTW_COLLECTIVE_AUTO, RTW_COLLECTIVE_PEER, RTW_COLLECTIVE_NCCL = 0, 1, 2
 RTW_COMM_ID_BYTES = 128
 RTW_TILE_W = RTW_TILE_H = 16

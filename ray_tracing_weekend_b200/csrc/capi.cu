@@ -1039,7 +1039,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
         uint4* cand = nullptr;
         // (wavefront only: in the pooled megakernel the extra branch of path_step costs more than the walks it saves — measured 56.5 ms
         // with the lists against 53.3 without on C2 / 100 spp; the images are identical either way)
-        if (cand_allowed && wavefront && cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0) {
+        if (cand_allowed && !(o->flags & RTW_FLAG_NO_CANDIDATES) && wavefront && cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0) {
             CU(s->d_cand.reserve((size_t)cam->image_width * cam->image_height));
             CU(launch_primary_candidates_f32(s->f32.view, to_camera<float>(cam), s->d_cand.p, st));
             cand = s->d_cand.p;

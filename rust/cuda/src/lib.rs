@@ -67,7 +67,7 @@ pub const RTW_E_UNSUPPORTED: c_int = -4; pub const RTW_E_NOMEM: c_int = -5;
 pub const RTW_F32: u32 = 0; pub const RTW_F64: u32 = 1;
 pub const RTW_MEGAKERNEL: u32 = 0; pub const RTW_WAVEFRONT: u32 = 1;
 pub const RTW_TMIN_REFERENCE: f64 = -1.0;
-pub const RTW_FLAG_FIX_NAN: u32 = 1; pub const RTW_FLAG_COUNT_EVENTS: u32 = 2; pub const RTW_FLAG_LANE_PER_PIXEL: u32 = 4;
+pub const RTW_FLAG_FIX_NAN: u32 = 1; pub const RTW_FLAG_COUNT_EVENTS: u32 = 2; pub const RTW_FLAG_LANE_PER_PIXEL: u32 = 4; pub const RTW_FLAG_NO_CANDIDATES: u32 = 8;
 pub const RTW_LAMBERTIAN: u32 = 0; pub const RTW_METAL: u32 = 1; pub const RTW_DIELECTRIC: u32 = 2; pub const RTW_INVISIBLE: u32 = 3;
 pub const RTW_DIFFUSE_LIGHT: u32 = 4; pub const RTW_ISOTROPIC: u32 = 5;
 pub const RTW_PRIM_SPHERE: u32 = 0; pub const RTW_PRIM_PLANE: u32 = 1; pub const RTW_PRIM_QUAD: u32 = 2; pub const RTW_PRIM_TRIANGLE: u32 = 3;

@@ -196,3 +196,39 @@ def test_cpp_host_writers_and_config(rtw, tmp_path):
     assert p6.startswith(b"P6\n5 3\n255\n") and np.array_equal(np.frombuffer(p6[len(b"P6\n5 3\n255\n"):], dtype=np.uint8).reshape(3, 5, 3), want)
     Image = pytest.importorskip("PIL.Image")
     assert np.array_equal(np.asarray(Image.open(tmp_path / "c.png").convert("RGB")), want)
+
+
+@pytest.fixture(scope="module")
+def dump_scenes_exe(rtw, tmp_path_factory):
+    lib_dir = os.path.dirname(rtw.library_path())
+    exe = tmp_path_factory.mktemp("dump_scenes") / "dump_scenes"
+    src = os.path.join(ROOT, "tests", "host_cpp", "dump_scenes.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", src, "-o", str(exe), "-L" + lib_dir, "-lrtw_cuda", "-Wl,-rpath," + lib_dir], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("name", ["simple_light", "cornell_box", "debugging_scene", "simple_transform", "checkered_spheres", "plane"])
+def test_scene_mirrors_agree_general(rtw, tmp_path, dump_scenes_exe, name):
+    """The scene constants live in hand-kept mirrors (C++ host/rtw_host.hpp for `rtw_bin`, Python scenes.py for the tests; the oracle's
+    general scenes are built FROM the Python description, tests/test_gpu_general.py).  Every general scene of the CLI must come out
+    of both generators as the same plain-data description, byte for byte: entity arrays, transforms, materials, textures, Perlin
+    tables, the two entry lists, the is-BVH flags and the camera builder."""
+    import ctypes as C
+    exe = dump_scenes_exe
+    out = tmp_path / (name + ".bin")
+    subprocess.run([str(exe), name, str(out)], check=True)
+    blob = out.read_bytes()
+    gen = getattr(rtw.scenes, name)
+    world, lights, cb = gen(SEED) if name in ("simple_light", "debugging_scene", "simple_transform") else gen()
+    desc = rtw.SceneDescription(world, lights)
+    pos = 0
+    for key in ("spheres", "planes", "quads", "cuboids", "transforms", "materials", "textures", "perlins", "world", "lights"):
+        n = int.from_bytes(blob[pos:pos + 8], "little"); pos += 8
+        assert n == getattr(desc.pod, "n_" + key), (name, key, n)
+        arr = desc._keep[key]
+        size = C.sizeof(arr._type_) * n
+        assert blob[pos:pos + size] == bytes(arr)[:size], (name, key)
+        pos += size
+    assert np.frombuffer(blob[pos:pos + 8], dtype=np.uint32).tolist() == [desc.pod.world_is_bvh, desc.pod.lights_is_bvh]
+    pos += 8
+    assert blob[pos:] == bytes(cb.pod), (name, "camera builder")

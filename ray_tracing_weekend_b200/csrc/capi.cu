@@ -182,6 +182,7 @@ struct rtw_scene {
     DevBuf<double> d_rgb_sum; DevBuf<uint8_t> d_rgb8;
     DevBuf<unsigned long long> d_accum; DevBuf<uint32_t> d_poison;   // pooled megakernel accumulators
     DevBuf<uint4> d_cand;                                            // candidate lists of the camera rays, rebuilt by every render call
+    DevBuf<uint32_t> d_order;                                        // chunk order of the work queue (costly chunks first), rebuilt by every render call
     DevBuf<double> d_in2, d_in3; DevBuf<uint32_t> d_u3, d_u4;          // rtw_shade_batch inputs
     DevBuf<double> d_in0, d_in1, d_out0, d_out1, d_out2, d_out3, d_out4; DevBuf<uint32_t> d_u0, d_u1, d_u2, d_k; DevBuf<int32_t> d_prim;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -886,7 +887,7 @@ void rtw_scene_destroy(rtw_scene* s) {
     s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release(); s->d_panic.release();
     cached_free(s->d_work, sizeof(unsigned int), s->device);
     cached_free(s->d_counters, sizeof(DeviceCounters), s->device);
-    s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release(); s->d_cand.release();
+    s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release(); s->d_cand.release(); s->d_order.release();
     s->d_in2.release(); s->d_in3.release(); s->d_u3.release(); s->d_u4.release();
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
@@ -1009,7 +1010,6 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             PoolParams Q{};
             Q.accum = accum_p; Q.poison = poison_p;
             Q.pixels_per_chunk = pool_pixels_per_chunk(spp_here);
-        Q.sample_cap = pool_sample_cap(cam->samples_per_pixel);
             Q.sample_cap = pool_sample_cap(cam->samples_per_pixel);
             uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
             Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
@@ -1044,6 +1044,16 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             CU(launch_primary_candidates_f32(s->f32.view, to_camera<float>(cam), s->d_cand.p, st));
             cand = s->d_cand.p;
             launches++;
+            // ... and they say which chunks of the path stream can meet a sphere: those go first (chunk_order_kernel)
+            static const bool order_allowed = [] { const char* e = std::getenv("RTW_NO_CHUNK_ORDER"); return !(e && std::atoi(e) == 1); }();
+            if (order_allowed && Q.n_chunks < 0x7fffffffu) {
+                CU(s->d_order.reserve((size_t)Q.n_chunks + 2));
+                CU(launch_chunk_order_f32(cand, s->f32.view, to_camera<float>(cam), rank, world, (cam->image_width + kTileW - 1) / kTileW,
+                                          rtw_tiles_total(cam->image_width, cam->image_height), n_slots, Q.pixels_per_chunk, Q.n_chunks,
+                                          s->d_order.p, st));
+                Q.chunk_order = s->d_order.p;
+                launches++;
+            }
         }
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
             P.cand = cand;

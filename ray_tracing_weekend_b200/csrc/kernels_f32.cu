@@ -148,6 +148,16 @@ cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const C
     primary_candidates_kernel<0><<<grid, kCandBlock * kCandBlock, 0, s>>>(scene, cam, cand);
     return cudaGetLastError();
 }
+cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
+                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
+                                   uint32_t* order, cudaStream_t s) {
+    if (!n_chunks) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(order + n_chunks, 0, 2 * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    chunk_order_kernel<0><<<(n_chunks + 255) / 256, 256, 0, s>>>(cand, scene, cam, rank, world, tiles_x, tiles_total, n_slots, pixels_per_chunk,
+                                                                 n_chunks, order);
+    return cudaGetLastError();
+}
 // samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units
 // (2^28 radiance units) in total, whichever way they are split over lanes, launches and ranks
 float pool_sample_cap(uint32_t spp_total) {

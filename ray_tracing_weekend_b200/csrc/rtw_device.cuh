@@ -265,7 +265,7 @@ RTW_HD int32_t encode_leaf(uint32_t first, uint32_t count) { return count == 0 ?
 // lights.pdf_value sums over ALL lights the ray crosses (hittable_list.rs:408-412), so the walk needs no ordering and no range
 // shrinking — its whole state is one index plus the running sum, which is what lets the wavefront's CONNECT stage keep two walks
 // per lane in flight and suspend / resume them.
-struct __align__(16) LNode { float c[3], hx, hy, hz; int32_t skip, leaf; };
+struct __align__(32) LNode { float c[3], hx, hy, hz; int32_t skip, leaf; };
 constexpr int32_t kLNodeInner = -1, kLNodeEmpty = -2, kLNodeLight = -3;
 static_assert(sizeof(LNode) == 32, "two 16-byte loads per node");
 
@@ -319,6 +319,25 @@ RTW_D uint32_t lds32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+// 32 bytes with ONE request to the L1/TEX pipe (sm_100: ld.global.v8, SASS LDG.E.ENL2.256); p must be 32-byte aligned, read-only data
+struct F8 { float4 a, b; };
+RTW_D F8 ldg256(const void* p) {
+    F8 r;
+#ifndef RTW_NO_LDG256
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#else
+    r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+    return r;
+}
+// 16 bytes of read-only global data.  Unlike __ldg (asm volatile in the CUDA headers) an unused result is dropped by the compiler, so a
+// record can be fetched as a whole and only the chunks a code path reads turn into loads.
+RTW_D float4 ldg128(const void* p) {
+    float4 v;
+    asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 RTW_D void unpack_node(float4 a, float4 b, float4 c, float4 d, Node<float>& nd) {
     nd.la[0] = a.x; nd.la[1] = a.y; nd.la[2] = a.z; nd.lb[0] = a.w;
     nd.lb[1] = b.x; nd.lb[2] = b.y; nd.ra[0] = b.z; nd.ra[1] = b.w;
@@ -328,8 +347,18 @@ RTW_D void unpack_node(float4 a, float4 b, float4 c, float4 d, Node<float>& nd) 
 // accessors: generic (any T) / FP32 vectorised / FP32 shared
 template <class T> RTW_D void load_node(const SceneView<T>& sc, int32_t cur, Node<T>& nd) { nd = cur < sc.n_top ? sc.top_nodes[cur] : sc.nodes[cur]; }
 RTW_D void load_node(const SceneView<float>& sc, int32_t cur, Node<float>& nd) {
+#ifndef RTW_NO_LDG256
+    if (cur < sc.n_top) {                                    // the BFS prefix a kernel has staged in shared memory (n_top > 0 only then)
+        const uint32_t p = (uint32_t)__cvta_generic_to_shared(sc.top_nodes) + (uint32_t)cur * 64u;
+        unpack_node(lds128(p), lds128(p + 16), lds128(p + 32), lds128(p + 48), nd);
+    } else {                                                 // global memory: two 256-bit loads (cudaMalloc'ed, 64-byte records)
+        const F8 lo = ldg256(sc.nodes + cur), hi = ldg256(reinterpret_cast<const char*>(sc.nodes + cur) + 32);
+        unpack_node(lo.a, lo.b, hi.a, hi.b, nd);
+    }
+#else
     const float4* p = reinterpret_cast<const float4*>(cur < sc.n_top ? sc.top_nodes + cur : sc.nodes + cur);
     unpack_node(p[0], p[1], p[2], p[3], nd);
+#endif
 }
 RTW_D void load_node(const SceneViewSh<float>& sc, int32_t cur, Node<float>& nd) {
     uint32_t p = sc.s_nodes + (uint32_t)cur * sc.s_node_stride;
@@ -353,21 +382,22 @@ RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
 // General scenes (rtw_general.cuh): one table of list entries (entity kind + index + optional Transformed<T>) under one BVH.
 enum PrimKind : uint32_t { P_SPHERE = 0, P_PLANE = 1, P_QUAD = 2, P_TRIANGLE = 3, P_CUBOID = 4, P_NO_LIGHTS = 7 };
 enum MatKindG : uint32_t { DIFFUSE_LIGHT = 4, ISOTROPIC = 5 };
-template <class T> struct GQuad { V3<T> q, u, v, w, normal; T area; };       // Quad / Triangle / one Cuboid face (quadrilateral.rs:23-32)
+// (general-scene records are 16-byte aligned and padded to whole 16-byte chunks: the FP32 kernels fetch them with 128-bit loads, g_rec)
+template <class T> struct alignas(16) GQuad { V3<T> q, u, v, w, normal; T area; };       // Quad / Triangle / one Cuboid face (quadrilateral.rs:23-32)
 // get_plane_uv (plane.rs:41-55) rotates (p - point) about k = normalize(normal x +y) by theta = angle(normal, +y) unless theta <= EPSILON;
 // theta, cos, sin and k depend on the plane only and are evaluated on the host in f64 (the same libm calls the reference makes per hit)
-template <class T> struct GPlane { V3<T> point, normal, k; T cos_theta, sin_theta; uint32_t rotated, pad; };
-template <class T> struct GXform { T fwd[9], ft[3], inv[9], it[3]; };         // Transformation and its inverse (transformations.rs:96-136)
-template <class T> struct GPrim {
+template <class T> struct alignas(16) GPlane { V3<T> point, normal, k; T cos_theta, sin_theta; uint32_t rotated, pad; };
+template <class T> struct alignas(16) GXform { T fwd[9], ft[3], inv[9], it[3]; };         // Transformation and its inverse (transformations.rs:96-136)
+template <class T> struct alignas(16) GPrim {
     T box[6];                // the entry's own world-space box (min, max): bounded_hit's test on the exact path
     uint32_t kind, first;    // entity kind; index into spheres / plane_geo / quads (cuboid: first of its six quads)
     uint32_t mat, id;        // material index; position in the world list (the primitive id the batch calls report)
     int32_t xform;           // -1, or index into xforms: the entry is a Transformed<T>
     uint32_t pad;
 };
-template <class T> struct GMat { T albedo[3], param; uint32_t kind, texture; };                 // texture: 0 = SolidColour(albedo), k = textures[k-1]
+template <class T> struct alignas(16) GMat { T albedo[3], param; uint32_t kind, texture; };                 // texture: 0 = SolidColour(albedo), k = textures[k-1]
 enum TexKind : uint32_t { TEX_NOISE = 1, TEX_CHECKER = 2 };
-template <class T> struct GTex { uint32_t kind, perlin, even, odd; T scale, even_c[3], odd_c[3]; };   // texture.rs:24-102
+template <class T> struct alignas(16) GTex { uint32_t kind, perlin, even, odd; T scale, even_c[3], odd_c[3]; };   // texture.rs:24-102
 template <class T> struct GPerlin { T rand_vec[256][3]; uint8_t perm_x[256], perm_y[256], perm_z[256]; };
 template <class T> struct SceneViewG {
     const Node<T>* nodes;          // BVH over `prims` (leaf ranges index it)

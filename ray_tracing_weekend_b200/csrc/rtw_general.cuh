@@ -7,6 +7,26 @@
 
 namespace rtw {
 
+// One scene record.  The exact path reads it in place.  The FP32 kernels fetch it with 128-bit non-coherent loads (LDG.E.128.CONSTANT):
+// the records are read-only, 16-byte aligned and whole 16-byte chunks long (rtw_device.cuh), while member-by-member reads through a
+// `const R&` compiled to one generic 32-bit load per float — 16 per tested quad, 12 per list entry (SASS of round 1: 247 scalar loads
+// in the kernel) — in kernels that sit at the instruction-cache knee.
+template <class T> struct GRec {
+    template <class R> static RTW_D const R& get(const R* p) { return *p; }
+};
+#ifndef RTW_G_SCALAR_LOADS
+template <> struct GRec<float> {
+    template <class R> static RTW_D R get(const R* p) {
+        static_assert(sizeof(R) % 16 == 0 && alignof(R) >= 16, "general-scene records are whole 16-byte chunks");
+        union U { R r; float4 q[sizeof(R) / 16]; RTW_D U() {} } u;
+        const float4* src = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(R) / 16); ++i) u.q[i] = ldg128(src + i);
+        return u.r;
+    }
+};
+#endif
+
 // ---- Transformed<T> (entities/transformations.rs:14-29, geometry/src/transformations.rs:118-126) ----------------
 template <class T> RTW_D V3<T> g_mat_vec(const T* m, V3<T> v) {                      // matrix3.rs:88-100: row . v
     return mk<T>(dot(mk<T>(m[0], m[1], m[2]), v), dot(mk<T>(m[3], m[4], m[5]), v), dot(mk<T>(m[6], m[7], m[8]), v));
@@ -67,7 +87,8 @@ RTW_D bool g_quad_hit(const GQuad<T>& Q, bool tri, const Ray<T>& r, T tmin, T tm
 // Hittable::hit of one list entry in the entity's own space; *sub = the quad that was hit (cuboid face)
 template <class T, bool EXACT, bool COUNT>
 RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>& r, T tmin, T tmax, T* t_out, uint32_t* sub, Tally& tl) {
-    Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
+    Ray<T> rr = r;
+    if (pr.xform >= 0) { const auto& X = GRec<T>::get(sc.xforms + pr.xform); rr = g_instance_ray<T>(X, r); }
     *sub = pr.first;
     switch (pr.kind) {
     case P_SPHERE: {
@@ -77,7 +98,7 @@ RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>&
         else return sphere_root_fast(sc.spheres[pr.first], rr, frcp(a), tmin, tmax, t_out);
     }
     case P_PLANE: {                                                                     // plane.rs:61-76, one-sided
-        const GPlane<T>& pl = sc.plane_geo[pr.first];
+        const auto& pl = GRec<T>::get(sc.plane_geo + pr.first);
         T denom = g_dot(rr.d, pl.normal);
         if (!(denom > M<T, EXACT>::EPS)) return false;
         T t = -g_dot(rr.o - pl.point, pl.normal) / denom;
@@ -96,7 +117,8 @@ RTW_D bool g_prim_hit(const SceneViewG<T>& sc, const GPrim<T>& pr, const Ray<T>&
 #pragma unroll 1
         for (uint32_t f = 0; f < faces; ++f) {
             T t;
-            if (g_quad_hit<T, EXACT>(sc.quads[pr.first + f], tri, rr, tmin, tmax, &t) && (!any || t < best)) { any = true; best = t; *sub = pr.first + f; }
+            const auto& Q = GRec<T>::get(sc.quads + pr.first + f);
+            if (g_quad_hit<T, EXACT>(Q, tri, rr, tmin, tmax, &t) && (!any || t < best)) { any = true; best = t; *sub = pr.first + f; }
         }
         *t_out = best;
         return any;
@@ -292,7 +314,7 @@ template <class T> RTW_D V3<T> g_texture(const SceneViewG<T>& sc, const GMat<T>&
 
 // ---- closest hit over the planes + the BVH of bounded entries ----------------------------------------------------
 // The winner as two words: code >= 0: index into sc.prims, code <= -2: unbounded entry -2 - code; sub = the quad that was hit.
-template <class T> RTW_D const GPrim<T>& g_entry(const SceneViewG<T>& sc, int32_t code) { return code >= 0 ? sc.prims[code] : sc.unbounded[-2 - code]; }
+template <class T> RTW_D const GPrim<T>* g_entry(const SceneViewG<T>& sc, int32_t code) { return code >= 0 ? sc.prims + code : sc.unbounded + (-2 - code); }
 
 template <class T, bool EXACT, bool COUNT>
 RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, const GPrim<T>** best_out, uint32_t* sub_out, T* t_out,
@@ -319,7 +341,8 @@ RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T t
 #pragma unroll 1
         for (; i < end; ++i) {
             const bool unb = i < nu;
-            const GPrim<T>& pr = unb ? sc.unbounded[i] : sc.prims[i - nu];
+            const GPrim<T>* pp = unb ? sc.unbounded + i : sc.prims + (i - nu);
+            const auto& pr = GRec<T>::get(pp);
             // The entry's own box, where it is part of the result.  Unbounded entries: bounded_hit (hittable.rs:191-196) with
             // Plane::get_aabbox (plane.rs:78-107) — an axis-aligned plane's box is the slab {axis = 0} whatever the plane's offset,
             // tested in both precisions.  Bounded entries: the exact path repeats bounded_hit with the un-shrunk range; the fast
@@ -332,7 +355,7 @@ RTW_D bool g_closest_entry(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T t
             }
             T t; uint32_t sub;
             if (g_prim_hit<T, EXACT, COUNT>(sc, pr, r, tmin, tmax, &t, &sub, tl) && (!found || t < best_t)) {
-                found = true; best_t = t; best = &pr; best_sub = sub;
+                found = true; best_t = t; best = pp; best_sub = sub;
             }
         }
         while (cur >= 0) {
@@ -383,6 +406,14 @@ RTW_D bool g_closest_prim(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tm
     return true;
 }
 
+// the normal alone: words 12..14 of the record (one 128-bit load in FP32)
+template <class T> RTW_D V3<T> g_quad_normal(const GQuad<T>* Q) { return Q->normal; }
+#ifndef RTW_G_SCALAR_LOADS
+template <> RTW_D V3<float> g_quad_normal<float>(const GQuad<float>* Q) {
+    const float4 v = ldg128(reinterpret_cast<const float4*>(Q) + 3);
+    return mk<float>(v.x, v.y, v.z);
+}
+#endif
 // (u, v) of a hit, read by CheckerTexture only — out of line like the texture lookup itself (code size, see g_texture_lookup)
 template <class T, bool EXACT>
 __device__ __noinline__ V3<T> g_hit_uv(const SceneViewG<T>& sc, const GPrim<T>& pr, uint32_t best_sub, V3<T> pi, V3<T> outward) {
@@ -390,7 +421,7 @@ __device__ __noinline__ V3<T> g_hit_uv(const SceneViewG<T>& sc, const GPrim<T>& 
     T* u = &uu; T* v = &vv;
     if (pr.kind == P_SPHERE) g_sphere_uv<T, EXACT>(outward.x, outward.y, outward.z, u, v);               // of the outward normal, sphere.rs:83-84
     else if (pr.kind == P_PLANE) {                                         // get_plane_uv, plane.rs:41-55
-        const GPlane<T>& pl = sc.plane_geo[pr.first];
+        const auto& pl = GRec<T>::get(sc.plane_geo + pr.first);
         if (!pl.rotated) { *u = pi.x; *v = pi.z; }                         // the normal is +y
         else {                                                             // Rodrigues' rotation onto +y, then f64::fract of x and z
             V3<T> w = pi - pl.point;
@@ -398,7 +429,7 @@ __device__ __noinline__ V3<T> g_hit_uv(const SceneViewG<T>& sc, const GPrim<T>& 
             *u = rot.x - trunc(rot.x); *v = rot.z - trunc(rot.z);
         }
     } else {                                                               // get_quad_uv, quadrilateral.rs:58-63
-        const GQuad<T>& Q = sc.quads[best_sub];
+        const auto& Q = GRec<T>::get(sc.quads + best_sub);
         V3<T> pq = pi - Q.q;
         *u = dot(cross(pq, Q.v), Q.w); *v = dot(cross(Q.u, pq), Q.w);
     }
@@ -407,8 +438,10 @@ __device__ __noinline__ V3<T> g_hit_uv(const SceneViewG<T>& sc, const GPrim<T>& 
 
 // HitRecord::new (hittable.rs:102-129) for the winner, in the entity's space, then p back to world space (transformations.rs:21-27)
 template <class T, bool EXACT>
-RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>& pr, uint32_t best_sub, T best_t, Hit<T>* h) {
-    Ray<T> rr = pr.xform >= 0 ? g_instance_ray<T>(sc.xforms[pr.xform], r) : r;
+RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>* entry, uint32_t best_sub, T best_t, Hit<T>* h) {
+    const auto& pr = GRec<T>::get(entry);
+    Ray<T> rr = r;
+    if (pr.xform >= 0) { const auto& X = GRec<T>::get(sc.xforms + pr.xform); rr = g_instance_ray<T>(X, r); }
     h->t = best_t;
     V3<T> p = pr.kind == P_SPHERE ? at(rr, best_t) : g_at(rr, best_t);
     V3<T> outward;
@@ -417,15 +450,15 @@ RTW_D void g_hit_record(const SceneViewG<T>& sc, const Ray<T>& r, const GPrim<T>
         if constexpr (EXACT) outward = (p - mk<T>(s.x, s.y, s.z)) / s.w;
         else outward = (p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
     } else if (pr.kind == P_PLANE) outward = sc.plane_geo[pr.first].normal;
-    else outward = sc.quads[best_sub].normal;
+    else outward = g_quad_normal<T>(sc.quads + best_sub);
     h->front_face = dot(rr.d, outward) < T(0);
     h->normal = h->front_face ? outward : -outward;
     if (pr.xform >= 0) {
-        const GXform<T>& X = sc.xforms[pr.xform];
+        const auto& X = GRec<T>::get(sc.xforms + pr.xform);
         p = g_mat_vec<T>(X.fwd, p) + mk<T>(X.ft[0], X.ft[1], X.ft[2]);
     }
     h->p = p;
-    const GMat<T>& m = sc.mats[pr.mat];
+    const auto& m = GRec<T>::get(sc.mats + pr.mat);
     h->gkind = m.kind;
     h->info = (pr.id << 2) | (m.kind & 3u);
     h->param = m.param;
@@ -444,7 +477,7 @@ template <class T, bool EXACT, bool COUNT>
 RTW_D bool g_closest_hit(const SceneViewG<T>& sc, const Ray<T>& r, T tmin, T tmax, Hit<T>* h, int32_t* stack, int stride, Tally& tl) {
     const GPrim<T>* best; uint32_t sub; T t;
     if (!g_closest_entry<T, EXACT, COUNT>(sc, r, tmin, tmax, &best, &sub, &t, stack, stride, tl)) return false;
-    g_hit_record<T, EXACT>(sc, r, *best, sub, t, h);
+    g_hit_record<T, EXACT>(sc, r, best, sub, t, h);
     return true;
 }
 
@@ -456,7 +489,7 @@ RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tal
     Ray<T> r{origin, dir};
     T a = sqlen(dir);
     for (int i = 0; i < sc.n_lights; ++i) {
-        const GPrim<T>& pr = sc.lights[i];
+        const auto& pr = GRec<T>::get(sc.lights + i);
         T v = T(0);
         if (pr.xform < 0) {                                        // Transformed<T>, Cuboid, Plane: Hittable default 0 (hittable.rs:175-177)
             if (pr.kind == P_SPHERE) {                             // sphere.rs:101-111
@@ -478,7 +511,7 @@ RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tal
                 }
             } else if (pr.kind == P_QUAD || pr.kind == P_TRIANGLE) {   // quadrilateral.rs:100-112
                 if (COUNT) tl.light_tests++;
-                const GQuad<T>& Q = sc.quads[pr.first];
+                const auto& Q = GRec<T>::get(sc.quads + pr.first);
                 T t;
                 if (g_quad_hit<T, EXACT>(Q, pr.kind == P_TRIANGLE, r, T(0), Mt::inf(), &t)) {
                     T distance_squared = t * t * a;
@@ -501,11 +534,11 @@ RTW_D T g_lights_pdf_value(const SceneViewG<T>& sc, V3<T> origin, V3<T> dir, Tal
 }
 template <class T, bool EXACT>
 RTW_D V3<T> g_lights_random(const SceneViewG<T>& sc, V3<T> origin, Stream<EXACT>& rng) {
-    const GPrim<T>& pr = sc.lights[uindex(rng, (uint32_t)sc.n_lights)];
+    const auto& pr = GRec<T>::get(sc.lights + uindex(rng, (uint32_t)sc.n_lights));
     if (pr.xform < 0) {
         if (pr.kind == P_SPHERE) return sphere_random<T, EXACT>(sc.spheres[pr.first], origin, rng);
         if (pr.kind == P_QUAD || pr.kind == P_TRIANGLE) {         // quadrilateral.rs:114-118, triangles.rs:108-117
-            const GQuad<T>& Q = sc.quads[pr.first];
+            const auto& Q = GRec<T>::get(sc.quads + pr.first);
             T r1 = open01(rng), r2 = open01(rng);
             if (pr.kind == P_TRIANGLE && r1 + r2 > T(1)) { r1 = T(1) - r1; r2 = T(1) - r2; }
             return ((Q.q + Q.u * r1) + Q.v * r2) - origin;

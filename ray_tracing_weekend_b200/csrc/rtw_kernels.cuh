@@ -354,9 +354,8 @@ RTW_D int32_t light_walk_step(const SC& sc, float4 a, float4 b, V3<float> origin
 template <bool COUNT, class SC>
 RTW_D int32_t light_walk(const SC& sc, V3<float> origin, V3<float> nd, const RayAux& aux, int32_t cur, float& acc, uint32_t max_steps, Tally& tl) {
     for (uint32_t step = 0; cur >= 0 && step < max_steps; ++step) {
-        const float4* p = reinterpret_cast<const float4*>(sc.light_nodes + cur);
-        const float4 a = __ldg(p), b = __ldg(p + 1);
-        cur = light_walk_step<COUNT>(sc, a, b, origin, nd, aux, cur, acc, tl);
+        const F8 n = ldg256(sc.light_nodes + cur);
+        cur = light_walk_step<COUNT>(sc, n.a, n.b, origin, nd, aux, cur, acc, tl);
     }
     return cur;
 }
@@ -366,11 +365,11 @@ template <bool COUNT, class SC>
 RTW_D void light_walk_pair(const SC& sc, V3<float> o0, V3<float> n0, const RayAux& x0, int32_t& c0, float& acc0,
                            V3<float> o1, V3<float> n1, const RayAux& x1, int32_t& c1, float& acc1, uint32_t max_steps, Tally& tl) {
     for (uint32_t step = 0; (c0 >= 0 || c1 >= 0) && step < max_steps; ++step) {
-        const float4* p0 = reinterpret_cast<const float4*>(sc.light_nodes + (c0 >= 0 ? c0 : 0));
-        const float4* p1 = reinterpret_cast<const float4*>(sc.light_nodes + (c1 >= 0 ? c1 : 0));
-        const float4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
-        if (c0 >= 0) c0 = light_walk_step<COUNT>(sc, a0, b0, o0, n0, x0, c0, acc0, tl);
-        if (c1 >= 0) c1 = light_walk_step<COUNT>(sc, a1, b1, o1, n1, x1, c1, acc1, tl);
+        // one 256-bit load per node (LDG.E.ENL2.256): the walk is bound by the L1/TEX pipe (ncu, C4: 76 % busy), which handles a
+        // node's two 16-byte halves as two requests
+        const F8 m0 = ldg256(sc.light_nodes + (c0 >= 0 ? c0 : 0)), m1 = ldg256(sc.light_nodes + (c1 >= 0 ? c1 : 0));
+        if (c0 >= 0) c0 = light_walk_step<COUNT>(sc, m0.a, m0.b, o0, n0, x0, c0, acc0, tl);
+        if (c1 >= 0) c1 = light_walk_step<COUNT>(sc, m1.a, m1.b, o1, n1, x1, c1, acc1, tl);
     }
 }
 
@@ -783,7 +782,9 @@ struct PoolParams {
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
     float sample_cap;               // samples of this radiance or more set the overflow flag instead of being added (pool_sample_cap)
+    const uint32_t* chunk_order;    // [n_chunks] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x7fffffff (chunk_order_kernel)
 };
+constexpr uint32_t kChunkCheap = 0x80000000u;
 
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
 // ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
@@ -1035,6 +1036,57 @@ __global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_ke
         else out = make_uint4(ids[0], ids[1], ids[2], ids[3]);
     }
     cand[j * cam.width + i] = out;
+}
+
+// Order of the work queue: longest processing time first.  A path that only sees background ends in GENERATE; a path that meets a
+// sphere bounces on for up to max_depth vertices (zero-weight paths are followed to the end like in the reference), and with
+// warp-private queues the frame is over when the LAST such path is — ~0.7 ms after the stream has run dry on `simple`, whatever the
+// sample count (depth 1: none of it), i.e. 3 % of the 24 ms one of eight GPUs spends on its share.  The candidate lists already say
+// which pixels can meet a sphere; a one-sided plane is met iff one of the pixel's corner rays meets it (the set of such directions is
+// a half-space).  Chunks with such a pixel are dealt out first, the background-only chunks last — flagged kChunkCheap, on which a warp
+// switches to "old paths first" — so the long paths end while the cheap tail of the stream still keeps every warp busy.
+// Scheduling only: paths, RNG streams and the fixed-point sums do not depend on who traces what when.
+// order[n_chunks] / order[n_chunks + 1]: the two cursors (zeroed by the host).
+template <int UNUSED = 0>
+__global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, CameraT<float> cam, uint32_t rank, uint32_t world, uint32_t tiles_x,
+                                   uint32_t tiles_total, uint32_t n_slots, uint32_t G, uint32_t n_chunks, uint32_t* order) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    bool costly = false;
+    const uint32_t q1 = min(n_slots, (c + 1u) * G);
+    for (uint32_t q = c * G; q < q1 && !costly; ++q) {
+        const uint32_t tile = (q >> 8) * world + rank, in = q & 255u;
+        if (tile >= tiles_total) continue;
+        uint32_t ttx, tty;
+        slot_tile(tile, tiles_x, &ttx, &tty);
+        const uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
+        if (i >= cam.width || j >= cam.height) continue;
+        if (__ldg(cand + (size_t)j * cam.width + i).x != kCandNone) { costly = true; break; }
+        for (int k = 0; k < sc.n_planes && !costly; ++k) {
+            const PlaneT<float>& pl = sc.planes[k];
+            const float side = -dot(cam.center - pl.point, pl.normal);
+#pragma unroll
+            for (int corner = 0; corner < 4; ++corner) {
+                const float fi = (float)i + ((corner & 1) ? 0.5f : -0.5f), fj = (float)j + ((corner & 2) ? 0.5f : -0.5f);
+                const V3<float> d = (cam.pixel00 + cam.du * fi) + cam.dv * fj - cam.center;
+                const float denom = dot(d, pl.normal);
+                if (denom > 0.f && side >= 0.f) costly = true;
+            }
+        }
+    }
+    // ballot-aggregated cursors: one atomic per warp and class
+    const uint32_t lane = threadIdx.x & 31u, active = __activemask();
+    const uint32_t mc = __ballot_sync(active, costly), mh = active & ~mc;
+    uint32_t base_c = 0, base_h = 0;
+    const uint32_t leader = (uint32_t)__ffs(active) - 1u;
+    if (lane == leader) {
+        if (mc) base_c = atomicAdd(order + n_chunks, (uint32_t)__popc(mc));
+        if (mh) base_h = atomicAdd(order + n_chunks + 1, (uint32_t)__popc(mh));
+    }
+    base_c = __shfl_sync(active, base_c, (int)leader); base_h = __shfl_sync(active, base_h, (int)leader);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (costly) order[base_c + (uint32_t)__popc(mc & lt)] = c;
+    else order[n_chunks - 1u - (base_h + (uint32_t)__popc(mh & lt))] = c | kChunkCheap;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 uint32_t pool_pixels_per_chunk(uint32_t spp);
 float pool_sample_cap(uint32_t spp_total);
 cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, uint4* cand, cudaStream_t s);
+// order[0 .. n_chunks): the work queue's chunk order (costly chunks first), order[n_chunks .. n_chunks + 2): scratch cursors
+cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
+                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
+                                   uint32_t* order, cudaStream_t s);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t wavefront_max_bvh_depth();

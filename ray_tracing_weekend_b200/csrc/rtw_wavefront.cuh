@@ -151,12 +151,16 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     uint32_t n_free = NPW, n_ext = 0, n_lamb = 0, n_metal = 0, n_diel = 0, n_conn = 0;
     uint32_t chunk_next = 0, chunk_end = 0, chunk_q0 = 0;
     bool exhausted = (spp == 0 || cam.max_depth == 0);       // max_depth == 0: every path returns 0 (camera.rs:470-472)
+    bool cheap_phase = false;                                // the queue has reached its background-only chunks (chunk_order_kernel)
     for (uint32_t i = lane; i < NPW; i += 32) S.list[WF_FREE][i] = (uint8_t)i;
 
     for (;;) {
         __syncwarp();
         // ---- pick the stage with the longest list (free slots only count while the stream has paths left) ----
         uint32_t nf = (exhausted && chunk_next == chunk_end) ? 0u : n_free;
+        // cheap tail of the stream: old paths first, whatever the length of their lists — new paths there end in GENERATE anyway, and
+        // every pass spent on an old one now is a pass that does not keep the frame waiting after the stream has run dry
+        if (cheap_phase && (n_ext | n_lamb | n_metal | n_diel | n_conn)) nf = 0u;
         int stage = WF_FREE;
         uint32_t best = nf;
         if (n_ext > best) { best = n_ext; stage = WF_EXT; }
@@ -173,6 +177,11 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 if (lane == 0) c = atomicAdd(P.work_counter, 1u);
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c >= Q.n_chunks) { exhausted = true; continue; }
+                if (Q.chunk_order) {
+                    c = __ldg(Q.chunk_order + c);
+                    cheap_phase = (c & kChunkCheap) != 0u;
+                    c &= ~kChunkCheap;
+                }
                 chunk_q0 = c * G;
                 uint32_t npx = min(G, n_slots - chunk_q0);
                 chunk_next = 0; chunk_end = npx * spp;
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     hit = g_closest_prim<T, EXACT, COUNT>(sc, r, P.tmin, M<T, EXACT>::inf(), &bestp, &sub, &best_t, stack, BLOCK, tl);
                     if (hit) {
                         S.ht[slot] = best_t; S.hp[slot] = bestp; S.hs[slot] = sub;
-                        uint32_t k = sc.mats[g_entry<T>(sc, bestp).mat].kind;
+                        uint32_t k = sc.mats[g_entry<T>(sc, bestp)->mat].kind;
                         // DiffuseLight / Invisible never scatter (mult * emitted + res, camera.rs:484-486): they ride the first shade
                         // list, where g_shade returns V_ABSORB — a second inlined hit record here cost more in instruction fetch
                         // than the extra pass does

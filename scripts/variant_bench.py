@@ -5,7 +5,7 @@ knobs from the environment (RTW_SH_NODE_STRIDE, ...).  Every variant runs in its
 process), renders the same frame, and reports the best / median kernel time plus a SHA-1 of the resolved image so that
 "bit-identical to the baseline" is checked, not assumed.
 
-  python scripts/variant_bench.py [--config C2|C1|C4|C5] [--spp N] [--reps K] name[:lib][,ENV=val...] ...
+  python scripts/variant_bench.py [--config C2|C1|C4|C5|cornell_box|simple_light|debugging_scene|simple_transform|checkered_spheres] [--spp N] [--reps K] name[:lib][,ENV=val...] ...
   python scripts/variant_bench.py --child ...        (internal)
 """
 import hashlib
@@ -14,6 +14,8 @@ import os
 import subprocess
 import sys
 
+GENERAL = {"cornell_box": (1024, 1024), "simple_light": (1920, 1080), "debugging_scene": (1920, 1080), "simple_transform": (1920, 1080),
+           "checkered_spheres": (1920, 1080)}
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 SEED = 20261018
@@ -24,6 +26,13 @@ def child(config, spp, reps, mode):
     import ray_tracing_weekend_b200 as R
     w, h = 1920, 1080
     cam_edit = None
+    if config in GENERAL:                       # the reference's other scenes through the general path (scripts/general_configs.py sizes)
+        w, h = GENERAL[config]
+        gen = getattr(R.scenes, config)
+        world, lights, cb = gen() if config in ("cornell_box", "checkered_spheres") else gen(SEED)
+        sc = R.Scene(world, lights)
+        cam = cb.with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h).with_samples_per_pixel(spp).build()
+        return run(R, sc, cam, reps, mode)
     if config == "C1":
         arrays, w, h = R.scenes.simple_arrays(SEED), 400, 225
     elif config == "C5":
@@ -38,6 +47,10 @@ def child(config, spp, reps, mode):
     if cam_edit:
         cb = cam_edit(cb)
     cam = cb.build()
+    return run(R, sc, cam, reps, mode)
+
+
+def run(R, sc, cam, reps, mode):
     opts = R.RenderOptions(seed=SEED, mode=R.RTW_WAVEFRONT if mode == "wavefront" else R.RTW_MEGAKERNEL)
     times, st, rgb8 = [], None, None
     for k in range(reps + 1):

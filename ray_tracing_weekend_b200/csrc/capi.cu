@@ -201,6 +201,8 @@ void multi_release(rtw_scene* s);
 inline double light_w(double r) { return r; }
 inline float light_w(float r) { volatile float r2 = r * r; return r2; }
 
+constexpr size_t kIsolationMaxSpheres = 4096;
+
 template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_device = false) {
     const host::Bvh& b = s->bvh;
     std::vector<Node<T>> nodes(world_on_device ? 0 : b.nodes.size());
@@ -223,6 +225,24 @@ template <class T> int upload_scene(rtw_scene* s, SceneDev<T>& d, bool world_on_
         sph[k] = Vec4T<T>{(T)q.cx, (T)q.cy, (T)q.cz, (T)q.r};
         mat[k] = Vec4T<T>{(T)m.r, (T)m.g, (T)m.b, (T)m.param};
         info[k] = ((uint32_t)(np + src) << 2) | (m.kind & 3u);
+    }
+    // kSphereIsolated (see closest_prim_self): no other sphere's SURFACE comes near the ball of this one — a ray that leaves the sphere
+    // and meets it again cannot meet anything else first.  Distance from c_s to the surface of o is | |c_s - c_o| - r_o |; the ball is
+    // inflated by 0.1 % plus 1e-4 of the lengths involved, far beyond the FP32 error of a root.  O(n^2) on the host, small scenes only.
+    static const bool iso_allowed = [] { const char* e = std::getenv("RTW_NO_SELF_HIT"); return !(e && std::atoi(e) == 1); }();   // A/B measurements
+    if (sizeof(T) == 4 && iso_allowed && ns_host <= kIsolationMaxSpheres && ns + np < (1u << 29)) {
+        for (size_t k = 0; k < ns_host; ++k) {
+            const rtw_sphere& a = s->spheres[b.order[k]];
+            bool isolated = a.r > 0. && std::isfinite(a.r);
+            for (size_t j = 0; j < ns_host && isolated; ++j) {
+                if (j == k) continue;
+                const rtw_sphere& o = s->spheres[b.order[j]];
+                const double dx = a.cx - o.cx, dy = a.cy - o.cy, dz = a.cz - o.cz, D = std::sqrt(dx * dx + dy * dy + dz * dz);
+                const double R = a.r * 1.001 + 1e-4 * (D + std::fabs(o.r)) + 1e-6;
+                if (!(std::fabs(D - std::fabs(o.r)) > R)) isolated = false;
+            }
+            if (isolated) info[k] |= kSphereIsolated;
+        }
     }
     // lights: insertion order; on the FP32 path a long list gets its own BVH (leaf order) so that
     // lights.pdf_value is not O(#lights) per diffuse bounce

@@ -238,6 +238,9 @@ template <> struct M<float, false> {
 // ---------------------------------------------------------------------------------------------
 // Flattened scene.  Spheres are stored in BVH-leaf order ("sorted" index); info = prim_id << 2 | kind.
 enum MatKind : uint32_t { LAMBERTIAN = 0, METAL = 1, DIELECTRIC = 2, INVISIBLE = 3 };
+// bit 31 of a sphere's info word (FP32 scene copy only; set by the host for small scenes): the sphere is ISOLATED — no other sphere's
+// surface comes near its ball — see closest_prim_self
+constexpr uint32_t kSphereIsolated = 0x80000000u;
 
 template <class T> struct Vec4T { T x, y, z, w; };
 template <> struct __align__(16) Vec4T<float> { float x, y, z, w; };

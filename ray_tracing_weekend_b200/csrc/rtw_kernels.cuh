@@ -126,7 +126,7 @@ RTW_D void hit_record(const SC& sc, const Ray<T>& r, int32_t best, T best_t, Hit
         if constexpr (EXACT) outward = (h->p - mk<T>(s.x, s.y, s.z)) / s.w;            // sphere.rs:82-83
         else outward = (h->p - mk<T>(s.x, s.y, s.z)) * frcp(s.w);
         Vec4T<T> m = load_sphere_mat(sc, best);
-        h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = load_sphere_info(sc, best);
+        h->albedo = mk<T>(m.x, m.y, m.z); h->param = m.w; h->info = load_sphere_info(sc, best) & ~kSphereIsolated;
     } else {
         const PlaneT<T>& pl = sc.planes[-2 - best];
         outward = pl.normal;
@@ -183,6 +183,28 @@ RTW_D bool closest_prim_candidates(const SC& sc, const Ray<float>& r, float tmin
     *best_out = best;
     *t_out = best_t;
     return found;
+}
+
+// A ray that LEAVES sphere `from` (the hit point of the previous vertex) and meets the same sphere again — self-intersection at the
+// reference's tmin (about half the diffuse bounces), a refracted ray crossing its glass sphere, a zero-weight path
+// bouncing on inside one — travels inside that sphere's (slightly inflated) ball from origin to hit point: both ends lie on its
+// surface and a ball is convex.  If the sphere is ISOLATED (kSphereIsolated: no other sphere's surface comes near that ball, checked
+// on the host with a margin far beyond FP32 rounding) no other sphere can be met first, so this root IS the tree walk's argmin: same
+// function, same arguments, same bits.  Planes are unbounded and tested like in closest_prim.  Returns false when the walk is needed.
+template <bool COUNT, class SC>
+RTW_D bool closest_prim_self(const SC& sc, const Ray<float>& r, int32_t from, float tmin, float tmax, int32_t* best_out, float* t_out, Tally& tl) {
+    if (from < 0 || !(load_sphere_info(sc, from) & kSphereIsolated)) return false;
+    if (COUNT) tl.sphere_tests++;
+    float t;
+    if (!sphere_root_fast(load_sphere(sc, from), r, frcp(sqlen(r.d)), tmin, tmax, &t)) return false;
+    bool found = false;
+    float best_t = tmax;
+    int32_t best = -1;
+    closest_plane<float, false, SC>(sc, r, tmin, tmax, found, best_t, best);
+    if (!found || t < best_t) { best_t = t; best = from; }
+    *best_out = best;
+    *t_out = best_t;
+    return true;
 }
 
 template <class T, bool EXACT, bool COUNT, class SC>

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
             const bool active = lane < n;
             uint32_t slot = active ? S.list[stage][cnt + lane] : 0u;
             bool to_ext = false, to_free = false, to_conn = false;
+            uint32_t again = 0xffu;                           // the next ray's closest hit is already known (closest_prim_self): 0..2 material list
             if (active) {
                 Ray<T> r{mk<T>(S.ox[slot], S.oy[slot], S.oz[slot]), mk<T>(S.dx[slot], S.dy[slot], S.dz[slot])};
                 Hit<T> h;
@@ -427,12 +428,32 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                     if (wf_advance<COUNT>(S, slot, kind, next, w, emitted, mult, dep, &fin_value, tl)) {
                         wf_finish(Q, acc, S.q[slot], fin_value, P.flags);
                         to_free = true;
-                    } else to_ext = true;
+                    } else {
+                        to_ext = true;
+                        if constexpr (!GEN) {
+                            // the ray leaves an isolated sphere and meets it again: no EXTEND pass, straight back to a shade list
+                            if (!(P.flags & 8u)) {            // RTW_FLAG_NO_CANDIDATES: every ray walks the tree
+                                T best_t; int32_t bestp;
+                                if (closest_prim_self<COUNT>(sc, next, S.hp[slot], P.tmin, M<T, EXACT>::inf(), &bestp, &best_t, tl)) {
+                                    nrays++;
+                                    S.ht[slot] = best_t; S.hp[slot] = bestp;
+                                    uint32_t k = bestp >= 0 ? (load_sphere_info(sc, bestp) & 3u) : (sc.planes[-2 - bestp].info & 3u);
+                                    again = k == LAMBERTIAN ? 0u : (k == METAL ? 1u : 2u);
+                                    to_ext = false;
+                                }
+                            }
+                        }
+                    }
                 }
             }
             __syncwarp();
             if constexpr (CONN) wf_push(S.conn, n_conn, to_conn, slot, lt_mask);
             wf_push(S.list[WF_EXT], n_ext, to_ext, slot, lt_mask);
+            if constexpr (!GEN) {
+                wf_push(S.list[WF_LAMB], n_lamb, again == 0u, slot, lt_mask);
+                wf_push(S.list[WF_METAL], n_metal, again == 1u, slot, lt_mask);
+                wf_push(S.list[WF_DIEL], n_diel, again == 2u, slot, lt_mask);
+            }
             wf_push(S.list[WF_FREE], n_free, to_free, slot, lt_mask);
         }
     }

@@ -173,3 +173,9 @@ uint32_t pool_pixels_per_chunk(uint32_t spp) {
     return g < 1 ? 1 : (g > 256 ? 256 : g);
 }
 }
+#ifdef RTW_TIMELINE
+extern "C" __attribute__((visibility("default"))) int rtw_debug_timeline(unsigned long long* out, size_t n_words) {
+    const size_t cap = sizeof(rtw::rtw_timeline) / sizeof(unsigned long long);
+    return (int)cudaMemcpyFromSymbol(out, rtw::rtw_timeline, sizeof(unsigned long long) * (n_words < cap ? n_words : cap));
+}
+#endif

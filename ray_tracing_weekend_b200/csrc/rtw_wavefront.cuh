@@ -112,6 +112,13 @@ RTW_D int wf_advance(WS& S, uint32_t slot, uint32_t kind, const Ray<float>& next
 #endif
 constexpr uint32_t kConnQuantum = RTW_CONN_QUANTUM;
 
+#ifdef RTW_TIMELINE
+// diagnostic build (scripts/timeline_probe.py): per warp, %globaltimer at kernel entry / first background-only chunk / queue dry / exit,
+// the paths still in flight when the queue ran dry and the stage passes made after that
+__device__ unsigned long long rtw_timeline[148 * 32 * 8];
+RTW_D unsigned long long wf_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>, bool CONN = false>
 __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float, SCENE> P, PoolParams Q) {
     using T = float;
@@ -153,9 +160,17 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     bool exhausted = (spp == 0 || cam.max_depth == 0);       // max_depth == 0: every path returns 0 (camera.rs:470-472)
     bool cheap_phase = false;                                // the queue has reached its background-only chunks (chunk_order_kernel)
     for (uint32_t i = lane; i < NPW; i += 32) S.list[WF_FREE][i] = (uint8_t)i;
+#ifdef RTW_TIMELINE
+    unsigned long long tl_t[4] = {wf_now(), 0ull, 0ull, 0ull};
+    uint32_t tl_inflight = 0, tl_passes = 0;
+#endif
 
     for (;;) {
         __syncwarp();
+#ifdef RTW_TIMELINE
+        if (cheap_phase && !tl_t[1]) tl_t[1] = wf_now();
+        if (exhausted && chunk_next == chunk_end) { if (!tl_t[2]) { tl_t[2] = wf_now(); tl_inflight = NPW - n_free; } tl_passes++; }
+#endif
         // ---- pick the stage with the longest list (free slots only count while the stream has paths left) ----
         uint32_t nf = (exhausted && chunk_next == chunk_end) ? 0u : n_free;
         // cheap tail of the stream: old paths first, whatever the length of their lists — new paths there end in GENERATE anyway, and
@@ -458,6 +473,13 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
         }
     }
     wf_acc_flush(Q, acc);
+#ifdef RTW_TIMELINE
+    tl_t[3] = wf_now();
+    if (lane == 0) {
+        unsigned long long* o = rtw_timeline + ((size_t)blockIdx.x * 32 + warp) * 8;
+        o[0] = tl_t[0]; o[1] = tl_t[1]; o[2] = tl_t[2]; o[3] = tl_t[3]; o[4] = tl_inflight; o[5] = tl_passes; o[6] = npaths; o[7] = nrays;
+    }
+#endif
     flush_counters<COUNT>(P.counters, npaths, nrays, tl);
 }
 

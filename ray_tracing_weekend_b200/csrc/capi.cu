@@ -182,6 +182,7 @@ struct rtw_scene {
     DevBuf<double> d_rgb_sum; DevBuf<uint8_t> d_rgb8;
     DevBuf<unsigned long long> d_accum; DevBuf<uint32_t> d_poison;   // pooled megakernel accumulators
     DevBuf<uint4> d_cand;                                            // candidate lists of the camera rays, rebuilt by every render call
+    DevBuf<unsigned char> d_cand_blocks;                             // ... and the per-block lists of their first level
     DevBuf<uint32_t> d_order;                                        // chunk order of the work queue (costly chunks first), rebuilt by every render call
     DevBuf<double> d_in2, d_in3; DevBuf<uint32_t> d_u3, d_u4;          // rtw_shade_batch inputs
     DevBuf<double> d_in0, d_in1, d_out0, d_out1, d_out2, d_out3, d_out4; DevBuf<uint32_t> d_u0, d_u1, d_u2, d_k; DevBuf<int32_t> d_prim;
@@ -907,7 +908,7 @@ void rtw_scene_destroy(rtw_scene* s) {
     s->f32.release(); s->f64.release(); s->g32.release(); s->g64.release(); s->d_panic.release();
     cached_free(s->d_work, sizeof(unsigned int), s->device);
     cached_free(s->d_counters, sizeof(DeviceCounters), s->device);
-    s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release(); s->d_cand.release(); s->d_order.release();
+    s->d_rgb_sum.release(); s->d_rgb8.release(); s->d_accum.release(); s->d_poison.release(); s->d_cand.release(); s->d_cand_blocks.release(); s->d_order.release();
     s->d_in2.release(); s->d_in3.release(); s->d_u3.release(); s->d_u4.release();
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
@@ -1061,7 +1062,9 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
         // with the lists against 53.3 without on C2 / 100 spp; the images are identical either way)
         if (cand_allowed && !(o->flags & RTW_FLAG_NO_CANDIDATES) && wavefront && cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0) {
             CU(s->d_cand.reserve((size_t)cam->image_width * cam->image_height));
-            CU(launch_primary_candidates_f32(s->f32.view, to_camera<float>(cam), s->d_cand.p, st));
+            CU(s->d_cand_blocks.reserve(primary_candidates_scratch_bytes(cam->image_width, cam->image_height)));
+            CU(launch_primary_candidates_f32(s->f32.view, to_camera<float>(cam), s->d_cand_blocks.p, s->d_cand.p, st));
+            launches++;
             cand = s->d_cand.p;
             launches++;
             // ... and they say which chunks of the path stream can meet a sphere: those go first (chunk_order_kernel)

@@ -142,10 +142,18 @@ cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uin
     return count ? launch_render_wavefront_impl<true>(P, Q, bvh_depth, sm_count, s, info)
                  : launch_render_wavefront_impl<false>(P, Q, bvh_depth, sm_count, s, info);
 }
-cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, uint4* cand, cudaStream_t s) {
+size_t primary_candidates_scratch_bytes(uint32_t width, uint32_t height) {
+    return (size_t)((width + kCandBlock - 1) / kCandBlock) * ((height + kCandBlock - 1) / kCandBlock) * sizeof(CandBlockList);
+}
+cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, void* scratch, uint4* cand, cudaStream_t s) {
     if (!cam.width || !cam.height) return cudaSuccess;
     dim3 grid((cam.width + kCandBlock - 1) / kCandBlock, (cam.height + kCandBlock - 1) / kCandBlock);
-    primary_candidates_kernel<0><<<grid, kCandBlock * kCandBlock, 0, s>>>(scene, cam, cand);
+    const uint32_t n_blocks = grid.x * grid.y;
+    CandBlockList* lists = reinterpret_cast<CandBlockList*>(scratch);
+    block_candidates_kernel<0><<<(n_blocks + 127) / 128, 128, 0, s>>>(scene, cam, grid.x, n_blocks, lists);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    primary_candidates_kernel<0><<<grid, kCandBlock * kCandBlock, 0, s>>>(scene, cam, lists, cand);
     return cudaGetLastError();
 }
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,

@@ -1011,28 +1011,44 @@ RTW_D int cone_walk(const SceneView<float>& sc, V3<float> apex, V3<float> axis, 
     }
     return n;
 }
-// Two levels: one CTA per 8 x 8-pixel block.  Thread 0 walks the tree once with the BLOCK's cone (up to 24 candidates, in shared
-// memory); then every thread filters that short list with its own pixel's cone.  Only a block with more than 24 candidates sends
-// its pixels down the tree one by one.  (The first version walked the tree once per pixel: 0.24 ms per 1080p frame — 1 % of the
-// 62-spp frame one of eight GPUs renders; this one takes a sixth of that.)
+// Two levels, two launches.  (1) One THREAD per 8 x 8-pixel block walks the tree with the block's cone and writes up to 24 candidates to a
+// scratch list.  (2) One thread per pixel filters its block's short list with its own cone; only a block with more than 24 candidates sends
+// its pixels down the tree one by one.  (First version: one walk per pixel, 0.24 ms per 1080p frame.  Second: one CTA per block whose thread 0
+// walked while 63 threads waited — at most 32 walks in flight per SM, 0.20 ms under ncu.  A walk is a chain of ~50 dependent node loads, so
+// what it needs is many of them in flight: here 2 048 per SM.)
 constexpr int kCandBlock = 8, kCandBlockCap = 24;
+struct CandBlockList { uint32_t n; uint32_t ids[kCandBlockCap]; };          // n = kCandBlockCap + 1: more than fit
+RTW_D float cand_half_pixel(const CameraT<float>& cam) { return 0.5f * (fsqrt(dot(cam.du, cam.du)) + fsqrt(dot(cam.dv, cam.dv))) * 1.001f; }   // >= half a pixel's diagonal
 template <int UNUSED = 0>
-__global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_kernel(SceneView<float> sc, CameraT<float> cam, uint4* cand) {
-    __shared__ uint32_t block_ids[kCandBlockCap];
-    __shared__ int block_n;
-    const uint32_t bx = blockIdx.x * kCandBlock, by = blockIdx.y * kCandBlock;
-    const float px = 0.5f * (fsqrt(dot(cam.du, cam.du)) + fsqrt(dot(cam.dv, cam.dv))) * 1.001f;       // >= half a pixel's diagonal
-    if (threadIdx.x == 0) {
-        const V3<float> dc = (cam.pixel00 + cam.du * ((float)bx + 3.5f)) + cam.dv * ((float)by + 3.5f) - cam.center;
-        const float len = fsqrt(dot(dc, dc)), hd = 8.f * px;           // pixel centres up to 3.5 away per axis + half a pixel of jitter
-        int n = kCandBlockCap + 1;
-        if (len > 4.f * hd) {
-            const float tan_a = hd * frcp(len - hd) * 1.001f;
-            n = cone_walk<kCandBlockCap>(sc, cam.center, dc * frcp(len), tan_a, fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f, block_ids);
-        }
-        block_n = n;
+__global__ void __launch_bounds__(128) block_candidates_kernel(SceneView<float> sc, CameraT<float> cam, uint32_t blocks_x, uint32_t n_blocks, CandBlockList* lists) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t bx = (b % blocks_x) * kCandBlock, by = (b / blocks_x) * kCandBlock;
+    const float px = cand_half_pixel(cam);
+    const V3<float> dc = (cam.pixel00 + cam.du * ((float)bx + 3.5f)) + cam.dv * ((float)by + 3.5f) - cam.center;
+    const float len = fsqrt(dot(dc, dc)), hd = 8.f * px;           // pixel centres up to 3.5 away per axis + half a pixel of jitter
+    uint32_t ids[kCandBlockCap];
+    int n = kCandBlockCap + 1;
+    if (len > 4.f * hd) {
+        const float tan_a = hd * frcp(len - hd) * 1.001f;
+        n = cone_walk<kCandBlockCap>(sc, cam.center, dc * frcp(len), tan_a, fsqrt(fmaf(tan_a, tan_a, 1.f)) * 1.0001f, ids);
+    }
+    CandBlockList& out = lists[b];
+    out.n = (uint32_t)n;
+    for (int k = 0; k < kCandBlockCap; ++k) if (k < n) out.ids[k] = ids[k];
+}
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_kernel(SceneView<float> sc, CameraT<float> cam, const CandBlockList* lists, uint4* cand) {
+    __shared__ CandBlockList bl;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(lists + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+        if (threadIdx.x < sizeof(CandBlockList) / 4) reinterpret_cast<uint32_t*>(&bl)[threadIdx.x] = __ldg(src + threadIdx.x);
     }
     __syncthreads();
+    const int block_n = (int)bl.n;
+    const uint32_t* block_ids = bl.ids;
+    const uint32_t bx = blockIdx.x * kCandBlock, by = blockIdx.y * kCandBlock;
+    const float px = cand_half_pixel(cam);
     const uint32_t i = bx + threadIdx.x % kCandBlock, j = by + threadIdx.x / kCandBlock;
     if (i >= cam.width || j >= cam.height) return;
     const V3<float> dc = (cam.pixel00 + cam.du * (float)i) + cam.dv * (float)j - cam.center;

@@ -24,7 +24,9 @@ RTW_DECLARE_LAUNCHERS(f32, float)
 cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t pool_pixels_per_chunk(uint32_t spp);
 float pool_sample_cap(uint32_t spp_total);
-cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, uint4* cand, cudaStream_t s);
+// scratch: primary_candidates_scratch_bytes(width, height) bytes of device memory (the per-block lists of the first level)
+size_t primary_candidates_scratch_bytes(uint32_t width, uint32_t height);
+cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, void* scratch, uint4* cand, cudaStream_t s);
 // order[0 .. n_chunks): the work queue's chunk order (costly chunks first), order[n_chunks .. n_chunks + 2): scratch cursors
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
                                    uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,

@@ -380,8 +380,10 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 const uint32_t walking = __popc(__ballot_sync(0xffffffffu, cur[0] >= 0)) + __popc(__ballot_sync(0xffffffffu, cur[1] >= 0));
                 if (walking == 0 && !__any_sync(0xffffffffu, active[0] || active[1])) break;
                 if (walking != 0 && n_conn == 0) {
-                    // nothing to refill with: yield if another stage has at least as many paths waiting as walks remain
-                    const uint32_t nf = (exhausted && chunk_next == chunk_end) ? 0u : n_free;
+                    // nothing to refill with: yield if another stage has at least as many paths waiting as walks remain (free slots count
+                    // exactly when the stage selection above would let GENERATE run — not on the queue's background-only tail, where
+                    // old paths go first: yielding to a stage that is not going to run would bounce between here and there forever)
+                    const uint32_t nf = ((exhausted && chunk_next == chunk_end) || cheap_phase) ? 0u : n_free;
                     const uint32_t other = max(max(n_ext, nf), max(n_lamb, max(n_metal, n_diel)));
                     if (other >= walking) {
                         // finished-but-not-yet-completed walks are completed by the next pass of the loop head; suspend the rest

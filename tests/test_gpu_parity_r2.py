@@ -300,3 +300,23 @@ def test_connect_stage_is_bit_identical(rtw):
     assert np.array_equal(out["wavefront"][0], out["megakernel"][0]) and np.array_equal(out["wavefront"][1], out["megakernel"][1])
     assert out["wavefront"][2]["rays"] == out["megakernel"][2]["rays"] and out["wavefront"][2]["paths"] == w * h * spp
     assert (out["wavefront"][0] > 0).any()
+
+
+@pytest.mark.timeout(300)
+def test_connect_stage_with_background_tail(rtw):
+    """A CONNECT scene whose frame is mostly sky: the work queue ends with background-only chunks, on which a warp runs old paths first.
+    (The CONNECT stage used to yield to GENERATE there while the stage selection refused to run it: a livelock that the all-covered
+    frame of the test above never reached — found by the 1 M-sphere bench.)  Same image as the megakernel."""
+    arr = rtw.scenes.simple_arrays(SEED, 112)
+    sc = rtw.Scene.from_arrays(arr["spheres"], arr["sphere_materials"], arr["planes"], arr["plane_materials"], arr["lights"])
+    w, h, spp = 192, 108, 8
+    cam = (arr["cam"].with_vfov(40.).with_aspect_ratio(w / h).with_max_depth(50).with_image_width(w).with_image_height(h)
+           .with_samples_per_pixel(spp).with_lookfrom((60., 30., 60.)).with_lookat((0., 25., 0.)).with_focus_dist(85.).build())
+    out = {}
+    for name, mode in (("wavefront", rtw.RTW_WAVEFRONT), ("megakernel", rtw.RTW_MEGAKERNEL)):
+        _, rgb8, st = sc.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F32, mode=mode), want_sum=False, want_rgb8=True)
+        out[name] = (rgb8.copy(), st)
+    sc.close()
+    assert np.array_equal(out["wavefront"][0], out["megakernel"][0]) and out["wavefront"][1]["rays"] == out["megakernel"][1]["rays"]
+    sky = (out["wavefront"][0] == out["wavefront"][0][0, 0]).all(axis=2).mean()
+    assert 0.05 < sky < 0.98, sky         # the frame has both a sky part and a part that reaches the lights

@@ -350,10 +350,10 @@ def run_cuda(args):
                      d2h_bytes_per_step=WIDTH * HEIGHT * 3 + 88, steps=e2e_steps, ms_per_step=e2e_s / e2e_steps * 1e3),
             # per step: tiles partition = render (+ fixed-point -> tiles conversion) per rank + untile on rank 0; samples partition =
             # render per rank + resolve on rank 0
-            # per step and rank: candidate pre-pass (2 launches) + queue-order kernel (wavefront) + render kernel (+ fixed-point -> tiles conversion on the tile partition); on
+            # per step and rank: candidate pre-pass (2 launches) + queue order + queue split + background-chunk kernel (wavefront) + render kernel (+ fixed-point -> tiles conversion on the tile partition); on
             # rank 0 one untile / resolve kernel
             gpu_launches=args.steps * (((1 if (renderer.partition == "samples" or (args.lane_per_pixel and args.mode == "megakernel")) else 2)
-                                        + (3 if (args.mode == "wavefront" and not args.lane_per_pixel) else 0)) * world + 1),
+                                        + (5 if (args.mode == "wavefront" and not args.lane_per_pixel) else 0)) * world + 1),
             clocks=clocks,
             events_per_step={k: total[k] for k in keys},
             other_renderer=other,

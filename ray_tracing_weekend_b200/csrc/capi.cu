@@ -1069,13 +1069,22 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             launches++;
             // ... and they say which chunks of the path stream can meet a sphere: those go first (chunk_order_kernel)
             static const bool order_allowed = [] { const char* e = std::getenv("RTW_NO_CHUNK_ORDER"); return !(e && std::atoi(e) == 1); }();
-            if (order_allowed && Q.n_chunks < 0x7fffffffu) {
-                CU(s->d_order.reserve((size_t)Q.n_chunks + 2));
+            if (order_allowed && Q.n_chunks > 0 && Q.n_chunks < 0x3fffffffu) {
+                CU(s->d_order.reserve((size_t)Q.n_chunks + 4));
                 CU(launch_chunk_order_f32(cand, s->f32.view, to_camera<float>(cam), rank, world, (cam->image_width + kTileW - 1) / kTileW,
                                           rtw_tiles_total(cam->image_width, cam->image_height), n_slots, Q.pixels_per_chunk, Q.n_chunks,
                                           s->d_order.p, st));
                 Q.chunk_order = s->d_order.p;
                 launches++;
+                // ... and the background-only chunks beyond a tail of ~8 k paths per warp leave the wavefront's queue for a kernel of their own
+                static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 8192L; }();
+                if (tail_per_warp >= 0) {
+                    const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
+                    const uint64_t tail = ((uint64_t)tail_per_warp * 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) + per_chunk - 1) / per_chunk;
+                    CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), st));
+                    Q.queue_len = s->d_order.p + Q.n_chunks + 2;
+                    launches += 2;
+                }
             }
         }
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {

@@ -47,6 +47,10 @@ cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, u
     e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info)
            : launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
+    if (Q.queue_len) {                                      // the background-only chunks the queue does not hold (chunk_split_kernel)
+        e = launch_render_background_f32(P, Q, Q.chunk_order, sm_count, s);
+        if (e != cudaSuccess) return e;
+    }
     return pool_finalize(P, Q, s);
 }
 // scenes with a LARGE light BVH run the CONNECT variant (for short walks the stage costs more than it saves: C5, 399 lights, 29.8 ms
@@ -164,6 +168,14 @@ cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& sc
     if (e != cudaSuccess) return e;
     chunk_order_kernel<0><<<(n_chunks + 255) / 256, 256, 0, s>>>(cand, scene, cam, rank, world, tiles_x, tiles_total, n_slots, pixels_per_chunk,
                                                                  n_chunks, order);
+    return cudaGetLastError();
+}
+cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s) {
+    chunk_split_kernel<0><<<(n_chunks + 255u) / 256u, 256, 0, s>>>(order, n_chunks, tail_chunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s) {
+    render_background_kernel<0><<<(sm_count > 0 ? sm_count : 148) * 4, kBackgroundBlock, 0, s>>>(P, Q, order, Q.n_chunks);
     return cudaGetLastError();
 }
 // samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units

@@ -804,9 +804,10 @@ struct PoolParams {
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
     float sample_cap;               // samples of this radiance or more set the overflow flag instead of being added (pool_sample_cap)
-    const uint32_t* chunk_order;    // [n_chunks] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x7fffffff (chunk_order_kernel)
+    const uint32_t* chunk_order;    // [n_chunks + 4] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x7fffffff (chunk_order_kernel)
+    const uint32_t* queue_len;      // device word or NULL: the queue has been split (chunk_split_kernel) — entries flagged kChunkEnd belong to render_background_kernel
 };
-constexpr uint32_t kChunkCheap = 0x80000000u;
+constexpr uint32_t kChunkCheap = 0x80000000u, kChunkEnd = 0x40000000u;
 
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
 // ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
@@ -1125,6 +1126,92 @@ __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, Camer
     const uint32_t lt = (1u << lane) - 1u;
     if (costly) order[base_c + (uint32_t)__popc(mc & lt)] = c;
     else order[n_chunks - 1u - (base_h + (uint32_t)__popc(mh & lt))] = c | kChunkCheap;
+}
+
+// The background-only chunks need none of the wavefront's machinery — no path slots, no stage lists: their camera rays have an empty
+// candidate list and no plane in reach, so each path is one ray, one plane test and the background colour.  chunk_split_kernel
+// leaves the LAST `tail_chunks` of them in the wavefront's queue (that tail is what lets every warp finish its old paths while it still
+// has new ones to generate, see chunk_order_kernel) and hands the rest to render_background_kernel: one warp per chunk, lanes
+// striding over a pixel's samples — the same Philox stream, the same get_ray, the same plane test as GENERATE — and ONE set of
+// reductions per pixel (n x the fixed-point background sample; integer arithmetic, so the sum is what n separate additions give).
+// Should a plane be met after all (the classification has margins; this is the belt to its braces) the path is traced to its end
+// right here with the megakernel's path_step.
+// order[n_chunks + 0 / 1]: the cursors of chunk_order_kernel = number of costly / cheap chunks; + 2: queue length; + 3: background chunks
+template <int UNUSED = 0>
+__global__ void chunk_split_kernel(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;             // one thread per queue position
+    const uint32_t n_costly = order[n_chunks], n_cheap = order[n_chunks + 1];
+    const uint32_t keep = min(n_cheap, tail_chunks), queue_len = n_costly + keep;
+    if (p == 0) { order[n_chunks + 2] = queue_len; order[n_chunks + 3] = n_cheap - keep; }
+    // the positions behind the wavefront's last chunk hold the background chunks — flagged, so that a warp fetching
+    // one knows the queue has ended (the queue counter only grows: every later fetch lands on a flagged entry or beyond n_chunks)
+    if (p >= queue_len && p < n_chunks) order[p] |= kChunkEnd;
+}
+
+template <class SC>
+__device__ __noinline__ void background_slow_path(const SC& sc, const RenderParams<float>& P, const PoolParams& Q, uint32_t q, uint32_t pixel, uint32_t i,
+                                                  uint32_t j, uint32_t sample, int32_t* stack, int stride, uint32_t& nrays, Tally& tl) {
+    Stream<false> rng(P.seed, pixel, sample, 0u);
+    PathState<float> ps;
+    ps.r = get_ray<float, false>(P.cam, i, j, rng);
+    ps.mult = mk<float>(1, 1, 1); ps.res = mk<float>(0, 0, 0); ps.depth = P.cam.max_depth;
+    V3<float> value;
+    while (!path_step<float, false, false, SC>(sc, P.cam, P.seed, P.tmin, pixel, sample, ps, &value, stack, stride, nrays, tl)) {}
+    if (P.flags & 1u) value = fix_nan(value);
+    uint32_t bad = 0;
+    pool_flush(Q, q, pool_fixed(Q, value.x, 0, bad), pool_fixed(Q, value.y, 1, bad), pool_fixed(Q, value.z, 2, bad));
+    if (bad) atomicOr(Q.poison + q, bad);
+}
+
+constexpr int kBackgroundBlock = 256;
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(kBackgroundBlock) render_background_kernel(RenderParams<float> P, PoolParams Q, const uint32_t* order, uint32_t n_chunks) {
+    __shared__ int32_t stack_s[kStackDepth * kBackgroundBlock];              // only the slow path walks a tree
+    const SceneView<float>& sc = P.scene;
+    const CameraT<float>& cam = P.cam;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * kBackgroundBlock + threadIdx.x) >> 5, n_warps = (gridDim.x * kBackgroundBlock) >> 5;
+    const uint32_t n_bg = __ldg(order + n_chunks + 3);
+    const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH), spp = cam.spp, G = Q.pixels_per_chunk;
+    uint32_t npaths = 0, nrays = 0;
+    Tally tl;
+    V3<float> value = mk<float>(1.f, 1.f, 1.f) * cam.background + mk<float>(0.f, 0.f, 0.f);      // mult * background + res (camera.rs:473-475)
+    if (P.flags & 1u) value = fix_nan(value);
+    for (uint32_t k = warp; k < n_bg; k += n_warps) {
+        const uint32_t c = __ldg(order + (n_chunks - 1u - k)) & ~(kChunkCheap | kChunkEnd);
+        const uint32_t q0 = c * G, npx = min(G, n_slots - q0);
+        for (uint32_t pin = 0; pin < npx; ++pin) {
+            const uint32_t q = q0 + pin;
+            const uint32_t tile = (q >> 8) * P.world + P.rank, in = q & 255u;
+            uint32_t ttx, tty;
+            slot_tile(tile, P.tiles_x, &ttx, &tty);
+            const uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
+            if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) continue;
+            const uint32_t pixel = j * cam.width + i;
+            uint32_t miss = 0;
+            for (uint32_t s0 = lane; s0 < spp; s0 += 32u) {
+                const uint32_t sample = s0 + cam.sample_offset;
+                Stream<false> rng(P.seed, pixel, sample, 0u);
+                const Ray<float> r = get_ray<float, false>(cam, i, j, rng);
+                bool found = false;
+                float best_t = M<float, false>::inf();
+                int32_t best = -1;
+                closest_plane<float, false, SceneView<float>>(sc, r, P.tmin, M<float, false>::inf(), found, best_t, best);
+                npaths++;
+                if (!found) { miss++; nrays++; }
+                else background_slow_path(sc, P, Q, q, pixel, i, j, sample, stack_s + threadIdx.x, kBackgroundBlock, nrays, tl);
+            }
+            miss = warp_sum(miss);
+            if (lane == 0 && miss) {
+                uint32_t bad = 0;
+                const unsigned long long n = miss;
+                pool_flush(Q, q, n * pool_fixed(Q, value.x, 0, bad), n * pool_fixed(Q, value.y, 1, bad), n * pool_fixed(Q, value.z, 2, bad));
+                if (bad) atomicOr(Q.poison + q, bad);
+                if (P.flags & 2u) tl.missed += miss;          // RTW_FLAG_COUNT_EVENTS
+            }
+        }
+    }
+    flush_counters<true>(P.counters, npaths, nrays, tl);
 }
 
 // ---------------------------------------------------------------------------------------------

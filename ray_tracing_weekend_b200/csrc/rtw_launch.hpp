@@ -28,6 +28,10 @@ float pool_sample_cap(uint32_t spp_total);
 size_t primary_candidates_scratch_bytes(uint32_t width, uint32_t height);
 cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, void* scratch, uint4* cand, cudaStream_t s);
 // order[0 .. n_chunks): the work queue's chunk order (costly chunks first), order[n_chunks .. n_chunks + 2): scratch cursors
+// after launch_chunk_order_f32: split the background-only chunks between the wavefront's queue (the last tail_chunks of them; order[n_chunks + 2]
+// receives the queue length) and launch_render_background_f32 (the rest), which must run with the same RenderParams / PoolParams as the render
+cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s);
+cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s);
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
                                    uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
                                    uint32_t* order, cudaStream_t s);

@@ -194,6 +194,9 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 if (c >= Q.n_chunks) { exhausted = true; continue; }
                 if (Q.chunk_order) {
                     c = __ldg(Q.chunk_order + c);
+                    // the first of the chunks that belong to render_background_kernel: the queue ends here.  (A flag in the entry the warp
+                    // fetches anyway: holding the queue length in a register instead cost this kernel 2 %, profiles/r2_background_kernel_ab.jsonl)
+                    if (c & kChunkEnd) { exhausted = true; continue; }
                     cheap_phase = (c & kChunkCheap) != 0u;
                     c &= ~kChunkCheap;
                 }

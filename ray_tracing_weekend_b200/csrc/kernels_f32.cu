@@ -71,6 +71,10 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
     if (shape == 3) return launch_render_wavefront_shape<COUNT, 640, 112, false>(P, Q, bvh_depth, sm_count, s, info);
     if (shape == 4) return launch_render_wavefront_shape<COUNT, 704, 96, false>(P, Q, bvh_depth, sm_count, s, info);
     if (shape == 5) return launch_render_wavefront_shape<COUNT, 768, 88, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 6) return launch_render_wavefront_shape<COUNT, 576, 128, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 7) return launch_render_wavefront_shape<COUNT, 512, 144, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 8) return launch_render_wavefront_shape<COUNT, 640, 104, false>(P, Q, bvh_depth, sm_count, s, info);
+    if (shape == 9) return launch_render_wavefront_shape<COUNT, 448, 160, false>(P, Q, bvh_depth, sm_count, s, info);
 #endif
     if (P.scene.n_light_nodes > 0 && P.scene.connect_stage && connect_stage_allowed()) {
 #ifdef RTW_CONN_SWEEP

@@ -179,7 +179,13 @@ cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t 
     return cudaGetLastError();
 }
 cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s) {
-    render_background_kernel<0><<<(sm_count > 0 ? sm_count : 148) * 4, kBackgroundBlock, 0, s>>>(P, Q, order, Q.n_chunks);
+    static int per_sm = 0;                                  // resident CTAs per SM (64 registers: the slow path may spill, the loop does not)
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_background_kernel<0>, kBackgroundBlock, 0) != cudaSuccess || n < 1) n = 2;
+        per_sm = n;
+    }
+    render_background_kernel<0><<<(sm_count > 0 ? sm_count : 148) * per_sm, kBackgroundBlock, 0, s>>>(P, Q, order, Q.n_chunks);
     return cudaGetLastError();
 }
 // samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units

@@ -1165,7 +1165,7 @@ __device__ __noinline__ void background_slow_path(const SC& sc, const RenderPara
 
 constexpr int kBackgroundBlock = 256;
 template <int UNUSED = 0>
-__global__ void __launch_bounds__(kBackgroundBlock) render_background_kernel(RenderParams<float> P, PoolParams Q, const uint32_t* order, uint32_t n_chunks) {
+__global__ void __launch_bounds__(kBackgroundBlock, 4) render_background_kernel(RenderParams<float> P, PoolParams Q, const uint32_t* order, uint32_t n_chunks) {
     __shared__ int32_t stack_s[kStackDepth * kBackgroundBlock];              // only the slow path walks a tree
     const SceneView<float>& sc = P.scene;
     const CameraT<float>& cam = P.cam;

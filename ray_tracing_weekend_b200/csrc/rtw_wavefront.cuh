@@ -178,15 +178,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
         if (cheap_phase && (n_ext | n_lamb | n_metal | n_diel | n_conn)) nf = 0u;
         int stage = WF_FREE;
         uint32_t best = nf;
-#if defined(RTW_EXT_BIAS) && RTW_EXT_BIAS == 1
-        { const uint32_t key = n_ext >= 32u ? n_ext : (n_ext * 3u) >> 2; if (key > best) { best = key; stage = WF_EXT; } }
-#elif defined(RTW_EXT_BIAS) && RTW_EXT_BIAS == 2
-        { const uint32_t key = n_ext >= 32u ? 255u : n_ext >> 1; if (key > best) { best = key; stage = WF_EXT; } }
-#elif defined(RTW_EXT_BIAS) && RTW_EXT_BIAS == 3
-        { const uint32_t key = n_ext >= 32u ? 255u : n_ext; if (key > best) { best = key; stage = WF_EXT; } }
-#else
         if (n_ext > best) { best = n_ext; stage = WF_EXT; }
-#endif
         if (n_lamb > best) { best = n_lamb; stage = WF_LAMB; }
         if (n_metal > best) { best = n_metal; stage = WF_METAL; }
         if (n_diel > best) { best = n_diel; stage = WF_DIEL; }

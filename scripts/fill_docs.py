@@ -1,6 +1,6 @@
 """Fill the @@PLACEHOLDER@@ numbers of scripts/templates/*.tmpl from a bench.py JSON line (+ an optional JSON dict of extra values) and write
 DESIGN.md, profiles/README.md and README.md.  usage: fill_docs.py bench_line.json [extra.json]"""
-import json,sys,re
+import json,sys,re,os
 d=json.loads(open(sys.argv[1]).read())
 extra=json.loads(open(sys.argv[2]).read()) if len(sys.argv)>2 else {}
 rf=d['roofline']
@@ -14,6 +14,16 @@ vals={
  'C3_MS': f"{d['c3']['ms_per_step']:.0f}", 'C3_GRAYS': f"{d['c3']['mrays_per_s']/1e3:.1f}",
 }
 vals.update(extra)
+# multi-GPU lines, when they exist
+for n in (2, 4, 8):
+    f=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', f'r2_bench_n{n}.json')
+    if os.path.exists(f):
+        m=json.loads(open(f).read())
+        vals.update({f'N{n}_MRAYS': f"{m['value']:,.0f}".replace(',',' '), f'N{n}_MS': f"{m['ms_per_step']:.2f}", f'N{n}_KMS': f"{m['kernel_ms_per_step']:.2f}",
+                     f'N{n}_X': f"{d['ms_per_step']/m['ms_per_step']:.2f}", f'N{n}_E2E': f"{m['e2e']['value']:,.0f}".replace(',',' '),
+                     f'N{n}_C3': f"{m['c3']['ms_per_step']:.0f}" if m.get('c3') else '—'})
+    else:
+        vals.update({f'N{n}_{k}': 'not measured' for k in ('MRAYS','MS','KMS','X','E2E','C3')})
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for t, p in (('DESIGN.md.tmpl', 'DESIGN.md'), ('profiles_README.md.tmpl', 'profiles/README.md'), ('README.md.tmpl', 'README.md')):

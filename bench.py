@@ -174,13 +174,17 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(tot)
     total = {k: float(v) for k, v in zip(keys, tot.tolist())}
-    local_flops = algorithmic_flops(cnt)
+    local_flops = algorithmic_flops(total) / world           # every rank's share of the frame's events (the library may split the frame by pixels)
     # the same frame with every camera ray walking the BVH (RTW_FLAG_NO_CANDIDATES): the event counts of the plain tree-walk algorithm
     # SURVEY 8(d) describes.  `roofline.achieved` uses the events the timed kernel EXECUTES (above); this count is reported beside it.
     tw = None
     if mode == R.RTW_WAVEFRONT and not args.lane_per_pixel:
         twc = renderer.render_local(R.RenderOptions(seed=SEED, precision=R.RTW_F32, mode=mode, flags=R.RTW_FLAG_COUNT_EVENTS | R.RTW_FLAG_NO_CANDIDATES | base_flags), want_stats=True)
-        tw = dict(flop_per_launch=algorithmic_flops(twc), node_visits=twc["node_visits"], sphere_tests=twc["sphere_tests"])
+        twt = torch.tensor([twc[k] for k in keys], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(twt)
+        twtot = {k: float(v) for k, v in zip(keys, twt.tolist())}
+        tw = dict(flop_per_launch=algorithmic_flops(twtot) / world, node_visits=twtot["node_visits"] / world, sphere_tests=twtot["sphere_tests"] / world)
 
     for _ in range(args.warmup):
         renderer.render()
@@ -203,17 +207,14 @@ def run_cuda(args):
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    renderer.check()                                         # a path that would make the reference panic surfaces here
+    last_kernel_ms = renderer.check()                        # a path that would make the reference panic surfaces here
     step_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
     if renderer.comm is not None:
-        # the library call fuses kernel + collective: the kernel's own time comes from the same number of untimed local renders
-        for k in range(args.steps):
-            flush.fill_(k & 0xff)
-            ev[k][2].record()
-            renderer.render_local()
-            ev[k][3].record()
-        barrier()
-    kern_ms = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps))
+        # the library call fuses kernels + collective: the kernels' own time is the CUDA-event time the library took around this rank's
+        # render kernels in the last timed step (rtw_scene_sync)
+        kern_ms = float(last_kernel_ms) * args.steps
+    else:
+        kern_ms = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps))
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,7 +333,8 @@ def run_cuda(args):
             metric="Mrays/s", value=mrays, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=step_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=WORKLOAD, mode=("wavefront (warp-private queues in shared memory)" if args.mode == "wavefront" else
-                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=((f"samples of every pixel split over {world} GPU(s) (fixed-point accumulators) + 1 NCCL reduce" if renderer.partition == "samples"
+                              "megakernel (lane per pixel, diagnostic)" if args.lane_per_pixel else "megakernel (pooled path stream)"), parallelism=((f"pixels (chunks of the per-frame ordered work queue) dealt to {world} GPU(s), all samples each, into whole-image fixed-point accumulators + 1 NCCL reduce" if (renderer.partition == "samples" and renderer.comm is not None and args.mode == "wavefront" and not args.lane_per_pixel and os.environ.get("RTW_MULTI_PARTITION") != "samples")
+                                      else f"samples of every pixel split over {world} GPU(s) (fixed-point accumulators) + 1 NCCL reduce" if renderer.partition == "samples"
                                       else f"tiles16x16 interleaved over {world} GPU(s) + 1 NCCL gather") +
                                      ("; collective inside the C library (rtw_render_rank_device)" if renderer.comm is not None else ("; collective through torch.distributed" if world > 1 else ""))),
                         tmin="RTW_TMIN_REFERENCE: machine epsilon of the working precision (the reference uses f64::EPSILON in f64)", l2="256 MiB fill between timed steps (scene is 40 KB, shared-memory resident)"),

@@ -586,7 +586,10 @@ void read_stats(const DeviceCounters& c, rtw_stats* st) {
     st->absorbed = c.absorbed; st->missed = c.missed; st->depth_out = c.depth_out;
 }
 
-struct SampleRange { uint32_t begin = 0, count = 0; bool set = false; };     // sample partition: this launch's samples of every pixel
+// sample partition: this launch's samples of every pixel.  own_world > 1 (rtw_render_multi / rtw_render_rank): GPU own_rank of own_world
+// renders its share of ONE frame — ALL samples of the pixels it owns when the work queue is ordered per frame (chunk_order_kernel deals
+// the chunks out), else its share of every pixel's samples (render_device_impl decides and rewrites the range)
+struct SampleRange { uint32_t begin = 0, count = 0; bool set = false; uint32_t own_rank = 0, own_world = 1; };
 
 template <class T, class DEV, class Launch>
 int render_tiles_t(rtw_scene* s, DEV& d, const rtw_camera* cam, const rtw_opts* o, uint32_t rank, uint32_t world, T* tiles,
@@ -1023,6 +1026,22 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
     }
     unsigned long long* accum_p = ext_accum ? ext_accum : s->d_accum.p;
     uint32_t* poison_p = ext_accum ? ext_poison : s->d_poison.p;
+    if (sr.own_world > 1) {
+        // one frame over several GPUs: pixels if this call will order its work queue (same conditions as below), samples otherwise
+        static const bool pixels_allowed = [] { const char* e = std::getenv("RTW_MULTI_PARTITION"); return !(e && std::string(e) == "samples"); }();
+        static const bool cand_ok = [] { const char* e = std::getenv("RTW_NO_PRIMARY_CANDIDATES"); return !(e && std::atoi(e) == 1); }();
+        static const bool order_ok = [] { const char* e = std::getenv("RTW_NO_CHUNK_ORDER"); return !(e && std::atoi(e) == 1); }();
+        const uint32_t spp_all = cam->samples_per_pixel;
+        const uint64_t chunks = ((uint64_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH) / std::max<uint32_t>(1u, pool_pixels_per_chunk(spp_all)) + 1;
+        const bool by_pixels = pixels_allowed && cand_ok && order_ok && !s->general && pooled && o->mode == RTW_WAVEFRONT && !(o->flags & RTW_FLAG_NO_CANDIDATES) &&
+                               cam->max_depth <= 0xffffu && std::max(s->bvh.depth, s->light_bvh_depth) <= wavefront_max_bvh_depth() &&
+                               cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0 && chunks < 0x3fffffffu;
+        if (by_pixels) { sr.begin = 0; sr.count = spp_all; sr.set = true; }
+        else {
+            const uint32_t b = (uint32_t)((uint64_t)spp_all * sr.own_rank / sr.own_world), e = (uint32_t)((uint64_t)spp_all * (sr.own_rank + 1) / sr.own_world);
+            sr.begin = b; sr.count = e - b; sr.set = true; sr.own_rank = 0; sr.own_world = 1;
+        }
+    }
     const uint32_t spp_here = sr.set ? sr.count : cam->samples_per_pixel;
     CU(cudaEventRecord(s->ev[0], st));
     if (s->general) {
@@ -1070,21 +1089,20 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             // ... and they say which chunks of the path stream can meet a sphere: those go first (chunk_order_kernel)
             static const bool order_allowed = [] { const char* e = std::getenv("RTW_NO_CHUNK_ORDER"); return !(e && std::atoi(e) == 1); }();
             if (order_allowed && Q.n_chunks > 0 && Q.n_chunks < 0x3fffffffu) {
-                CU(s->d_order.reserve((size_t)Q.n_chunks + 4));
+                CU(s->d_order.reserve(2 * (size_t)Q.n_chunks + 4));
                 CU(launch_chunk_order_f32(cand, s->f32.view, to_camera<float>(cam), rank, world, (cam->image_width + kTileW - 1) / kTileW,
                                           rtw_tiles_total(cam->image_width, cam->image_height), n_slots, Q.pixels_per_chunk, Q.n_chunks,
-                                          s->d_order.p, st));
+                                          sr.own_rank, sr.own_world, s->d_order.p, st));
                 Q.chunk_order = s->d_order.p;
-                launches++;
                 // ... and the background-only chunks beyond a tail of ~8 k paths per warp leave the wavefront's queue for a kernel of their own
+                // (RTW_CHEAP_TAIL_PATHS=-1: they all stay in the queue)
                 static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 8192L; }();
-                if (tail_per_warp >= 0) {
-                    const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
-                    const uint64_t tail = ((uint64_t)tail_per_warp * 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) + per_chunk - 1) / per_chunk;
-                    CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), st));
-                    Q.queue_len = s->d_order.p + Q.n_chunks + 2;
-                    launches += 2;
-                }
+                const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
+                const uint64_t tail = tail_per_warp < 0 ? 0xffffffffull
+                                                        : ((uint64_t)tail_per_warp * 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) + per_chunk - 1) / per_chunk;
+                CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), st));
+                if (tail_per_warp >= 0) Q.queue_len = s->d_order.p + 2 * (size_t)Q.n_chunks + 2;
+                launches += 3;
             }
         }
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {

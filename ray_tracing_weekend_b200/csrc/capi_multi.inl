@@ -281,9 +281,7 @@ int rtw_render_multi(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, int
             MultiReplica* r = s->replicas[g];
             CU(cudaSetDevice(r->device));
             CU(r->block.reserve(words));
-            uint32_t begin, count;
-            sample_share(spp, g, N, &begin, &count);
-            SampleRange sr; sr.begin = begin; sr.count = count; sr.set = true;
+            SampleRange sr; sr.own_rank = g; sr.own_world = N;        // its pixels, or its samples of every pixel (render_device_impl)
             rc = render_device_impl(r->scene, cam, o, 0, 1, nullptr, r->stream, nullptr, sr, r->block.p, reinterpret_cast<uint32_t*>(r->block.p + 3 * slots));
             if (rc) return rc;
             CU(cudaEventRecord(r->rendered, r->stream));
@@ -399,9 +397,7 @@ int rtw_render_rank_device(rtw_scene* s, const rtw_camera* cam, const rtw_opts* 
         const size_t slots = rtw_accum_slots(w, h), words = block_words(slots);
         CU(s->d_block.reserve(words));
         uint32_t* poison = reinterpret_cast<uint32_t*>(s->d_block.p + 3 * slots);
-        uint32_t begin, count;
-        sample_share(spp, rank, N, &begin, &count);
-        SampleRange sr; sr.begin = begin; sr.count = count; sr.set = true;
+        SampleRange sr; sr.own_rank = rank; sr.own_world = N;         // its pixels, or its samples of every pixel (render_device_impl)
         rc = render_device_impl(s, cam, o, 0, 1, nullptr, st, nullptr, sr, s->d_block.p, poison);
         if (rc) return rc;
         if (N > 1) NC(nccl().Reduce(s->d_block.p, s->d_block.p, words, kNcclUint64, kNcclSum, 0, c->comm, st));

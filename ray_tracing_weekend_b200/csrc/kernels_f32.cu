@@ -166,12 +166,12 @@ cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const C
 }
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
                                    uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
-                                   uint32_t* order, cudaStream_t s) {
+                                   uint32_t own_rank, uint32_t own_world, uint32_t* order, cudaStream_t s) {
     if (!n_chunks) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(order + n_chunks, 0, 2 * sizeof(uint32_t), s);
+    cudaError_t e = cudaMemsetAsync(order + 2 * (size_t)n_chunks, 0, 2 * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     chunk_order_kernel<0><<<(n_chunks + 255) / 256, 256, 0, s>>>(cand, scene, cam, rank, world, tiles_x, tiles_total, n_slots, pixels_per_chunk,
-                                                                 n_chunks, order);
+                                                                 n_chunks, own_rank, own_world, order);
     return cudaGetLastError();
 }
 cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s) {

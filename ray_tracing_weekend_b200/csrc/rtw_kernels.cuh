@@ -804,7 +804,7 @@ struct PoolParams {
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
     float sample_cap;               // samples of this radiance or more set the overflow flag instead of being added (pool_sample_cap)
-    const uint32_t* chunk_order;    // [n_chunks + 4] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x7fffffff (chunk_order_kernel)
+    const uint32_t* chunk_order;    // [2 n_chunks + 4] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x3fffffff (chunk_order_kernel)
     const uint32_t* queue_len;      // device word or NULL: the queue has been split (chunk_split_kernel) — entries flagged kChunkEnd belong to render_background_kernel
 };
 constexpr uint32_t kChunkCheap = 0x80000000u, kChunkEnd = 0x40000000u;
@@ -1086,11 +1086,19 @@ __global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_ke
 // switches to "old paths first" — so the long paths end while the cheap tail of the stream still keeps every warp busy.
 // Scheduling only: paths, RNG streams and the fixed-point sums do not depend on who traces what when.
 // order[n_chunks] / order[n_chunks + 1]: the two cursors (zeroed by the host).
+// Buffer: order[0 .. n) = the queue (costly chunks from the front; chunk_split_kernel appends the background tail and end marks),
+// order[n .. 2n) = the background-only chunks, order[2n + 0 / 1] = their counts (cursors, zeroed by the host), + 2 / 3 = see chunk_split_kernel.
+// own_world > 1 (several GPUs, one frame): this GPU only takes the chunks it OWNS — chunk c belongs to GPU (c + (c >> 4)) % own_world, a
+// diagonal 1-chunk interleave — and renders ALL samples of their pixels.  Every GPU's accumulators then cover a disjoint set of pixels and
+// the frame's one integer reduce puts them together; unlike a split of every pixel's samples, the per-pixel costs of a frame (candidate
+// lookups, partial-sum flushes, queue transactions) are paid once, not once per GPU.
 template <int UNUSED = 0>
 __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, CameraT<float> cam, uint32_t rank, uint32_t world, uint32_t tiles_x,
-                                   uint32_t tiles_total, uint32_t n_slots, uint32_t G, uint32_t n_chunks, uint32_t* order) {
+                                   uint32_t tiles_total, uint32_t n_slots, uint32_t G, uint32_t n_chunks, uint32_t own_rank, uint32_t own_world,
+                                   uint32_t* order) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
+    if (own_world > 1u && (c + (c >> 4)) % own_world != own_rank) return;
     bool costly = false;
     const uint32_t q1 = min(n_slots, (c + 1u) * G);
     for (uint32_t q = c * G; q < q1 && !costly; ++q) {
@@ -1119,13 +1127,13 @@ __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, Camer
     uint32_t base_c = 0, base_h = 0;
     const uint32_t leader = (uint32_t)__ffs(active) - 1u;
     if (lane == leader) {
-        if (mc) base_c = atomicAdd(order + n_chunks, (uint32_t)__popc(mc));
-        if (mh) base_h = atomicAdd(order + n_chunks + 1, (uint32_t)__popc(mh));
+        if (mc) base_c = atomicAdd(order + 2u * n_chunks, (uint32_t)__popc(mc));
+        if (mh) base_h = atomicAdd(order + 2u * n_chunks + 1u, (uint32_t)__popc(mh));
     }
     base_c = __shfl_sync(active, base_c, (int)leader); base_h = __shfl_sync(active, base_h, (int)leader);
     const uint32_t lt = (1u << lane) - 1u;
     if (costly) order[base_c + (uint32_t)__popc(mc & lt)] = c;
-    else order[n_chunks - 1u - (base_h + (uint32_t)__popc(mh & lt))] = c | kChunkCheap;
+    else order[n_chunks + base_h + (uint32_t)__popc(mh & lt)] = c | kChunkCheap;
 }
 
 // The background-only chunks need none of the wavefront's machinery — no path slots, no stage lists: their camera rays have an empty
@@ -1136,16 +1144,19 @@ __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, Camer
 // reductions per pixel (n x the fixed-point background sample; integer arithmetic, so the sum is what n separate additions give).
 // Should a plane be met after all (the classification has margins; this is the belt to its braces) the path is traced to its end
 // right here with the megakernel's path_step.
-// order[n_chunks + 0 / 1]: the cursors of chunk_order_kernel = number of costly / cheap chunks; + 2: queue length; + 3: background chunks
+// order[2n + 0 / 1]: number of costly / background-only chunks (the cursors of chunk_order_kernel); + 2: queue length; + 3: chunks of
+// render_background_kernel (the first that many entries of order[n ..))
 template <int UNUSED = 0>
 __global__ void chunk_split_kernel(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;             // one thread per queue position
-    const uint32_t n_costly = order[n_chunks], n_cheap = order[n_chunks + 1];
+    const uint32_t n_costly = order[2u * n_chunks], n_cheap = order[2u * n_chunks + 1u];
     const uint32_t keep = min(n_cheap, tail_chunks), queue_len = n_costly + keep;
-    if (p == 0) { order[n_chunks + 2] = queue_len; order[n_chunks + 3] = n_cheap - keep; }
-    // the positions behind the wavefront's last chunk hold the background chunks — flagged, so that a warp fetching
-    // one knows the queue has ended (the queue counter only grows: every later fetch lands on a flagged entry or beyond n_chunks)
-    if (p >= queue_len && p < n_chunks) order[p] |= kChunkEnd;
+    if (p == 0) { order[2u * n_chunks + 2u] = queue_len; order[2u * n_chunks + 3u] = n_cheap - keep; }
+    if (p >= n_chunks) return;
+    // the last `keep` background chunks follow the costly ones in the queue; every position behind them carries the end mark (the queue
+    // counter only grows: a warp that fetches one knows the queue has ended)
+    if (p >= n_costly && p < queue_len) order[p] = order[n_chunks + (n_cheap - keep) + (p - n_costly)];
+    else if (p >= queue_len) order[p] = kChunkEnd;
 }
 
 template <class SC>
@@ -1171,14 +1182,14 @@ __global__ void __launch_bounds__(kBackgroundBlock, 4) render_background_kernel(
     const CameraT<float>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * kBackgroundBlock + threadIdx.x) >> 5, n_warps = (gridDim.x * kBackgroundBlock) >> 5;
-    const uint32_t n_bg = __ldg(order + n_chunks + 3);
+    const uint32_t n_bg = __ldg(order + 2u * n_chunks + 3u);
     const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH), spp = cam.spp, G = Q.pixels_per_chunk;
     uint32_t npaths = 0, nrays = 0;
     Tally tl;
     V3<float> value = mk<float>(1.f, 1.f, 1.f) * cam.background + mk<float>(0.f, 0.f, 0.f);      // mult * background + res (camera.rs:473-475)
     if (P.flags & 1u) value = fix_nan(value);
     for (uint32_t k = warp; k < n_bg; k += n_warps) {
-        const uint32_t c = __ldg(order + (n_chunks - 1u - k)) & ~(kChunkCheap | kChunkEnd);
+        const uint32_t c = __ldg(order + n_chunks + k) & ~(kChunkCheap | kChunkEnd);
         const uint32_t q0 = c * G, npx = min(G, n_slots - q0);
         for (uint32_t pin = 0; pin < npx; ++pin) {
             const uint32_t q = q0 + pin;

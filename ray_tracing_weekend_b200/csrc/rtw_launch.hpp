@@ -27,14 +27,14 @@ float pool_sample_cap(uint32_t spp_total);
 // scratch: primary_candidates_scratch_bytes(width, height) bytes of device memory (the per-block lists of the first level)
 size_t primary_candidates_scratch_bytes(uint32_t width, uint32_t height);
 cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, void* scratch, uint4* cand, cudaStream_t s);
-// order[0 .. n_chunks): the work queue's chunk order (costly chunks first), order[n_chunks .. n_chunks + 2): scratch cursors
-// after launch_chunk_order_f32: split the background-only chunks between the wavefront's queue (the last tail_chunks of them; order[n_chunks + 2]
-// receives the queue length) and launch_render_background_f32 (the rest), which must run with the same RenderParams / PoolParams as the render
-cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s);
-cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s);
+// order: 2 * n_chunks + 4 words (chunk_order_kernel); own_rank / own_world: this GPU's share of the chunks (0 / 1: all of them)
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
                                    uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
-                                   uint32_t* order, cudaStream_t s);
+                                   uint32_t own_rank, uint32_t own_world, uint32_t* order, cudaStream_t s);
+// after launch_chunk_order_f32 (always): append the last tail_chunks background-only chunks to the queue and mark its end; the rest of them is
+// what launch_render_background_f32 renders — with the same RenderParams / PoolParams as the wavefront (order + 2 n_chunks + 2: queue length)
+cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s);
+cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 uint32_t wavefront_max_bvh_depth();

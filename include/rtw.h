@@ -286,8 +286,10 @@ RTW_API int rtw_resolve_accum_device(const void* d_accum, const void* d_poison, 
  *
  * (A) one process, N GPUs: rtw_render_multi.  The scene is replicated onto devices[0..n_gpus) (NULL: CUDA devices 0..n_gpus-1;
  *     devices[0] is the root and should be the device the scene was created on), every GPU renders its share on its own stream
- *     and the root returns the image.  RTW_F32 (fixed-point renderers): sample partition — GPU g renders samples
- *     [spp*g/N, spp*(g+1)/N) of every pixel; the collective is
+ *     and the root returns the image.  RTW_F32 (fixed-point renderers): every GPU renders into a whole-image block of fixed-point
+ *     accumulators — ALL samples of the pixels it owns when the frame's work queue is ordered (sphere scenes, wavefront renderer,
+ *     pinhole camera: chunk c of the queue belongs to GPU (c + (c >> 4)) mod N), else samples [spp*g/N, spp*(g+1)/N) of every pixel
+ *     (RTW_MULTI_PARTITION=samples in the environment forces that split) — and the collective is
  *       RTW_COLLECTIVE_PEER: one fused kernel per GPU over NVLink peer memory — GPU g sums pixel slots [S*g/N, S*(g+1)/N) of all N
  *                            accumulator blocks through peer loads, resolves them and stores the pixels into the root's image
  *                            (reduce-scatter + resolve + gather in one pass; needs peer access between all pairs)

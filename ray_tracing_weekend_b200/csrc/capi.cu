@@ -1026,6 +1026,13 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
     }
     unsigned long long* accum_p = ext_accum ? ext_accum : s->d_accum.p;
     uint32_t* poison_p = ext_accum ? ext_poison : s->d_poison.p;
+    {
+        // diagnostic (scripts/timeline_probe.py, variant_bench.py): RTW_DEBUG_OWN="r,n" makes a plain single-GPU render behave like GPU r of n
+        // of rtw_render_multi — it renders only the chunks that GPU would own (the image is partial; the timing is that GPU's)
+        static const int dbg_own[2] = {[] { const char* e = std::getenv("RTW_DEBUG_OWN"); return e ? std::atoi(e) : 0; }(),
+                                       [] { const char* e = std::getenv("RTW_DEBUG_OWN"); const char* c = e ? std::strchr(e, ',') : nullptr; return c ? std::atoi(c + 1) : 1; }()};
+        if (dbg_own[1] > 1 && sr.own_world == 1 && !sr.set && world == 1) { sr.own_rank = (uint32_t)dbg_own[0] % (uint32_t)dbg_own[1]; sr.own_world = (uint32_t)dbg_own[1]; }
+    }
     if (sr.own_world > 1) {
         // one frame over several GPUs: pixels if this call will order its work queue (same conditions as below), samples otherwise
         static const bool pixels_allowed = [] { const char* e = std::getenv("RTW_MULTI_PARTITION"); return !(e && std::string(e) == "samples"); }();
@@ -1105,6 +1112,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
                 launches += 3;
             }
         }
+        if (sr.own_world > 1 && !Q.chunk_order) return fail(RTW_E_UNSUPPORTED, "frame too large for the pixel split of a multi-GPU render (set RTW_MULTI_PARTITION=samples)");
         auto launch = [&](RenderParams<float> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
             P.cand = cand;
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)

@@ -1042,7 +1042,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
         const uint64_t chunks = ((uint64_t)rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH) / std::max<uint32_t>(1u, pool_pixels_per_chunk(spp_all)) + 1;
         const bool by_pixels = pixels_allowed && cand_ok && order_ok && !s->general && pooled && o->mode == RTW_WAVEFRONT && !(o->flags & RTW_FLAG_NO_CANDIDATES) &&
                                cam->max_depth <= 0xffffu && std::max(s->bvh.depth, s->light_bvh_depth) <= wavefront_max_bvh_depth() &&
-                               cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0 && chunks < 0x3fffffffu;
+                               cam->defocus_angle <= 2.220446049250313e-16 && s->f32.view.n_spheres > 0 && chunks < kChunkMask;
         if (by_pixels) { sr.begin = 0; sr.count = spp_all; sr.set = true; }
         else {
             const uint32_t b = (uint32_t)((uint64_t)spp_all * sr.own_rank / sr.own_world), e = (uint32_t)((uint64_t)spp_all * (sr.own_rank + 1) / sr.own_world);
@@ -1060,6 +1060,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             Q.sample_cap = pool_sample_cap(cam->samples_per_pixel);
             uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
             Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+            Q.queue_cap = Q.n_chunks;
             const bool wavefront = o->mode == RTW_WAVEFRONT && cam->max_depth <= 0xffffu && s->bvh.depth + 2 <= 24;
             auto launch = [&](RenderParams<float, SceneViewG<float>> P, bool count, int sms, cudaStream_t str, LaunchInfo* info) {
                 return wavefront ? launch_render_wavefront_general_f32(P, Q, s->bvh.depth, count, sms, str, info)
@@ -1076,6 +1077,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
         Q.sample_cap = pool_sample_cap(cam->samples_per_pixel);
         uint32_t n_slots = rtw_tiles_per_rank(cam->image_width, cam->image_height, world) * kTileW * kTileH;
         Q.n_chunks = (n_slots + Q.pixels_per_chunk - 1) / Q.pixels_per_chunk;
+        Q.queue_cap = Q.n_chunks;
         // the wavefront packs the remaining depth into 16 bits; deeper paths take the (bit-identical) megakernel
         // ... and a tree too deep for the wavefront's shared-memory stacks (a device-built LBVH can be) does too
         const uint32_t bvh_depth = std::max(s->bvh.depth, s->light_bvh_depth);
@@ -1095,20 +1097,27 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             launches++;
             // ... and they say which chunks of the path stream can meet a sphere: those go first (chunk_order_kernel)
             static const bool order_allowed = [] { const char* e = std::getenv("RTW_NO_CHUNK_ORDER"); return !(e && std::atoi(e) == 1); }();
-            if (order_allowed && Q.n_chunks > 0 && Q.n_chunks < 0x3fffffffu) {
-                CU(s->d_order.reserve(2 * (size_t)Q.n_chunks + 4));
+            if (order_allowed && Q.n_chunks > 0 && Q.n_chunks < kChunkMask) {
+                // ... the last costly chunks — two per warp — go out in pieces (kChunkSubs) when a chunk is long enough to be worth cutting
+                // (RTW_SPLIT_CHUNKS_PER_WARP=0: none)
+                static const long split_per_warp = [] { const char* e = std::getenv("RTW_SPLIT_CHUNKS_PER_WARP"); return e ? std::atol(e) : 2L; }();
+                const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
+                const uint64_t warps = 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148);
+                const uint32_t split_chunks = per_chunk >= 32u * kChunkSubs && split_per_warp > 0
+                                                  ? (uint32_t)std::min<uint64_t>((uint64_t)split_per_warp * warps, Q.n_chunks) : 0u;
+                const uint32_t cap = Q.n_chunks + chunk_order_extra(split_chunks);
+                CU(s->d_order.reserve(chunk_order_words(Q.n_chunks, cap)));
                 CU(launch_chunk_order_f32(cand, s->f32.view, to_camera<float>(cam), rank, world, (cam->image_width + kTileW - 1) / kTileW,
-                                          rtw_tiles_total(cam->image_width, cam->image_height), n_slots, Q.pixels_per_chunk, Q.n_chunks,
+                                          rtw_tiles_total(cam->image_width, cam->image_height), n_slots, Q.pixels_per_chunk, Q.n_chunks, cap,
                                           sr.own_rank, sr.own_world, s->d_order.p, st));
                 Q.chunk_order = s->d_order.p;
+                Q.queue_cap = cap;
                 // ... and the background-only chunks beyond a tail of ~8 k paths per warp leave the wavefront's queue for a kernel of their own
                 // (RTW_CHEAP_TAIL_PATHS=-1: they all stay in the queue)
                 static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 8192L; }();
-                const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
-                const uint64_t tail = tail_per_warp < 0 ? 0xffffffffull
-                                                        : ((uint64_t)tail_per_warp * 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148) + per_chunk - 1) / per_chunk;
-                CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), st));
-                if (tail_per_warp >= 0) Q.queue_len = s->d_order.p + 2 * (size_t)Q.n_chunks + 2;
+                const uint64_t tail = tail_per_warp < 0 ? 0xffffffffull : ((uint64_t)tail_per_warp * warps + per_chunk - 1) / per_chunk;
+                CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, cap, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), split_chunks, st));
+                if (tail_per_warp >= 0) Q.queue_len = s->d_order.p + cap + 2 * (size_t)Q.n_chunks + 2;
                 launches += 3;
             }
         }

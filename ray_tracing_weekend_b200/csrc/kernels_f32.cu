@@ -18,9 +18,9 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_pool_general_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_general_impl<false>(P, Q, sm_count, s, info);
 }
-template <bool COUNT, bool SH, int BLOCK, int NP, bool CONN>
+template <bool COUNT, bool SH, int BLOCK, int NP, bool CONN, int LN>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH, SceneView<float>, CONN>;
+    auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH, SceneView<float>, CONN, LN>;
     int grid = 0;
     cudaError_t e = persistent_grid(kernel, BLOCK, smem, sm_count, &grid, info);
     if (e != cudaSuccess) return e;
@@ -44,8 +44,10 @@ cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, u
     size_t smem = fixed + scene;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
-    e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info)
-           : launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN>(P, Q, smem, sm_count, s, info);
+    // (all-shared scenes: one instantiation per kind of light list, LightMode)
+    e = !sh ? launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN, -1>(P, Q, smem, sm_count, s, info)
+            : (CONN || P.scene.n_light_nodes > 0) ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, 1>(P, Q, smem, sm_count, s, info)
+                                                  : launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, CONN ? 1 : 0>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     if (Q.queue_len) {                                      // the background-only chunks the queue does not hold (chunk_split_kernel)
         e = launch_render_background_f32(P, Q, Q.chunk_order, sm_count, s);
@@ -165,19 +167,21 @@ cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const C
     return cudaGetLastError();
 }
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
-                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
+                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks, uint32_t cap,
                                    uint32_t own_rank, uint32_t own_world, uint32_t* order, cudaStream_t s) {
     if (!n_chunks) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(order + 2 * (size_t)n_chunks, 0, 2 * sizeof(uint32_t), s);
+    cudaError_t e = cudaMemsetAsync(order + cap + 2 * (size_t)n_chunks, 0, 2 * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     chunk_order_kernel<0><<<(n_chunks + 255) / 256, 256, 0, s>>>(cand, scene, cam, rank, world, tiles_x, tiles_total, n_slots, pixels_per_chunk,
-                                                                 n_chunks, own_rank, own_world, order);
+                                                                 n_chunks, cap, own_rank, own_world, order);
     return cudaGetLastError();
 }
-cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s) {
-    chunk_split_kernel<0><<<(n_chunks + 255u) / 256u, 256, 0, s>>>(order, n_chunks, tail_chunks);
+cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t cap, uint32_t tail_chunks, uint32_t split_chunks, cudaStream_t s) {
+    chunk_split_kernel<0><<<(cap + 255u) / 256u, 256, 0, s>>>(order, n_chunks, cap, tail_chunks, split_chunks);
     return cudaGetLastError();
 }
+size_t chunk_order_words(uint32_t n_chunks, uint32_t cap) { return order_words(n_chunks, cap); }
+uint32_t chunk_order_extra(uint32_t split_chunks) { return order_extra(split_chunks); }
 cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s) {
     static int per_sm = 0;                                  // resident CTAs per SM (64 registers: the slow path may spill, the loop does not)
     if (per_sm == 0) {

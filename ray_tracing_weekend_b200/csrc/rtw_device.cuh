@@ -380,6 +380,15 @@ RTW_D Vec4T<float> load_light(const SceneViewSh<float>& sc, int32_t i) {
     if (sc.n_light_nodes > 0) return as_vec4(__ldg(reinterpret_cast<const float4*>(sc.lights + i)));
     return as_vec4(lds128(sc.s_lights + (uint32_t)i * 16u));
 }
+// Compile-time knowledge of whether the scene has a light BVH (the wavefront is instantiated for either case, so that neither carries the
+// other's code: the kernel sits at the instruction cache's capacity).  LN: 0 = flat light list, 1 = light BVH; a plain view decides at run time.
+template <class B, int LN> struct LightMode : B { static constexpr int kLightMode = LN; };
+template <class SC> struct light_mode { static constexpr int value = -1; };
+template <class B, int LN> struct light_mode<LightMode<B, LN>> { static constexpr int value = LN; };
+template <int LN> RTW_D Vec4T<float> load_light(const LightMode<SceneViewSh<float>, LN>& sc, int32_t i) {
+    if constexpr (LN == 1) return as_vec4(__ldg(reinterpret_cast<const float4*>(sc.lights + i)));
+    else return as_vec4(lds128(sc.s_lights + (uint32_t)i * 16u));
+}
 
 // ---------------------------------------------------------------------------------------------
 // General scenes (rtw_general.cuh): one table of list entries (entity kind + index + optional Transformed<T>) under one BVH.

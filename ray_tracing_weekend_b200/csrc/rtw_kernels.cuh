@@ -427,10 +427,41 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
         return acc / (T)sc.n_lights;
     } else {
         V3<T> nd = Mt::normalize(dir);
-        if (sc.n_light_nodes > 0) {
+        constexpr int lm = light_mode<SC>::value;
+        if (lm < 0 ? sc.n_light_nodes > 0 : lm == 1) {
             RayAux aux;
             ray_aux(Ray<float>{origin, nd}, aux);
             light_walk<COUNT>(sc, origin, nd, aux, light_walk_start(origin, nd), acc, 0xffffffffu, tl);
+        } else if constexpr (lm == 0) {
+            // (the wavefront without a light BVH) two passes: which lights does the ray's line cross — a bit per light, no branch — then the
+            // terms of those lights, in the same order and from the same operands as light_term: the sum is bit for bit the one-pass loop's.
+            // The one-pass loop enters its hit branch for one or two lanes at a time, ~12 times per warp and pass (ncu: 10 % of the kernel's
+            // samples at 1.5 active lanes); here the lanes' hits are worked off together.  C2: 156.8 -> 154.4 ms (profiles/r2_light_defer_ab.jsonl)
+            for (int base = 0; base < sc.n_lights; base += 32) {
+                const int n = min(32, sc.n_lights - base);
+                uint32_t m = 0;
+                for (int i = 0; i < n; ++i) {
+                    const Vec4T<float> s = load_light(sc, base + i);
+                    const float cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
+                    const float towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
+                    const float lx = fmaf(-towards, nd.x, cx), ly = fmaf(-towards, nd.y, cy), lz = fmaf(-towards, nd.z, cz);
+                    if (fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, s.w))) > 0.f) m |= 1u << i;
+                }
+                if (COUNT) tl.light_tests += (uint32_t)n;
+                while (m) {
+                    const int i = __ffs((int)m) - 1;
+                    m &= m - 1u;
+                    const Vec4T<float> s = load_light(sc, base + i);
+                    const float cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
+                    const float towards = fmaf(nd.x, cx, fmaf(nd.y, cy, nd.z * cz));
+                    const float distance_squared = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
+                    if (towards >= 0.f || distance_squared <= s.w) {
+                        const float cos_theta_max = Mt::sqrt_(1.f - s.w * frcp(distance_squared));
+                        const float solid_angle = 2.f * Mt::PI * (1.f - cos_theta_max);
+                        acc += frcp(solid_angle);
+                    }
+                }
+            }
         } else {
             for (int i = 0; i < sc.n_lights; ++i) light_term<COUNT>(load_light(sc, i), origin, nd, acc, tl);
         }
@@ -804,10 +835,20 @@ struct PoolParams {
     uint32_t pixels_per_chunk;      // G: pixel slots per work chunk (1 when spp is large)
     uint32_t n_chunks;
     float sample_cap;               // samples of this radiance or more set the overflow flag instead of being added (pool_sample_cap)
-    const uint32_t* chunk_order;    // [2 n_chunks + 4] or NULL: the k-th chunk handed out by the queue is chunk_order[k] & 0x3fffffff (chunk_order_kernel)
+    const uint32_t* chunk_order;    // NULL or the ordered queue (order_words(): layout at chunk_order_kernel): its k-th entry is a chunk (kChunkMask), flags
+                                    // (kChunkCheap / kChunkEnd) and, for the last costly chunks, which eighth of the chunk's paths it stands for (kChunkSubShift)
     const uint32_t* queue_len;      // device word or NULL: the queue has been split (chunk_split_kernel) — entries flagged kChunkEnd belong to render_background_kernel
+    uint32_t queue_cap;             // positions of the queue: n_chunks, or n_chunks + order_extra() when chunk_order is set
 };
 constexpr uint32_t kChunkCheap = 0x80000000u, kChunkEnd = 0x40000000u;
+// The LAST costly chunks of the queue are handed out in kChunkSubs pieces (entry bits 26..29: 0 = the whole chunk, k = piece k - 1): at 500
+// samples per pixel a chunk is one pixel's 500 paths, ~2 ms of a warp's time, and the warps would reach the end of the costly work up to one
+// chunk apart.  (Cutting EVERY chunk costs 2-3 % — profiles/r2_sample_blocks_ab.jsonl; only the end of the queue needs the fine grain.)
+constexpr uint32_t kChunkSubShift = 26u, kChunkSubs = 8u, kChunkMask = (1u << kChunkSubShift) - 1u;
+// order buffer, in words: [0, cap) the queue | [cap, cap + n) background-only chunks | [cap + n, cap + 2n) costly chunks as chunk_order_kernel
+// found them | 4 words: their two counts (the kernel's cursors, zeroed by the host), the queue's length, the chunks of render_background_kernel
+RTW_HD uint32_t order_extra(uint32_t split_chunks) { return split_chunks * (kChunkSubs - 1u); }
+RTW_HD size_t order_words(uint32_t n_chunks, uint32_t cap) { return (size_t)cap + 2u * (size_t)n_chunks + 4u; }
 
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
 // ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
@@ -1085,16 +1126,15 @@ __global__ void __launch_bounds__(kCandBlock * kCandBlock) primary_candidates_ke
 // a half-space).  Chunks with such a pixel are dealt out first, the background-only chunks last — flagged kChunkCheap, on which a warp
 // switches to "old paths first" — so the long paths end while the cheap tail of the stream still keeps every warp busy.
 // Scheduling only: paths, RNG streams and the fixed-point sums do not depend on who traces what when.
-// order[n_chunks] / order[n_chunks + 1]: the two cursors (zeroed by the host).
-// Buffer: order[0 .. n) = the queue (costly chunks from the front; chunk_split_kernel appends the background tail and end marks),
-// order[n .. 2n) = the background-only chunks, order[2n + 0 / 1] = their counts (cursors, zeroed by the host), + 2 / 3 = see chunk_split_kernel.
+// This kernel sorts the chunks into the two regions behind the queue (layout: order_words() above; the two cursors are zeroed by the host);
+// chunk_split_kernel then writes the queue itself.
 // own_world > 1 (several GPUs, one frame): this GPU only takes the chunks it OWNS — chunk c belongs to GPU (c + (c >> 4)) % own_world, a
 // diagonal 1-chunk interleave — and renders ALL samples of their pixels.  Every GPU's accumulators then cover a disjoint set of pixels and
 // the frame's one integer reduce puts them together; unlike a split of every pixel's samples, the per-pixel costs of a frame (candidate
 // lookups, partial-sum flushes, queue transactions) are paid once, not once per GPU.
 template <int UNUSED = 0>
 __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, CameraT<float> cam, uint32_t rank, uint32_t world, uint32_t tiles_x,
-                                   uint32_t tiles_total, uint32_t n_slots, uint32_t G, uint32_t n_chunks, uint32_t own_rank, uint32_t own_world,
+                                   uint32_t tiles_total, uint32_t n_slots, uint32_t G, uint32_t n_chunks, uint32_t cap, uint32_t own_rank, uint32_t own_world,
                                    uint32_t* order) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
@@ -1126,14 +1166,17 @@ __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, Camer
     const uint32_t mc = __ballot_sync(active, costly), mh = active & ~mc;
     uint32_t base_c = 0, base_h = 0;
     const uint32_t leader = (uint32_t)__ffs(active) - 1u;
+    uint32_t* cheap = order + cap;
+    uint32_t* found = cheap + n_chunks;
+    uint32_t* meta = found + n_chunks;
     if (lane == leader) {
-        if (mc) base_c = atomicAdd(order + 2u * n_chunks, (uint32_t)__popc(mc));
-        if (mh) base_h = atomicAdd(order + 2u * n_chunks + 1u, (uint32_t)__popc(mh));
+        if (mc) base_c = atomicAdd(meta, (uint32_t)__popc(mc));
+        if (mh) base_h = atomicAdd(meta + 1u, (uint32_t)__popc(mh));
     }
     base_c = __shfl_sync(active, base_c, (int)leader); base_h = __shfl_sync(active, base_h, (int)leader);
     const uint32_t lt = (1u << lane) - 1u;
-    if (costly) order[base_c + (uint32_t)__popc(mc & lt)] = c;
-    else order[n_chunks + base_h + (uint32_t)__popc(mh & lt)] = c | kChunkCheap;
+    if (costly) found[base_c + (uint32_t)__popc(mc & lt)] = c;
+    else cheap[base_h + (uint32_t)__popc(mh & lt)] = c | kChunkCheap;
 }
 
 // The background-only chunks need none of the wavefront's machinery — no path slots, no stage lists: their camera rays have an empty
@@ -1144,19 +1187,27 @@ __global__ void chunk_order_kernel(const uint4* cand, SceneView<float> sc, Camer
 // reductions per pixel (n x the fixed-point background sample; integer arithmetic, so the sum is what n separate additions give).
 // Should a plane be met after all (the classification has margins; this is the belt to its braces) the path is traced to its end
 // right here with the megakernel's path_step.
-// order[2n + 0 / 1]: number of costly / background-only chunks (the cursors of chunk_order_kernel); + 2: queue length; + 3: chunks of
-// render_background_kernel (the first that many entries of order[n ..))
+// meta[0 / 1]: number of costly / background-only chunks (the cursors of chunk_order_kernel); [2]: queue length; [3]: chunks of
+// render_background_kernel (the first that many entries of the background-only region).
+// The queue, front to back: the costly chunks whole, the last `split_chunks` of them in kChunkSubs pieces each, `tail_chunks` background-only
+// chunks, end marks.
 template <int UNUSED = 0>
-__global__ void chunk_split_kernel(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks) {
+__global__ void chunk_split_kernel(uint32_t* order, uint32_t n_chunks, uint32_t cap, uint32_t tail_chunks, uint32_t split_chunks) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;             // one thread per queue position
-    const uint32_t n_costly = order[2u * n_chunks], n_cheap = order[2u * n_chunks + 1u];
-    const uint32_t keep = min(n_cheap, tail_chunks), queue_len = n_costly + keep;
-    if (p == 0) { order[2u * n_chunks + 2u] = queue_len; order[2u * n_chunks + 3u] = n_cheap - keep; }
-    if (p >= n_chunks) return;
-    // the last `keep` background chunks follow the costly ones in the queue; every position behind them carries the end mark (the queue
-    // counter only grows: a warp that fetches one knows the queue has ended)
-    if (p >= n_costly && p < queue_len) order[p] = order[n_chunks + (n_cheap - keep) + (p - n_costly)];
-    else if (p >= queue_len) order[p] = kChunkEnd;
+    const uint32_t* cheap = order + cap;
+    const uint32_t* found = cheap + n_chunks;
+    uint32_t* meta = order + cap + 2u * (size_t)n_chunks;
+    const uint32_t n_costly = meta[0], n_cheap = meta[1];
+    const uint32_t n_split = min(n_costly, split_chunks), whole = n_costly - n_split, pieces = n_split * kChunkSubs;
+    const uint32_t keep = min(n_cheap, tail_chunks), queue_len = whole + pieces + keep;
+    if (p == 0) { meta[2] = queue_len; meta[3] = n_cheap - keep; }
+    if (p >= cap) return;
+    // every position behind the queue carries the end mark (the queue counter only grows: a warp that fetches one knows the queue has ended)
+    uint32_t e = kChunkEnd;
+    if (p < whole) e = found[p];
+    else if (p < whole + pieces) e = found[whole + (p - whole) / kChunkSubs] | (((p - whole) % kChunkSubs + 1u) << kChunkSubShift);
+    else if (p < queue_len) e = cheap[(n_cheap - keep) + (p - whole - pieces)];
+    order[p] = e;
 }
 
 template <class SC>
@@ -1177,19 +1228,20 @@ __device__ __noinline__ void background_slow_path(const SC& sc, const RenderPara
 constexpr int kBackgroundBlock = 256;
 template <int UNUSED = 0>
 __global__ void __launch_bounds__(kBackgroundBlock, 4) render_background_kernel(RenderParams<float> P, PoolParams Q, const uint32_t* order, uint32_t n_chunks) {
+    const uint32_t* cheap = order + Q.queue_cap;
     __shared__ int32_t stack_s[kStackDepth * kBackgroundBlock];              // only the slow path walks a tree
     const SceneView<float>& sc = P.scene;
     const CameraT<float>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * kBackgroundBlock + threadIdx.x) >> 5, n_warps = (gridDim.x * kBackgroundBlock) >> 5;
-    const uint32_t n_bg = __ldg(order + 2u * n_chunks + 3u);
+    const uint32_t n_bg = __ldg(cheap + 2u * (size_t)n_chunks + 3u);
     const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH), spp = cam.spp, G = Q.pixels_per_chunk;
     uint32_t npaths = 0, nrays = 0;
     Tally tl;
     V3<float> value = mk<float>(1.f, 1.f, 1.f) * cam.background + mk<float>(0.f, 0.f, 0.f);      // mult * background + res (camera.rs:473-475)
     if (P.flags & 1u) value = fix_nan(value);
     for (uint32_t k = warp; k < n_bg; k += n_warps) {
-        const uint32_t c = __ldg(order + n_chunks + k) & ~(kChunkCheap | kChunkEnd);
+        const uint32_t c = __ldg(cheap + k) & kChunkMask;
         const uint32_t q0 = c * G, npx = min(G, n_slots - q0);
         for (uint32_t pin = 0; pin < npx; ++pin) {
             const uint32_t q = q0 + pin;

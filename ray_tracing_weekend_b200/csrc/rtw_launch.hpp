@@ -27,13 +27,17 @@ float pool_sample_cap(uint32_t spp_total);
 // scratch: primary_candidates_scratch_bytes(width, height) bytes of device memory (the per-block lists of the first level)
 size_t primary_candidates_scratch_bytes(uint32_t width, uint32_t height);
 cudaError_t launch_primary_candidates_f32(const SceneView<float>& scene, const CameraT<float>& cam, void* scratch, uint4* cand, cudaStream_t s);
-// order: 2 * n_chunks + 4 words (chunk_order_kernel); own_rank / own_world: this GPU's share of the chunks (0 / 1: all of them)
+// order: chunk_order_words(n_chunks, cap) words, cap = n_chunks + chunk_order_extra(split_chunks) queue positions (layout: order_words() in
+// rtw_kernels.cuh); own_rank / own_world: this GPU's share of the chunks (0 / 1: all of them)
+size_t chunk_order_words(uint32_t n_chunks, uint32_t cap);
+uint32_t chunk_order_extra(uint32_t split_chunks);
 cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& scene, const CameraT<float>& cam, uint32_t rank, uint32_t world,
-                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks,
+                                   uint32_t tiles_x, uint32_t tiles_total, uint32_t n_slots, uint32_t pixels_per_chunk, uint32_t n_chunks, uint32_t cap,
                                    uint32_t own_rank, uint32_t own_world, uint32_t* order, cudaStream_t s);
-// after launch_chunk_order_f32 (always): append the last tail_chunks background-only chunks to the queue and mark its end; the rest of them is
-// what launch_render_background_f32 renders — with the same RenderParams / PoolParams as the wavefront (order + 2 n_chunks + 2: queue length)
-cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t tail_chunks, cudaStream_t s);
+// after launch_chunk_order_f32 (always): write the queue — the costly chunks (the last split_chunks of them in pieces), the last tail_chunks
+// background-only chunks, end marks; the rest of the background-only chunks is what launch_render_background_f32 renders — with the same
+// RenderParams / PoolParams as the wavefront (order + cap + 2 n_chunks + 2: queue length)
+cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t cap, uint32_t tail_chunks, uint32_t split_chunks, cudaStream_t s);
 cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);

@@ -119,7 +119,7 @@ __device__ unsigned long long rtw_timeline[148 * 32 * 8];
 RTW_D unsigned long long wf_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>, bool CONN = false>
+template <bool COUNT, int BLOCK, int NPW, bool SH, class SCENE = SceneView<float>, bool CONN = false, int LN = -1>
 __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams<float, SCENE> P, PoolParams Q) {
     using T = float;
     constexpr bool EXACT = false;
@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
     const uint32_t stack_depth = P.stack_depth;
     int32_t* stack_base = reinterpret_cast<int32_t*>(smem_raw);
     unsigned char* cur_p = smem_raw + sizeof(int32_t) * stack_depth * BLOCK;
-    using SC = typename std::conditional<SH, SceneViewSh<T>, SCENE>::type;
+    using SC0 = typename std::conditional<SH, SceneViewSh<T>, SCENE>::type;
+    using SC = typename std::conditional<(SH && LN >= 0), LightMode<SC0, LN>, SC0>::type;       // light BVH or not: known at compile time (LightMode)
+    static_assert(!(CONN && LN == 0), "the CONNECT stage walks the light BVH");
     SC sc;
     if constexpr (GEN) sc = P.scene;
     else {
@@ -191,24 +193,30 @@ __global__ void __launch_bounds__(BLOCK, 1) render_wavefront_kernel(RenderParams
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(P.work_counter, 1u);
                 c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= Q.n_chunks) { exhausted = true; continue; }
+                if (c >= Q.queue_cap) { exhausted = true; continue; }
+                uint32_t piece = 0;
                 if (Q.chunk_order) {
                     c = __ldg(Q.chunk_order + c);
                     // the first of the chunks that belong to render_background_kernel: the queue ends here.  (A flag in the entry the warp
                     // fetches anyway: holding the queue length in a register instead cost this kernel 2 %, profiles/r2_background_kernel_ab.jsonl)
                     if (c & kChunkEnd) { exhausted = true; continue; }
                     cheap_phase = (c & kChunkCheap) != 0u;
-                    c &= ~kChunkCheap;
+                    piece = (c >> kChunkSubShift) & (2u * kChunkSubs - 1u);
+                    c &= kChunkMask;
                 }
                 chunk_q0 = c * G;
                 uint32_t npx = min(G, n_slots - chunk_q0);
                 chunk_next = 0; chunk_end = npx * spp;
+                if (piece) {                                  // one of the last costly chunks: this entry stands for an eighth of its paths
+                    chunk_next = (piece - 1u) * chunk_end / kChunkSubs;
+                    chunk_end = piece * chunk_end / kChunkSubs;
+                }
                 if (G == 1) {       // skip padding pixels (outside the image / padding tiles) as a whole
                     uint32_t tile = (chunk_q0 >> 8) * P.world + P.rank, in = chunk_q0 & 255u;
                     uint32_t ttx, tty;
                     slot_tile(tile, P.tiles_x, &ttx, &tty);
                     uint32_t i = ttx * kTileW + (in & 15u), j = tty * kTileH + (in >> 4);
-                    if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) chunk_end = 0;
+                    if (!(tile < P.tiles_total && i < cam.width && j < cam.height)) chunk_end = chunk_next;
                 }
                 if (chunk_next == chunk_end) continue;
             }

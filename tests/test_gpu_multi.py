@@ -96,3 +96,52 @@ def test_render_rank_two_processes(rtw, simple_scene, tmp_path, precision):
     ref_sum, ref8, _ = sc.render(cam, rtw.RenderOptions(seed=SEED, precision=rtw.RTW_F64 if precision == "f64" else rtw.RTW_F32))
     sc.close()
     assert np.array_equal(ref_sum, np.load(out), equal_nan=True) and np.array_equal(ref8, np.load(out + ".rgb8.npy"))
+
+
+_OWN_CHILD = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import ray_tracing_weekend_b200 as R
+SEED = 20261018
+world, lights, cb = R.scenes.simple(SEED)
+sc = R.Scene(world, lights)
+cam = cb.with_vfov(40.).with_aspect_ratio(16 / 9).with_max_depth(50).with_image_width(192).with_image_height(108).with_samples_per_pixel(int(sys.argv[3])).build()
+s, rgb8, st = sc.render(cam, R.RenderOptions(seed=SEED, precision=R.RTW_F32))
+np.savez(sys.argv[2], rgb_sum=s, rays=st["rays"], paths=st["paths"])
+sc.close()
+'''
+
+
+@pytest.mark.parametrize("spp", [8, 160])
+def test_pixel_ownership_covers_the_frame_once(rtw, tmp_path, spp):
+    """The multi-GPU split of one frame by OWNED chunks (chunk_order_kernel), checked on ONE GPU: with RTW_DEBUG_OWN=r,n a plain render
+    produces what GPU r of n would — the owned pixels at all their samples, zeros elsewhere.  The n partial frames must be disjoint and
+    add up to the full frame bit for bit (rgb sums, ray and path counts): every chunk has exactly one owner.  (On a multi-GPU box
+    test_render_multi_two_gpus_bit_identical checks the same through rtw_render_multi.)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "own_child.py"
+    script.write_text(_OWN_CHILD)
+
+    def run(tag, own):
+        env = dict(os.environ)
+        env.pop("RTW_DEBUG_OWN", None)
+        if own:
+            env["RTW_DEBUG_OWN"] = own
+        out = tmp_path / f"{tag}.npz"
+        subprocess.run([sys.executable, str(script), root, str(out), str(spp)], env=env, check=True, timeout=300)
+        return np.load(out)
+    full = run("full", None)
+    n = 3
+    parts = [run(f"own{r}", f"{r},{n}") for r in range(n)]
+    covered = np.zeros(full["rgb_sum"].shape[:2], dtype=np.int32)
+    total = np.zeros_like(full["rgb_sum"])
+    for p in parts:
+        s = np.nan_to_num(p["rgb_sum"], nan=-1.0)            # a NaN-poisoned pixel is a rendered pixel
+        covered += (s != 0).any(axis=2)
+        total += np.where(np.isnan(p["rgb_sum"]), 0.0, p["rgb_sum"])
+    ref = full["rgb_sum"]
+    assert covered.max() <= 1                                # no pixel rendered by two owners
+    assert np.array_equal(np.isnan(ref), np.any([np.isnan(p["rgb_sum"]) for p in parts], axis=0))
+    assert np.array_equal(np.where(np.isnan(ref), 0.0, ref), total)
+    assert sum(int(p["rays"]) for p in parts) == int(full["rays"]) and sum(int(p["paths"]) for p in parts) == int(full["paths"])

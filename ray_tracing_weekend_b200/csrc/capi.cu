@@ -1114,7 +1114,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
                 Q.queue_cap = cap;
                 // ... and the background-only chunks beyond a tail of ~8 k paths per warp leave the wavefront's queue for a kernel of their own
                 // (RTW_CHEAP_TAIL_PATHS=-1: they all stay in the queue)
-                static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 8192L; }();
+                static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 4096L; }();
                 const uint64_t tail = tail_per_warp < 0 ? 0xffffffffull : ((uint64_t)tail_per_warp * warps + per_chunk - 1) / per_chunk;
                 CU(launch_chunk_split_f32(s->d_order.p, Q.n_chunks, cap, (uint32_t)std::min<uint64_t>(tail, 0xffffffffu), split_chunks, st));
                 if (tail_per_warp >= 0) Q.queue_len = s->d_order.p + cap + 2 * (size_t)Q.n_chunks + 2;

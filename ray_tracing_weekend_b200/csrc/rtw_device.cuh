@@ -94,8 +94,10 @@ static __device__ __noinline__ uint4 philox4x32_10_call(uint32_t c0, uint32_t c1
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 #endif
+// ... which is every kernel by now: one copy instead of five took 1.4 % off the wavefront's C2 frame and 6.5 % off C5's once the kernel had
+// been cut to the instruction cache's size (profiles/r2_code_size_combinations.jsonl); -DRTW_PHILOX_OUTLINE_ALL=false restores the inlined copies
 #ifndef RTW_PHILOX_OUTLINE_ALL
-#define RTW_PHILOX_OUTLINE_ALL false
+#define RTW_PHILOX_OUTLINE_ALL true
 #endif
 template <bool EXACT> struct Stream {
     uint32_t k0, k1, pixel, sample, vertex;
@@ -184,6 +186,7 @@ template <> struct M<double, true> {
     static RTW_HD double sqrt_(double a) { return sqrt(a); }
     static RTW_HD V3<double> normalize(V3<double> a) { return a / sqrt(sqlen(a)); }                  // vec.rs:84-94
     static RTW_HD double div_pi(double a) { return a / PI; }
+    static RTW_HD double div(double a, double b) { return a / b; }
     // sin/cos of phi = 2*PI*r: fixed IEEE operation sequence (Cody-Waite by pi/2 + fdlibm kernels),
     // no FMA — repeated bit for bit by any f64 implementation of the same sequence.
     static RTW_HD void sincos_2pi(double r, double* s, double* c) {
@@ -226,6 +229,12 @@ template <> struct M<float, false> {
 #endif
     }
     static RTW_HD float div_pi(float a) { return a * 0.318309886183790671538f; }
+    // a / b of the fast path: one SFU reciprocal (the IEEE quotient is ~12 instructions and a slow-path call per site)
+#ifdef RTW_IEEE_DIV
+    static RTW_HD float div(float a, float b) { return a / b; }
+#else
+    static RTW_HD float div(float a, float b) { return a * frcp(b); }
+#endif
     static RTW_HD void sincos_2pi(float r, float* s, float* c) {
 #ifdef __CUDA_ARCH__
         sincospif(2.f * r, s, c);

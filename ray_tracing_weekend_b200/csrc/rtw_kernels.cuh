@@ -172,6 +172,16 @@ RTW_D bool closest_prim_candidates(const SC& sc, const Ray<float>& r, float tmin
     int32_t best = -1;
     closest_plane<float, false, SC>(sc, r, tmin, tmax, found, best_t, best);
     const float inv_a = frcp(sqlen(r.d));
+#ifdef RTW_CAND_ROLL
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t id = k == 0 ? cand.x : (k == 1 ? cand.y : (k == 2 ? cand.z : cand.w));
+        if (id == kCandNone) break;
+        if (COUNT) tl.sphere_tests++;
+        float t;
+        if (sphere_root_fast(load_sphere(sc, (int32_t)id), r, inv_a, tmin, tmax, &t) && (!found || t < best_t)) { found = true; best_t = t; best = (int32_t)id; }
+    }
+#else
     const uint32_t ids[4] = {cand.x, cand.y, cand.z, cand.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -180,6 +190,7 @@ RTW_D bool closest_prim_candidates(const SC& sc, const Ray<float>& r, float tmin
         float t;
         if (sphere_root_fast(load_sphere(sc, (int32_t)ids[k]), r, inv_a, tmin, tmax, &t) && (!found || t < best_t)) { found = true; best_t = t; best = (int32_t)ids[k]; }
     }
+#endif
     *best_out = best;
     *t_out = best_t;
     return found;
@@ -440,6 +451,10 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
             for (int base = 0; base < sc.n_lights; base += 32) {
                 const int n = min(32, sc.n_lights - base);
                 uint32_t m = 0;
+#ifdef RTW_LIGHT_UNROLL
+                constexpr int unroll = RTW_LIGHT_UNROLL;
+#pragma unroll unroll
+#endif
                 for (int i = 0; i < n; ++i) {
                     const Vec4T<float> s = load_light(sc, base + i);
                     const float cx = s.x - origin.x, cy = s.y - origin.y, cz = s.z - origin.z;
@@ -479,7 +494,7 @@ RTW_D V3<T> sphere_random(const Vec4T<T>& s, V3<T> origin, Stream<EXACT>& rng) {
     T r1 = standard(rng);
     T r2 = standard(rng);
     const T radius_squared = W_IS_R2 ? s.w : s.w * s.w;    // the sphere path's FP32 light records carry r^2 (upload_scene)
-    T z = T(1) + r1 * (Mt::sqrt_(T(1) - radius_squared / (distance * distance)) - T(1));
+    T z = T(1) + r1 * (Mt::sqrt_(T(1) - Mt::div(radius_squared, distance * distance)) - T(1));
     T sn, cs;
     Mt::sincos_2pi(r2, &sn, &cs);
     T x = cs * Mt::sqrt_(T(1) - z * z);
@@ -495,6 +510,40 @@ enum VertexKind : uint32_t { V_MISS = 0, V_ABSORB = 1, V_SPECULAR = 2, V_DIFFUSE
 template <class T, bool EXACT, class SC>
 RTW_D V3<T> lambertian_sample(const SC& sc, const Hit<T>& h, Stream<EXACT>& rng, T* cos_v, T* scattering_pdf) {
     using Mt = M<T, EXACT>;
+#ifndef RTW_LAMB_MERGE
+#define RTW_LAMB_MERGE 0            // the light_mode the merged form is compiled for
+#endif
+    if constexpr (!EXACT && light_mode<SC>::value == RTW_LAMB_MERGE) {
+        // (the wavefront without a light BVH) the two halves of the mixture share ONE copy of the frame, the sincos and the transform — the
+        // kernel is bound by instruction fetch; each half computes what it computed before, from the same uniforms in the same order, so the
+        // direction is bit for bit the two-copy form's.  C2 143.9 -> 133.0 ms; the light-BVH kernel is slower with it (C5 50.8 -> 52.3)
+        V3<T> axis, dir;
+        T phi, rad, z;
+        if (standard(rng) < T(0.5)) {                       // Sphere::random (sphere.rs:114-127) of a light picked uniformly
+            const uint32_t idx = uindex(rng, (uint32_t)sc.n_lights);
+            const Vec4T<T> s = load_light(sc, (int32_t)idx);
+            axis = mk<T>(s.x - h.p.x, s.y - h.p.y, s.z - h.p.z);
+            const T distance = Mt::sqrt_(sqlen(axis));
+            const T r1 = standard(rng);
+            phi = standard(rng);
+            z = T(1) + r1 * (Mt::sqrt_(T(1) - Mt::div(s.w, distance * distance)) - T(1));      // s.w = r^2 on the fast path
+            rad = Mt::sqrt_(T(1) - z * z);
+        } else {                                            // CosineWeightedHemisphere, utils.rs:146-161
+            phi = standard(rng);
+            const T r2 = standard(rng);
+            axis = h.normal;
+            rad = Mt::sqrt_(r2);
+            z = Mt::sqrt_(T(1) - r2);
+        }
+        Onb<T, EXACT> uvw(axis);
+        T sn, cs;
+        Mt::sincos_2pi(phi, &sn, &cs);
+        dir = uvw.transform(mk<T>(cs * rad, sn * rad, z));
+        V3<T> nd = Mt::normalize(dir);
+        *scattering_pdf = Mt::max_(Mt::div_pi(dot(h.normal, nd)), T(0));
+        *cos_v = *scattering_pdf;
+        return dir;
+    }
     Onb<T, EXACT> uvw(h.normal);                            // CosinePdf::new, pdf.rs:39-43
     V3<T> dir;
     if (standard(rng) < T(0.5)) {                           // MixturePdf::generate, pdf.rs:94-100 (pdf1 = lights)
@@ -562,13 +611,13 @@ RTW_D uint32_t shade(const SC& sc, const Ray<T>& r, const Hit<T>& h, Stream<EXAC
     }
     if (kind == DIELECTRIC) {                                   // material.rs:457-488
         if (COUNT) tl.dielectric++;
-        T ratio = h.front_face ? T(1) / h.param : h.param;
+        T ratio = h.front_face ? Mt::div(T(1), h.param) : h.param;
         V3<T> unit = Mt::normalize(r.d);
         T cos_theta = Mt::min_(dot(unit, -h.normal), T(1));
         T sin_theta = Mt::sqrt_(T(1) - cos_theta * cos_theta);
         bool do_reflect = ratio * sin_theta > T(1);
         if (!do_reflect) {
-            T r0 = (T(1) - ratio) / (T(1) + ratio);             // reflectance, material.rs:450-454
+            T r0 = Mt::div(T(1) - ratio, T(1) + ratio);          // reflectance, material.rs:450-454
             r0 = r0 * r0;
             T om = T(1) - cos_theta;
             T p5 = ((om * om) * (om * om)) * om;

@@ -1102,7 +1102,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
                 // (RTW_SPLIT_CHUNKS_PER_WARP=0: none)
                 static const long split_per_warp = [] { const char* e = std::getenv("RTW_SPLIT_CHUNKS_PER_WARP"); return e ? std::atol(e) : 2L; }();
                 const uint64_t per_chunk = (uint64_t)Q.pixels_per_chunk * (spp_here ? spp_here : 1u);
-                const uint64_t warps = 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148);
+                const uint64_t warps = 24u * (uint64_t)(s->sm_count > 0 ? s->sm_count : 148);      // (20 per SM without a light BVH: the sizes below are not that fine)
                 const uint32_t split_chunks = per_chunk >= 32u * kChunkSubs && split_per_warp > 0
                                                   ? (uint32_t)std::min<uint64_t>((uint64_t)split_per_warp * warps, Q.n_chunks) : 0u;
                 const uint32_t cap = Q.n_chunks + chunk_order_extra(split_chunks);
@@ -1112,7 +1112,7 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
                                           sr.own_rank, sr.own_world, s->d_order.p, st));
                 Q.chunk_order = s->d_order.p;
                 Q.queue_cap = cap;
-                // ... and the background-only chunks beyond a tail of ~8 k paths per warp leave the wavefront's queue for a kernel of their own
+                // ... and the background-only chunks beyond a tail of ~4 k paths per warp leave the wavefront's queue for a kernel of their own
                 // (RTW_CHEAP_TAIL_PATHS=-1: they all stay in the queue)
                 static const long tail_per_warp = [] { const char* e = std::getenv("RTW_CHEAP_TAIL_PATHS"); return e ? std::atol(e) : 4096L; }();
                 const uint64_t tail = tail_per_warp < 0 ? 0xffffffffull : ((uint64_t)tail_per_warp * warps + per_chunk - 1) / per_chunk;

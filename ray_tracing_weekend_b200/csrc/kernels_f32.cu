@@ -9,6 +9,7 @@ namespace rtw {
 // wavefront launch shape: ONE CTA per SM (its warps never synchronise after the scene is staged), 24 warps,
 // 96 path slots per warp -> ~216 KB of shared memory for `simple`
 constexpr int kWfBlock = 768, kWfSlotsPerWarp = 96;
+constexpr int kWfBlockFlat = 640, kWfSlotsPerWarpFlat = 112;       // scenes without a light BVH
 }
 namespace rtw {
 RTW_DEFINE_LAUNCHERS(f32, float, false)
@@ -27,8 +28,11 @@ cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size
     kernel<<<grid, BLOCK, smem, s>>>(P, Q);
     return cudaGetLastError();
 }
-template <bool COUNT, int BLOCK, int NP, bool CONN>
+// LNS: what the all-shared kernel of this shape knows about the scene's lights at compile time (LightMode: 0 = flat list, 1 = light BVH)
+template <bool COUNT, int BLOCK, int NP, bool CONN, int LNS = (CONN ? 1 : 0)>
 cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, int sm_count, cudaStream_t s, LaunchInfo* info) {
+    static_assert(!(CONN && LNS != 1), "the CONNECT stage walks the light BVH");
+    if ((P.scene.n_light_nodes > 0) != (LNS == 1)) return cudaErrorInvalidConfiguration;
     // shared memory: per-thread traversal stacks + per-warp path slots; what is left (of 227 KB) stages the scene.
     // A walk pushes at most one entry per inner level below the stop code, so `bvh_depth` entries always suffice; two spare
     // entries are kept unless the tree is so deep that the stacks would not fit next to the path slots.
@@ -45,9 +49,8 @@ cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, u
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
     // (all-shared scenes: one instantiation per kind of light list, LightMode)
-    e = !sh ? launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN, -1>(P, Q, smem, sm_count, s, info)
-            : (CONN || P.scene.n_light_nodes > 0) ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, 1>(P, Q, smem, sm_count, s, info)
-                                                  : launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, CONN ? 1 : 0>(P, Q, smem, sm_count, s, info);
+    e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, LNS>(P, Q, smem, sm_count, s, info)
+           : launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN, -1>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     if (Q.queue_len) {                                      // the background-only chunks the queue does not hold (chunk_split_kernel)
         e = launch_render_background_f32(P, Q, Q.chunk_order, sm_count, s);
@@ -67,7 +70,7 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #ifdef RTW_WF_SWEEP
     // tuning build only (nvcc -DRTW_WF_SWEEP): launch shape from the environment
     const char* e = std::getenv("RTW_WF_SHAPE");
-    int shape = e ? std::atoi(e) : 0;
+    int shape = e && P.scene.n_light_nodes == 0 ? std::atoi(e) : 0;
     if (shape == 1) return launch_render_wavefront_shape<COUNT, 896, 64, false>(P, Q, bvh_depth, sm_count, s, info);
     if (shape == 2) return launch_render_wavefront_shape<COUNT, 832, 80, false>(P, Q, bvh_depth, sm_count, s, info);
     if (shape == 3) return launch_render_wavefront_shape<COUNT, 640, 112, false>(P, Q, bvh_depth, sm_count, s, info);
@@ -88,7 +91,10 @@ cudaError_t launch_render_wavefront_impl(RenderParams<float> P, PoolParams Q, ui
 #endif
         return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarpConnect, true>(P, Q, bvh_depth, sm_count, s, info);
     }
-    return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp, false>(P, Q, bvh_depth, sm_count, s, info);
+    // flat light list: 20 warps x 112 slots (swept again once the kernel fitted the instruction cache: 768x96 133.4 ms, 640x112 131.4, 576x128 134.4,
+    // 640x104 134.1, 832x80 143.0 on C2; C1 +2.9 %); the light-BVH kernel stays at 24 x 96 (C5: 50.7 ms against 52.2 / 54.3 at 640x112 / 576x128)
+    if (P.scene.n_light_nodes == 0) return launch_render_wavefront_shape<COUNT, kWfBlockFlat, kWfSlotsPerWarpFlat, false, 0>(P, Q, bvh_depth, sm_count, s, info);
+    return launch_render_wavefront_shape<COUNT, kWfBlock, kWfSlotsPerWarp, false, 1>(P, Q, bvh_depth, sm_count, s, info);
 }
 // general scenes: the same warp-private wavefront and launch shape, scene tables in global memory.  Swept on cornell_box while the kernel
 // was bound by instruction fetch: 512x96 460 ms, 512x128 450, 576x96 440, 640x96 408, 704x96 386, 768x96 364; again after its code
@@ -144,8 +150,8 @@ cudaError_t launch_peer_reduce_resolve_f32(const PeerBlocks& B, uint32_t slot_be
 }
 // deepest BVH the default wavefront shape can traverse: its per-thread stacks share the CTA's shared memory with the path slots
 uint32_t wavefront_max_bvh_depth() {
-    const size_t limit = 226 * 1024, state = wavefront_state_bytes<kWfBlock, kWfSlotsPerWarp>();
-    size_t entries = (limit - 1024 - state) / (sizeof(int32_t) * kWfBlock);
+    const size_t limit = 226 * 1024, state = wavefront_state_bytes<kWfBlock, kWfSlotsPerWarp>(), state_flat = wavefront_state_bytes<kWfBlockFlat, kWfSlotsPerWarpFlat>();
+    size_t entries = std::min((limit - 1024 - state) / (sizeof(int32_t) * kWfBlock), (limit - 1024 - state_flat) / (sizeof(int32_t) * kWfBlockFlat));
     return (uint32_t)std::min<size_t>(entries, kStackDepth - 2);
 }
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {

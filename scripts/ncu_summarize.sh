@@ -1,7 +1,7 @@
 #!/bin/bash
 # turn the round-2 capture of the headline kernel into the text files profiles/ keeps (run here, not on the GPU box)
 REP=${1:-gpurun_out/r2_prof_wavefront_bench.ncu-rep}
-K=render_wavefront_kernelILb0ELi768ELi96ELb1ENS_9SceneViewIfEELb0E
+K=render_wavefront_kernelILb0ELi640ELi112ELb1ENS_9SceneViewIfEELb0ELi0E
 ncu -i $REP --page details > profiles/r2_ncu_details_render_wavefront_kernel.txt
 (echo "# ncu --set full of render_wavefront_kernel inside \`python bench.py\` (BASELINE C2, 500 spp) at the round's last commit; per-line roll-up by scripts/ncu_lines.py"; python scripts/ncu_lines.py $REP $K --top 60 | cut -c1-220) > profiles/r2_ncu_lines_render_wavefront_kernel.txt
 ncu -i $REP --page raw --csv | python3 -c "

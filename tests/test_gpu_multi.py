@@ -112,7 +112,7 @@ sc.close()
 '''
 
 
-@pytest.mark.parametrize("spp", [8, 160])
+@pytest.mark.parametrize("spp", [8, 160, 320])     # 320: a chunk is one pixel and the last chunks of the queue go out in eighths (chunk_split_kernel)
 def test_pixel_ownership_covers_the_frame_once(rtw, tmp_path, spp):
     """The multi-GPU split of one frame by OWNED chunks (chunk_order_kernel), checked on ONE GPU: with RTW_DEBUG_OWN=r,n a plain render
     produces what GPU r of n would — the owned pixels at all their samples, zeros elsewhere.  The n partial frames must be disjoint and

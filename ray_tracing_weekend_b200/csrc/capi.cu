@@ -187,6 +187,8 @@ struct rtw_scene {
     DevBuf<double> d_in2, d_in3; DevBuf<uint32_t> d_u3, d_u4;          // rtw_shade_batch inputs
     DevBuf<double> d_in0, d_in1, d_out0, d_out1, d_out2, d_out3, d_out4; DevBuf<uint32_t> d_u0, d_u1, d_u2, d_k; DevBuf<int32_t> d_prim;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side_stream = nullptr;                              // render_background_kernel runs here, next to the wavefront kernel (set_background_side_stream)
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
     LaunchInfo last_launch;
     uint32_t last_launches = 1;
     uint32_t light_bvh_depth = 0;
@@ -787,6 +789,8 @@ int rtw_scene_create(const rtw_sphere* spheres, const uint32_t* sphere_material,
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int), nullptr);
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters), nullptr);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev_side[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     bool on_device = false;
     int rc = RTW_OK;
@@ -893,6 +897,8 @@ int rtw_scene_create_general(const rtw_scene_desc* d, rtw_scene** out) {
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_work), sizeof(unsigned int), nullptr);
     if (e == cudaSuccess) e = cached_malloc(reinterpret_cast<void**>(&s->d_counters), sizeof(DeviceCounters), nullptr);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev_side[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { fail(RTW_E_CUDA, cudaGetErrorString(e)); return bail(RTW_E_CUDA); }
     e = s->d_panic.reserve(1);
     if (e == cudaSuccess) e = cudaMemset(s->d_panic.p, 0, sizeof(uint32_t));
@@ -916,6 +922,8 @@ void rtw_scene_destroy(rtw_scene* s) {
     s->d_in0.release(); s->d_in1.release(); s->d_out0.release(); s->d_out1.release(); s->d_out2.release(); s->d_out3.release();
     s->d_out4.release(); s->d_u0.release(); s->d_u1.release(); s->d_u2.release(); s->d_k.release(); s->d_prim.release();
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : s->ev_side) if (ev) cudaEventDestroy(ev);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     delete s;
 }
 
@@ -1127,7 +1135,13 @@ int render_device_impl(rtw_scene* s, const rtw_camera* cam, const rtw_opts* o, u
             return wavefront ? launch_render_wavefront_f32(P, Q, bvh_depth, count, sms, str, info)
                              : launch_render_pool_f32(P, Q, count, sms, str, info);
         };
+        // RTW_SIDE_STREAM=1: render_background_kernel on a second stream NEXT TO the wavefront kernel (its CTAs fit beside the wavefront's one CTA per
+        // SM).  Measured and not the default: the frame's 5.4 ms of background work overlap, but the wavefront kernel loses more than that to the
+        // guest in its instruction cache and issue slots — C2 131.0 -> 144.0 ms, one of eight GPUs' share 17.02 -> 18.40 (profiles/r2_side_stream_ab.jsonl)
+        static const bool side_allowed = [] { const char* e = std::getenv("RTW_SIDE_STREAM"); return e && std::atoi(e) == 1; }();
+        if (side_allowed) set_background_side_stream(s->side_stream, s->ev_side[0], s->ev_side[1]);
         rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch, sr);
+        set_background_side_stream(nullptr, nullptr, nullptr);
         launches += 1;
     } else if (o->precision == RTW_F32) rc = render_tiles_t<float>(s, s->f32, cam, o, rank, world, (float*)d_tiles, st, launch_render_f32);
     else rc = render_tiles_t<double>(s, s->f64, cam, o, rank, world, (double*)d_tiles, st, launch_render_f64);

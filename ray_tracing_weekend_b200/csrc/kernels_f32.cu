@@ -19,6 +19,9 @@ cudaError_t launch_render_pool_f32(RenderParams<float> P, PoolParams Q, bool cou
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info) {
     return count ? launch_render_pool_general_impl<true>(P, Q, sm_count, s, info) : launch_render_pool_general_impl<false>(P, Q, sm_count, s, info);
 }
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static thread_local SideStream g_side;
+void set_background_side_stream(cudaStream_t stream, cudaEvent_t fork, cudaEvent_t join) { g_side.stream = stream; g_side.fork = fork; g_side.join = join; }
 template <bool COUNT, bool SH, int BLOCK, int NP, bool CONN, int LN>
 cudaError_t launch_render_wavefront_sh(RenderParams<float> P, PoolParams Q, size_t smem, int sm_count, cudaStream_t s, LaunchInfo* info) {
     auto kernel = render_wavefront_kernel<COUNT, BLOCK, NP, SH, SceneView<float>, CONN, LN>;
@@ -48,13 +51,31 @@ cudaError_t launch_render_wavefront_shape(RenderParams<float> P, PoolParams Q, u
     size_t smem = fixed + scene;
     cudaError_t e = pool_clear(P, Q, s);
     if (e != cudaSuccess) return e;
+    // render_background_kernel runs on the caller's second stream when there is one (set_background_side_stream): forked HERE — everything it reads
+    // has been written, the accumulators are clear — but launched behind the wavefront kernel, so that its small CTAs fill what the wavefront's one
+    // CTA per SM leaves free; joined before the finalize
+    const SideStream side = g_side;
+    const bool fork = Q.queue_len && side.stream && side.fork && side.join;
+    if (fork) {
+        e = cudaEventRecord(side.fork, s);
+        if (e != cudaSuccess) return e;
+    }
     // (all-shared scenes: one instantiation per kind of light list, LightMode)
     e = sh ? launch_render_wavefront_sh<COUNT, true, BLOCK, NP, CONN, LNS>(P, Q, smem, sm_count, s, info)
            : launch_render_wavefront_sh<COUNT, false, BLOCK, NP, CONN, -1>(P, Q, smem, sm_count, s, info);
     if (e != cudaSuccess) return e;
     if (Q.queue_len) {                                      // the background-only chunks the queue does not hold (chunk_split_kernel)
-        e = launch_render_background_f32(P, Q, Q.chunk_order, sm_count, s);
+        if (fork) {
+            e = cudaStreamWaitEvent(side.stream, side.fork, 0);
+            if (e != cudaSuccess) return e;
+        }
+        e = launch_render_background_f32(P, Q, Q.chunk_order, sm_count, fork ? side.stream : s);
         if (e != cudaSuccess) return e;
+        if (fork) {
+            e = cudaEventRecord(side.join, side.stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side.join, 0);
+            if (e != cudaSuccess) return e;
+        }
     }
     return pool_finalize(P, Q, s);
 }
@@ -195,7 +216,7 @@ cudaError_t launch_render_background_f32(const RenderParams<float>& P, const Poo
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_background_kernel<0>, kBackgroundBlock, 0) != cudaSuccess || n < 1) n = 2;
         per_sm = n;
     }
-    render_background_kernel<0><<<(sm_count > 0 ? sm_count : 148) * per_sm, kBackgroundBlock, 0, s>>>(P, Q, order, Q.n_chunks);
+    render_background_kernel<0><<<(sm_count > 0 ? sm_count : 148) * per_sm, kBackgroundBlock, 0, s>>>(P, Q, const_cast<uint32_t*>(order), Q.n_chunks);
     return cudaGetLastError();
 }
 // samples of this radiance or more set a pixel's overflow flag instead of being added: spp of them stay below 2^60 fixed-point units

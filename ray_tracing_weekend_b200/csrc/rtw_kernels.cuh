@@ -895,9 +895,9 @@ constexpr uint32_t kChunkCheap = 0x80000000u, kChunkEnd = 0x40000000u;
 // chunk apart.  (Cutting EVERY chunk costs 2-3 % — profiles/r2_sample_blocks_ab.jsonl; only the end of the queue needs the fine grain.)
 constexpr uint32_t kChunkSubShift = 26u, kChunkSubs = 8u, kChunkMask = (1u << kChunkSubShift) - 1u;
 // order buffer, in words: [0, cap) the queue | [cap, cap + n) background-only chunks | [cap + n, cap + 2n) costly chunks as chunk_order_kernel
-// found them | 4 words: their two counts (the kernel's cursors, zeroed by the host), the queue's length, the chunks of render_background_kernel
+// found them | 8 words, 5 used: their two counts (the kernel's cursors, zeroed by the host), the queue's length, the chunks of render_background_kernel, its cursor
 RTW_HD uint32_t order_extra(uint32_t split_chunks) { return split_chunks * (kChunkSubs - 1u); }
-RTW_HD size_t order_words(uint32_t n_chunks, uint32_t cap) { return (size_t)cap + 2u * (size_t)n_chunks + 4u; }
+RTW_HD size_t order_words(uint32_t n_chunks, uint32_t cap) { return (size_t)cap + 2u * (size_t)n_chunks + 8u; }
 
 // poison word: six flags (NaN r/g/b, overflow r/g/b), each the low bit of its own 4-bit field, so that the words of up to 15
 // ranks can be SUMMED by a reduce without one flag carrying into the next (a flag is set iff its field is non-zero)
@@ -1249,7 +1249,7 @@ __global__ void chunk_split_kernel(uint32_t* order, uint32_t n_chunks, uint32_t 
     const uint32_t n_costly = meta[0], n_cheap = meta[1];
     const uint32_t n_split = min(n_costly, split_chunks), whole = n_costly - n_split, pieces = n_split * kChunkSubs;
     const uint32_t keep = min(n_cheap, tail_chunks), queue_len = whole + pieces + keep;
-    if (p == 0) { meta[2] = queue_len; meta[3] = n_cheap - keep; }
+    if (p == 0) { meta[2] = queue_len; meta[3] = n_cheap - keep; meta[4] = 0u; }
     if (p >= cap) return;
     // every position behind the queue carries the end mark (the queue counter only grows: a warp that fetches one knows the queue has ended)
     uint32_t e = kChunkEnd;
@@ -1274,22 +1274,28 @@ __device__ __noinline__ void background_slow_path(const SC& sc, const RenderPara
     if (bad) atomicOr(Q.poison + q, bad);
 }
 
-constexpr int kBackgroundBlock = 256;
+// Launch shape: CTAs of 128 threads, 64 registers, no shared memory, chunks pulled from a cursor (+0.4 % on C2 over 256-thread CTAs striding over
+// the chunks).  Small enough to sit NEXT TO the wavefront's one CTA per SM — which was tried (RTW_SIDE_STREAM=1, capi.cu) and costs the wavefront
+// kernel more than the overlap returns.
+constexpr int kBackgroundBlock = 128;
 template <int UNUSED = 0>
-__global__ void __launch_bounds__(kBackgroundBlock, 4) render_background_kernel(RenderParams<float> P, PoolParams Q, const uint32_t* order, uint32_t n_chunks) {
+__global__ void __launch_bounds__(kBackgroundBlock, 8) render_background_kernel(RenderParams<float> P, PoolParams Q, uint32_t* order, uint32_t n_chunks) {
     const uint32_t* cheap = order + Q.queue_cap;
-    __shared__ int32_t stack_s[kStackDepth * kBackgroundBlock];              // only the slow path walks a tree
+    uint32_t* meta = order + Q.queue_cap + 2u * (size_t)n_chunks;
     const SceneView<float>& sc = P.scene;
     const CameraT<float>& cam = P.cam;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * kBackgroundBlock + threadIdx.x) >> 5, n_warps = (gridDim.x * kBackgroundBlock) >> 5;
-    const uint32_t n_bg = __ldg(cheap + 2u * (size_t)n_chunks + 3u);
+    const uint32_t n_bg = __ldg(meta + 3);
     const uint32_t n_slots = P.n_local_tiles * (kTileW * kTileH), spp = cam.spp, G = Q.pixels_per_chunk;
     uint32_t npaths = 0, nrays = 0;
     Tally tl;
     V3<float> value = mk<float>(1.f, 1.f, 1.f) * cam.background + mk<float>(0.f, 0.f, 0.f);      // mult * background + res (camera.rs:473-475)
     if (P.flags & 1u) value = fix_nan(value);
-    for (uint32_t k = warp; k < n_bg; k += n_warps) {
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(meta + 4, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_bg) break;
         const uint32_t c = __ldg(cheap + k) & kChunkMask;
         const uint32_t q0 = c * G, npx = min(G, n_slots - q0);
         for (uint32_t pin = 0; pin < npx; ++pin) {
@@ -1311,7 +1317,10 @@ __global__ void __launch_bounds__(kBackgroundBlock, 4) render_background_kernel(
                 closest_plane<float, false, SceneView<float>>(sc, r, P.tmin, M<float, false>::inf(), found, best_t, best);
                 npaths++;
                 if (!found) { miss++; nrays++; }
-                else background_slow_path(sc, P, Q, q, pixel, i, j, sample, stack_s + threadIdx.x, kBackgroundBlock, nrays, tl);
+                else {                                        // only this path walks a tree: its stack lives in local memory
+                    int32_t stack_l[kStackDepth];
+                    background_slow_path(sc, P, Q, q, pixel, i, j, sample, stack_l, 1, nrays, tl);
+                }
             }
             miss = warp_sum(miss);
             if (lane == 0 && miss) {

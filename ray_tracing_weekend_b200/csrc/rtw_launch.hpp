@@ -38,6 +38,9 @@ cudaError_t launch_chunk_order_f32(const uint4* cand, const SceneView<float>& sc
 // background-only chunks, end marks; the rest of the background-only chunks is what launch_render_background_f32 renders — with the same
 // RenderParams / PoolParams as the wavefront (order + cap + 2 n_chunks + 2: queue length)
 cudaError_t launch_chunk_split_f32(uint32_t* order, uint32_t n_chunks, uint32_t cap, uint32_t tail_chunks, uint32_t split_chunks, cudaStream_t s);
+// the calling thread's next wavefront launches run render_background_kernel on `stream`, forked from / joined to the render stream with the two
+// events (all NULL: on the render stream itself, after the wavefront kernel)
+void set_background_side_stream(cudaStream_t stream, cudaEvent_t fork, cudaEvent_t join);
 cudaError_t launch_render_background_f32(const RenderParams<float>& P, const PoolParams& Q, const uint32_t* order, int sm_count, cudaStream_t s);
 cudaError_t launch_render_pool_general_f32(RenderParams<float, SceneViewG<float>> P, PoolParams Q, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);
 cudaError_t launch_render_wavefront_f32(RenderParams<float> P, PoolParams Q, uint32_t bvh_depth, bool count, int sm_count, cudaStream_t s, LaunchInfo* info);

@@ -172,7 +172,7 @@ RTW_D bool closest_prim_candidates(const SC& sc, const Ray<float>& r, float tmin
     int32_t best = -1;
     closest_plane<float, false, SC>(sc, r, tmin, tmax, found, best_t, best);
     const float inv_a = frcp(sqlen(r.d));
-#ifdef RTW_CAND_ROLL
+#ifdef RTW_CAND_ROLL                       // tuning build (scripts/variant_bench.py): one inlined sphere test instead of four; slower, profiles/r2_code_size_combinations.jsonl
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const uint32_t id = k == 0 ? cand.x : (k == 1 ? cand.y : (k == 2 ? cand.z : cand.w));
@@ -451,7 +451,7 @@ RTW_D T lights_pdf_value(const SC& sc, V3<T> origin, V3<T> dir, Tally& tl) {
             for (int base = 0; base < sc.n_lights; base += 32) {
                 const int n = min(32, sc.n_lights - base);
                 uint32_t m = 0;
-#ifdef RTW_LIGHT_UNROLL
+#ifdef RTW_LIGHT_UNROLL                    // tuning build: unroll factor of the first pass (the compiler's own choice is 4); measured, ibid.
                 constexpr int unroll = RTW_LIGHT_UNROLL;
 #pragma unroll unroll
 #endif

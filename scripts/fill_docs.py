@@ -20,7 +20,7 @@ for n in (2, 4, 8):
     if os.path.exists(f):
         m=json.loads(open(f).read())
         vals.update({f'N{n}_MRAYS': f"{m['value']:,.0f}".replace(',',' '), f'N{n}_MS': f"{m['ms_per_step']:.2f}", f'N{n}_KMS': f"{m['kernel_ms_per_step']:.2f}",
-                     f'N{n}_X': f"{d['ms_per_step']/m['ms_per_step']:.2f}", f'N{n}_E2E': f"{m['e2e']['value']:,.0f}".replace(',',' '),
+                     f'N{n}_X': f"{float(extra.get('SCALING_N1_MS', d['ms_per_step']))/m['ms_per_step']:.2f}", f'N{n}_E2E': f"{m['e2e']['value']:,.0f}".replace(',',' '),
                      f'N{n}_C3': f"{m['c3']['ms_per_step']:.0f}" if m.get('c3') else '—'})
     else:
         vals.update({f'N{n}_{k}': 'not measured' for k in ('MRAYS','MS','KMS','X','E2E','C3')})
